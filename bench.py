@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py — re-ranked (query, doc) pairs/s of the Fast-Forward hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ffx|reference]
+
+One "step" = one pass of the hot path (gather passage vectors by id -> q.p dots -> per-doc
+MAXP -> interpolate with the lexical score -> per-query top-k) over one batch of synthetic
+input: BASELINE.json configs[2], "MS MARCO-doc scale Mode.MAXP: 3.2M docs / ~20M passages
+ragged, 5193 queries x 5000 candidates" (61 GB of fp32 vectors resident in HBM; 499 GB of
+algorithmic traffic per step, so nothing is L2-resident between steps).
+
+  value     whole-job pairs/s with the integer-coded inputs already in HBM (CUDA events on the
+            launching stream, max over ranks)
+  e2e       the same metric through the host-buffer C-ABI call (ffx_rerank_host): pinned host
+            inputs -> H2D -> kernel -> D2H of the ranked lists, all inside the timed region
+  roofline  algorithmic bytes per launch / mean launch time of the fused kernel vs the measured
+            HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the numpy restatement of the reference's algorithm (oracle/, "port") on a bounded
+            sample of the same workload, one process per host core
+
+`--impl reference` times that CPU port alone (rank 0 only) and prints the same line shape.
+Multi-GPU (torchrun): queries shard across ranks, the index is replicated, no data-path
+collective; scaling is weak (every rank re-ranks its own 5193 x 5000 pairs).
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "fast-forward-indexes_b200")
+sys.path.insert(0, PKG)
+
+METRIC = "re-ranked (query,doc) pairs/sec, MAXP k=5000"
+DIM = 768
+MODE_MAXP = 2
+
+WORKLOADS = {
+    # name: (n_docs, mean passages/doc, queries, candidates/query, cut k)
+    "c3_msmarco_doc_maxp": dict(n_docs=3_200_000, mean_psg=6.25, nq=5193, cands=5000, k=5000),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ffx", choices=["ffx", "reference"])
+    ap.add_argument("--workload", default="c3_msmarco_doc_maxp", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("FFX_BENCH_SCALE", "1")),
+                    help="shrink docs and queries (debug only; the line says so)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--alpha", type=float, default=0.1)
+    return ap.parse_args()
+
+
+def doc_lengths(n_docs, mean_psg, seed=0):
+    """Clipped geometric passages/doc, mean ~6.25, min 1, max 64."""
+    rng = np.random.default_rng(seed)
+    return np.clip(rng.geometric(1.0 / mean_psg, n_docs), 1, 64).astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the numpy port of the reference algorithm, one process per core
+# ------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_worker(args):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ff_oracle as fo
+
+    q_lo, q_hi, cands, k, alpha = args
+    vec, off, qv, cand, lex = _CPU["vec"], _CPU["off"], _CPU["qv"], _CPU["cand"], _CPU["lex"]
+    rows = _CPU["rows"]
+    sl = slice(q_lo * cands, q_hi * cands)
+    pair_q = np.repeat(np.arange(q_lo, q_hi), cands)
+    # index/base.py:445-459 batches queries; 2 queries/batch keeps temporaries ~200 MB
+    ff = fo.score_pairs(vec, off, rows, pair_q, cand[sl], qv, fo.MODE_MAXP, chunk_pairs=2 * cands)
+    it = fo.interpolate_f32(lex[sl], ff, alpha)
+    q_off = np.arange(q_hi - q_lo + 1) * cands
+    s, p = fo.topk_per_query(q_off, it, k)
+    return float(s[0, 0])
+
+
+def cpu_port_run(wl, alpha, q_per_core=4, cores=None):
+    """Times the numpy port on `cores` processes x `q_per_core` queries of the workload's
+    shape over a scaled-down index (cost per pair does not depend on the index size)."""
+    import multiprocessing as mp
+
+    cores = cores or os.cpu_count() or 1
+    cores = min(cores, 64)
+    n_docs = 40_000
+    cnt = doc_lengths(n_docs, wl["mean_psg"], seed=1)
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    rng = np.random.default_rng(2)
+    _CPU["vec"] = rng.standard_normal((int(off[-1]), DIM), dtype=np.float32)
+    _CPU["off"] = off
+    _CPU["rows"] = np.arange(off[-1], dtype=np.int64)
+    nq = cores * q_per_core
+    cands = wl["cands"]
+    _CPU["qv"] = rng.standard_normal((nq, DIM), dtype=np.float32)
+    _CPU["cand"] = np.concatenate([rng.choice(n_docs, cands, replace=False) for _ in range(nq)])
+    _CPU["lex"] = rng.uniform(0, 20, nq * cands).astype(np.float32)
+    jobs = [(c * q_per_core, (c + 1) * q_per_core, cands, wl["k"], alpha) for c in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(0, 1, cands, wl["k"], alpha)] * cores)  # warm the workers
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+    pairs = nq * cands
+    sample = (f"{nq} queries x {cands} candidates MAXP over a {n_docs}-doc / {int(off[-1])}-passage "
+              f"768-d fp32 host index, numpy port of index/base.py:279-314 + ranking.py:319,279-291, "
+              f"{cores} processes x {q_per_core} queries")
+    _CPU.clear()
+    return pairs / dt, dt, cores, sample, pairs
+
+
+# ------------------------------------------------------------------------------------------
+def clocks_start():
+    f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    try:
+        p = subprocess.Popen(
+            ["nvidia-smi", "--query-gpu=index,clocks.sm,clocks.max.sm,power.draw,"
+             "clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+            stdout=f, stderr=subprocess.DEVNULL)
+    except OSError:
+        return None, f.name
+    return p, f.name
+
+
+def clocks_stop(p, path, device_index):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    if p is not None:
+        p.terminate()
+        try:
+            p.wait(timeout=5)
+        except Exception:
+            p.kill()
+    try:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9 or not c[0].isdigit() or int(c[0]) != device_index:
+                continue
+            sm.append(float(c[1]))
+            mx.append(float(c[2]))
+            for nme, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+    except OSError:
+        pass
+    finally:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+    return out
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the fused kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, times = [], []
+    for step in range(args.warmup + args.steps):
+        v, dt, cores, sample, pairs = cpu_port_run(wl, args.alpha, q_per_core=8)
+        if step >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    value = float(np.mean(vals)) if vals else 0.0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)) if times else None,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "mode": "MAXP", "dim": DIM, "candidates_per_query": wl["cands"],
+                   "cut_k": wl["k"], "alpha": args.alpha,
+                   "note": "each step = a bounded sample of the workload on the host cores"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ffx(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    from fast_forward import _ffx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if _ffx.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: libffx has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_docs = max(1000, int(wl["n_docs"] * args.scale))
+    nq = max(296, int(wl["nq"] * args.scale)) if args.scale < 1 else wl["nq"]
+    cands, k = wl["cands"], wl["k"]
+    cnt = doc_lengths(n_docs, wl["mean_psg"], seed=0)
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    n_rows = int(off[-1])
+
+    # ---- index: synthetic N(0,1) fp32 rows generated on the device, staged into the store
+    t_stage = time.perf_counter()
+    idx = _ffx.DeviceIndex(DIM, capacity=n_rows, device=local)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234)  # identical replicas on every rank
+    chunk = 1 << 20
+    for r0 in range(0, n_rows, chunk):
+        nr = min(chunk, n_rows - r0)
+        t = torch.randn((nr, DIM), device=dev, dtype=torch.float32, generator=gen)
+        torch.cuda.synchronize()
+        idx.stage_device(r0, nr, t.data_ptr())
+        del t
+    idx.set_docs(off)
+    torch.cuda.empty_cache()
+    t_stage = time.perf_counter() - t_stage
+
+    # ---- queries of this rank: stratified distinct candidates, uniform over the corpus
+    gen.manual_seed(99 + rank)
+    qv = torch.randn((nq, DIM), device=dev, dtype=torch.float32, generator=gen)
+    bucket = n_docs // cands
+    if bucket < 1:
+        raise RuntimeError("corpus smaller than the candidate list")
+    perm = torch.rand((nq, cands), device=dev, generator=gen).argsort(dim=1)
+    within = torch.randint(0, bucket, (nq, cands), device=dev, generator=gen)
+    cand = (perm * bucket + within).to(torch.int32).contiguous().view(-1)
+    del perm, within
+    lex = (torch.rand((nq * cands,), device=dev, generator=gen) * 20).contiguous()
+    q_off = (torch.arange(nq + 1, device=dev, dtype=torch.int64) * cands).contiguous()
+    topk_s = torch.empty((nq, k), device=dev, dtype=torch.float32)
+    topk_p = torch.empty((nq, k), device=dev, dtype=torch.int32)
+    n_pairs = nq * cands
+    d_cnt = torch.from_numpy(cnt).to(dev)
+    rows_touched = int(d_cnt[cand.long()].sum().item())
+    del d_cnt
+    # rows*D*4 + 16 B/pair (cand, lex, span) + per query (query vector + top-k out)
+    algo_bytes = rows_touched * DIM * 4 + n_pairs * 16 + nq * (DIM * 4 + k * 8)
+
+    stream = torch.cuda.current_stream()
+
+    def step():
+        idx.rerank_device(MODE_MAXP, qv.data_ptr(), nq, q_off.data_ptr(), cand.data_ptr(), lex.data_ptr(),
+                          args.alpha, k, cands, 0, 0, topk_s.data_ptr(), topk_p.data_ptr(),
+                          stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    clk_p, clk_path = clocks_start() if rank == 0 else (None, None)
+    launches0 = _ffx.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(stream)
+    barrier()
+    launches = _ffx.launch_count() - launches0
+    per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    clocks = clocks_stop(clk_p, clk_path, local) if rank == 0 else None
+
+    # sanity on the timed output: ranked lists are sorted and are permutations of the block
+    s_host = topk_s[:4].cpu().numpy()
+    p_host = topk_p[:4].cpu().numpy()
+    assert (np.diff(s_host, axis=1) <= 0).all(), "top-k not sorted"
+    assert all(len(set(r.tolist())) == k for r in p_host) and p_host.min() >= 0 and p_host.max() < cands
+
+    # ---- e2e: host buffers through ffx_rerank_host (H2D + kernel + D2H inside the timed region)
+    h_q = _ffx.PinnedBuffer((nq, DIM), np.float32)
+    h_off = _ffx.PinnedBuffer((nq + 1,), np.int64)
+    h_cand = _ffx.PinnedBuffer((n_pairs,), np.int32)
+    h_lex = _ffx.PinnedBuffer((n_pairs,), np.float32)
+    h_ts = _ffx.PinnedBuffer((nq, k), np.float32)
+    h_tp = _ffx.PinnedBuffer((nq, k), np.int32)
+    h_q.array[:] = qv.cpu().numpy()
+    h_off.array[:] = q_off.cpu().numpy()
+    h_cand.array[:] = cand.cpu().numpy()
+    h_lex.array[:] = lex.cpu().numpy()
+    out = {"topk_score": h_ts.array, "topk_pos": h_tp.array}
+
+    def e2e_step():
+        idx.rerank_host(MODE_MAXP, h_q.array, h_off.array, h_cand.array, h_lex.array, args.alpha, k,
+                        want_ff=False, want_int=False, out=out)
+
+    e2e_step()
+    assert (h_tp.array[:4] == p_host).all(), "host-buffer path disagrees with the device path"
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = h_q.array.nbytes + h_off.array.nbytes + h_cand.array.nbytes + h_lex.array.nbytes
+    d2h = h_ts.array.nbytes + h_tp.array.nbytes
+
+    times = torch.tensor([total_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = times.tolist()
+
+    if rank == 0:
+        value = world * n_pairs * args.steps / (total_ms * 1e-3)
+        e2e_value = world * n_pairs * args.steps / (e2e_ms * 1e-3)
+        kern_ms = float(np.mean(per_step_ms))
+        achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+        peak, peak_src = measured_peak()
+        traffic = ncu_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": args.workload if args.scale == 1 else f"{args.workload} (SCALED x{args.scale}: debug)",
+                "mode": "MAXP", "dim": DIM, "docs": n_docs, "passages": n_rows, "index_gb": n_rows * DIM * 4 / 1e9,
+                "queries_per_gpu": nq, "candidates_per_query": cands, "cut_k": k, "alpha": args.alpha,
+                "parallelism": f"query-dp{world} (replicated index, no data-path collective)",
+                "l2": "inputs larger than L2 (61 GB index, 499 GB touched per step)",
+                "index_stage_s": round(t_stage, 2),
+            },
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "kernel": "ffx_score_kernel<2,12,true> (fused gather-dot-MAXP-interpolate-topk)",
+                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_ms, "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, dt, cores, sample, _ = cpu_port_run(wl, args.alpha, q_per_core=16)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                    "sample": sample, "seconds": round(dt, 2)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    idx.close()
+
+
+def main():
+    args = parse()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ffx(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,741 @@
+// ffx.cu — host side of libffx.so: the C ABI declared in include/ffx.h.
+//
+// Owns the HBM-resident index (row store, doc -> rows spans, PQ codebooks), stages rows
+// through a pinned double buffer, plans and launches the kernels of ffx_kernels.cuh /
+// ffx_adc.cuh.  No torch, no CPU compute path: every scoring entry point needs a CUDA
+// device and fails with FFX_ERR_CUDA without one.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ffx.h"
+#include "ffx_adc.cuh"
+#include "ffx_kernels.cuh"
+#include "ffx_layout.h"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define FFX_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            cudaGetLastError();                                                             \
+            return fail(e_ == cudaErrorMemoryAllocation ? FFX_ERR_OOM : FFX_ERR_CUDA,       \
+                        "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                   \
+    } while (0)
+
+#define FFX_TRY(expr)          \
+    do {                       \
+        int rc_ = (expr);      \
+        if (rc_ != FFX_OK) return rc_; \
+    } while (0)
+
+constexpr int64_t kStageBytes = 32ll << 20;  // per pinned / device staging buffer
+
+struct Scratch {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+int scratch_reserve(Scratch &s, size_t bytes) {
+    if (bytes <= s.bytes) return FFX_OK;
+    if (s.p) {
+        FFX_CUDA(cudaDeviceSynchronize());
+        FFX_CUDA(cudaFree(s.p));
+        s.p = nullptr;
+        s.bytes = 0;
+    }
+    bytes = (bytes + (1u << 20)) & ~static_cast<size_t>((1u << 20) - 1);
+    FFX_CUDA(cudaMalloc(&s.p, bytes));
+    s.bytes = bytes;
+    return FFX_OK;
+}
+
+inline int next_pow2(int64_t v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+struct ffx_index {
+    int device = 0;
+    int row_kind = FFX_ROWS_F32;
+    int64_t dim = 0;
+    int64_t capacity = 0;
+    int64_t num_rows = 0;
+    ffx_plan plan{0, 0};
+    size_t row_bytes = 0;
+    void *store = nullptr;
+    int sm_count = 148;
+
+    // doc -> rows
+    int64_t n_docs = 0;
+    uint2 *doc_span = nullptr;
+    int32_t *doc_rows = nullptr;
+    int indirect = 0;
+
+    // PQ / OPQ
+    int M = 0, Ks = 0, Ds = 0;
+    float *codewords = nullptr;
+    float *R = nullptr;
+
+    // staging: pinned double buffer + device landing buffers (fp32 rows are permuted
+    // from the landing buffer into the lane-major store)
+    cudaStream_t stream = nullptr;
+    void *pinned[2] = {nullptr, nullptr};
+    void *landing[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+
+    Scratch work;     // kernel scratch of ffx_rerank (scores / keys / rotated queries)
+    Scratch hostio;   // device mirrors of ffx_rerank_host's host buffers
+};
+
+namespace {
+
+int bind(const ffx_index *idx) {
+    FFX_CUDA(cudaSetDevice(idx->device));
+    return FFX_OK;
+}
+
+int ensure_staging(ffx_index *idx) {
+    if (idx->pinned[0]) return FFX_OK;
+    for (int i = 0; i < 2; i++) {
+        FFX_CUDA(cudaMallocHost(&idx->pinned[i], kStageBytes));
+        if (idx->row_kind == FFX_ROWS_F32 && idx->plan.cpl)
+            FFX_CUDA(cudaMalloc(&idx->landing[i], kStageBytes));
+        FFX_CUDA(cudaEventCreateWithFlags(&idx->done[i], cudaEventDisableTiming));
+    }
+    return FFX_OK;
+}
+
+void release_staging(ffx_index *idx) {
+    for (int i = 0; i < 2; i++) {
+        if (idx->pinned[i]) cudaFreeHost(idx->pinned[i]);
+        if (idx->landing[i]) cudaFree(idx->landing[i]);
+        if (idx->done[i]) cudaEventDestroy(idx->done[i]);
+        idx->pinned[i] = idx->landing[i] = nullptr;
+        idx->done[i] = nullptr;
+    }
+}
+
+int permute_grid(int64_t elems, int sm_count) {
+    const int64_t blocks = (elems + 255) / 256;
+    return static_cast<int>(std::min<int64_t>(blocks, static_cast<int64_t>(sm_count) * 16));
+}
+
+// original order (device) -> store rows [row0, row0+nrows)
+int launch_to_store(ffx_index *idx, int64_t row0, int64_t nrows, const void *src_dev) {
+    char *dst = static_cast<char *>(idx->store) + static_cast<size_t>(row0) * idx->row_bytes;
+    if (idx->row_kind == FFX_ROWS_F32 && idx->plan.cpl) {
+        ffx::ffx_permute_rows_kernel<<<permute_grid(nrows * idx->dim, idx->sm_count), 256, 0,
+                                       idx->stream>>>(
+            reinterpret_cast<float *>(dst), static_cast<const float *>(src_dev), nrows,
+            static_cast<int>(idx->dim), idx->plan.cpl, idx->plan.steps, 1, nullptr);
+        g_launches++;
+        FFX_CUDA(cudaGetLastError());
+    } else {
+        FFX_CUDA(cudaMemcpyAsync(dst, src_dev, static_cast<size_t>(nrows) * idx->row_bytes,
+                                 cudaMemcpyDeviceToDevice, idx->stream));
+    }
+    return FFX_OK;
+}
+
+// ---- kernel dispatch -------------------------------------------------------------------
+template <int CPL, int S>
+int launch_score(const ffx::ScoreArgs &a, bool fuse, int grid, size_t smem, cudaStream_t st) {
+    if (fuse) {
+        auto kern = ffx::ffx_score_kernel<CPL, S, true>;
+        FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        kern<<<grid, ffx::kThreads, smem, st>>>(a);
+    } else {
+        ffx::ffx_score_kernel<CPL, S, false><<<grid, ffx::kThreads, 0, st>>>(a);
+    }
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
+int dispatch_score(const ffx_plan &p, const ffx::ScoreArgs &a, bool fuse, int grid, size_t smem,
+                   cudaStream_t st) {
+#define FFX_CASE(C, S_) \
+    if (p.cpl == C && p.steps == S_) return launch_score<C, S_>(a, fuse, grid, smem, st)
+    FFX_CASE(1, 12);
+    FFX_CASE(1, 16);
+    FFX_CASE(2, 10);
+    FFX_CASE(2, 12);
+    FFX_CASE(2, 14);
+    FFX_CASE(2, 16);
+    FFX_CASE(4, 12);
+    FFX_CASE(4, 16);
+#undef FFX_CASE
+    return fail(FFX_ERR_UNSUPPORTED, "no lane-major kernel for plan (%d,%d)", p.cpl, p.steps);
+}
+
+int launch_topk(const float *scores, const int64_t *q_off, int64_t nq, int k, int cpad,
+                Scratch &work, size_t work_off, float *out_s, int32_t *out_p, cudaStream_t st) {
+    unsigned long long *gkeys = nullptr;
+    size_t smem = static_cast<size_t>(cpad) * 8;
+    if (cpad > ffx::kMaxFusedCand) {
+        gkeys = reinterpret_cast<unsigned long long *>(static_cast<char *>(work.p) + work_off);
+        smem = 0;
+    }
+    if (smem > 48 * 1024)
+        FFX_CUDA(cudaFuncSetAttribute(ffx::ffx_topk_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    ffx::ffx_topk_kernel<<<static_cast<unsigned>(nq), ffx::kThreads, smem, st>>>(
+        scores, q_off, k, cpad, gkeys, out_s, out_p);
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int ffx_abi_version(void) { return FFX_ABI_VERSION; }
+
+const char *ffx_last_error(void) { return g_err.c_str(); }
+
+int ffx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int64_t ffx_launch_count(void) { return g_launches.load(); }
+
+int ffx_host_alloc(void **out, int64_t bytes) {
+    if (!out || bytes < 0) return fail(FFX_ERR_INVALID, "ffx_host_alloc: bad arguments");
+    *out = nullptr;
+    if (bytes == 0) return FFX_OK;
+    FFX_CUDA(cudaMallocHost(out, static_cast<size_t>(bytes)));
+    return FFX_OK;
+}
+
+int ffx_host_free(void *p) {
+    if (p) FFX_CUDA(cudaFreeHost(p));
+    return FFX_OK;
+}
+
+// ---- index ---------------------------------------------------------------------------
+int ffx_index_create(int device, int row_kind, int64_t dim, int64_t capacity_rows,
+                     ffx_index **out) {
+    if (!out) return fail(FFX_ERR_INVALID, "ffx_index_create: out is NULL");
+    *out = nullptr;
+    if (row_kind != FFX_ROWS_F32 && row_kind != FFX_ROWS_PQ_U8)
+        return fail(FFX_ERR_INVALID, "ffx_index_create: unknown row kind %d", row_kind);
+    if (dim <= 0 || dim > (1 << 20) || capacity_rows < 0 || capacity_rows > 0xffffffffll)
+        return fail(FFX_ERR_INVALID, "ffx_index_create: bad dim/capacity (%lld, %lld)",
+                    static_cast<long long>(dim), static_cast<long long>(capacity_rows));
+    const int n_dev = ffx_device_count();
+    if (n_dev <= 0) return fail(FFX_ERR_CUDA, "no CUDA device (ffx has no CPU path)");
+    if (device < 0 || device >= n_dev)
+        return fail(FFX_ERR_INVALID, "ffx_index_create: device %d of %d", device, n_dev);
+    FFX_CUDA(cudaSetDevice(device));
+
+    ffx_index *idx = new ffx_index();
+    idx->device = device;
+    idx->row_kind = row_kind;
+    idx->dim = dim;
+    if (row_kind == FFX_ROWS_F32) {
+        idx->plan = ffx_plan_for_dim(dim);
+        idx->row_bytes = static_cast<size_t>(dim) * 4;
+    } else {
+        idx->row_bytes = static_cast<size_t>(dim);
+    }
+    cudaDeviceGetAttribute(&idx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete idx;
+        return fail(FFX_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    *out = idx;
+    int rc = ffx_index_reserve(idx, capacity_rows);
+    if (rc != FFX_OK) {
+        ffx_index_destroy(idx);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+int ffx_index_destroy(ffx_index *idx) {
+    if (!idx) return FFX_OK;
+    cudaSetDevice(idx->device);
+    cudaDeviceSynchronize();
+    release_staging(idx);
+    cudaFree(idx->store);
+    cudaFree(idx->doc_span);
+    cudaFree(idx->doc_rows);
+    cudaFree(idx->codewords);
+    cudaFree(idx->R);
+    cudaFree(idx->work.p);
+    cudaFree(idx->hostio.p);
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+    cudaGetLastError();
+    delete idx;
+    return FFX_OK;
+}
+
+int ffx_index_reserve(ffx_index *idx, int64_t capacity_rows) {
+    if (!idx) return fail(FFX_ERR_INVALID, "ffx_index_reserve: NULL index");
+    if (capacity_rows > 0xffffffffll)
+        return fail(FFX_ERR_INVALID, "ffx_index_reserve: more than 2^32 rows");
+    if (capacity_rows <= idx->capacity) return FFX_OK;
+    FFX_TRY(bind(idx));
+    void *fresh = nullptr;
+    // 256 B slack: the kernels may issue (masked) vector loads just past the last row
+    FFX_CUDA(cudaMalloc(&fresh, static_cast<size_t>(capacity_rows) * idx->row_bytes + 256));
+    if (idx->store) {
+        if (idx->num_rows > 0)
+            FFX_CUDA(cudaMemcpyAsync(fresh, idx->store,
+                                     static_cast<size_t>(idx->num_rows) * idx->row_bytes,
+                                     cudaMemcpyDeviceToDevice, idx->stream));
+        FFX_CUDA(cudaStreamSynchronize(idx->stream));
+        FFX_CUDA(cudaFree(idx->store));
+    }
+    idx->store = fresh;
+    idx->capacity = capacity_rows;
+    return FFX_OK;
+}
+
+int ffx_index_stage_rows(ffx_index *idx, int64_t row0, int64_t nrows, const void *rows,
+                         int src_on_device) {
+    if (!idx || (!rows && nrows > 0) || row0 < 0 || nrows < 0)
+        return fail(FFX_ERR_INVALID, "ffx_index_stage_rows: bad arguments");
+    if (row0 + nrows > idx->capacity)
+        return fail(FFX_ERR_INVALID, "ffx_index_stage_rows: rows [%lld, %lld) exceed capacity %lld",
+                    static_cast<long long>(row0), static_cast<long long>(row0 + nrows),
+                    static_cast<long long>(idx->capacity));
+    if (nrows == 0) return FFX_OK;
+    FFX_TRY(bind(idx));
+    if (src_on_device) {
+        // the caller's producer ran on some other stream: order after everything queued so far
+        FFX_CUDA(cudaDeviceSynchronize());
+        FFX_TRY(launch_to_store(idx, row0, nrows, rows));
+        FFX_CUDA(cudaStreamSynchronize(idx->stream));
+    } else {
+        FFX_TRY(ensure_staging(idx));
+        const int64_t rows_per_buf = std::max<int64_t>(1, kStageBytes / static_cast<int64_t>(idx->row_bytes));
+        if (static_cast<int64_t>(idx->row_bytes) > kStageBytes)
+            return fail(FFX_ERR_UNSUPPORTED, "row of %zu bytes exceeds the staging buffer", idx->row_bytes);
+        const bool permute = idx->row_kind == FFX_ROWS_F32 && idx->plan.cpl;
+        int b = 0;
+        for (int64_t r = 0; r < nrows; r += rows_per_buf, b ^= 1) {
+            const int64_t nr = std::min(rows_per_buf, nrows - r);
+            const size_t bytes = static_cast<size_t>(nr) * idx->row_bytes;
+            FFX_CUDA(cudaEventSynchronize(idx->done[b]));  // buffer b free again
+            memcpy(idx->pinned[b], static_cast<const char *>(rows) + static_cast<size_t>(r) * idx->row_bytes, bytes);
+            if (permute) {
+                FFX_CUDA(cudaMemcpyAsync(idx->landing[b], idx->pinned[b], bytes,
+                                         cudaMemcpyHostToDevice, idx->stream));
+                FFX_TRY(launch_to_store(idx, row0 + r, nr, idx->landing[b]));
+            } else {
+                FFX_CUDA(cudaMemcpyAsync(static_cast<char *>(idx->store) +
+                                             static_cast<size_t>(row0 + r) * idx->row_bytes,
+                                         idx->pinned[b], bytes, cudaMemcpyHostToDevice, idx->stream));
+            }
+            FFX_CUDA(cudaEventRecord(idx->done[b], idx->stream));
+        }
+        FFX_CUDA(cudaStreamSynchronize(idx->stream));
+    }
+    idx->num_rows = std::max(idx->num_rows, row0 + nrows);
+    return FFX_OK;
+}
+
+int ffx_index_read_rows(ffx_index *idx, const int64_t *rows, int64_t n, void *out) {
+    if (!idx || n < 0 || (n > 0 && (!rows || !out)))
+        return fail(FFX_ERR_INVALID, "ffx_index_read_rows: bad arguments");
+    for (int64_t i = 0; i < n; i++)
+        if (rows[i] < 0 || rows[i] >= idx->num_rows)
+            return fail(FFX_ERR_INVALID, "ffx_index_read_rows: row %lld out of range",
+                        static_cast<long long>(rows[i]));
+    if (n == 0) return FFX_OK;
+    FFX_TRY(bind(idx));
+    const int64_t per = std::max<int64_t>(1, kStageBytes / static_cast<int64_t>(idx->row_bytes));
+    const size_t chunk_rows = static_cast<size_t>(std::min(per, n));
+    const size_t ids_bytes = (chunk_rows * 8 + 255) & ~static_cast<size_t>(255);
+    FFX_TRY(scratch_reserve(idx->work, ids_bytes + chunk_rows * idx->row_bytes));
+    int64_t *d_rows = static_cast<int64_t *>(idx->work.p);
+    char *d_out = static_cast<char *>(idx->work.p) + ids_bytes;
+    for (int64_t r = 0; r < n; r += per) {
+        const int64_t nr = std::min(per, n - r);
+        FFX_CUDA(cudaMemcpyAsync(d_rows, rows + r, static_cast<size_t>(nr) * 8,
+                                 cudaMemcpyHostToDevice, idx->stream));
+        if (idx->row_kind == FFX_ROWS_F32) {
+            ffx::ffx_permute_rows_kernel<<<permute_grid(nr * idx->dim, idx->sm_count), 256, 0,
+                                           idx->stream>>>(
+                reinterpret_cast<float *>(d_out), static_cast<const float *>(idx->store), nr,
+                static_cast<int>(idx->dim), idx->plan.cpl, idx->plan.steps, 0, d_rows);
+        } else {
+            ffx::ffx_gather_bytes_kernel<<<permute_grid(nr * idx->dim, idx->sm_count), 256, 0,
+                                           idx->stream>>>(
+                reinterpret_cast<uint8_t *>(d_out), static_cast<const uint8_t *>(idx->store), nr,
+                static_cast<int64_t>(idx->row_bytes), d_rows);
+        }
+        g_launches++;
+        FFX_CUDA(cudaGetLastError());
+        FFX_CUDA(cudaMemcpyAsync(static_cast<char *>(out) + static_cast<size_t>(r) * idx->row_bytes,
+                                 d_out, static_cast<size_t>(nr) * idx->row_bytes,
+                                 cudaMemcpyDeviceToHost, idx->stream));
+        FFX_CUDA(cudaStreamSynchronize(idx->stream));
+    }
+    return FFX_OK;
+}
+
+int64_t ffx_index_num_rows(const ffx_index *idx) { return idx ? idx->num_rows : -1; }
+int64_t ffx_index_capacity(const ffx_index *idx) { return idx ? idx->capacity : -1; }
+int64_t ffx_index_dim(const ffx_index *idx) { return idx ? idx->dim : -1; }
+int ffx_index_has_fast_path(const ffx_index *idx) {
+    return idx && idx->row_kind == FFX_ROWS_F32 && idx->plan.cpl != 0;
+}
+
+int ffx_index_set_docs(ffx_index *idx, int64_t n_docs, const int64_t *doc_off,
+                       const int64_t *doc_rows) {
+    if (!idx || n_docs < 0 || (n_docs > 0 && !doc_off))
+        return fail(FFX_ERR_INVALID, "ffx_index_set_docs: bad arguments");
+    if (n_docs > 0x7fffffffll) return fail(FFX_ERR_INVALID, "ffx_index_set_docs: too many documents");
+    FFX_TRY(bind(idx));
+    FFX_CUDA(cudaDeviceSynchronize());
+    cudaFree(idx->doc_span);
+    cudaFree(idx->doc_rows);
+    idx->doc_span = nullptr;
+    idx->doc_rows = nullptr;
+    idx->n_docs = 0;
+    idx->indirect = 0;
+    if (n_docs == 0) return FFX_OK;
+
+    const int64_t total = doc_off[n_docs];
+    if (doc_off[0] != 0 || total < 0 || total > 0xffffffffll)
+        return fail(FFX_ERR_INVALID, "ffx_index_set_docs: bad offsets");
+    bool contiguous = true;
+    for (int64_t d = 0; d < n_docs; d++) {
+        const int64_t b = doc_off[d], e = doc_off[d + 1];
+        if (e <= b) return fail(FFX_ERR_INVALID, "ffx_index_set_docs: document %lld has no rows",
+                                static_cast<long long>(d));
+        if (doc_rows) {
+            for (int64_t i = b; i < e; i++) {
+                if (doc_rows[i] < 0 || doc_rows[i] >= idx->capacity)
+                    return fail(FFX_ERR_INVALID, "ffx_index_set_docs: row %lld out of range",
+                                static_cast<long long>(doc_rows[i]));
+                if (i > b && doc_rows[i] != doc_rows[i - 1] + 1) contiguous = false;
+            }
+        } else if (e > idx->capacity) {
+            return fail(FFX_ERR_INVALID, "ffx_index_set_docs: offsets exceed the row store");
+        }
+    }
+    std::vector<uint2> span(static_cast<size_t>(n_docs));
+    for (int64_t d = 0; d < n_docs; d++) {
+        const int64_t b = doc_off[d];
+        const uint32_t cnt = static_cast<uint32_t>(doc_off[d + 1] - b);
+        const uint32_t first = contiguous ? static_cast<uint32_t>(doc_rows ? doc_rows[b] : b)
+                                          : static_cast<uint32_t>(b);
+        span[static_cast<size_t>(d)] = make_uint2(first, cnt);
+    }
+    FFX_CUDA(cudaMalloc(&idx->doc_span, span.size() * sizeof(uint2)));
+    FFX_CUDA(cudaMemcpy(idx->doc_span, span.data(), span.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    if (!contiguous) {
+        std::vector<int32_t> rows32(static_cast<size_t>(total));
+        for (int64_t i = 0; i < total; i++)
+            rows32[static_cast<size_t>(i)] = static_cast<int32_t>(static_cast<uint32_t>(doc_rows[i]));
+        FFX_CUDA(cudaMalloc(&idx->doc_rows, rows32.size() * 4 + 256));
+        FFX_CUDA(cudaMemcpy(idx->doc_rows, rows32.data(), rows32.size() * 4, cudaMemcpyHostToDevice));
+        idx->indirect = 1;
+    }
+    idx->n_docs = n_docs;
+    return FFX_OK;
+}
+
+int ffx_index_set_pq(ffx_index *idx, int M, int Ks, int Ds, const float *codewords, const float *R) {
+    if (!idx || !codewords || M <= 0 || Ks <= 0 || Ds <= 0)
+        return fail(FFX_ERR_INVALID, "ffx_index_set_pq: bad arguments");
+    if (idx->row_kind != FFX_ROWS_PQ_U8)
+        return fail(FFX_ERR_STATE, "ffx_index_set_pq: index does not hold PQ codes");
+    if (M != idx->dim) return fail(FFX_ERR_INVALID, "ffx_index_set_pq: M=%d but rows have %lld codes",
+                                   M, static_cast<long long>(idx->dim));
+    if (Ks > 256) return fail(FFX_ERR_UNSUPPORTED, "ffx_index_set_pq: Ks=%d > 256 (uint8 codes)", Ks);
+    if (static_cast<size_t>(M) * Ks * 4 > 200 * 1024)
+        return fail(FFX_ERR_UNSUPPORTED, "ffx_index_set_pq: LUT of %d x %d floats exceeds shared memory", M, Ks);
+    FFX_TRY(bind(idx));
+    FFX_CUDA(cudaDeviceSynchronize());
+    cudaFree(idx->codewords);
+    cudaFree(idx->R);
+    idx->codewords = idx->R = nullptr;
+    const size_t cw = static_cast<size_t>(M) * Ks * Ds * 4;
+    FFX_CUDA(cudaMalloc(&idx->codewords, cw));
+    FFX_CUDA(cudaMemcpy(idx->codewords, codewords, cw, cudaMemcpyHostToDevice));
+    if (R) {
+        const size_t D = static_cast<size_t>(M) * Ds;
+        FFX_CUDA(cudaMalloc(&idx->R, D * D * 4));
+        FFX_CUDA(cudaMemcpy(idx->R, R, D * D * 4, cudaMemcpyHostToDevice));
+    }
+    idx->M = M;
+    idx->Ks = Ks;
+    idx->Ds = Ds;
+    return FFX_OK;
+}
+
+// ---- the hot path ----------------------------------------------------------------------
+int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const int64_t *q_off,
+               const int32_t *cand, const float *lex, double alpha, int k, int64_t max_cand,
+               float *out_ff, float *out_int, float *out_topk_score, int32_t *out_topk_pos,
+               void *stream) {
+    if (!idx) return fail(FFX_ERR_INVALID, "ffx_rerank: NULL index");
+    if (mode < FFX_MODE_PASSAGE || mode > FFX_MODE_AVEP)
+        return fail(FFX_ERR_INVALID, "ffx_rerank: unknown mode %d", mode);
+    if (nq < 0 || k < 0 || max_cand < 0 || nq > 0x7fffffffll || max_cand > (1ll << 30))
+        return fail(FFX_ERR_INVALID, "ffx_rerank: bad sizes");
+    if (nq == 0) return FFX_OK;
+    if (!qvecs || !q_off || (!cand && max_cand > 0))
+        return fail(FFX_ERR_INVALID, "ffx_rerank: NULL input");
+    if (k > 0 && (!out_topk_score || !out_topk_pos))
+        return fail(FFX_ERR_INVALID, "ffx_rerank: k > 0 needs top-k outputs");
+    if (mode != FFX_MODE_PASSAGE && idx->n_docs == 0 && max_cand > 0)
+        return fail(FFX_ERR_STATE, "ffx_rerank: document modes need ffx_index_set_docs first");
+    if (idx->row_kind == FFX_ROWS_PQ_U8 && !idx->codewords)
+        return fail(FFX_ERR_STATE, "ffx_rerank: PQ index without codebooks (ffx_index_set_pq)");
+    FFX_TRY(bind(idx));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    const int cpad = next_pow2(std::max<int64_t>(max_cand, 1));
+    const bool pq = idx->row_kind == FFX_ROWS_PQ_U8;
+    const bool fast = !pq && idx->plan.cpl != 0;
+    const int64_t D = pq ? static_cast<int64_t>(idx->M) * idx->Ds : idx->dim;
+    const float alpha32 = static_cast<float>(alpha);
+    const float beta32 = static_cast<float>(1.0 - alpha);
+
+    // one CTA per query with the top-k fused needs enough queries to fill the machine
+    const int64_t slots = static_cast<int64_t>(idx->sm_count) * 2;
+    const bool fuse = fast && k > 0 && cpad <= ffx::kMaxFusedCand && nq >= slots;
+
+    // scratch plan: [scores n_total?][keys nq*cpad?][qeff nq*D?]
+    const bool need_scores = k > 0 && !fuse && !out_int;
+    const bool need_gkeys = k > 0 && !fuse && cpad > ffx::kMaxFusedCand;
+    size_t off_scores = 0, off_keys = 0, off_qeff = 0, total = 0;
+    int64_t n_total = 0;
+    if (need_scores) {
+        // the pair count lives in device memory (q_off[nq]); bound it by nq * max_cand
+        n_total = nq * max_cand;
+        off_scores = total;
+        total += (static_cast<size_t>(n_total) * 4 + 255) & ~static_cast<size_t>(255);
+    }
+    if (need_gkeys) {
+        off_keys = total;
+        total += static_cast<size_t>(nq) * cpad * 8;
+    }
+    if (pq && idx->R) {
+        off_qeff = total;
+        total += static_cast<size_t>(nq) * D * 4;
+    }
+    if (total) FFX_TRY(scratch_reserve(idx->work, total));
+    char *work = static_cast<char *>(idx->work.p);
+    float *scores = out_int ? out_int : (need_scores ? reinterpret_cast<float *>(work + off_scores) : nullptr);
+
+    // tiles: split a query over several CTAs when there are few queries
+    int tiles = 1, tile = static_cast<int>(std::max<int64_t>(max_cand, 1));
+    if (!fuse) {
+        const int64_t want = slots * 4;
+        tiles = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((want + nq - 1) / nq,
+                                                                        (max_cand + 31) / 32)));
+        tile = static_cast<int>((std::max<int64_t>(max_cand, 1) + tiles - 1) / tiles);
+        tile = (tile + 31) & ~31;
+        tiles = static_cast<int>((std::max<int64_t>(max_cand, 1) + tile - 1) / tile);
+    }
+    if (nq * tiles > 0x7fffffffll) return fail(FFX_ERR_UNSUPPORTED, "ffx_rerank: grid too large");
+
+    if (max_cand > 0) {
+        if (pq) {
+            const float *qeff = qvecs;
+            if (idx->R) {
+                float *qe = reinterpret_cast<float *>(work + off_qeff);
+                ffx::ffx_rotate_queries_kernel<<<static_cast<unsigned>(nq), 256,
+                                                 static_cast<size_t>(D) * 4, st>>>(
+                    qvecs, idx->R, static_cast<int>(D), qe);
+                g_launches++;
+                FFX_CUDA(cudaGetLastError());
+                qeff = qe;
+            }
+            ffx::AdcArgs a{};
+            a.codes = static_cast<const uint8_t *>(idx->store);
+            a.codewords = idx->codewords;
+            a.qeff = qeff;
+            a.M = idx->M;
+            a.Ks = idx->Ks;
+            a.Ds = idx->Ds;
+            a.doc_span = idx->doc_span;
+            a.doc_rows = idx->doc_rows;
+            a.indirect = idx->indirect;
+            a.mode = mode;
+            a.q_off = q_off;
+            a.cand = cand;
+            a.lex = lex;
+            a.alpha = alpha32;
+            a.beta = beta32;
+            a.out_ff = out_ff;
+            a.out_int = scores;
+            a.tiles_per_query = tiles;
+            a.tile = tile;
+            const size_t smem = static_cast<size_t>(idx->M) * idx->Ks * 4;
+            FFX_CUDA(cudaFuncSetAttribute(ffx::ffx_adc_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+            ffx::ffx_adc_kernel<<<static_cast<unsigned>(nq * tiles), ffx::kThreads, smem, st>>>(a);
+            g_launches++;
+            FFX_CUDA(cudaGetLastError());
+        } else {
+            ffx::ScoreArgs a{};
+            a.vectors = static_cast<const float *>(idx->store);
+            a.doc_span = idx->doc_span;
+            a.doc_rows = idx->doc_rows;
+            a.indirect = idx->indirect;
+            a.mode = mode;
+            a.dim = idx->dim;
+            a.qvecs = qvecs;
+            a.q_off = q_off;
+            a.cand = cand;
+            a.lex = lex;
+            a.alpha = alpha32;
+            a.beta = beta32;
+            a.k = k;
+            a.out_ff = out_ff;
+            a.out_int = fuse ? out_int : scores;
+            a.topk_score = out_topk_score;
+            a.topk_pos = out_topk_pos;
+            a.tiles_per_query = tiles;
+            a.tile = tile;
+            a.cpad = cpad;
+            if (fast) {
+                FFX_TRY(dispatch_score(idx->plan, a, fuse, static_cast<int>(nq * tiles),
+                                       fuse ? static_cast<size_t>(cpad) * 8 : 0, st));
+            } else {
+                // generic exact kernel: one thread per pair over the [0, nq*max_cand) bound;
+                // the kernel reads the true pair count from q_off[nq]
+                const int64_t bound = nq * max_cand;
+                ffx::ffx_score_generic_kernel<<<static_cast<unsigned>((bound + 127) / 128), 128, 0, st>>>(
+                    a, nq, bound);
+                g_launches++;
+                FFX_CUDA(cudaGetLastError());
+            }
+        }
+    }
+    if (k > 0 && !fuse)
+        FFX_TRY(launch_topk(scores, q_off, nq, k, cpad, idx->work, off_keys, out_topk_score,
+                            out_topk_pos, st));
+    return FFX_OK;
+}
+
+int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
+                    const int64_t *q_off, const int32_t *cand, const float *lex, double alpha,
+                    int k, float *out_ff, float *out_int, float *out_topk_score,
+                    int32_t *out_topk_pos) {
+    if (!idx) return fail(FFX_ERR_INVALID, "ffx_rerank_host: NULL index");
+    if (nq < 0) return fail(FFX_ERR_INVALID, "ffx_rerank_host: nq < 0");
+    if (nq == 0) return FFX_OK;
+    if (!qvecs || !q_off) return fail(FFX_ERR_INVALID, "ffx_rerank_host: NULL input");
+    if (q_off[0] != 0) return fail(FFX_ERR_INVALID, "ffx_rerank_host: q_off[0] must be 0");
+    int64_t max_cand = 0;
+    for (int64_t q = 0; q < nq; q++) {
+        const int64_t c = q_off[q + 1] - q_off[q];
+        if (c < 0) return fail(FFX_ERR_INVALID, "ffx_rerank_host: q_off not monotone");
+        max_cand = std::max(max_cand, c);
+    }
+    const int64_t n = q_off[nq];
+    if (n > 0 && !cand) return fail(FFX_ERR_INVALID, "ffx_rerank_host: NULL candidates");
+    const bool pq = idx->row_kind == FFX_ROWS_PQ_U8;
+    const int64_t D = pq ? static_cast<int64_t>(idx->M) * idx->Ds : idx->dim;
+    // candidate range check: an out-of-range id must never reach the kernel
+    const int64_t limit = mode == FFX_MODE_PASSAGE ? idx->num_rows : idx->n_docs;
+    for (int64_t i = 0; i < n; i++)
+        if (cand[i] < 0 || cand[i] >= limit)
+            return fail(FFX_ERR_INVALID, "ffx_rerank_host: candidate %d at pair %lld out of range [0, %lld)",
+                        cand[i], static_cast<long long>(i), static_cast<long long>(limit));
+    FFX_TRY(bind(idx));
+
+    auto pad = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+    const size_t b_q = pad(static_cast<size_t>(nq) * D * 4), b_off = pad(static_cast<size_t>(nq + 1) * 8);
+    const size_t b_n = pad(static_cast<size_t>(n) * 4), b_k = pad(static_cast<size_t>(nq) * k * 4);
+    size_t total = b_q + b_off + b_n /*cand*/ + (lex ? b_n : 0) + (out_ff ? b_n : 0) +
+                   (out_int ? b_n : 0) + (k > 0 ? 2 * b_k : 0);
+    FFX_TRY(scratch_reserve(idx->hostio, total));
+    char *p = static_cast<char *>(idx->hostio.p);
+    auto take = [&](size_t b) { char *r = p; p += b; return r; };
+    float *d_q = reinterpret_cast<float *>(take(b_q));
+    int64_t *d_off = reinterpret_cast<int64_t *>(take(b_off));
+    int32_t *d_cand = reinterpret_cast<int32_t *>(take(b_n));
+    float *d_lex = lex ? reinterpret_cast<float *>(take(b_n)) : nullptr;
+    float *d_ff = out_ff ? reinterpret_cast<float *>(take(b_n)) : nullptr;
+    float *d_int = out_int ? reinterpret_cast<float *>(take(b_n)) : nullptr;
+    float *d_ts = k > 0 ? reinterpret_cast<float *>(take(b_k)) : nullptr;
+    int32_t *d_tp = k > 0 ? reinterpret_cast<int32_t *>(take(b_k)) : nullptr;
+
+    cudaStream_t st = idx->stream;
+    FFX_CUDA(cudaMemcpyAsync(d_q, qvecs, static_cast<size_t>(nq) * D * 4, cudaMemcpyHostToDevice, st));
+    FFX_CUDA(cudaMemcpyAsync(d_off, q_off, static_cast<size_t>(nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n > 0) {
+        FFX_CUDA(cudaMemcpyAsync(d_cand, cand, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));
+        if (lex) FFX_CUDA(cudaMemcpyAsync(d_lex, lex, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));
+    }
+    FFX_TRY(ffx_rerank(idx, mode, d_q, nq, d_off, d_cand, d_lex, alpha, k, max_cand, d_ff, d_int,
+                       d_ts, d_tp, st));
+    if (n > 0) {
+        if (out_ff) FFX_CUDA(cudaMemcpyAsync(out_ff, d_ff, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, st));
+        if (out_int) FFX_CUDA(cudaMemcpyAsync(out_int, d_int, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (k > 0) {
+        FFX_CUDA(cudaMemcpyAsync(out_topk_score, d_ts, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
+        FFX_CUDA(cudaMemcpyAsync(out_topk_pos, d_tp, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
+    }
+    FFX_CUDA(cudaStreamSynchronize(st));
+    return FFX_OK;
+}
+
+int ffx_merge_topk(int device, const float *shard_scores, const int32_t *shard_pos, int n_shards,
+                   int64_t nq, int k, float *out_score, int32_t *out_pos, void *stream) {
+    if (n_shards <= 0 || nq < 0 || k <= 0 || !shard_scores || !shard_pos || !out_score || !out_pos)
+        return fail(FFX_ERR_INVALID, "ffx_merge_topk: bad arguments");
+    if (nq == 0) return FFX_OK;
+    const int cpad = next_pow2(static_cast<int64_t>(n_shards) * k);
+    const size_t smem = static_cast<size_t>(cpad) * 8;
+    if (smem > 200 * 1024)
+        return fail(FFX_ERR_UNSUPPORTED, "ffx_merge_topk: %d shards x k=%d exceeds shared memory", n_shards, k);
+    FFX_CUDA(cudaSetDevice(device));
+    if (smem > 48 * 1024)
+        FFX_CUDA(cudaFuncSetAttribute(ffx::ffx_merge_topk_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    ffx::ffx_merge_topk_kernel<<<static_cast<unsigned>(nq), ffx::kThreads, smem,
+                                 static_cast<cudaStream_t>(stream)>>>(
+        shard_scores, shard_pos, n_shards, nq, k, cpad, out_score, out_pos);
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
+}  // extern "C"

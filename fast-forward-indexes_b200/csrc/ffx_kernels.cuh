@@ -1,0 +1,428 @@
+// ffx_kernels.cuh — sm_100a kernels of the re-ranking hot path.
+//
+//   ffx_score_kernel<CPL,S,FUSE>  gather passage rows by id, q.p dots with numpy's exact
+//                                 pairwise tree, segmented max / Kahan-mean / first per
+//                                 document, interpolation with the lexical score and (FUSE)
+//                                 the per-query top-k, in ONE pass over HBM
+//   ffx_score_generic_kernel      same semantics for dimensions without a lane-major plan
+//   ffx_topk_kernel               per-query top-k when a query is split over several CTAs
+//   ffx_permute_rows_kernel       staging: original row order -> lane-major store (and back)
+//
+// Replaces index/base.py:279-314, index/util.py:84-113, ranking.py:319 and
+// ranking.py:115-117,285-291 of the reference.  HBM-bound (0.5 FLOP/B): no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ffx.h"
+#include "ffx_layout.h"
+
+namespace ffx {
+
+constexpr int kThreads = 256;            // 8 warps per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxFusedCand = 16384;     // fused top-k keeps <= 128 KB of keys in smem
+
+struct ScoreArgs {
+    const float *vectors;     // lane-major fp32 rows (identity layout for the generic kernel)
+    const uint2 *doc_span;    // per document: (first row | offset into doc_rows, count)
+    const int32_t *doc_rows;  // only when indirect
+    int indirect;
+    int mode;
+    int64_t dim;
+    const float *qvecs;       // [nq, D] original element order
+    const int64_t *q_off;     // [nq+1]
+    const int32_t *cand;      // [n]
+    const float *lex;         // [n] or nullptr
+    float alpha, beta;        // fl32(alpha), fl32(1 - alpha)
+    int k;
+    float *out_ff, *out_int;  // [n] or nullptr
+    float *topk_score;        // [nq, k]
+    int32_t *topk_pos;
+    int tiles_per_query;      // 1 when FUSE
+    int tile;                 // candidates per tile
+    int cpad;                 // FUSE: next pow2 >= max candidates per query
+};
+
+// ---------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 r;  // read-once data: keep it out of L1
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float f4c(const float4 &v, int c) {
+    return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+}
+
+// Monotone key: larger score first, then smaller position first, when sorted DESCENDING.
+// -0.0 is folded onto +0.0 (pandas ties them); NaN sorts last.  Key 0 is "empty".
+__device__ __forceinline__ unsigned long long topk_key(float s, uint32_t pos) {
+    if (s == 0.f) s = 0.f;
+    uint32_t u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    if (s != s) u = 1u;
+    return (static_cast<unsigned long long>(u) << 32) | static_cast<uint32_t>(~pos);
+}
+__device__ __forceinline__ float key_score(unsigned long long key) {
+    uint32_t u = static_cast<uint32_t>(key >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ int32_t key_pos(unsigned long long key) {
+    return static_cast<int32_t>(~static_cast<uint32_t>(key));
+}
+
+// In-CTA bitonic sort, descending; `keys` may live in shared or global memory.
+__device__ inline void bitonic_sort_desc(unsigned long long *keys, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const bool desc = (lo & k) == 0;
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a < b) == desc && a != b) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ void write_topk(const unsigned long long *keys, int n_valid, int k,
+                                           float *out_s, int32_t *out_p) {
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const bool ok = i < n_valid;
+        out_s[i] = ok ? key_score(keys[i]) : -INFINITY;
+        out_p[i] = ok ? key_pos(keys[i]) : -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// one (query, passage) dot product, bit-identical to np.sum(q * d) (N1)
+// ---------------------------------------------------------------------------------------
+template <int CPL, int S>
+__device__ __forceinline__ float lane_chain_sum(const float (&q)[CPL * S],
+                                                const float4 (&v)[CPL * S / 4]) {
+    float acc[CPL];
+#pragma unroll
+    for (int ch = 0; ch < CPL; ch++) acc[ch] = __fmul_rn(q[ch], f4c(v[ch >> 2], ch & 3));
+#pragma unroll
+    for (int s = 1; s < S; s++) {
+#pragma unroll
+        for (int ch = 0; ch < CPL; ch++) {
+            const int m = s * CPL + ch;
+            acc[ch] = __fadd_rn(acc[ch], __fmul_rn(q[m], f4c(v[m >> 2], m & 3)));
+        }
+    }
+#pragma unroll
+    for (int w = 1; w < CPL; w <<= 1) {
+#pragma unroll
+        for (int ch = 0; ch < CPL; ch += 2 * w) acc[ch] = __fadd_rn(acc[ch], acc[ch + w]);
+    }
+    return acc[0];
+}
+
+__device__ __forceinline__ float warp_tree_sum(float t) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) t = __fadd_rn(t, __shfl_xor_sync(kFull, t, off));
+    return __fadd_rn(0.f, t);  // the reduction starts from the identity 0
+}
+
+// Running per-document reduce (index/base.py:306-312).  Rows arrive in insertion order.
+struct DocReduce {
+    float acc, comp;
+    __device__ __forceinline__ void init() { acc = 0.f; comp = 0.f; }
+    __device__ __forceinline__ void add(float s, bool first, int mode) {
+        if (mode == FFX_MODE_AVEP) {  // pandas group_mean: fp32 Kahan (N2)
+            const float y = __fsub_rn(s, comp);
+            const float t = __fadd_rn(acc, y);
+            comp = __fsub_rn(__fsub_rn(t, acc), y);
+            if (comp != comp) comp = 0.f;
+            acc = t;
+        } else if (first || (mode == FFX_MODE_MAXP && s > acc)) {
+            acc = s;
+        }
+    }
+    __device__ __forceinline__ float finish(uint32_t cnt, int mode) const {
+        return mode == FFX_MODE_AVEP ? __fdiv_rn(acc, static_cast<float>(cnt)) : acc;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// the fused hot kernel
+// ---------------------------------------------------------------------------------------
+template <int CPL, int S, bool FUSE>
+__global__ void __launch_bounds__(kThreads, 2) ffx_score_kernel(const ScoreArgs a) {
+    constexpr int EPL = CPL * S;       // elements per lane per row
+    constexpr int NV4 = EPL / 4;       // 128-bit loads per lane per row
+    constexpr int ROW_F4 = 32 * NV4;   // float4s per row
+    static_assert(EPL % 4 == 0, "lane slice must be whole float4s");
+
+    extern __shared__ unsigned long long s_keys[];  // FUSE only: cpad keys
+    __shared__ int s_next;
+
+    const int lane = threadIdx.x & 31;
+    const int64_t q_idx = blockIdx.x / a.tiles_per_query;
+    const int t_idx = blockIdx.x % a.tiles_per_query;
+    const int64_t q_begin = a.q_off[q_idx];
+    const int n_query = static_cast<int>(a.q_off[q_idx + 1] - q_begin);
+    const int c0 = t_idx * a.tile;
+    const int n_tile = min(a.tile, n_query - c0);
+    if (!FUSE && n_tile <= 0) return;
+
+    if (threadIdx.x == 0) s_next = 0;
+    if (FUSE) {
+        for (int i = n_query + threadIdx.x; i < a.cpad; i += kThreads) s_keys[i] = 0ull;
+    }
+
+    // this lane's slice of the query vector, gathered once from the original order
+    float q[EPL];
+    {
+        const float *qv = a.qvecs + q_idx * (32 * EPL);
+#pragma unroll
+        for (int m = 0; m < EPL; m++) {
+            const int g = lane * CPL + (m % CPL);
+            q[m] = __ldg(qv + (g >> 3) * (8 * S) + 8 * (m / CPL) + (g & 7));
+        }
+    }
+    __syncthreads();
+
+    const float4 *rows4 = reinterpret_cast<const float4 *>(a.vectors);
+    const bool indirect = a.indirect && a.mode != FFX_MODE_PASSAGE;
+
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_next, 32);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n_tile) break;
+        const int nb = min(32, n_tile - base);
+        const int64_t my_pair = q_begin + c0 + base + lane;
+
+        // lane j resolves candidate j of the batch: id -> (first row, count)
+        uint32_t my_start = 0, my_cnt = 0;
+        float my_lex = 0.f;
+        if (lane < nb) {
+            const int32_t u = __ldg(a.cand + my_pair);
+            if (a.mode == FFX_MODE_PASSAGE) {
+                my_start = static_cast<uint32_t>(u);
+                my_cnt = 1;
+            } else {
+                const uint2 sp = __ldg(a.doc_span + u);
+                my_start = sp.x;
+                my_cnt = a.mode == FFX_MODE_FIRSTP ? 1u : sp.y;
+            }
+            if (a.lex) my_lex = __ldg(a.lex + my_pair);
+        }
+
+        float my_ff = 0.f;
+        for (int j = 0; j < nb; j++) {
+            const uint32_t start = __shfl_sync(kFull, my_start, j);
+            const uint32_t cnt = __shfl_sync(kFull, my_cnt, j);
+            DocReduce red;
+            red.init();
+            for (uint32_t r0 = 0; r0 < cnt; r0 += 32) {
+                const uint32_t nr = min(32u, cnt - r0);
+                uint32_t my_row = start + r0 + lane;
+                if (indirect) my_row = lane < nr ? __ldg(a.doc_rows + start + r0 + lane) : 0u;
+                for (uint32_t r = 0; r < nr; r += 2) {
+                    const bool two = r + 1 < nr;  // warp-uniform
+                    const uint32_t row_a = __shfl_sync(kFull, my_row, r);
+                    const uint32_t row_b = __shfl_sync(kFull, my_row, two ? r + 1 : r);
+                    const float4 *pa = rows4 + static_cast<size_t>(row_a) * ROW_F4 + lane;
+                    const float4 *pb = rows4 + static_cast<size_t>(row_b) * ROW_F4 + lane;
+                    float4 va[NV4], vb[NV4];
+#pragma unroll
+                    for (int i = 0; i < NV4; i++) va[i] = ldg_stream(pa + i * 32);
+                    if (two) {
+#pragma unroll
+                        for (int i = 0; i < NV4; i++) vb[i] = ldg_stream(pb + i * 32);
+                    }
+                    const float sa = warp_tree_sum(lane_chain_sum<CPL, S>(q, va));
+                    red.add(sa, r0 + r == 0, a.mode);
+                    if (two) {
+                        const float sb = warp_tree_sum(lane_chain_sum<CPL, S>(q, vb));
+                        red.add(sb, false, a.mode);
+                    }
+                }
+            }
+            const float ff = red.finish(cnt, a.mode);
+            if (lane == j) my_ff = ff;
+        }
+
+        // lane j now holds candidate j's score: coalesced epilogue
+        if (lane < nb) {
+            float inter = my_ff;
+            if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, my_lex), __fmul_rn(a.beta, my_ff));
+            if (a.out_ff) a.out_ff[my_pair] = my_ff;
+            if (a.out_int) a.out_int[my_pair] = inter;
+            if (FUSE) {
+                const uint32_t pos = static_cast<uint32_t>(c0 + base + lane);
+                s_keys[pos] = topk_key(inter, pos);
+            }
+        }
+    }
+
+    if (FUSE) {
+        __syncthreads();
+        bitonic_sort_desc(s_keys, a.cpad);
+        write_topk(s_keys, n_query, a.k, a.topk_score + q_idx * a.k, a.topk_pos + q_idx * a.k);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// generic exact kernel (any D, identity layout): one thread per pair
+// ---------------------------------------------------------------------------------------
+__device__ inline float pairwise_dot_generic(const float *q, const float *d, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; i++) res = __fadd_rn(res, __fmul_rn(q[i], d[i]));
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = __fmul_rn(q[j], d[j]);
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = __fadd_rn(r[j], __fmul_rn(q[i + j], d[i + j]));
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; i++) res = __fadd_rn(res, __fmul_rn(q[i], d[i]));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(pairwise_dot_generic(q, d, n2), pairwise_dot_generic(q + n2, d + n2, n - n2));
+}
+
+__global__ void __launch_bounds__(128) ffx_score_generic_kernel(const ScoreArgs a, int64_t nq,
+                                                                int64_t n_pairs) {
+    const int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (p >= n_pairs || p >= a.q_off[nq]) return;  // n_pairs is only an upper bound
+    // query of this pair: binary search in q_off
+    int64_t lo = 0, hi = nq;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a.q_off[mid] <= p) lo = mid; else hi = mid;
+    }
+    const float *qv = a.qvecs + lo * a.dim;
+    const int32_t u = a.cand[p];
+    uint32_t start, cnt;
+    if (a.mode == FFX_MODE_PASSAGE) {
+        start = static_cast<uint32_t>(u);
+        cnt = 1;
+    } else {
+        const uint2 sp = a.doc_span[u];
+        start = sp.x;
+        cnt = a.mode == FFX_MODE_FIRSTP ? 1u : sp.y;
+    }
+    const bool indirect = a.indirect && a.mode != FFX_MODE_PASSAGE;
+    DocReduce red;
+    red.init();
+    for (uint32_t r = 0; r < cnt; r++) {
+        const uint32_t row = indirect ? static_cast<uint32_t>(a.doc_rows[start + r]) : start + r;
+        const float s = __fadd_rn(
+            0.f, pairwise_dot_generic(qv, a.vectors + static_cast<size_t>(row) * a.dim,
+                                      static_cast<int>(a.dim)));
+        red.add(s, r == 0, a.mode);
+    }
+    const float ff = red.finish(cnt, a.mode);
+    float inter = ff;
+    if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, a.lex[p]), __fmul_rn(a.beta, ff));
+    if (a.out_ff) a.out_ff[p] = ff;
+    if (a.out_int) a.out_int[p] = inter;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-query top-k over already interpolated scores (split path, generic path, merges)
+// ---------------------------------------------------------------------------------------
+// keys: shared memory when cpad <= kMaxFusedCand, else `gkeys + q*cpad` in global memory.
+__global__ void __launch_bounds__(kThreads) ffx_topk_kernel(const float *scores,
+                                                            const int64_t *q_off, int k, int cpad,
+                                                            unsigned long long *gkeys,
+                                                            float *out_s, int32_t *out_p) {
+    extern __shared__ unsigned long long s_keys[];
+    const int64_t q = blockIdx.x;
+    const int64_t b = q_off[q];
+    const int n = static_cast<int>(q_off[q + 1] - b);
+    unsigned long long *keys = gkeys ? gkeys + q * cpad : s_keys;
+    for (int i = threadIdx.x; i < cpad; i += blockDim.x)
+        keys[i] = i < n ? topk_key(scores[b + i], static_cast<uint32_t>(i)) : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(keys, cpad);
+    write_topk(keys, n, k, out_s + q * k, out_p + q * k);
+}
+
+// Merge per-shard top-k lists [n_shards, nq, k] -> [nq, k]; positions are global positions
+// inside the query's candidate block, so the ordering rule is the same key.
+__global__ void __launch_bounds__(kThreads) ffx_merge_topk_kernel(const float *sh_s,
+                                                                  const int32_t *sh_p,
+                                                                  int n_shards, int64_t nq, int k,
+                                                                  int cpad, float *out_s,
+                                                                  int32_t *out_p) {
+    extern __shared__ unsigned long long s_keys[];
+    const int64_t q = blockIdx.x;
+    const int total = n_shards * k;
+    for (int i = threadIdx.x; i < cpad; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < total) {
+            const int sh = i / k, j = i % k;
+            const int64_t src = (static_cast<int64_t>(sh) * nq + q) * k + j;
+            const int32_t pos = sh_p[src];
+            if (pos >= 0) key = topk_key(sh_s[src], static_cast<uint32_t>(pos));
+        }
+        s_keys[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort_desc(s_keys, cpad);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const bool ok = s_keys[i] != 0ull;
+        out_s[q * k + i] = ok ? key_score(s_keys[i]) : -INFINITY;
+        out_p[q * k + i] = ok ? key_pos(s_keys[i]) : -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// staging: element permutation between original order and the lane-major store
+// ---------------------------------------------------------------------------------------
+// to_store != 0: dst(store row, staged k) = src(row, orig(k)); else the inverse.
+// `rows` (optional) lists the store rows to read when gathering back.
+__global__ void ffx_permute_rows_kernel(float *dst, const float *src, int64_t nrows, int dim,
+                                        int cpl, int steps, int to_store, const int64_t *rows) {
+    const int64_t total = nrows * dim;
+    for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = t / dim;
+        const int k = static_cast<int>(t % dim);
+        const int e = cpl ? ffx_orig_index(cpl, steps, k) : k;
+        if (to_store) {
+            dst[r * dim + k] = src[r * dim + e];
+        } else {
+            const int64_t sr = rows ? rows[r] : r;
+            dst[r * dim + e] = src[sr * dim + k];
+        }
+    }
+}
+
+__global__ void ffx_gather_bytes_kernel(uint8_t *dst, const uint8_t *src, int64_t nrows,
+                                        int64_t row_bytes, const int64_t *rows) {
+    const int64_t total = nrows * row_bytes;
+    for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = t / row_bytes;
+        dst[t] = src[rows[r] * row_bytes + (t % row_bytes)];
+    }
+}
+
+}  // namespace ffx

@@ -1,0 +1,48 @@
+// ffx_layout.h — the lane-major row layout shared by host staging code and the kernels.
+//
+// numpy reduces a D-element fp32 row with a fixed pairwise tree (DESIGN.md "N1"): the row is
+// cut into NB = 2^t leaf blocks of 8*S elements (8*S <= 128); inside a leaf, accumulator j
+// (0..7) sums elements j, 8+j, 16+j, ... sequentially ("chain" (b, j), S terms); the 8
+// accumulators and then the NB leaves are combined by a balanced binary tree.
+//
+// A warp reproduces that tree when lane l owns CPL = NB/4 whole chains
+//     g = l*CPL + ch,  block b = g / 8,  accumulator j = g % 8
+// and the combine is the xor-butterfly 1,2,4,8,16.  So that a lane's chains arrive with
+// perfectly coalesced 128-bit loads, the STORE keeps every row permuted: the i-th float4 of
+// lane l sits at float offset (i*32 + l)*4 and holds lane-local elements m = 4i..4i+3, with
+// lane-local element m = step s = m / CPL of chain ch = m % CPL.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FFX_HD __host__ __device__
+#else
+#define FFX_HD
+#endif
+
+struct ffx_plan {
+    int cpl;    // chains per lane (1, 2, 4, 8); 0 = no fast plan (identity layout)
+    int steps;  // S: terms per chain
+};
+
+// D = 32 * cpl * steps.  Only shapes whose numpy tree is uniform qualify.
+static inline ffx_plan ffx_plan_for_dim(int64_t dim) {
+    static const struct { int dim, cpl, steps; } table[] = {
+        {384, 1, 12}, {512, 1, 16}, {640, 2, 10}, {768, 2, 12},
+        {896, 2, 14}, {1024, 2, 16}, {1536, 4, 12}, {2048, 4, 16},
+    };
+    for (unsigned i = 0; i < sizeof(table) / sizeof(table[0]); i++)
+        if (table[i].dim == dim) return ffx_plan{table[i].cpl, table[i].steps};
+    return ffx_plan{0, 0};
+}
+
+// staged float offset k inside a row  ->  original element index
+FFX_HD static inline int ffx_orig_index(int cpl, int steps, int k) {
+    const int i = k >> 7;          // which float4 of the lane
+    const int l = (k & 127) >> 2;  // lane
+    const int c = k & 3;
+    const int m = 4 * i + c;       // lane-local element
+    const int s = m / cpl, ch = m % cpl;
+    const int g = l * cpl + ch;
+    return (g >> 3) * (8 * steps) + 8 * s + (g & 7);
+}

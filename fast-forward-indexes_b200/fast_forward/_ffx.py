@@ -1,0 +1,243 @@
+"""ctypes binding of libffx.so (the C ABI in include/ffx.h) + a thin numpy-level wrapper.
+
+There is no CPU implementation behind this module: if the shared library has not been built
+(`python -c "import __graft_entry__ as g; g.build()"`) or no CUDA device is visible, the
+calls raise — nothing silently falls back to numpy.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libffx.so")
+
+ROWS_F32, ROWS_PQ_U8 = 0, 1
+MODE_PASSAGE, MODE_MAXP, MODE_FIRSTP, MODE_AVEP = 1, 2, 3, 4
+
+# every symbol include/ffx.h declares: name -> (restype, argtypes)
+_P, _I, _L, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
+SYMBOLS = {
+    "ffx_abi_version": (_I, []),
+    "ffx_last_error": (C.c_char_p, []),
+    "ffx_device_count": (_I, []),
+    "ffx_host_alloc": (_I, [C.POINTER(_P), _L]),
+    "ffx_host_free": (_I, [_P]),
+    "ffx_index_create": (_I, [_I, _I, _L, _L, C.POINTER(_P)]),
+    "ffx_index_destroy": (_I, [_P]),
+    "ffx_index_reserve": (_I, [_P, _L]),
+    "ffx_index_stage_rows": (_I, [_P, _L, _L, _P, _I]),
+    "ffx_index_read_rows": (_I, [_P, _P, _L, _P]),
+    "ffx_index_num_rows": (_L, [_P]),
+    "ffx_index_capacity": (_L, [_P]),
+    "ffx_index_dim": (_L, [_P]),
+    "ffx_index_has_fast_path": (_I, [_P]),
+    "ffx_index_set_docs": (_I, [_P, _L, _P, _P]),
+    "ffx_index_set_pq": (_I, [_P, _I, _I, _I, _P, _P]),
+    "ffx_rerank": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _L, _P, _P, _P, _P, _P]),
+    "ffx_rerank_host": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _P, _P, _P, _P]),
+    "ffx_merge_topk": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _P]),
+    "ffx_launch_count": (_L, []),
+}
+
+_lib = None
+
+
+class FFXError(RuntimeError):
+    """A libffx call failed (status code + message of ffx_last_error)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libffx error {code}: {message}")
+        self.code = code
+
+
+def lib():
+    """Load libffx.so once.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not built. Build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` from the repository root; fast_forward has no CPU scoring path."
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.ffx_abi_version() != 1:
+            raise ImportError("libffx.so ABI version mismatch; rebuild it")
+        _lib = handle
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise FFXError(code, lib().ffx_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    return lib().ffx_device_count()
+
+
+def launch_count() -> int:
+    return lib().ffx_launch_count()
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return C.c_void_p(a.ctypes.data)
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class PinnedBuffer:
+    """Page-locked host memory from ffx_host_alloc, exposed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._p = C.c_void_p()
+        check(lib().ffx_host_alloc(C.byref(self._p), nbytes))
+        if nbytes:
+            buf = (C.c_char * nbytes).from_address(self._p.value)
+            self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+        else:
+            self.array = np.empty(self.shape, self.dtype)
+
+    def free(self):
+        if self._p is not None and self._p.value:
+            self.array = None
+            lib().ffx_host_free(self._p)
+        self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceIndex:
+    """An HBM-resident row store + doc->rows map + optional PQ codebooks (one ffx_index)."""
+
+    def __init__(self, dim: int, capacity: int = 0, row_kind: int = ROWS_F32, device: int = 0):
+        self._h = C.c_void_p()
+        self.row_kind = row_kind
+        self.dim = int(dim)
+        self.device = device
+        check(lib().ffx_index_create(device, row_kind, self.dim, int(capacity), C.byref(self._h)))
+
+    # -- lifetime -----------------------------------------------------------------------
+    def close(self):
+        if self._h is not None and self._h.value:
+            lib().ffx_index_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError("index closed")
+        return self._h
+
+    # -- storage ------------------------------------------------------------------------
+    def __len__(self):
+        return int(lib().ffx_index_num_rows(self.handle))
+
+    @property
+    def capacity(self):
+        return int(lib().ffx_index_capacity(self.handle))
+
+    @property
+    def has_fast_path(self):
+        return bool(lib().ffx_index_has_fast_path(self.handle))
+
+    def reserve(self, capacity: int):
+        check(lib().ffx_index_reserve(self.handle, int(capacity)))
+
+    def stage(self, row0: int, rows: np.ndarray):
+        dt = np.float32 if self.row_kind == ROWS_F32 else np.uint8
+        rows = _arr(rows, dt)
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise ValueError(f"expected rows of shape [n, {self.dim}], got {rows.shape}")
+        check(lib().ffx_index_stage_rows(self.handle, int(row0), rows.shape[0], _ptr(rows), 0))
+
+    def stage_device(self, row0: int, nrows: int, device_ptr: int):
+        check(lib().ffx_index_stage_rows(self.handle, int(row0), int(nrows), C.c_void_p(device_ptr), 1))
+
+    def read_rows(self, rows) -> np.ndarray:
+        rows = _arr(rows, np.int64)
+        dt = np.float32 if self.row_kind == ROWS_F32 else np.uint8
+        out = np.empty((len(rows), self.dim), dt)
+        check(lib().ffx_index_read_rows(self.handle, _ptr(rows), len(rows), _ptr(out)))
+        return out
+
+    def set_docs(self, doc_off, doc_rows=None):
+        doc_off = _arr(doc_off, np.int64)
+        doc_rows = None if doc_rows is None else _arr(doc_rows, np.int64)
+        check(lib().ffx_index_set_docs(self.handle, len(doc_off) - 1, _ptr(doc_off), _ptr(doc_rows)))
+
+    def set_pq(self, codewords, R=None):
+        codewords = _arr(codewords, np.float32)
+        M, Ks, Ds = codewords.shape
+        R = None if R is None else _arr(R, np.float32)
+        check(lib().ffx_index_set_pq(self.handle, M, Ks, Ds, _ptr(codewords), _ptr(R)))
+
+    # -- the hot path -------------------------------------------------------------------
+    def rerank_host(self, mode, qvecs, q_off, cand, lex=None, alpha=0.0, k=0, want_ff=True,
+                    want_int=False, out=None):
+        """ffx_rerank_host on numpy (or pinned) buffers.  Returns a dict with the requested
+        outputs: ff [n], int [n], topk_score / topk_pos [nq, k]."""
+        qvecs = _arr(qvecs, np.float32)
+        q_off = _arr(q_off, np.int64)
+        cand = _arr(cand, np.int32)
+        lex = None if lex is None else _arr(lex, np.float32)
+        nq, n = len(q_off) - 1, len(cand)
+        out = {} if out is None else out
+        ff = out.get("ff") if want_ff else None
+        if want_ff and ff is None:
+            ff = out["ff"] = np.empty(n, np.float32)
+        it = out.get("int") if want_int else None
+        if want_int and it is None:
+            it = out["int"] = np.empty(n, np.float32)
+        ts = tp = None
+        if k > 0:
+            ts = out.get("topk_score")
+            tp = out.get("topk_pos")
+            if ts is None:
+                ts = out["topk_score"] = np.empty((nq, k), np.float32)
+            if tp is None:
+                tp = out["topk_pos"] = np.empty((nq, k), np.int32)
+        check(lib().ffx_rerank_host(self.handle, int(mode), _ptr(qvecs), nq, _ptr(q_off), _ptr(cand),
+                                    _ptr(lex), float(alpha), int(k), _ptr(ff), _ptr(it), _ptr(ts),
+                                    _ptr(tp)))
+        return out
+
+    def rerank_device(self, mode, qvecs_ptr, nq, q_off_ptr, cand_ptr, lex_ptr, alpha, k, max_cand,
+                      out_ff_ptr=0, out_int_ptr=0, topk_score_ptr=0, topk_pos_ptr=0, stream=0):
+        """ffx_rerank on raw device pointers (ints); asynchronous on `stream`."""
+        vp = lambda x: C.c_void_p(x) if x else None  # noqa: E731
+        check(lib().ffx_rerank(self.handle, int(mode), vp(qvecs_ptr), int(nq), vp(q_off_ptr),
+                               vp(cand_ptr), vp(lex_ptr), float(alpha), int(k), int(max_cand),
+                               vp(out_ff_ptr), vp(out_int_ptr), vp(topk_score_ptr), vp(topk_pos_ptr),
+                               vp(stream)))
+
+
+def merge_topk(device, shard_scores_ptr, shard_pos_ptr, n_shards, nq, k, out_score_ptr, out_pos_ptr,
+               stream=0):
+    check(lib().ffx_merge_topk(int(device), C.c_void_p(shard_scores_ptr), C.c_void_p(shard_pos_ptr),
+                               int(n_shards), int(nq), int(k), C.c_void_p(out_score_ptr),
+                               C.c_void_p(out_pos_ptr), C.c_void_p(stream) if stream else None))

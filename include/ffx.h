@@ -1,0 +1,150 @@
+/* ffx.h — C ABI of the B200-native Fast-Forward re-ranking engine (libffx.so).
+ *
+ * The reference (mrjleo/fast-forward-indexes v0.8.0) is pure Python and has no FFI seam;
+ * its seam is the `Index` class contract.  Each entry point below replaces one piece of
+ * that contract on the re-ranking hot path; the citation is the reference code it stands
+ * in for (paths relative to /root/reference/src/fast_forward/).  The Python drop-in shell
+ * (fast-forward-indexes_b200/fast_forward/) binds these with ctypes — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; no torch / numpy types cross this boundary
+ *   - every call returns 0 on success or a negative ffx_status; the message for the last
+ *     failure on the calling thread is ffx_last_error(); nothing throws across the ABI
+ *   - the caller owns every host buffer; the library owns all device memory it allocates
+ *   - id strings never cross the ABI: the host shell maps ids to integers with the exact
+ *     semantics of index/util.py:12-42 and raises IndexError itself
+ *   - calls on one ffx_index must be serialised by the caller (the reference is
+ *     single-threaded as well)
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ */
+#ifndef FFX_H_
+#define FFX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFX_ABI_VERSION 1
+
+typedef struct ffx_index ffx_index;
+
+typedef enum {
+    FFX_OK = 0,
+    FFX_ERR_INVALID = -1,    /* bad argument */
+    FFX_ERR_CUDA = -2,       /* CUDA runtime error (message has the cudaError string) */
+    FFX_ERR_OOM = -3,        /* device or pinned-host allocation failed */
+    FFX_ERR_STATE = -4,      /* call not valid in the index's current state */
+    FFX_ERR_UNSUPPORTED = -5 /* shape outside what the kernels implement */
+} ffx_status;
+
+/* index/base.py:18-24 (`Mode`); same numeric values */
+typedef enum {
+    FFX_MODE_PASSAGE = 1,
+    FFX_MODE_MAXP = 2,
+    FFX_MODE_FIRSTP = 3,
+    FFX_MODE_AVEP = 4
+} ffx_mode;
+
+typedef enum {
+    FFX_ROWS_F32 = 0,  /* fp32 vectors, `dim` floats per row */
+    FFX_ROWS_PQ_U8 = 1 /* PQ/OPQ codes, `dim` = M code bytes per row (Ks <= 256) */
+} ffx_row_kind;
+
+/* ---- library ---------------------------------------------------------------------- */
+int ffx_abi_version(void);
+const char *ffx_last_error(void);
+/* number of CUDA devices visible; 0 when there is none (then nothing else will work) */
+int ffx_device_count(void);
+
+/* Pinned host memory for buffers that cross PCIe every call (candidate lists, query
+ * vectors, outputs).  Plain malloc'ed buffers work too, just slower. */
+int ffx_host_alloc(void **out, int64_t bytes);
+int ffx_host_free(void *p);
+
+/* ---- index storage ---------------------------------------------------------------- */
+/* Replaces `InMemoryIndex.__init__` chunk allocation (index/memory.py:23-56): one
+ * device-resident row store with room for `capacity_rows` rows on CUDA device `device`. */
+int ffx_index_create(int device, int row_kind, int64_t dim, int64_t capacity_rows, ffx_index **out);
+int ffx_index_destroy(ffx_index *idx);
+/* Grow the store (index/memory.py:103-108, the alloc_size chunk growth); keeps contents. */
+int ffx_index_reserve(ffx_index *idx, int64_t capacity_rows);
+/* Replaces the chunk copy of `InMemoryIndex._add` (index/memory.py:97-119) and the slice
+ * loop of `OnDiskIndex.to_memory` (index/disk.py:190-204): rows [row0, row0+nrows) take
+ * `rows` (row-major, fp32 or uint8 per row_kind).  Host sources go through a pinned double
+ * buffer; `src_on_device != 0` means `rows` is a device pointer on the index's device.
+ * The store keeps fp32 rows in a lane-major permuted layout; callers only ever
+ * see the original element order. */
+int ffx_index_stage_rows(ffx_index *idx, int64_t row0, int64_t nrows, const void *rows,
+                         int src_on_device);
+/* Replaces `ChunkIndexer.__call__`'s fancy-index gather (index/util.py:97-113): copies the
+ * listed rows, in order and in original element order, to host memory `out`. */
+int ffx_index_read_rows(ffx_index *idx, const int64_t *rows, int64_t n, void *out);
+int64_t ffx_index_num_rows(const ffx_index *idx);     /* highest staged row + 1 */
+int64_t ffx_index_capacity(const ffx_index *idx);
+int64_t ffx_index_dim(const ffx_index *idx);
+/* 1 when `dim` has a lane-major fast kernel, 0 when the generic exact kernel is used */
+int ffx_index_has_fast_path(const ffx_index *idx);
+
+/* Replaces `doc_id_to_idx` (index/memory.py:86-88, index/disk.py:408-417): document
+ * ordinal d owns rows doc_rows[doc_off[d] .. doc_off[d+1]) in insertion order.  When every
+ * document's rows are consecutive the library keeps only (first,count) spans. */
+int ffx_index_set_docs(ffx_index *idx, int64_t n_docs, const int64_t *doc_off,
+                       const int64_t *doc_rows);
+
+/* Replaces `Quantizer.decode` on the scoring path (quantizer/base.py:123-132 ->
+ * quantizer/nanopq.py:43-44,111-112): attaches nanopq-compatible codebooks
+ * `codewords[M][Ks][Ds]` and, for OPQ, the rotation `R[D][D]` (NULL for plain PQ) to an
+ * FFX_ROWS_PQ_U8 index.  Scoring then uses asymmetric distance computation. */
+int ffx_index_set_pq(ffx_index *idx, int M, int Ks, int Ds, const float *codewords,
+                     const float *R);
+
+/* ---- the hot path ----------------------------------------------------------------- */
+/* Replaces, in one pass, `Index._compute_scores` (index/base.py:279-314) including
+ * `_get_vectors` (index/memory.py:139-140), `Ranking.interpolate`'s arithmetic
+ * (ranking.py:319) and the per-query `Ranking.cut` (ranking.py:115-117, :285-291).
+ *
+ *   qvecs   [nq, D] fp32 query vectors (D = vector dimension, also for PQ indexes)
+ *   q_off   [nq+1]  pair offsets: query q owns pairs [q_off[q], q_off[q+1])
+ *   cand    [n]     candidate per pair: a document ordinal (MAXP/FIRSTP/AVEP, as given to
+ *                   ffx_index_set_docs) or a row number (PASSAGE)
+ *   lex     [n]     first-stage scores, or NULL for "no interpolation"
+ *   alpha           interpolated = fl32(fl32(alpha)*lex) + fl32(fl32(1-alpha)*ff)
+ *   k               per-query cut-off; 0 = no top-k
+ *   out_ff  [n]     semantic score per pair (may be NULL)
+ *   out_int [n]     interpolated score per pair (may be NULL; equals ff when lex==NULL)
+ *   out_topk_score / out_topk_pos [nq, k]: the k best interpolated scores per query in
+ *                   descending order, ties by ascending position inside the query's block;
+ *                   pos is that position; unused slots are (-inf, -1)
+ *
+ * fp32 scores are bit-identical to numpy's `np.sum(q * d, axis=1)` + pandas' groupby
+ * max / mean / first; PQ scores are ADC sums (tolerance in DESIGN.md).
+ *
+ * ffx_rerank: all pointers are DEVICE pointers on the index's device, the work is
+ * enqueued on `stream` (a cudaStream_t, NULL = default stream) and the call returns
+ * without synchronising.  `max_cand` must be >= the largest q_off[q+1]-q_off[q].
+ * ffx_rerank_host: all pointers are HOST pointers; copies in, runs, copies out and
+ * synchronises before returning. */
+int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const int64_t *q_off,
+               const int32_t *cand, const float *lex, double alpha, int k, int64_t max_cand,
+               float *out_ff, float *out_int, float *out_topk_score, int32_t *out_topk_pos,
+               void *stream);
+int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
+                    const int64_t *q_off, const int32_t *cand, const float *lex, double alpha,
+                    int k, float *out_ff, float *out_int, float *out_topk_score,
+                    int32_t *out_topk_pos);
+
+/* Exchange step of a doc-id-range sharded corpus: merges `n_shards` per-shard
+ * top-k lists [n_shards, nq, k] (scores + GLOBAL positions, device pointers) into
+ * [nq, k] with the same ordering rule.  Runs on `stream`. */
+int ffx_merge_topk(int device, const float *shard_scores, const int32_t *shard_pos, int n_shards,
+                   int64_t nq, int k, float *out_score, int32_t *out_pos, void *stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t ffx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFX_H_ */

@@ -1,0 +1,393 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libffx.so), against the
+oracle and against the golden vectors written by the unmodified reference.
+
+Bar: bit-exact for ids / candidate sets / positions and for fp32 scores (N1/N2/N3 make the
+fp32 path reproducible bit-for-bit); the PQ/OPQ ADC path reorders arithmetic and is held to
+rtol 1e-5 + atol 1e-5*|q||d| (stated in the test)."""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+import ff_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+MODES = {"PASSAGE": fo.MODE_PASSAGE, "MAXP": fo.MODE_MAXP, "FIRSTP": fo.MODE_FIRSTP,
+         "AVEP": fo.MODE_AVEP}
+
+
+def bits(x):
+    return np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def ffx():
+    import __graft_entry__ as g
+
+    g.build()
+    from fast_forward import _ffx
+
+    assert _ffx.device_count() >= 1, "gpu tests need a CUDA device"
+    return _ffx
+
+
+def c_scores(oracle_c, vec, u_off, u_rows, pair_q, pair_u, qv, mode):
+    vec = np.ascontiguousarray(vec, np.float32)
+    qv = np.ascontiguousarray(qv, np.float32)
+    u_off = np.ascontiguousarray(u_off, np.int64)
+    u_rows = np.ascontiguousarray(u_rows, np.int64)
+    pair_q = np.ascontiguousarray(pair_q, np.int64)
+    pair_u = np.ascontiguousarray(pair_u, np.int64)
+    out = np.empty(len(pair_q), np.float32)
+    P = ctypes.c_void_p
+    oracle_c.ffo_score_pairs(P(vec.ctypes.data), ctypes.c_int64(vec.shape[1]), P(u_off.ctypes.data),
+                             P(u_rows.ctypes.data), P(pair_q.ctypes.data), P(pair_u.ctypes.data),
+                             ctypes.c_int64(len(pair_q)), P(qv.ctypes.data), ctypes.c_int(mode),
+                             P(out.ctypes.data))
+    return out
+
+
+def units_for_mode(doc_off, doc_rows, n_rows, mode):
+    """Mode-resolved CSR for the oracle (index/util.py:29-41)."""
+    if mode == fo.MODE_PASSAGE:
+        return np.arange(n_rows + 1), np.arange(n_rows)
+    if mode == fo.MODE_FIRSTP:
+        return np.arange(len(doc_off)), doc_rows[doc_off[:-1]]
+    return doc_off, doc_rows
+
+
+def make_corpus(rng, n_docs, max_psg, dim, contiguous=True):
+    cnt = rng.integers(1, max_psg + 1, n_docs)
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    n_rows = int(off[-1])
+    rows = np.arange(n_rows, dtype=np.int64)
+    if not contiguous:  # documents own scattered rows, listed in increasing (insertion) order
+        owner = np.repeat(np.arange(n_docs), cnt)
+        rng.shuffle(owner)
+        order = np.argsort(owner, kind="stable")
+        rows = order.astype(np.int64)
+    vec = rng.standard_normal((n_rows, dim)).astype(np.float32)
+    return off, rows, vec
+
+
+def make_pairs(rng, nq, pool, lo, hi):
+    cnts = rng.integers(lo, hi + 1, nq)
+    q_off = np.concatenate([[0], np.cumsum(cnts)]).astype(np.int64)
+    cand = np.concatenate([rng.choice(pool, c, replace=False) for c in cnts] + [np.zeros(0, np.int64)])
+    return q_off, cand.astype(np.int32), np.repeat(np.arange(nq), cnts)
+
+
+# ------------------------------------------------------------------------------------------
+# golden vectors of the unmodified reference, through the C ABI
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", ["s11", "s12", "s13", "s14"])
+@pytest.mark.parametrize("mode", ["MAXP", "AVEP", "FIRSTP", "PASSAGE"])
+def test_golden_reference_vectors(ffx, golden_random, key, mode):
+    meta, arrays = golden_random
+    case = meta[key]
+    g = case["modes"][mode]
+    vec, qvecs = arrays[f"{key}/vectors"], arrays[f"{key}/qvecs"]
+    doc_names = list(dict.fromkeys(case["doc_ids"]))
+    doc_ord = {d: i for i, d in enumerate(doc_names)}
+    lists = [[] for _ in doc_names]
+    for row, d in enumerate(case["doc_ids"]):
+        lists[doc_ord[d]].append(row)
+    doc_off = np.concatenate([[0], np.cumsum([len(x) for x in lists])])
+    doc_rows = np.concatenate(lists)
+    psg_row = {p: i for i, p in enumerate(case["psg_ids"])}
+
+    idx = ffx.DeviceIndex(case["dim"], capacity=len(vec))
+    half = len(vec) // 2
+    idx.stage(0, vec[:half])
+    idx.stage(half, vec[half:])
+    idx.set_docs(doc_off, doc_rows)
+    assert idx.has_fast_path == (case["dim"] in (384, 768, 1024))
+
+    # integer-code the first-stage ranking: queries in order of appearance, candidates of a
+    # query in ascending id order (the order the reference's outer merge leaves ties in)
+    fs = g["first_stage"]
+    q_names = list(dict.fromkeys(fs["q_id"]))
+    per_q = {q: [] for q in q_names}
+    for q, i, s in zip(fs["q_id"], fs["id"], fs["score"]):
+        per_q[q].append((i, s))
+    cand, lex, q_off, names = [], [], [0], []
+    for q in q_names:
+        for i, s in sorted(per_q[q]):
+            cand.append(psg_row[i] if mode == "PASSAGE" else doc_ord[i])
+            lex.append(s)
+            names.append((q, i))
+        q_off.append(len(cand))
+    qv = np.stack([qvecs[int(q[1:])] for q in q_names])
+    k = case["cutoff"]
+    out = idx.rerank_host(MODES[mode], qv, q_off, cand, lex, case["alpha"], k, want_ff=True, want_int=True)
+
+    want_ff = {(q, i): b for q, i, b in zip(g["ff"]["q_id"], g["ff"]["id"], g["ff"]["score_bits"])}
+    got_ff = dict(zip(names, bits(out["ff"]).tolist()))
+    assert got_ff == want_ff
+    want_int = {(q, i): b for q, i, b in zip(g["interpolated"]["q_id"], g["interpolated"]["id"],
+                                             g["interpolated"]["score_bits"])}
+    assert dict(zip(names, bits(out["int"]).tolist())) == want_int
+    # cut: same rows, same order, same bits — per query, in the reference's frame order
+    got = []
+    for qi, q in enumerate(q_names):
+        for j in range(k):
+            p = out["topk_pos"][qi, j]
+            if p >= 0:
+                got.append((q, names[q_off[qi] + p][1], int(bits(out["topk_score"][qi, j:j + 1])[0])))
+    want = list(zip(g["cut"]["q_id"], g["cut"]["id"], g["cut"]["score_bits"]))
+    order = {q: n for n, q in enumerate(dict.fromkeys(g["cut"]["q_id"]))}
+    got.sort(key=lambda t: order[t[0]])  # stable: keeps our within-query order
+    assert got == want
+    idx.close()
+
+
+def test_reference_known_answers(ffx, golden_kat):
+    """reference tests/test_index.py:135-200 fixtures (5x5 lower-triangular, d0 has 2 rows)."""
+    V = np.tril(np.ones((5, 5), dtype=np.float32))
+    idx = ffx.DeviceIndex(5, capacity=5)
+    idx.stage(0, V)
+    idx.set_docs([0, 2, 3, 4, 5])
+    qv = np.ones((2, 5), np.float32)
+    q_off, cand = [0, 4, 8], [0, 1, 2, 3] * 2
+    for mode, d0 in (("MAXP", 2.0), ("FIRSTP", 1.0), ("AVEP", 1.5)):
+        ff = idx.rerank_host(MODES[mode], qv, q_off, cand)["ff"]
+        assert ff.tolist() == [d0, 3.0, 4.0, 5.0] * 2
+        want = golden_kat[f"full/{mode}"]
+        by = {(q, i): s for q, i, s in zip(want["q_id"], want["id"], want["score"])}
+        assert [by[("q1", f"d{c}")] for c in range(4)] == ff[:4].tolist()
+    ff = idx.rerank_host(fo.MODE_PASSAGE, qv, [0, 5, 10], list(range(5)) * 2)["ff"]
+    assert ff.tolist() == [1.0, 2.0, 3.0, 4.0, 5.0] * 2
+    idx.close()
+
+
+# ------------------------------------------------------------------------------------------
+# seeded random problems against the oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [768, 384, 512, 640, 896, 1024, 1536, 2048, 100, 5, 130])
+@pytest.mark.parametrize("contiguous", [True, False])
+def test_scores_bit_exact_all_modes(ffx, oracle_c, dim, contiguous):
+    rng = np.random.default_rng(dim * 2 + contiguous)
+    n_docs = 400
+    off, rows, vec = make_corpus(rng, n_docs, 9, dim, contiguous)
+    idx = ffx.DeviceIndex(dim, capacity=len(vec))
+    idx.stage(0, vec)
+    idx.set_docs(off, rows)
+    nq = 7
+    qv = rng.standard_normal((nq, dim)).astype(np.float32)
+    for name, mode in MODES.items():
+        pool = len(vec) if mode == fo.MODE_PASSAGE else n_docs
+        q_off, cand, pair_q = make_pairs(rng, nq, pool, 0, 150)
+        lex = (rng.integers(0, 40, len(cand)) / 2).astype(np.float32)
+        out = idx.rerank_host(mode, qv, q_off, cand, lex, 0.1, 12, want_ff=True, want_int=True)
+        u_off, u_rows = units_for_mode(off, rows, len(vec), mode)
+        ff = c_scores(oracle_c, vec, u_off, u_rows, pair_q, cand, qv, mode)
+        assert (bits(out["ff"]) == bits(ff)).all(), name
+        it = fo.interpolate_f32(lex, ff, 0.1)
+        assert (bits(out["int"]) == bits(it)).all(), name
+        ts, tp = fo.topk_per_query(q_off, it, 12)
+        assert (out["topk_pos"] == tp).all(), name
+        assert (bits(out["topk_score"]) == bits(ts)).all(), name
+    idx.close()
+
+
+def test_numpy_oracle_agrees_with_c_oracle_and_gpu(ffx, oracle_c):
+    """The numpy restatement (np.sum(q*d, axis=1) itself) on a mid-size problem."""
+    rng = np.random.default_rng(77)
+    off, rows, vec = make_corpus(rng, 300, 6, 768, True)
+    idx = ffx.DeviceIndex(768, capacity=len(vec))
+    idx.stage(0, vec)
+    idx.set_docs(off)
+    qv = rng.standard_normal((5, 768)).astype(np.float32)
+    q_off, cand, pair_q = make_pairs(rng, 5, 300, 50, 120)
+    for mode in (fo.MODE_MAXP, fo.MODE_AVEP):
+        ff_np = fo.score_pairs(vec, off, rows, pair_q, cand, qv, mode)
+        ff_c = c_scores(oracle_c, vec, off, rows, pair_q, cand, qv, mode)
+        ff_gpu = idx.rerank_host(mode, qv, q_off, cand)["ff"]
+        assert (bits(ff_np) == bits(ff_c)).all() and (bits(ff_gpu) == bits(ff_np)).all()
+    idx.close()
+
+
+@pytest.mark.parametrize("mode", ["MAXP", "AVEP", "PASSAGE"])
+def test_fused_topk_path_many_queries(ffx, oracle_c, mode):
+    """nq >= 2 CTAs/SM x SMs switches to the fused score+interpolate+top-k kernel."""
+    rng = np.random.default_rng(5)
+    m = MODES[mode]
+    off, rows, vec = make_corpus(rng, 2000, 8, 768, True)
+    idx = ffx.DeviceIndex(768, capacity=len(vec))
+    idx.stage(0, vec)
+    idx.set_docs(off)
+    nq = 320
+    pool = len(vec) if m == fo.MODE_PASSAGE else 2000
+    qv = rng.standard_normal((nq, 768)).astype(np.float32)
+    q_off, cand, pair_q = make_pairs(rng, nq, pool, 0, 300)
+    lex = (rng.integers(0, 8, len(cand)) * 4).astype(np.float32)  # heavy ties with alpha=1
+    u_off, u_rows = units_for_mode(off, rows, len(vec), m)
+    ff = c_scores(oracle_c, vec, u_off, u_rows, pair_q, cand, qv, m)
+    for alpha, k in ((0.1, 100), (1.0, 37), (0.0, 512)):
+        out = idx.rerank_host(m, qv, q_off, cand, lex, alpha, k, want_ff=True, want_int=True)
+        it = fo.interpolate_f32(lex, ff, alpha)
+        ts, tp = fo.topk_per_query(q_off, it, k)
+        assert (bits(out["ff"]) == bits(ff)).all()
+        assert (bits(out["int"]) == bits(it)).all()
+        assert (out["topk_pos"] == tp).all()
+        assert (bits(out["topk_score"]) == bits(ts)).all()
+        # top-k only (no per-pair outputs) must give the same lists
+        out2 = idx.rerank_host(m, qv, q_off, cand, lex, alpha, k, want_ff=False, want_int=False)
+        assert (out2["topk_pos"] == tp).all() and (bits(out2["topk_score"]) == bits(ts)).all()
+    idx.close()
+
+
+def test_edge_cases(ffx):
+    rng = np.random.default_rng(1)
+    vec = rng.standard_normal((64, 768)).astype(np.float32)
+    idx = ffx.DeviceIndex(768, capacity=64)
+    idx.stage(0, vec)
+    idx.set_docs(np.arange(0, 65, 2))
+    qv = rng.standard_normal((3, 768)).astype(np.float32)
+    # no queries / no pairs / empty query in the middle / k larger than the candidate count
+    assert idx.rerank_host(fo.MODE_MAXP, qv[:0], [0], [], k=0)["ff"].shape == (0,)
+    out = idx.rerank_host(fo.MODE_MAXP, qv, [0, 0, 0, 0], [], None, 0.0, 4)
+    assert (out["topk_pos"] == -1).all() and np.isneginf(out["topk_score"]).all()
+    out = idx.rerank_host(fo.MODE_MAXP, qv, [0, 3, 3, 5], [1, 2, 3, 4, 5], None, 0.0, 4)
+    assert (out["topk_pos"][1] == -1).all() and (out["topk_pos"][0, 3] == -1)
+    assert sorted(out["topk_pos"][0, :3].tolist()) == [0, 1, 2]
+    assert (out["topk_pos"][2, 2:] == -1).all()
+    # out-of-range candidates never reach the kernel
+    with pytest.raises(ffx.FFXError):
+        idx.rerank_host(fo.MODE_MAXP, qv, [0, 1, 1, 1], [32])
+    with pytest.raises(ffx.FFXError):
+        idx.rerank_host(fo.MODE_PASSAGE, qv, [0, 1, 1, 1], [64])
+    with pytest.raises(ffx.FFXError):
+        idx.rerank_host(fo.MODE_PASSAGE, qv, [0, 1, 1, 1], [-1])
+    # a long document (more rows than a warp) and a very long candidate list (global-key top-k)
+    idx.set_docs([0, 40, 64])
+    ff = idx.rerank_host(fo.MODE_AVEP, qv, [0, 2, 2, 2], [0, 1])["ff"]
+    s = (vec.astype(np.float32) @ qv[0])
+    want = fo.score_pairs(vec, np.array([0, 40, 64]), np.arange(64), [0, 0], [0, 1], qv, fo.MODE_AVEP)
+    assert (bits(ff) == bits(want)).all() and np.allclose(ff, [s[:40].mean(), s[40:].mean()], rtol=1e-4)
+    idx.close()
+
+
+def test_large_candidate_lists_use_global_keys(ffx, oracle_c):
+    rng = np.random.default_rng(8)
+    vec = rng.standard_normal((30000, 384)).astype(np.float32)
+    idx = ffx.DeviceIndex(384, capacity=len(vec))
+    idx.stage(0, vec)
+    qv = rng.standard_normal((2, 384)).astype(np.float32)
+    q_off = np.array([0, 20000, 20007])
+    cand = np.concatenate([rng.permutation(30000)[:20000], np.arange(7)]).astype(np.int32)
+    lex = np.round(rng.standard_normal(len(cand)) * 3).astype(np.float32)
+    out = idx.rerank_host(fo.MODE_PASSAGE, qv, q_off, cand, lex, 0.9, 1000, want_ff=True)
+    ff = c_scores(oracle_c, vec, np.arange(30001), np.arange(30000), np.repeat([0, 1], [20000, 7]),
+                  cand, qv, fo.MODE_PASSAGE)
+    ts, tp = fo.topk_per_query(q_off, fo.interpolate_f32(lex, ff, 0.9), 1000)
+    assert (bits(out["ff"]) == bits(ff)).all()
+    assert (out["topk_pos"] == tp).all() and (bits(out["topk_score"]) == bits(ts)).all()
+    idx.close()
+
+
+# ------------------------------------------------------------------------------------------
+# storage
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [768, 100, 2048])
+def test_stage_read_roundtrip_and_growth(ffx, dim):
+    rng = np.random.default_rng(dim)
+    vec = rng.standard_normal((5000, dim)).astype(np.float32)
+    idx = ffx.DeviceIndex(dim, capacity=1000)
+    idx.stage(0, vec[:1000])
+    idx.reserve(5000)  # index/memory.py:103-108 growth keeps contents
+    idx.stage(1000, vec[1000:])
+    assert len(idx) == 5000 and idx.capacity == 5000
+    rows = rng.integers(0, 5000, 700)
+    assert (idx.read_rows(rows) == vec[rows]).all()
+    assert idx.read_rows([]).shape == (0, dim)
+    with pytest.raises(ffx.FFXError):
+        idx.read_rows([5000])
+    with pytest.raises(ffx.FFXError):
+        idx.stage(4999, vec[:2])
+    idx.close()
+
+
+def test_staging_larger_than_the_pinned_buffer(ffx):
+    rng = np.random.default_rng(3)
+    vec = rng.standard_normal((40000, 768)).astype(np.float32)  # 123 MB > 2 x 32 MB buffers
+    idx = ffx.DeviceIndex(768, capacity=len(vec))
+    idx.stage(0, vec)
+    rows = np.concatenate([[0, 39999], rng.integers(0, 40000, 300)])
+    assert (idx.read_rows(rows) == vec[rows]).all()
+    idx.close()
+
+
+# ------------------------------------------------------------------------------------------
+# PQ / OPQ asymmetric distance
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rotate", [False, True])
+@pytest.mark.parametrize("M,Ks,Ds", [(96, 256, 8), (8, 16, 4), (12, 256, 3)])
+def test_adc_matches_decode_then_dot(ffx, M, Ks, Ds, rotate):
+    """quantizer/nanopq.py:43-44,111-112 + index/base.py:292-303.  ADC sums M LUT entries
+    instead of D products, so scores differ from decode-then-dot by reassociation only:
+    tolerance rtol 1e-5 (north_star) + atol 1e-5 * |q| * |d|."""
+    rng = np.random.default_rng(M + Ks)
+    D = M * Ds
+    n_docs = 500
+    off, rows, _ = make_corpus(rng, n_docs, 7, 4, True)
+    n_rows = int(off[-1])
+    codes = rng.integers(0, Ks, (n_rows, M)).astype(np.uint8)
+    cw = rng.standard_normal((M, Ks, Ds)).astype(np.float32)
+    R = np.linalg.qr(rng.standard_normal((D, D)))[0].astype(np.float32) if rotate else None
+    idx = ffx.DeviceIndex(M, capacity=n_rows, row_kind=ffx.ROWS_PQ_U8)
+    idx.stage(0, codes)
+    assert (idx.read_rows([0, n_rows - 1]) == codes[[0, n_rows - 1]]).all()
+    idx.set_docs(off)
+    idx.set_pq(cw, R)
+    nq = 6
+    qv = rng.standard_normal((nq, D)).astype(np.float32)
+    dec = fo.pq_decode(codes, cw) if R is None else fo.opq_decode(codes, cw, R)
+    row_norm = np.linalg.norm(dec, axis=1)
+    for name, mode in MODES.items():
+        pool = n_rows if mode == fo.MODE_PASSAGE else n_docs
+        q_off, cand, pair_q = make_pairs(rng, nq, pool, 10, 200)
+        lex = rng.uniform(0, 20, len(cand)).astype(np.float32)
+        out = idx.rerank_host(mode, qv, q_off, cand, lex, 0.2, 10, want_ff=True, want_int=True)
+        u_off, u_rows = units_for_mode(off, rows, n_rows, mode)
+        want = fo.score_pairs(dec.astype(np.float64), u_off, u_rows, pair_q, cand, qv.astype(np.float64), mode)
+        scale = np.array([row_norm[u_rows[u_off[c]:u_off[c + 1]]].max() for c in cand]) * \
+            np.linalg.norm(qv, axis=1)[pair_q]
+        err = np.abs(out["ff"] - want)
+        assert (err <= 1e-5 * np.abs(want) + 1e-5 * scale).all(), name
+        it = fo.interpolate_f32(lex, out["ff"], 0.2)
+        assert (bits(out["int"]) == bits(it)).all()
+        ts, tp = fo.topk_per_query(q_off, it, 10)
+        assert (out["topk_pos"] == tp).all()
+    idx.close()
+
+
+# ------------------------------------------------------------------------------------------
+# shard merge (doc-id-range sharded corpora)
+# ------------------------------------------------------------------------------------------
+def test_merge_topk_equals_global_topk(ffx):
+    import torch
+
+    rng = np.random.default_rng(21)
+    nq, C, k, S = 50, 600, 64, 4
+    scores = np.round(rng.standard_normal((nq, C)) * 4).astype(np.float32) / 2  # ties across shards
+    q_off = np.arange(nq + 1) * C
+    ws, wp = fo.topk_per_query(q_off, scores.ravel(), k)
+    sh_s = np.full((S, nq, k), -np.inf, np.float32)
+    sh_p = np.full((S, nq, k), -1, np.int32)
+    owner = rng.integers(0, S, (nq, C))
+    for s in range(S):
+        for q in range(nq):
+            pos = np.nonzero(owner[q] == s)[0]
+            order = pos[np.argsort(-scores[q, pos], kind="stable")][:k]
+            sh_s[s, q, :len(order)] = scores[q, order]
+            sh_p[s, q, :len(order)] = order
+    d_s, d_p = torch.from_numpy(sh_s).cuda(), torch.from_numpy(sh_p).cuda()
+    o_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    o_p = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ffx.merge_topk(0, d_s.data_ptr(), d_p.data_ptr(), S, nq, k, o_s.data_ptr(), o_p.data_ptr())
+    torch.cuda.synchronize()
+    assert (o_p.cpu().numpy() == wp).all() and (bits(o_s.cpu().numpy()) == bits(ws)).all()
