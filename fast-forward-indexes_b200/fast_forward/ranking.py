@@ -1,0 +1,229 @@
+"""`Ranking` — TREC-style rankings on a pandas frame, drop-in for the reference class.
+
+Mirrors `fast_forward.ranking.Ranking` of mrjleo/fast-forward-indexes v0.8.0
+(src/fast_forward/ranking.py:64-409): same constructor contract, same public methods, same
+frame invariants (`_df` has columns q_id, id, score[, query]; rows ordered by q_id DESC then
+score DESC with a stable sort; scores in `dtype`).
+
+What differs underneath: a ranking produced by `Index.__call__` remembers the integer-coded
+candidate lists it was computed from (`_origin`).  `first_stage.interpolate(ff_out, alpha)`
+followed by `.cut(k)` then runs interpolation and the per-query ordering on the GPU
+(`ffx_rerank` epilogue kernels through libffx) instead of a pandas outer merge on two string
+keys plus a lexsort — the result is the frame the reference would produce.
+"""
+
+from __future__ import annotations
+
+import logging
+from collections.abc import Iterator, Mapping
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+
+LOGGER = logging.getLogger(__name__)
+
+Run = Mapping[str, Mapping[str, float]]
+
+_KEYS = ["q_id", "id"]
+
+
+def _with_queries(df: pd.DataFrame, queries: Mapping[str, str]) -> pd.DataFrame:
+    """Left-join query texts onto a ranking frame (ranking.py:16-28)."""
+    missing = set(pd.unique(df["q_id"])) - set(queries)
+    if missing:
+        raise ValueError("Queries are incomplete.")
+    lookup = pd.DataFrame({"q_id": list(queries.keys()), "query": list(queries.values())})
+    return df.merge(lookup, how="left", on="q_id")
+
+
+def _rank_column(df: pd.DataFrame) -> pd.Series:
+    """1-based rank of each row inside its query group (ranking.py:31-42)."""
+    return (df.groupby("q_id").cumcount() + 1).rename("rank")
+
+
+def _minmax(df: pd.DataFrame) -> pd.DataFrame:
+    """Min-max normalise the score column over the WHOLE frame (ranking.py:45-61)."""
+    out = df.copy()
+    lo, hi = out["score"].min(), out["score"].max()
+    if lo == hi:
+        LOGGER.warning("all scores are equal, setting scores to 0")
+        out["score"] = 0
+    else:
+        out["score"] = (out["score"] - lo) / (hi - lo)
+    return out
+
+
+class Ranking:
+    """Rankings of documents/passages w.r.t. queries."""
+
+    def __init__(
+        self,
+        df: pd.DataFrame,
+        name: str | None = None,
+        queries: Mapping[str, str] | None = None,
+        dtype: np.dtype = np.dtype(np.float32),
+        copy: bool = True,
+        is_sorted: bool = False,
+    ) -> None:
+        """Create a ranking from a frame with columns q_id, id, score (optionally query).
+
+        Rows with NaN scores are dropped; a (q_id, id) pair may appear only once
+        (ValueError); `queries` must cover every q_id (ValueError).  ranking.py:67-121.
+        """
+        self.name = name
+        self._origin = None  # set by Index.__call__ (device-side provenance)
+
+        if df.duplicated(subset=_KEYS).any():
+            raise ValueError("Only one score per query-document/passage pair is allowed.")
+
+        keep = ["q_id", "id", "score"] + (["query"] if "query" in df.columns else [])
+        frame = df.loc[:, keep].dropna()
+        if copy:
+            frame = frame.copy()
+        for col, want in (("score", dtype), ("q_id", str), ("id", str)):
+            if frame[col].dtype != want:
+                frame[col] = frame[col].astype(want)
+        if not is_sorted:
+            # q_id DESC (as strings), score DESC, stable: ties keep the incoming order
+            frame.sort_values(by=["q_id", "score"], ascending=False, inplace=True)
+        frame.reset_index(drop=True, inplace=True)
+
+        self._q_ids = set(pd.unique(frame["q_id"]))
+        self._df = frame if queries is None else _with_queries(frame, queries)
+
+    # ------------------------------------------------------------------ container protocol
+    @property
+    def has_queries(self) -> bool:
+        """Whether query texts are attached."""
+        return "query" in self._df.columns
+
+    @property
+    def q_ids(self) -> set[str]:
+        """Query IDs with at least one scored document."""
+        return self._q_ids
+
+    def __getitem__(self, q_id: str) -> dict[str, float]:
+        rows = self._df.loc[self._df["q_id"] == q_id, ["id", "score"]]
+        return dict(rows.values)
+
+    def __len__(self) -> int:
+        return len(self._q_ids)
+
+    def __iter__(self) -> Iterator[str]:
+        yield from self._q_ids
+
+    def __contains__(self, key: object) -> bool:
+        return key in self._q_ids
+
+    def __eq__(self, o: object) -> bool:
+        """Same (q_id, id, score) triples, exact float equality (ranking.py:171-186)."""
+        if not isinstance(o, Ranking):
+            return False
+        cols = ["q_id", "id", "score"]
+        mine = self._df.sort_values(_KEYS).reset_index(drop=True)[cols]
+        theirs = o._df.sort_values(_KEYS).reset_index(drop=True)[cols]
+        return mine.equals(theirs)
+
+    __hash__ = None  # mutable container
+
+    def __repr__(self) -> str:
+        return repr(self._df)
+
+    # ------------------------------------------------------------------ arithmetic
+    def _derive(self, frame: pd.DataFrame, is_sorted: bool, copy: bool = False) -> "Ranking":
+        return Ranking(frame, name=self.name, dtype=self._df.dtypes["score"], copy=copy,
+                       is_sorted=is_sorted)
+
+    def _outer(self, other: pd.DataFrame, mine: pd.DataFrame | None = None) -> pd.DataFrame:
+        """Outer join on (q_id, id); a score missing on either side counts as 0."""
+        left = self._df if mine is None else mine
+        return left.merge(other, on=_KEYS, suffixes=(None, "_other"), how="outer").fillna(0)
+
+    def __add__(self, o: "Ranking | float") -> "Ranking":
+        """Add a constant or another ranking's scores (ranking.py:188-217)."""
+        if isinstance(o, Ranking):
+            joined = self._outer(o._df)
+            joined["score"] = joined["score"] + joined["score_other"]
+            return self._derive(joined, is_sorted=False)
+        if isinstance(o, (int, float)):
+            frame = self._df.copy()
+            frame["score"] += o
+            return self._derive(frame, is_sorted=True)
+        return NotImplemented
+
+    __radd__ = __add__
+
+    def __mul__(self, o: float) -> "Ranking":
+        """Multiply the scores by a constant (ranking.py:221-239)."""
+        if not isinstance(o, (int, float)):
+            return NotImplemented
+        frame = self._df.copy()
+        frame["score"] *= o
+        return self._derive(frame, is_sorted=True)
+
+    __rmul__ = __mul__
+
+    # ------------------------------------------------------------------ transformations
+    def attach_queries(self, queries: Mapping[str, str]) -> "Ranking":
+        """Return a copy with query texts attached (ValueError if incomplete)."""
+        return Ranking(self._df, self.name, queries=queries, dtype=self._df.dtypes["score"],
+                       copy=True, is_sorted=True)
+
+    def normalize(self) -> "Ranking":
+        """Min-max normalise scores into [0, 1] (all-equal scores become 0)."""
+        return self._derive(_minmax(self._df), is_sorted=True)
+
+    def cut(self, cutoff: int) -> "Ranking":
+        """Keep the `cutoff` best rows of every query (ranking.py:279-291)."""
+        top = self._df.groupby("q_id").head(cutoff).reset_index(drop=True)
+        return self._derive(top, is_sorted=True, copy=True)
+
+    def interpolate(self, other: "Ranking", alpha: float, normalize: bool = False) -> "Ranking":
+        """`score = alpha * self.score + (1 - alpha) * other.score` (ranking.py:293-326).
+
+        Scores missing on either side count as 0.  When `other` was computed by an index
+        from this very ranking, the arithmetic and the ordering run on the GPU.
+        """
+        origin = getattr(other, "_origin", None)
+        if origin is not None and not normalize and origin.matches(self):
+            return origin.interpolate(self, other, float(alpha))
+
+        a = _minmax(self._df) if normalize else self._df
+        b = _minmax(other._df) if normalize else other._df
+        joined = self._outer(b, mine=a)
+        joined["score"] = alpha * joined["score"] + (1 - alpha) * joined["score_other"]
+        return self._derive(joined, is_sorted=False)
+
+    def rr_scores(self, k: int = 60) -> "Ranking":
+        """Reciprocal-rank scores `1 / (rank + k)` (ranking.py:328-346)."""
+        frame = self._df.copy()
+        frame["score"] = 1 / (_rank_column(self._df) + k)
+        return self._derive(frame, is_sorted=True)
+
+    # ------------------------------------------------------------------ I/O
+    def save(self, target: Path) -> None:
+        """Write a TREC run file: q_id Q0 id rank score name (ranking.py:348-366)."""
+        out = self._df.join(_rank_column(self._df))
+        out["name"] = str(self.name)
+        out["q0"] = "Q0"
+        target.parent.mkdir(parents=True, exist_ok=True)
+        out.to_csv(target, sep="\t", columns=["q_id", "q0", "id", "rank", "score", "name"],
+                   index=False, header=False)
+
+    @classmethod
+    def from_run(cls, run: Run, name: str | None = None, queries: Mapping[str, str] | None = None,
+                 dtype: np.dtype = np.dtype(np.float32)) -> "Ranking":
+        """Build a ranking from `{q_id: {id: score}}` (ranking.py:368-386)."""
+        # column-major stack of the (id x q_id) table: the row order the reference produces
+        table = pd.DataFrame.from_dict(dict(run)).stack().reset_index()
+        table.columns = ("id", "q_id", "score")
+        return cls(table, name=name, queries=queries, dtype=dtype, copy=False)
+
+    @classmethod
+    def from_file(cls, f: Path, queries: Mapping[str, str] | None = None,
+                  dtype: np.dtype = np.dtype(np.float32)) -> "Ranking":
+        """Read a whitespace-separated TREC run file (ranking.py:388-409)."""
+        table = pd.read_csv(f, sep=r"\s+", skipinitialspace=True, header=None,
+                            names=["q_id", "q0", "id", "rank", "score", "name"])
+        return cls(table, name=table["name"][0], queries=queries, dtype=dtype, copy=False)
