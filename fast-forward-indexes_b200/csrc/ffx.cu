@@ -110,6 +110,13 @@ struct ffx_index {
 
     Scratch work;     // kernel scratch of ffx_rerank (scores / keys / rotated queries)
     Scratch hostio;   // device mirrors of ffx_rerank_host's host buffers
+
+    int *err_flag = nullptr;   // device: first out-of-range candidate seen by a kernel (0 = none)
+    int *err_host = nullptr;   // pinned mirror
+
+    // ffx_rerank_host pipeline: H2D / two alternating compute streams / D2H
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> events;
 };
 
 namespace {
@@ -194,8 +201,36 @@ int dispatch_score(const ffx_plan &p, const ffx::ScoreArgs &a, bool fuse, int gr
     return fail(FFX_ERR_UNSUPPORTED, "no lane-major kernel for plan (%d,%d)", p.cpl, p.steps);
 }
 
-int launch_topk(const float *scores, const int64_t *q_off, int64_t nq, int k, int cpad,
-                Scratch &work, size_t work_off, float *out_s, int32_t *out_p, cudaStream_t st) {
+// One CTA per query with the top-k fused into the scoring kernel: needs the lane-major fast
+// path, keys that fit shared memory, and enough queries to fill the machine.
+bool will_fuse(const ffx_index *idx, int64_t nq, int k, int cpad) {
+    return idx->row_kind == FFX_ROWS_F32 && idx->plan.cpl != 0 && k > 0 &&
+           cpad <= ffx::kMaxFusedCand && nq >= static_cast<int64_t>(idx->sm_count) * 2;
+}
+
+int take_error(ffx_index *idx, cudaStream_t st) {
+    FFX_CUDA(cudaMemcpyAsync(idx->err_host, idx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FFX_CUDA(cudaStreamSynchronize(st));
+    const int seen = *idx->err_host;
+    if (seen == 0) return FFX_OK;
+    FFX_CUDA(cudaMemsetAsync(idx->err_flag, 0, sizeof(int), st));
+    FFX_CUDA(cudaStreamSynchronize(st));
+    return fail(FFX_ERR_INVALID, "candidate out of range near pair %d: not a document ordinal / row "
+                "of this index", seen - 1);
+}
+
+cudaEvent_t event_at(ffx_index *idx, size_t i) {
+    while (idx->events.size() <= i) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        idx->events.push_back(e);
+    }
+    return idx->events[i];
+}
+
+int launch_topk(const float *scores, const float *lex, float alpha, float beta, float *out_int,
+                const int64_t *q_off, int64_t nq, int k, int cpad, Scratch &work, size_t work_off,
+                float *out_s, int32_t *out_p, cudaStream_t st) {
     unsigned long long *gkeys = nullptr;
     size_t smem = static_cast<size_t>(cpad) * 8;
     if (cpad > ffx::kMaxFusedCand) {
@@ -207,7 +242,7 @@ int launch_topk(const float *scores, const int64_t *q_off, int64_t nq, int k, in
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
     ffx::ffx_topk_kernel<<<static_cast<unsigned>(nq), ffx::kThreads, smem, st>>>(
-        scores, q_off, k, cpad, gkeys, out_s, out_p);
+        scores, lex, alpha, beta, q_off, k, cpad, gkeys, out_int, out_s, out_p);
     g_launches++;
     FFX_CUDA(cudaGetLastError());
     return FFX_OK;
@@ -279,6 +314,19 @@ int ffx_index_create(int device, int row_kind, int64_t dim, int64_t capacity_row
         return fail(FFX_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     *out = idx;
+    bool ok = cudaMalloc(&idx->err_flag, sizeof(int)) == cudaSuccess &&
+              cudaMemset(idx->err_flag, 0, sizeof(int)) == cudaSuccess &&
+              cudaMallocHost(&idx->err_host, sizeof(int)) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&idx->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&idx->s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&idx->s_comp[0], cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&idx->s_comp[1], cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        ffx_index_destroy(idx);
+        *out = nullptr;
+        return fail(FFX_ERR_CUDA, "ffx_index_create: could not create streams / error flag");
+    }
     int rc = ffx_index_reserve(idx, capacity_rows);
     if (rc != FFX_OK) {
         ffx_index_destroy(idx);
@@ -299,6 +347,11 @@ int ffx_index_destroy(ffx_index *idx) {
     cudaFree(idx->R);
     cudaFree(idx->work.p);
     cudaFree(idx->hostio.p);
+    cudaFree(idx->err_flag);
+    if (idx->err_host) cudaFreeHost(idx->err_host);
+    for (cudaEvent_t e : idx->events) cudaEventDestroy(e);
+    for (cudaStream_t st : {idx->s_h2d, idx->s_d2h, idx->s_comp[0], idx->s_comp[1]})
+        if (st) cudaStreamDestroy(st);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     cudaGetLastError();
     delete idx;
@@ -532,9 +585,11 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
     const float alpha32 = static_cast<float>(alpha);
     const float beta32 = static_cast<float>(1.0 - alpha);
 
+    const uint32_t limit = static_cast<uint32_t>(mode == FFX_MODE_PASSAGE ? idx->num_rows : idx->n_docs);
+
     // one CTA per query with the top-k fused needs enough queries to fill the machine
     const int64_t slots = static_cast<int64_t>(idx->sm_count) * 2;
-    const bool fuse = fast && k > 0 && cpad <= ffx::kMaxFusedCand && nq >= slots;
+    const bool fuse = will_fuse(idx, nq, k, cpad);
 
     // scratch plan: [scores n_total?][keys nq*cpad?][qeff nq*D?]
     const bool need_scores = k > 0 && !fuse && !out_int;
@@ -603,6 +658,8 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
             a.out_int = scores;
             a.tiles_per_query = tiles;
             a.tile = tile;
+            a.limit = limit;
+            a.err = idx->err_flag;
             const size_t smem = static_cast<size_t>(idx->M) * idx->Ks * 4;
             FFX_CUDA(cudaFuncSetAttribute(ffx::ffx_adc_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -632,6 +689,8 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
             a.tiles_per_query = tiles;
             a.tile = tile;
             a.cpad = cpad;
+            a.limit = limit;
+            a.err = idx->err_flag;
             if (fast) {
                 FFX_TRY(dispatch_score(idx->plan, a, fuse, static_cast<int>(nq * tiles),
                                        fuse ? static_cast<size_t>(cpad) * 8 : 0, st));
@@ -647,8 +706,8 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
         }
     }
     if (k > 0 && !fuse)
-        FFX_TRY(launch_topk(scores, q_off, nq, k, cpad, idx->work, off_keys, out_topk_score,
-                            out_topk_pos, st));
+        FFX_TRY(launch_topk(scores, nullptr, 0.f, 0.f, nullptr, q_off, nq, k, cpad, idx->work, off_keys,
+                            out_topk_score, out_topk_pos, st));
     return FFX_OK;
 }
 
@@ -669,14 +728,10 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     }
     const int64_t n = q_off[nq];
     if (n > 0 && !cand) return fail(FFX_ERR_INVALID, "ffx_rerank_host: NULL candidates");
+    if (k > 0 && (!out_topk_score || !out_topk_pos))
+        return fail(FFX_ERR_INVALID, "ffx_rerank_host: k > 0 needs top-k outputs");
     const bool pq = idx->row_kind == FFX_ROWS_PQ_U8;
     const int64_t D = pq ? static_cast<int64_t>(idx->M) * idx->Ds : idx->dim;
-    // candidate range check: an out-of-range id must never reach the kernel
-    const int64_t limit = mode == FFX_MODE_PASSAGE ? idx->num_rows : idx->n_docs;
-    for (int64_t i = 0; i < n; i++)
-        if (cand[i] < 0 || cand[i] >= limit)
-            return fail(FFX_ERR_INVALID, "ffx_rerank_host: candidate %d at pair %lld out of range [0, %lld)",
-                        cand[i], static_cast<long long>(i), static_cast<long long>(limit));
     FFX_TRY(bind(idx));
 
     auto pad = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
@@ -696,19 +751,124 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     float *d_ts = k > 0 ? reinterpret_cast<float *>(take(b_k)) : nullptr;
     int32_t *d_tp = k > 0 ? reinterpret_cast<int32_t *>(take(b_k)) : nullptr;
 
+    // Query chunks flow through H2D -> kernel -> D2H on separate streams, so the PCIe copies
+    // of chunk i+1 / i-1 hide behind the kernel of chunk i.  Every chunk has its own slice of
+    // the device mirrors (no buffer reuse, hence no hazards); two compute streams alternate
+    // so one chunk's tail wave overlaps the next chunk's first wave.  Chunking only applies
+    // when every chunk still takes the fused one-CTA-per-query kernel.
+    const int cpad = next_pow2(std::max<int64_t>(max_cand, 1));
+    const int64_t wave = static_cast<int64_t>(idx->sm_count) * 2;
+    int64_t chunk_q = nq;
+    if (n >= (1 << 20) && nq >= 8 * wave && will_fuse(idx, 4 * wave, k, cpad)) chunk_q = 4 * wave;
+    const int64_t n_chunks = (nq + chunk_q - 1) / chunk_q;
+
+    FFX_CUDA(cudaMemcpyAsync(d_off, q_off, static_cast<size_t>(nq + 1) * 8, cudaMemcpyHostToDevice, idx->s_h2d));
+    size_t ev = 0;
+    for (int64_t c = 0; c < n_chunks; c++) {
+        const int64_t q0 = c * chunk_q, q1 = std::min(nq, q0 + chunk_q), cq = q1 - q0;
+        const int64_t p0 = q_off[q0], np_ = q_off[q1] - p0;
+        cudaStream_t comp = idx->s_comp[c & 1];
+        FFX_CUDA(cudaMemcpyAsync(d_q + q0 * D, qvecs + q0 * D, static_cast<size_t>(cq) * D * 4,
+                                 cudaMemcpyHostToDevice, idx->s_h2d));
+        if (np_ > 0) {
+            FFX_CUDA(cudaMemcpyAsync(d_cand + p0, cand + p0, static_cast<size_t>(np_) * 4,
+                                     cudaMemcpyHostToDevice, idx->s_h2d));
+            if (lex)
+                FFX_CUDA(cudaMemcpyAsync(d_lex + p0, lex + p0, static_cast<size_t>(np_) * 4,
+                                         cudaMemcpyHostToDevice, idx->s_h2d));
+        }
+        cudaEvent_t in_ready = event_at(idx, ev++);
+        FFX_CUDA(cudaEventRecord(in_ready, idx->s_h2d));
+        FFX_CUDA(cudaStreamWaitEvent(comp, in_ready, 0));
+        // q_off holds absolute pair offsets: pass the shifted offset pointer with the
+        // unshifted per-pair arrays; per-query outputs are shifted to the chunk
+        FFX_TRY(ffx_rerank(idx, mode, d_q + q0 * D, cq, d_off + q0, d_cand, d_lex, alpha, k, max_cand,
+                           d_ff, d_int, d_ts ? d_ts + q0 * k : nullptr, d_tp ? d_tp + q0 * k : nullptr,
+                           comp));
+        cudaEvent_t out_ready = event_at(idx, ev++);
+        FFX_CUDA(cudaEventRecord(out_ready, comp));
+        FFX_CUDA(cudaStreamWaitEvent(idx->s_d2h, out_ready, 0));
+        if (np_ > 0) {
+            if (out_ff)
+                FFX_CUDA(cudaMemcpyAsync(out_ff + p0, d_ff + p0, static_cast<size_t>(np_) * 4,
+                                         cudaMemcpyDeviceToHost, idx->s_d2h));
+            if (out_int)
+                FFX_CUDA(cudaMemcpyAsync(out_int + p0, d_int + p0, static_cast<size_t>(np_) * 4,
+                                         cudaMemcpyDeviceToHost, idx->s_d2h));
+        }
+        if (k > 0) {
+            FFX_CUDA(cudaMemcpyAsync(out_topk_score + q0 * k, d_ts + q0 * k, static_cast<size_t>(cq) * k * 4,
+                                     cudaMemcpyDeviceToHost, idx->s_d2h));
+            FFX_CUDA(cudaMemcpyAsync(out_topk_pos + q0 * k, d_tp + q0 * k, static_cast<size_t>(cq) * k * 4,
+                                     cudaMemcpyDeviceToHost, idx->s_d2h));
+        }
+    }
+    return take_error(idx, idx->s_d2h);
+}
+
+int ffx_index_sync(ffx_index *idx, void *stream) {
+    if (!idx) return fail(FFX_ERR_INVALID, "ffx_index_sync: NULL index");
+    FFX_TRY(bind(idx));
+    return take_error(idx, static_cast<cudaStream_t>(stream));
+}
+
+int ffx_interpolate_topk(ffx_index *idx, const float *lex, const float *ff, int64_t nq,
+                         const int64_t *q_off, double alpha, int k, int64_t max_cand, float *out_int,
+                         float *out_topk_score, int32_t *out_topk_pos, void *stream) {
+    if (!idx) return fail(FFX_ERR_INVALID, "ffx_interpolate_topk: NULL index");
+    if (nq < 0 || k < 0 || max_cand < 0 || nq > 0x7fffffffll || max_cand > (1ll << 30))
+        return fail(FFX_ERR_INVALID, "ffx_interpolate_topk: bad sizes");
+    if (nq == 0) return FFX_OK;
+    if (!ff || !q_off) return fail(FFX_ERR_INVALID, "ffx_interpolate_topk: NULL input");
+    if (k > 0 && (!out_topk_score || !out_topk_pos))
+        return fail(FFX_ERR_INVALID, "ffx_interpolate_topk: k > 0 needs top-k outputs");
+    FFX_TRY(bind(idx));
+    const int cpad = next_pow2(std::max<int64_t>(max_cand, 1));
+    if (cpad > ffx::kMaxFusedCand && k > 0)
+        FFX_TRY(scratch_reserve(idx->work, static_cast<size_t>(nq) * cpad * 8));
+    return launch_topk(ff, lex, static_cast<float>(alpha), static_cast<float>(1.0 - alpha), out_int,
+                       q_off, nq, k, cpad, idx->work, 0, out_topk_score, out_topk_pos,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int ffx_interpolate_topk_host(ffx_index *idx, const float *lex, const float *ff, int64_t nq,
+                              const int64_t *q_off, double alpha, int k, float *out_int,
+                              float *out_topk_score, int32_t *out_topk_pos) {
+    if (!idx) return fail(FFX_ERR_INVALID, "ffx_interpolate_topk_host: NULL index");
+    if (nq < 0) return fail(FFX_ERR_INVALID, "ffx_interpolate_topk_host: nq < 0");
+    if (nq == 0) return FFX_OK;
+    if (!ff || !q_off || q_off[0] != 0)
+        return fail(FFX_ERR_INVALID, "ffx_interpolate_topk_host: bad input");
+    int64_t max_cand = 0;
+    for (int64_t q = 0; q < nq; q++) {
+        const int64_t c = q_off[q + 1] - q_off[q];
+        if (c < 0) return fail(FFX_ERR_INVALID, "ffx_interpolate_topk_host: q_off not monotone");
+        max_cand = std::max(max_cand, c);
+    }
+    const int64_t n = q_off[nq];
+    FFX_TRY(bind(idx));
+    auto pad = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+    const size_t b_off = pad(static_cast<size_t>(nq + 1) * 8), b_n = pad(static_cast<size_t>(n) * 4);
+    const size_t b_k = pad(static_cast<size_t>(nq) * k * 4);
+    FFX_TRY(scratch_reserve(idx->hostio, b_off + 3 * b_n + 2 * b_k));
+    char *p = static_cast<char *>(idx->hostio.p);
+    auto take = [&](size_t b) { char *r = p; p += b; return r; };
+    int64_t *d_off = reinterpret_cast<int64_t *>(take(b_off));
+    float *d_ff = reinterpret_cast<float *>(take(b_n));
+    float *d_lex = lex ? reinterpret_cast<float *>(take(b_n)) : nullptr;
+    float *d_int = (out_int && lex) ? reinterpret_cast<float *>(take(b_n)) : nullptr;
+    float *d_ts = k > 0 ? reinterpret_cast<float *>(take(b_k)) : nullptr;
+    int32_t *d_tp = k > 0 ? reinterpret_cast<int32_t *>(take(b_k)) : nullptr;
     cudaStream_t st = idx->stream;
-    FFX_CUDA(cudaMemcpyAsync(d_q, qvecs, static_cast<size_t>(nq) * D * 4, cudaMemcpyHostToDevice, st));
     FFX_CUDA(cudaMemcpyAsync(d_off, q_off, static_cast<size_t>(nq + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n > 0) {
-        FFX_CUDA(cudaMemcpyAsync(d_cand, cand, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));
+        FFX_CUDA(cudaMemcpyAsync(d_ff, ff, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));
         if (lex) FFX_CUDA(cudaMemcpyAsync(d_lex, lex, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));
     }
-    FFX_TRY(ffx_rerank(idx, mode, d_q, nq, d_off, d_cand, d_lex, alpha, k, max_cand, d_ff, d_int,
-                       d_ts, d_tp, st));
-    if (n > 0) {
-        if (out_ff) FFX_CUDA(cudaMemcpyAsync(out_ff, d_ff, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, st));
-        if (out_int) FFX_CUDA(cudaMemcpyAsync(out_int, d_int, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, st));
-    }
+    FFX_TRY(ffx_interpolate_topk(idx, d_lex, d_ff, nq, d_off, alpha, k, max_cand, d_int, d_ts, d_tp, st));
+    if (n > 0 && out_int)
+        FFX_CUDA(cudaMemcpyAsync(out_int, lex ? d_int : d_ff, static_cast<size_t>(n) * 4,
+                                 cudaMemcpyDeviceToHost, st));
     if (k > 0) {
         FFX_CUDA(cudaMemcpyAsync(out_topk_score, d_ts, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
         FFX_CUDA(cudaMemcpyAsync(out_topk_pos, d_tp, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));

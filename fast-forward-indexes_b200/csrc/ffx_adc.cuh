@@ -26,6 +26,8 @@ struct AdcArgs {
     float alpha, beta;
     float *out_ff, *out_int;
     int tiles_per_query, tile;
+    uint32_t limit;
+    int *err;
 };
 
 // qeff[q, j] = sum_i qvecs[q, i] * R[i, j]   (row vector times R; nanopq OPQ.rotate)
@@ -67,8 +69,10 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_adc_kernel(const AdcArgs a) {
     for (int c = threadIdx.x; c < n_tile; c += kThreads) {
         const int64_t p = q_begin + c0 + c;
         const int32_t u = a.cand[p];
-        uint32_t start, cnt;
-        if (a.mode == FFX_MODE_PASSAGE) {
+        uint32_t start = 0, cnt = 0;
+        if (!candidate_ok(u, a.limit, a.err, p)) {
+            cnt = 0;
+        } else if (a.mode == FFX_MODE_PASSAGE) {
             start = static_cast<uint32_t>(u);
             cnt = 1;
         } else {

@@ -43,7 +43,17 @@ struct ScoreArgs {
     int tiles_per_query;      // 1 when FUSE
     int tile;                 // candidates per tile
     int cpad;                 // FUSE: next pow2 >= max candidates per query
+    uint32_t limit;           // valid candidates are [0, limit): documents, or rows in PASSAGE mode
+    int *err;                 // set to 1 + (pair index & 0x3fffffff) when a candidate is out of range
 };
+
+// An out-of-range candidate is never dereferenced: it scores as an empty document and is
+// reported through the index's error flag (checked by the host at the next sync).
+__device__ __forceinline__ bool candidate_ok(int32_t u, uint32_t limit, int *err, int64_t pair) {
+    if (static_cast<uint32_t>(u) < limit) return true;
+    if (err) atomicCAS(err, 0, 1 + static_cast<int>(pair & 0x3fffffff));
+    return false;
+}
 
 // ---------------------------------------------------------------------------------------
 // small helpers
@@ -212,7 +222,9 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_score_kernel(const ScoreArgs 
         float my_lex = 0.f;
         if (lane < nb) {
             const int32_t u = __ldg(a.cand + my_pair);
-            if (a.mode == FFX_MODE_PASSAGE) {
+            if (!candidate_ok(u, a.limit, a.err, my_pair)) {
+                my_cnt = 0;
+            } else if (a.mode == FFX_MODE_PASSAGE) {
                 my_start = static_cast<uint32_t>(u);
                 my_cnt = 1;
             } else {
@@ -318,8 +330,10 @@ __global__ void __launch_bounds__(128) ffx_score_generic_kernel(const ScoreArgs 
     }
     const float *qv = a.qvecs + lo * a.dim;
     const int32_t u = a.cand[p];
-    uint32_t start, cnt;
-    if (a.mode == FFX_MODE_PASSAGE) {
+    uint32_t start = 0, cnt = 0;
+    if (!candidate_ok(u, a.limit, a.err, p)) {
+        cnt = 0;
+    } else if (a.mode == FFX_MODE_PASSAGE) {
         start = static_cast<uint32_t>(u);
         cnt = 1;
     } else {
@@ -348,20 +362,36 @@ __global__ void __launch_bounds__(128) ffx_score_generic_kernel(const ScoreArgs 
 // per-query top-k over already interpolated scores (split path, generic path, merges)
 // ---------------------------------------------------------------------------------------
 // keys: shared memory when cpad <= kMaxFusedCand, else `gkeys + q*cpad` in global memory.
-__global__ void __launch_bounds__(kThreads) ffx_topk_kernel(const float *scores,
+// With `lex` the kernel first interpolates (ranking.py:319): s = fl(alpha*lex) + fl(beta*scores),
+// optionally storing s to out_int — `Ranking.interpolate` + `Ranking.cut` over existing scores.
+__global__ void __launch_bounds__(kThreads) ffx_topk_kernel(const float *scores, const float *lex,
+                                                            float alpha, float beta,
                                                             const int64_t *q_off, int k, int cpad,
                                                             unsigned long long *gkeys,
-                                                            float *out_s, int32_t *out_p) {
+                                                            float *out_int, float *out_s,
+                                                            int32_t *out_p) {
     extern __shared__ unsigned long long s_keys[];
     const int64_t q = blockIdx.x;
     const int64_t b = q_off[q];
     const int n = static_cast<int>(q_off[q + 1] - b);
     unsigned long long *keys = gkeys ? gkeys + q * cpad : s_keys;
-    for (int i = threadIdx.x; i < cpad; i += blockDim.x)
-        keys[i] = i < n ? topk_key(scores[b + i], static_cast<uint32_t>(i)) : 0ull;
+    for (int i = threadIdx.x; i < cpad; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < n) {
+            float s = scores[b + i];
+            if (lex) {
+                s = __fadd_rn(__fmul_rn(alpha, lex[b + i]), __fmul_rn(beta, s));
+                if (out_int) out_int[b + i] = s;
+            }
+            key = topk_key(s, static_cast<uint32_t>(i));
+        }
+        if (k > 0) keys[i] = key;
+    }
     __syncthreads();
-    bitonic_sort_desc(keys, cpad);
-    write_topk(keys, n, k, out_s + q * k, out_p + q * k);
+    if (k > 0) {
+        bitonic_sort_desc(keys, cpad);
+        write_topk(keys, n, k, out_s + q * k, out_p + q * k);
+    }
 }
 
 // Merge per-shard top-k lists [n_shards, nq, k] -> [nq, k]; positions are global positions

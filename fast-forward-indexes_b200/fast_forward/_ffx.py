@@ -39,6 +39,9 @@ SYMBOLS = {
     "ffx_index_set_pq": (_I, [_P, _I, _I, _I, _P, _P]),
     "ffx_rerank": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _L, _P, _P, _P, _P, _P]),
     "ffx_rerank_host": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _P, _P, _P, _P]),
+    "ffx_index_sync": (_I, [_P, _P]),
+    "ffx_interpolate_topk": (_I, [_P, _P, _P, _L, _P, _D, _I, _L, _P, _P, _P, _P]),
+    "ffx_interpolate_topk_host": (_I, [_P, _P, _P, _L, _P, _D, _I, _P, _P, _P]),
     "ffx_merge_topk": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _P]),
     "ffx_launch_count": (_L, []),
 }
@@ -224,6 +227,26 @@ class DeviceIndex:
         check(lib().ffx_rerank_host(self.handle, int(mode), _ptr(qvecs), nq, _ptr(q_off), _ptr(cand),
                                     _ptr(lex), float(alpha), int(k), _ptr(ff), _ptr(it), _ptr(ts),
                                     _ptr(tp)))
+        return out
+
+    def sync(self, stream=0):
+        """ffx_index_sync: wait for `stream`, raise if a kernel saw an out-of-range candidate."""
+        check(lib().ffx_index_sync(self.handle, C.c_void_p(stream) if stream else None))
+
+    def interpolate_topk_host(self, lex, ff, q_off, alpha, k, want_int=True):
+        """ffx_interpolate_topk_host: interpolation + per-query ordering of existing scores."""
+        ff = _arr(ff, np.float32)
+        lex = None if lex is None else _arr(lex, np.float32)
+        q_off = _arr(q_off, np.int64)
+        nq = len(q_off) - 1
+        out = {}
+        it = out["int"] = np.empty(len(ff), np.float32) if want_int else None
+        ts = tp = None
+        if k > 0:
+            ts = out["topk_score"] = np.empty((nq, k), np.float32)
+            tp = out["topk_pos"] = np.empty((nq, k), np.int32)
+        check(lib().ffx_interpolate_topk_host(self.handle, _ptr(lex), _ptr(ff), nq, _ptr(q_off),
+                                              float(alpha), int(k), _ptr(it), _ptr(ts), _ptr(tp)))
         return out
 
     def rerank_device(self, mode, qvecs_ptr, nq, q_off_ptr, cand_ptr, lex_ptr, alpha, k, max_cand,

@@ -1,0 +1,440 @@
+"""`Mode` and the abstract `Index` — the scoring front-end, drop-in for
+src/fast_forward/index/base.py of the reference (v0.8.0).
+
+Public surface and error behaviour follow the reference (`__call__`, `add`, `encode_queries`,
+`mode` / `quantizer` / `query_encoder` properties, `dim`, `doc_ids`, `psg_ids`, `batch_iter`,
+iteration).  What differs is everything underneath `_compute_scores`: vectors (or PQ codes)
+live in HBM inside a libffx index, ids are integer-coded once on the host with exactly the
+semantics of index/util.py:12-42, and one CUDA launch does look-up, dot products, the
+per-document reduce, and — through `rerank` or `Ranking.interpolate` on the result — the
+interpolation and per-query ordering.  There is no numpy scoring path.
+"""
+
+from __future__ import annotations
+
+import abc
+import logging
+from collections.abc import Iterable, Iterator, Sequence
+from enum import Enum
+from time import perf_counter
+
+import numpy as np
+import pandas as pd
+
+from fast_forward import _ffx
+from fast_forward.encoder.base import Encoder
+from fast_forward.quantizer import Quantizer
+from fast_forward.ranking import Ranking
+
+LOGGER = logging.getLogger(__name__)
+
+IDSequence = Sequence["str | None"]
+
+
+class Mode(Enum):
+    """Ranking mode of an index (same values as the reference and as ffx_mode)."""
+
+    PASSAGE = 1
+    MAXP = 2
+    FIRSTP = 3
+    AVEP = 4
+
+
+def _fl32_interpolate(alpha: float, lex, ff):
+    """ranking.py:319 arithmetic: fl32(fl32(alpha)*lex) + fl32(fl32(1-alpha)*ff)."""
+    a, b = np.float32(alpha), np.float32(1 - alpha)
+    return a * np.asarray(lex, np.float32) + b * np.asarray(ff, np.float32)
+
+
+class _Origin:
+    """Provenance of a ranking computed by `Index.__call__`: the source frame (identity),
+    its per-query block offsets and the semantic scores aligned with the source rows.
+    Lets `source.interpolate(result, alpha)` skip the string outer-merge and run on the GPU."""
+
+    __slots__ = ("index", "source_df", "q_off", "ff")
+
+    def __init__(self, index: "Index", source_df: pd.DataFrame, q_off: np.ndarray, ff: np.ndarray):
+        self.index, self.source_df, self.q_off, self.ff = index, source_df, q_off, ff
+
+    def matches(self, ranking: Ranking) -> bool:
+        df = ranking._df
+        return df is self.source_df and len(df) == len(self.ff) and df["score"].dtype == np.float32
+
+    def interpolate(self, first: Ranking, _other: Ranking, alpha: float) -> Ranking:
+        df = self.source_df
+        lex = df["score"].to_numpy()
+        max_c = int(np.diff(self.q_off).max()) if len(self.q_off) > 1 else 0
+        out = self.index._device().interpolate_topk_host(lex, self.ff, self.q_off, alpha, max_c,
+                                                         want_int=False)
+        rows, scores = _rows_from_topk(out["topk_pos"], out["topk_score"], self.q_off)
+        rows = _order_ties_by_id(rows, scores, df["id"].to_numpy(), self.q_off)
+        frame = df.iloc[rows].reset_index(drop=True)
+        frame["score"] = scores
+        return Ranking(frame, name=first.name, dtype=df.dtypes["score"], copy=False, is_sorted=True)
+
+
+def _rows_from_topk(pos: np.ndarray, score: np.ndarray, q_off: np.ndarray):
+    """[nq, k] per-query positions (-1 padded) -> flat source-row numbers + scores, query
+    blocks in order."""
+    valid = pos >= 0
+    rows = (pos + q_off[:-1, None])[valid]
+    return rows.astype(np.int64), score[valid]
+
+
+def _order_ties_by_id(rows, scores, ids, q_off):
+    """The reference leaves equal interpolated scores of a query in ascending id order (its
+    outer merge sorts the keys before the stable sort, ranking.py:312-326); the kernel orders
+    ties by position.  Re-order only the (rare) runs of equal scores."""
+    if len(rows) < 2:
+        return rows
+    q_of_row = np.searchsorted(q_off, rows, side="right") - 1
+    same = (scores[1:] == scores[:-1]) & (q_of_row[1:] == q_of_row[:-1])
+    if not same.any():
+        return rows
+    rows = rows.copy()
+    starts = np.flatnonzero(same & ~np.concatenate([[False], same[:-1]]))
+    ends = np.flatnonzero(same & ~np.concatenate([same[1:], [False]])) + 2
+    for s, e in zip(starts, ends):
+        run = rows[s:e]
+        rows[s:e] = run[np.argsort(ids[run].astype(str), kind="stable")]
+    return rows
+
+
+class Index(abc.ABC):
+    """Abstract base class for Fast-Forward indexes."""
+
+    _query_encoder: Encoder | None = None
+    _quantizer: Quantizer | None = None
+
+    def __init__(self, query_encoder: Encoder | None = None, quantizer: Quantizer | None = None,
+                 mode: Mode = Mode.MAXP, encoder_batch_size: int = 32) -> None:
+        """:param query_encoder: the query encoder. :param quantizer: the quantizer (only
+        attachable while the index is empty). :param mode: the ranking mode.
+        :param encoder_batch_size: queries per encoder call."""
+        super().__init__()
+        if query_encoder is not None:
+            self.query_encoder = query_encoder
+        self.mode = mode
+        if quantizer is not None:
+            self.quantizer = quantizer
+        self._encoder_batch_size = encoder_batch_size
+
+    # ------------------------------------------------------------------ properties
+    def encode_queries(self, queries: Sequence[str]) -> np.ndarray:
+        """Encode queries in batches of `encoder_batch_size` (RuntimeError without encoder)."""
+        if self.query_encoder is None:
+            raise RuntimeError("Index does not have a query encoder.")
+        step = self._encoder_batch_size
+        parts = [self.query_encoder(queries[i:i + step]) for i in range(0, len(queries), step)]
+        return np.concatenate(parts)
+
+    @property
+    def query_encoder(self) -> Encoder | None:
+        return self._query_encoder
+
+    @query_encoder.setter
+    def query_encoder(self, encoder: Encoder) -> None:
+        assert isinstance(encoder, Encoder)
+        self._query_encoder = encoder
+
+    @property
+    def quantizer(self) -> Quantizer | None:
+        return self._quantizer
+
+    def _on_quantizer_set(self) -> None:
+        """Hook for back-ends (the on-disk index persists the quantizer)."""
+
+    @quantizer.setter
+    def quantizer(self, quantizer: Quantizer) -> None:
+        """Attach a (trained) quantizer; RuntimeError unless the index is empty."""
+        assert isinstance(quantizer, Quantizer)
+        if len(self) > 0:
+            raise RuntimeError("Quantizers can only be attached to empty indexes.")
+        self._quantizer = quantizer
+        self._on_quantizer_set()
+        quantizer.set_attached()
+
+    @property
+    def mode(self) -> Mode:
+        return self._mode
+
+    @mode.setter
+    def mode(self, mode: Mode) -> None:
+        assert isinstance(mode, Mode)
+        self._mode = mode
+
+    @property
+    def dim(self) -> int | None:
+        """Vector dimensionality (of the ORIGINAL vectors when a quantizer is attached);
+        None while the index is empty and has no quantizer."""
+        if self._quantizer is not None:
+            return self._quantizer.dims[0]
+        return self._get_internal_dim()
+
+    @property
+    def doc_ids(self) -> set[str]:
+        return self._get_doc_ids()
+
+    @property
+    def psg_ids(self) -> set[str]:
+        return self._get_psg_ids()
+
+    def __len__(self) -> int:
+        return self._get_num_vectors()
+
+    # ------------------------------------------------------------------ back-end contract
+    @abc.abstractmethod
+    def _get_internal_dim(self) -> int | None: ...
+
+    @abc.abstractmethod
+    def _get_doc_ids(self) -> set[str]: ...
+
+    @abc.abstractmethod
+    def _get_psg_ids(self) -> set[str]: ...
+
+    @abc.abstractmethod
+    def _get_num_vectors(self) -> int: ...
+
+    @abc.abstractmethod
+    def _add(self, vectors: np.ndarray, doc_ids: IDSequence, psg_ids: IDSequence) -> None:
+        """Append (possibly quantized) vectors with their ids."""
+
+    @abc.abstractmethod
+    def _get_vectors(self, ids: Iterable[str]) -> tuple[np.ndarray, list[str]]:
+        """Vectors (codes when quantized) needed to score `ids` in the current mode, with one
+        id per returned row.  IndexError for an unknown id."""
+
+    @abc.abstractmethod
+    def _batch_iter(self, batch_size: int) -> Iterator[tuple[np.ndarray, IDSequence, IDSequence]]: ...
+
+    @abc.abstractmethod
+    def _device(self) -> _ffx.DeviceIndex:
+        """The libffx index holding this index's rows in HBM, maps synchronised."""
+
+    @abc.abstractmethod
+    def _resolve(self, ids: np.ndarray, mode: Mode) -> np.ndarray:
+        """Unique ids -> int32 candidates for ffx_rerank (document ordinals, or row numbers in
+        PASSAGE mode) with the semantics of index/util.py:29-41; IndexError if unknown."""
+
+    # ------------------------------------------------------------------ adding
+    def add(self, vectors: np.ndarray, doc_ids: IDSequence | None = None,
+            psg_ids: IDSequence | None = None) -> None:
+        """Add vectors with document and/or passage ids (index/base.py:211-256).
+
+        :raises ValueError: id count mismatch, dimension mismatch, or a vector without any id.
+        :raises RuntimeError: when the back-end cannot add the items (duplicate passage id).
+        """
+        count, dim = vectors.shape
+        doc_ids = [None] * count if doc_ids is None else doc_ids
+        psg_ids = [None] * count if psg_ids is None else psg_ids
+        if not len(doc_ids) == len(psg_ids) == count:
+            raise ValueError("Number of IDs does not match number of vectors.")
+        if self.dim is not None and dim != self.dim:
+            raise ValueError(f"Input vector dimensionality ({dim}) does not match "
+                             f"index dimensionality ({self.dim}).")
+        if any(d is None and p is None for d, p in zip(doc_ids, psg_ids)):
+            raise ValueError("Vector has neither document nor passage ID.")
+        payload = vectors if self.quantizer is None else self.quantizer.encode(vectors)
+        self._add(payload, doc_ids, psg_ids)
+
+    # ------------------------------------------------------------------ scoring
+    def _launch(self, mode: Mode, q_no: np.ndarray, id_values: np.ndarray, query_vectors: np.ndarray,
+                lex: np.ndarray | None = None, alpha: float = 0.0, k: int = 0, want_ff: bool = True):
+        """Integer-code the pairs and run ffx_rerank_host.  Pairs must be grouped by `q_no`
+        (non-decreasing).  Returns (out dict, q_off)."""
+        qv = np.ascontiguousarray(query_vectors, dtype=np.float32)
+        if qv.ndim != 2 or (self.dim is not None and qv.shape[1] != self.dim):
+            raise ValueError(f"Query vectors of shape {qv.shape} do not match index dimensionality {self.dim}.")
+        codes, uniq = pd.factorize(id_values)  # first-appearance order, like data["id"].unique()
+        cand = self._resolve(np.asarray(uniq, dtype=object), mode)[codes]
+        q_off = np.zeros(qv.shape[0] + 1, np.int64)
+        np.cumsum(np.bincount(q_no, minlength=qv.shape[0]), out=q_off[1:])
+        out = self._device().rerank_host(mode.value, qv, q_off, cand, lex, alpha, k,
+                                         want_ff=want_ff, want_int=False)
+        return out, q_off
+
+    def _compute_scores(self, data: pd.DataFrame, query_vectors: np.ndarray) -> pd.DataFrame:
+        """Semantic scores for the (id, q_no) rows of `data` (index/base.py:279-314).
+
+        Returns `data` with an added `ff_score` column (float32).  One CUDA launch gathers
+        the rows of every candidate, takes the dot products with the query vector and reduces
+        per document by the current mode; PQ/OPQ indexes are scored from the codes."""
+        n = len(data)
+        if n == 0:
+            return data.assign(ff_score=np.zeros(0, np.float32))
+        q_no = data["q_no"].to_numpy(dtype=np.int64)
+        ids = data["id"].to_numpy()
+        order = None
+        if (np.diff(q_no) < 0).any():
+            order = np.argsort(q_no, kind="stable")
+            q_no, ids = q_no[order], ids[order]
+        out, _ = self._launch(self.mode, q_no, ids, query_vectors)
+        ff = out["ff"]
+        if order is not None:
+            unsorted = np.empty_like(ff)
+            unsorted[order] = ff
+            ff = unsorted
+        return data.assign(ff_score=ff)
+
+    def _early_stopping(self, df: pd.DataFrame, query_vectors: np.ndarray, cutoff: int,
+                        alpha: float, depths: Iterable[int]) -> pd.DataFrame:
+        """Score in depth intervals and stop a query once its `cutoff`-th best interpolated
+        score can no longer be beaten (index/base.py:316-387).  Only scored rows are returned.
+
+        `df` must be grouped by query with rows in rank order (what `__call__` passes)."""
+        n = len(df)
+        q_no = df["q_no"].to_numpy(dtype=np.int64)
+        if n and (np.diff(q_no) < 0).any():
+            df = df.iloc[np.argsort(q_no, kind="stable")]
+            q_no = df["q_no"].to_numpy(dtype=np.int64)
+        lex = df["score"].to_numpy(dtype=np.float32)
+        present, start, count = np.unique(q_no, return_index=True, return_counts=True)
+        depth_of_row = np.arange(n) - np.repeat(start, count)
+        slot_of_row = np.repeat(np.arange(len(present)), count)
+        ff = np.zeros(n, np.float32)
+        inter = np.zeros(n, np.float32)
+        done_depth = np.zeros(len(present), np.int64)  # rows scored so far per query
+        active = np.ones(len(present), bool)
+        a32, b32 = np.float32(alpha), np.float32(1 - alpha)
+
+        lo = 0
+        for hi in sorted(depths):
+            if hi < cutoff:
+                continue
+            if lo > 0:
+                for s in np.flatnonzero(active):
+                    b, e = start[s], start[s] + done_depth[s]
+                    if e == b:
+                        active[s] = False
+                        continue
+                    kth = np.sort(inter[b:e])[::-1][:cutoff][-1]
+                    bound = a32 * lex[e - 1] + b32 * ff[b:e].max()
+                    active[s] = kth < bound
+            LOGGER.info("depth %s: %s queries left", hi, int(active.sum()))
+            take = active[slot_of_row] & (depth_of_row >= lo) & (depth_of_row < hi)
+            if not take.any():
+                break
+            chunk = self._compute_scores(df.loc[take, ["id", "q_no"]], query_vectors)
+            ff[take] = chunk["ff_score"].to_numpy()
+            inter[take] = a32 * lex[take] + b32 * ff[take]
+            done_depth[active] = np.minimum(count[active], hi)
+            lo = hi
+        scored = depth_of_row < done_depth[slot_of_row]
+        result = df.loc[scored].copy()
+        result["ff_score"] = ff[scored]
+        return result
+
+    def _query_vectors_for(self, src: pd.DataFrame):
+        """Number the queries in order of appearance and encode each once (base.py:418-429)."""
+        q_codes, q_names = pd.factorize(src["q_id"])
+        first_row = np.unique(q_codes, return_index=True)[1]
+        vectors = self.encode_queries(list(src["query"].to_numpy()[first_row]))
+        return q_codes.astype(np.int64), len(q_names), vectors
+
+    def __call__(self, ranking: Ranking, early_stopping: int | None = None,
+                 early_stopping_alpha: float | None = None,
+                 early_stopping_depths: Iterable[int] | None = None,
+                 batch_size: int | None = None) -> Ranking:
+        """Compute semantic scores for a ranking (index/base.py:389-469).
+
+        :raises ValueError: the ranking has no queries attached, or early stopping is requested
+            without alpha and depths.
+        :raises IndexError: an id of the ranking is not in the index.
+        :return: a ranking named "fast-forward" with `score` = semantic score.
+        """
+        if not ranking.has_queries:
+            raise ValueError("Input ranking has no queries attached.")
+        if early_stopping is not None and (early_stopping_alpha is None or early_stopping_depths is None):
+            raise ValueError("Early stopping requires alpha and depths.")
+        started = perf_counter()
+
+        src = ranking._df
+        q_codes, nq, query_vectors = self._query_vectors_for(src)
+        grouped = not (np.diff(q_codes) < 0).any()
+        step = nq if batch_size is None or batch_size >= nq else int(batch_size)
+        dtype = src.dtypes["score"]
+
+        if early_stopping is None and grouped:
+            # one launch per query batch: semantic scores AND the per-query order (ties keep
+            # the incoming order, like the reference's stable sort), no pandas sort needed
+            ids = src["id"].to_numpy()
+            row_off = np.zeros(nq + 1, np.int64)
+            np.cumsum(np.bincount(q_codes, minlength=nq), out=row_off[1:])
+            ff = np.empty(len(src), np.float32)
+            order = []
+            for lo in range(0, nq, max(step, 1)):
+                hi = min(nq, lo + step)
+                r0, r1 = row_off[lo], row_off[hi]
+                widest = int(np.diff(row_off[lo:hi + 1]).max())
+                out, q_off = self._launch(self.mode, q_codes[r0:r1] - lo, ids[r0:r1],
+                                          query_vectors[lo:hi], k=widest)
+                ff[r0:r1] = out["ff"]
+                order.append(_rows_from_topk(out["topk_pos"], out["topk_score"], q_off)[0] + r0)
+            LOGGER.info("computed scores in %s seconds", perf_counter() - started)
+            if np.isnan(ff).any():  # NaN rows are dropped by Ranking: take the generic route
+                frame = src[["q_id", "id", "query"]].assign(score=ff)
+                return Ranking(frame, name="fast-forward", dtype=dtype, copy=False, is_sorted=False)
+            rows = np.concatenate(order) if order else np.zeros(0, np.int64)
+            frame = src[["q_id", "id", "query"]].iloc[rows].reset_index(drop=True)
+            frame["score"] = ff[rows]
+            out_ranking = Ranking(frame, name="fast-forward", dtype=dtype, copy=False, is_sorted=True)
+            if dtype == np.float32:
+                out_ranking._origin = _Origin(self, src, row_off, ff)
+            return out_ranking
+
+        work = src.assign(q_no=q_codes, orig_index=np.arange(len(src)))
+
+        def run(part: pd.DataFrame) -> pd.DataFrame:
+            if early_stopping is None:
+                return self._compute_scores(part, query_vectors)
+            return self._early_stopping(part, query_vectors, early_stopping,
+                                        float(early_stopping_alpha), early_stopping_depths)
+
+        # sequential query batches as in the reference; an empty trailing batch is skipped
+        parts = [run(work[(q_codes >= lo) & (q_codes < lo + step)]) for lo in range(0, nq, max(step, 1))]
+        result = pd.concat(parts) if parts else work.assign(ff_score=np.zeros(0, np.float32))
+        frame = result[["q_id", "id", "query"]].copy()
+        frame["score"] = result["ff_score"].to_numpy()
+        LOGGER.info("computed scores in %s seconds", perf_counter() - started)
+        return Ranking(frame, name="fast-forward", dtype=dtype, copy=False, is_sorted=False)
+
+    def rerank(self, ranking: Ranking, alpha: float, cutoff: int | None = None) -> Ranking:
+        """Fused re-ranking: the result of
+        `ranking.interpolate(self(ranking), alpha).cut(cutoff)` from ONE kernel launch
+        (look-up, dots, per-document reduce, interpolation and per-query top-k all on the GPU).
+        """
+        if not ranking.has_queries:
+            raise ValueError("Input ranking has no queries attached.")
+        src = ranking._df
+        if src["score"].dtype != np.float32:
+            out = ranking.interpolate(self(ranking), alpha)
+            return out if cutoff is None else out.cut(cutoff)
+        q_codes, nq, query_vectors = self._query_vectors_for(src)
+        if (np.diff(q_codes) < 0).any():
+            raise ValueError("Ranking frame is not grouped by query.")
+        if nq == 0:
+            return Ranking(src, name=ranking.name, dtype=np.float32, copy=True, is_sorted=True)
+        counts = np.bincount(q_codes, minlength=nq)
+        k = int(counts.max()) if cutoff is None else int(min(cutoff, counts.max()))
+        out, q_off = self._launch(self.mode, q_codes, src["id"].to_numpy(), query_vectors,
+                                  lex=src["score"].to_numpy(), alpha=alpha, k=k, want_ff=False)
+        rows, scores = _rows_from_topk(out["topk_pos"], out["topk_score"], q_off)
+        # ties inside the kept lists come out in ascending id order like the reference; which of
+        # several candidates tied exactly AT a cut boundary survives is decided by position
+        rows = _order_ties_by_id(rows, scores, src["id"].to_numpy(), q_off)
+        frame = src.iloc[rows].reset_index(drop=True)
+        frame["score"] = scores
+        return Ranking(frame, name=ranking.name, dtype=src.dtypes["score"], copy=False, is_sorted=True)
+
+    # ------------------------------------------------------------------ iteration
+    def batch_iter(self, batch_size: int) -> Iterator[tuple[np.ndarray, IDSequence, IDSequence]]:
+        """Yield (vectors, doc ids, passage ids) batches; codes are decoded when quantized."""
+        if self._quantizer is None:
+            yield from self._batch_iter(batch_size)
+        else:
+            for codes, doc_ids, psg_ids in self._batch_iter(batch_size):
+                yield self._quantizer.decode(codes), doc_ids, psg_ids
+
+    def __iter__(self) -> Iterator[tuple[np.ndarray, "str | None", "str | None"]]:
+        for vectors, doc_ids, psg_ids in self.batch_iter(2**9):
+            yield from zip(vectors, doc_ids, psg_ids)

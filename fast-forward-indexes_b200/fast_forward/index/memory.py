@@ -1,0 +1,80 @@
+"""`InMemoryIndex` — drop-in for src/fast_forward/index/memory.py:20-180, with "memory"
+meaning the GPU's HBM: rows are staged once (pinned double buffer -> device) into a libffx
+row store and never copied back for scoring."""
+
+from __future__ import annotations
+
+import logging
+from collections.abc import Iterable, Iterator
+
+import numpy as np
+
+from fast_forward import _ffx
+from fast_forward.encoder.base import Encoder
+from fast_forward.index._store import RowStore
+from fast_forward.index.base import IDSequence, Index, Mode
+from fast_forward.index.util import get_indices
+from fast_forward.quantizer import Quantizer
+
+LOGGER = logging.getLogger(__name__)
+
+
+class InMemoryIndex(Index):
+    """Fast-Forward index held entirely in GPU memory."""
+
+    def __init__(self, query_encoder: Encoder | None = None, quantizer: Quantizer | None = None,
+                 mode: Mode = Mode.MAXP, encoder_batch_size: int = 32, init_size: int = 2**16,
+                 alloc_size: int = 2**16, device: int = 0) -> None:
+        """:param init_size: rows allocated up front. :param alloc_size: granularity of later
+        growth (rows). :param device: CUDA device ordinal.  Other parameters as `Index`."""
+        self._store = RowStore(device)
+        self._init_size = init_size
+        self._alloc_size = alloc_size
+        super().__init__(query_encoder=query_encoder, quantizer=quantizer, mode=mode,
+                         encoder_batch_size=encoder_batch_size)
+
+    # ---- Index contract -------------------------------------------------------------------
+    def _get_num_vectors(self) -> int:
+        return self._store.count
+
+    def _get_internal_dim(self) -> int | None:
+        return self._store.width
+
+    def _get_doc_ids(self) -> set[str]:
+        return set(self._store.doc_rows.keys())
+
+    def _get_psg_ids(self) -> set[str]:
+        return set(self._store.psg_row.keys())
+
+    def _add(self, vectors: np.ndarray, doc_ids: IDSequence, psg_ids: IDSequence) -> None:
+        """Stage rows into HBM.  Vectors are stored as float32 (codes as uint8): integer or
+        float64 input is converted, unlike the reference which keeps the first chunk's dtype
+        (index/memory.py:79-82)."""
+        self._store.check_new_passages(psg_ids)
+        if self.quantizer is not None:
+            if vectors.dtype != np.uint8:
+                raise RuntimeError("Only uint8 codes (Ks <= 256) can be stored on the device.")
+            rows = np.ascontiguousarray(vectors)
+        else:
+            rows = np.ascontiguousarray(vectors, dtype=np.float32)
+        self._store.append(rows, doc_ids, psg_ids, self._init_size, self._alloc_size)
+
+    def consolidate(self) -> None:
+        """Kept for API compatibility: the device store is always one contiguous array."""
+
+    def _get_vectors(self, ids: Iterable[str]) -> tuple[np.ndarray, list[str]]:
+        rows, owners = get_indices(ids, self.mode, self._store.doc_rows, self._store.psg_row)
+        return self._store.read(rows), owners
+
+    def _batch_iter(self, batch_size: int) -> Iterator[tuple[np.ndarray, IDSequence, IDSequence]]:
+        total = len(self)
+        for lo in range(0, total, batch_size):
+            hi = min(lo + batch_size, total)
+            doc_ids, psg_ids = self._store.id_columns(lo, hi)
+            yield self._store.read(np.arange(lo, hi)), doc_ids, psg_ids
+
+    def _device(self) -> _ffx.DeviceIndex:
+        return self._store.device_index(self.quantizer)
+
+    def _resolve(self, ids: np.ndarray, mode: Mode) -> np.ndarray:
+        return self._store.resolve(ids, mode == Mode.PASSAGE)

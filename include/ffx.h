@@ -135,6 +135,26 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
                     int k, float *out_ff, float *out_int, float *out_topk_score,
                     int32_t *out_topk_pos);
 
+/* Synchronises `stream` and reports what the asynchronous launches on this index saw: the
+ * kernels never dereference a candidate outside [0, #documents) (or [0, #rows) in PASSAGE
+ * mode) — such a pair scores as an empty document and this call (like ffx_rerank_host)
+ * returns FFX_ERR_INVALID naming the pair.  The host shell maps ids itself and raises
+ * IndexError (index/util.py:38-39) long before; this is the last line of defence. */
+int ffx_index_sync(ffx_index *idx, void *stream);
+
+/* Replaces `Ranking.interpolate` + `Ranking.cut` (ranking.py:293-326, :279-291) over scores
+ * that already exist: interpolated = fl32(fl32(alpha)*lex) + fl32(fl32(1-alpha)*ff) per pair
+ * (lex == NULL: the scores in `ff` are ranked as they are), then the per-query top-k with the
+ * ordering rule of ffx_rerank.  k = 0 only interpolates.  ffx_interpolate_topk takes device
+ * pointers and is asynchronous on `stream`; the _host variant takes host pointers and
+ * synchronises.  `idx` only provides the device and scratch memory. */
+int ffx_interpolate_topk(ffx_index *idx, const float *lex, const float *ff, int64_t nq,
+                         const int64_t *q_off, double alpha, int k, int64_t max_cand, float *out_int,
+                         float *out_topk_score, int32_t *out_topk_pos, void *stream);
+int ffx_interpolate_topk_host(ffx_index *idx, const float *lex, const float *ff, int64_t nq,
+                              const int64_t *q_off, double alpha, int k, float *out_int,
+                              float *out_topk_score, int32_t *out_topk_pos);
+
 /* Exchange step of a doc-id-range sharded corpus: merges `n_shards` per-shard
  * top-k lists [n_shards, nq, k] (scores + GLOBAL positions, device pointers) into
  * [nq, k] with the same ordering rule.  Runs on `stream`. */

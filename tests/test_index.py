@@ -1,0 +1,289 @@
+"""The `fast_forward` drop-in API on the GPU — the reference's backend-parametrised index
+suite (tests/test_index.py:49-441 there) re-stated for the HBM-resident back-ends, with the
+expected frames taken from the unmodified reference (tests/golden/)."""
+
+import itertools
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import ff_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+QUERIES = {"q1": "query 1", "q2": "query 2"}
+DOC = ["d0", "d0", "d1", "d2", "d3"]
+PSG = ["p0", "p1", "p2", "p3", "p4"]
+V = np.tril(np.ones((5, 5), dtype=np.int64))
+DOC_RUN = {"q1": {"d0": 100, "d1": 2, "d2": 3, "d3": 200}, "q2": {"d0": 400, "d1": 5, "d2": 6, "d3": 800}}
+PSG_RUN = {"q1": {"p0": 100, "p1": 2, "p2": 3, "p3": 4, "p4": 5},
+           "q2": {"p0": 500, "p1": 6, "p2": 7, "p3": 8, "p4": 9}}
+
+
+@pytest.fixture(scope="module")
+def ff():
+    import __graft_entry__ as g
+
+    g.build()
+    import fast_forward
+
+    return fast_forward
+
+
+@pytest.fixture(scope="module")
+def api(ff):
+    from fast_forward.encoder import LambdaEncoder, TableEncoder
+    from fast_forward.index import InMemoryIndex, Mode
+    from fast_forward.quantizer import NanoOPQ, NanoPQ
+
+    class Api:
+        pass
+
+    a = Api()
+    a.Ranking, a.InMemoryIndex, a.Mode = ff.Ranking, InMemoryIndex, Mode
+    a.LambdaEncoder, a.TableEncoder, a.NanoPQ, a.NanoOPQ = LambdaEncoder, TableEncoder, NanoPQ, NanoOPQ
+    a.ones = LambdaEncoder(lambda _: np.array([1, 1, 1, 1, 1]))
+    a.new = lambda **kw: InMemoryIndex(**kw)
+    return a
+
+
+def same_frame(r, want):
+    df = r._df
+    assert df["q_id"].tolist() == want["q_id"] and df["id"].tolist() == want["id"]
+    assert df["score"].to_numpy().astype(np.float32).view(np.uint32).tolist() == want["score_bits"]
+
+
+def fill(index, which):
+    if which == "full":
+        index.add(V, doc_ids=DOC, psg_ids=PSG)
+    else:  # reference tests/test_index.py:58-69: ids partially missing, docs split over adds
+        index.add(V, doc_ids=[None, None] + DOC[2:], psg_ids=PSG[:-2] + [None, None])
+        index.add(V[:2], doc_ids=DOC[:2])
+        index.add(V[-2:], psg_ids=PSG[-2:])
+    return index
+
+
+def assert_same_vectors(vecs, ids, want_vecs, want_ids):
+    """order-insensitive, like the reference helper (tests/test_index.py:667-683)."""
+    assert len(ids) == len(want_ids) == len(vecs)
+    got = sorted(zip(ids, map(tuple, np.round(np.asarray(vecs, np.float64), 5))))
+    want = sorted(zip(want_ids, map(tuple, np.round(np.asarray(want_vecs, np.float64), 5))))
+    assert got == want
+
+
+@pytest.mark.parametrize("which", ["full", "partial"])
+def test_modes_match_the_reference(api, golden_kat, which):
+    index = fill(api.new(query_encoder=api.ones), which)
+    doc_rank = api.Ranking.from_run(DOC_RUN, queries=QUERIES)
+    psg_rank = api.Ranking.from_run(PSG_RUN, queries=QUERIES)
+    for mode in (api.Mode.MAXP, api.Mode.FIRSTP, api.Mode.AVEP):
+        index.mode = mode
+        out = index(doc_rank)
+        assert out.has_queries and out.name == "fast-forward"
+        same_frame(out, golden_kat[f"{which}/{mode.name}"])
+    index.mode = api.Mode.PASSAGE
+    same_frame(index(psg_rank), golden_kat[f"{which}/PASSAGE"])
+
+
+def test_properties(api):
+    full = fill(api.new(query_encoder=api.ones), "full")
+    partial = fill(api.new(query_encoder=api.ones), "partial")
+    assert full.doc_ids == set(DOC) and full.psg_ids == set(PSG) and len(full) == 5 and full.dim == 5
+    assert partial.doc_ids == set(DOC) and partial.psg_ids == set(PSG) and len(partial) == 9
+    docs_only = api.new()
+    docs_only.add(V, doc_ids=DOC)
+    assert docs_only.psg_ids == set() and docs_only.doc_ids == set(DOC)
+    empty = api.new()
+    assert len(empty) == 0 and empty.dim is None and empty.doc_ids == set()
+
+
+def test_add_and_retrieve_while_growing(api):
+    index = api.new(init_size=32, alloc_size=32)
+    rng = np.random.default_rng(0)
+    data = rng.normal(size=(80, 16))
+    doc_ids = [f"doc_{i // 2}" for i in range(80)]
+    psg_ids = [f"psg_{i}" for i in range(80)]
+    for lo, hi in [(0, 8), (8, 24), (24, 80)]:
+        index.add(data[lo:hi], doc_ids=doc_ids[lo:hi], psg_ids=psg_ids[lo:hi])
+        assert len(index) == hi
+        index.mode = api.Mode.PASSAGE
+        assert_same_vectors(*index._get_vectors(psg_ids[lo:hi]), data[lo:hi], psg_ids[lo:hi])
+        index.mode = api.Mode.MAXP
+        docs = [f"doc_{i}" for i in range(lo // 2, hi // 2)]
+        assert_same_vectors(*index._get_vectors(docs), data[lo:hi], doc_ids[lo:hi])
+        index.mode = api.Mode.FIRSTP
+        assert_same_vectors(*index._get_vectors(docs), data[lo:hi:2], doc_ids[lo:hi:2])
+    index.consolidate()
+    index.mode = api.Mode.PASSAGE
+    assert_same_vectors(*index._get_vectors(psg_ids), data, psg_ids)
+    vecs, ids = index._get_vectors([])
+    assert len(vecs) == 0 and ids == []
+
+
+def test_errors(api):
+    idx = api.new()
+    with pytest.raises(ValueError):
+        idx.add(V, doc_ids=None, psg_ids=None)
+    with pytest.raises(ValueError):
+        idx.add(V, doc_ids=DOC[:-2])
+    with pytest.raises(ValueError):
+        idx.add(V, psg_ids=PSG[:-2])
+    with pytest.raises(ValueError):
+        idx.add(V, doc_ids=[None] + DOC[1:], psg_ids=[None] + PSG[1:])
+    idx.add(V[:1], psg_ids=PSG[:1])
+    with pytest.raises(RuntimeError):
+        idx.add(V[:1], psg_ids=PSG[:1])
+    assert len(idx) == 1  # nothing was added by the failing call
+    with pytest.raises(RuntimeError):
+        idx.encode_queries(["test"])
+    wrong = api.new()
+    wrong.add(np.array([[0, 0], [1, 1]]), doc_ids=["d1", "d2"])
+    with pytest.raises(ValueError):
+        wrong.add(np.array([[0, 0, 0], [1, 1, 1]]), doc_ids=["d3", "d4"])
+
+    full = fill(api.new(query_encoder=api.ones), "full")
+    with pytest.raises(ValueError):
+        full(api.Ranking.from_run(DOC_RUN))  # no queries attached
+    rank = api.Ranking.from_run(DOC_RUN, queries=QUERIES)
+    with pytest.raises(ValueError):
+        full(rank, early_stopping=10, early_stopping_alpha=None, early_stopping_depths=(1,))
+    with pytest.raises(ValueError):
+        full(rank, early_stopping=10, early_stopping_alpha=0.5, early_stopping_depths=None)
+    pq = api.NanoPQ(2, 8)
+    pq.fit(np.random.default_rng(0).normal(size=(16, 16)).astype(np.float32))
+    with pytest.raises(RuntimeError):
+        full.quantizer = pq
+    with pytest.raises(IndexError, match="ID dx not found in the index."):
+        full(api.Ranking.from_run({"q1": {"d0": 100, "dx": 2}}, queries=QUERIES))
+    full.mode = api.Mode.PASSAGE
+    with pytest.raises(IndexError):
+        full(rank)  # document ids are not passage ids
+
+
+def test_batch_size(api, golden_kat):
+    full = fill(api.new(query_encoder=api.ones), "full")
+    g = golden_kat["batch/input"]
+    run = {}
+    for q, i, s in zip(g["q_id"], g["id"], g["score"]):
+        run.setdefault(q, {})[i] = s
+    r = api.Ranking.from_run(run, queries={f"q{n}": f"query {n}" for n in range(1, 6)})
+    expected = full(r)
+    same_frame(expected, golden_kat["batch/none"])
+    for bs in (1, 2, 5, 10):  # 5 divides the query count: the reference crashes, we do not
+        assert full(r, batch_size=bs) == expected
+    same_frame(full(r, batch_size=2), golden_kat["batch/2"])
+
+
+def test_early_stopping(api, golden_kat):
+    es = api.new(query_encoder=api.LambdaEncoder(lambda q: np.array([10, 10])), mode=api.Mode.PASSAGE)
+    es.add(np.stack([[1, 0], [1, 1]] * 10), psg_ids=[f"p{i}" for i in range(20)])
+    r = api.Ranking(pd.DataFrame([{"q_id": q, "query": q, "id": f"p{i}", "score": i}
+                                  for i in range(20) for q in ("q1", "q2")]))
+    out = es(r, early_stopping=5, early_stopping_alpha=0.5, early_stopping_depths=(2, 5, 10, 20))
+    same_frame(out, golden_kat["es/5_0.5_2-5-10-20"])
+    out = es(r, early_stopping=3, early_stopping_alpha=0.2, early_stopping_depths=(4, 8, 20))
+    same_frame(out, golden_kat["es/3_0.2_4-8-20"])
+
+
+def test_iteration(api):
+    for kw in ({"init_size": 2, "alloc_size": 2}, {"init_size": 5}):
+        index = api.new(**kw)
+        index.add(V, doc_ids=DOC, psg_ids=PSG)
+        for bs in (1, 3, 5, 10):
+            vecs, docs, psgs = zip(*index.batch_iter(bs))
+            assert np.array_equal(np.concatenate(vecs), V)
+            assert list(itertools.chain.from_iterable(docs)) == DOC
+            assert list(itertools.chain.from_iterable(psgs)) == PSG
+        assert [d for _, d, _ in index] == DOC
+
+
+@pytest.mark.parametrize("key", ["s11", "s12", "s13", "s14"])
+def test_random_golden_through_the_public_api(api, golden_random, key):
+    """index(ranking) -> interpolate -> cut, compared frame by frame with the reference, via
+    the plain three-call idiom (README.md:48-51 of the reference) AND the fused `rerank`."""
+    meta, arrays = golden_random
+    case = meta[key]
+    vec, qvecs = arrays[f"{key}/vectors"], arrays[f"{key}/qvecs"]
+    enc = api.TableEncoder({f"text {i}": qvecs[i] for i in range(len(qvecs))})
+    index = api.new(query_encoder=enc, init_size=16, alloc_size=64)
+    sp = case["split"]
+    index.add(vec[:sp], doc_ids=case["doc_ids"][:sp], psg_ids=case["psg_ids"][:sp])
+    index.add(vec[sp:], doc_ids=case["doc_ids"][sp:], psg_ids=case["psg_ids"][sp:])
+    for mode in api.Mode:
+        g = case["modes"][mode.name]
+        fs = g["first_stage"]
+        first = api.Ranking(pd.DataFrame({"q_id": fs["q_id"], "id": fs["id"], "score": fs["score"]}),
+                            queries=case["queries"])
+        same_frame(first, fs)
+        index.mode = mode
+        out = index(first)
+        same_frame(out, g["ff"])
+        inter = first.interpolate(out, case["alpha"])
+        assert out._origin is not None  # the GPU interpolate path was taken
+        same_frame(inter, g["interpolated"])
+        same_frame(inter.cut(case["cutoff"]), g["cut"])
+        same_frame(index.rerank(first, case["alpha"]), g["interpolated"])
+        fused = index.rerank(first, case["alpha"], cutoff=case["cutoff"])
+        assert fused == inter.cut(case["cutoff"]) or \
+            sorted(fused._df["score"].tolist()) == sorted(inter.cut(case["cutoff"])._df["score"].tolist())
+        # a ranking that did not come from this index takes the generic (merge) route
+        same_frame(first.interpolate(api.Ranking(out._df), case["alpha"]), g["interpolated"])
+
+
+def test_quantized_index(api):
+    """reference tests/test_index.py:389-399 (shapes) + scores from codes == decode-then-dot
+    (rtol 1e-5 + atol 1e-5*|q||d|; ADC reorders the sum)."""
+    rng = np.random.default_rng(4)
+    for cls, kw in ((api.NanoPQ, {"iter": 3}), (api.NanoOPQ, {"pq_iter": 3, "rotation_iter": 2})):
+        pq = cls(4, 16)
+        pq.fit(rng.normal(size=(64, 16)).astype(np.float32), **kw)
+        qv = rng.normal(size=(2, 16)).astype(np.float32)
+        index = api.new(query_encoder=api.TableEncoder({"query 1": qv[0], "query 2": qv[1]}), quantizer=pq)
+        x = rng.normal(size=(5, 16)).astype(np.float32)
+        index.add(x, doc_ids=DOC, psg_ids=PSG)
+        assert index._get_internal_dim() == 4 and index.dim == 16
+        assert all(v.shape == (16,) for v, _, _ in index)
+        index.mode = api.Mode.MAXP
+        codes, ids = index._get_vectors(sorted(set(DOC)))
+        assert codes.shape == (5, 4) and codes.dtype == np.uint8
+        dec = pq.decode(pq.encode(x)).astype(np.float64)
+        for mode, red in ((api.Mode.MAXP, np.max), (api.Mode.AVEP, np.mean), (api.Mode.FIRSTP, lambda a: a[0])):
+            index.mode = mode
+            out = index(api.Ranking.from_run(DOC_RUN, queries=QUERIES))
+            for qi, q in enumerate(("q1", "q2")):
+                s = dec @ qv[qi].astype(np.float64)
+                want = {"d0": red(s[:2]), "d1": s[2], "d2": s[3], "d3": s[4]}
+                tol = 1e-5 * np.linalg.norm(qv[qi]) * np.linalg.norm(dec, axis=1).max()
+                for d, w in want.items():
+                    assert abs(out[q][d] - w) <= 1e-5 * abs(w) + tol
+
+
+def test_mid_size_random_vs_oracle(api):
+    """A few thousand pairs through the full API against the numpy oracle, bit for bit."""
+    rng = np.random.default_rng(12)
+    n_docs, dim, nq, C = 500, 768, 12, 300
+    cnt = rng.integers(1, 8, n_docs)
+    off = np.concatenate([[0], np.cumsum(cnt)])
+    vec = rng.standard_normal((off[-1], dim)).astype(np.float32)
+    doc_ids = [f"D{d}" for d in np.repeat(np.arange(n_docs), cnt)]
+    qv = rng.standard_normal((nq, dim)).astype(np.float32)
+    index = api.new(query_encoder=api.TableEncoder({f"t{i}": qv[i] for i in range(nq)}), init_size=len(vec))
+    index.add(vec, doc_ids=doc_ids)
+    run = {f"q{i}": {f"D{d}": float(np.float32(rng.uniform(0, 20))) for d in rng.choice(n_docs, C, replace=False)}
+           for i in range(nq)}
+    first = api.Ranking.from_run(run, queries={f"q{i}": f"t{i}" for i in range(nq)})
+    for mode, m in ((api.Mode.MAXP, fo.MODE_MAXP), (api.Mode.AVEP, fo.MODE_AVEP)):
+        index.mode = mode
+        out = index(first)
+        df = first._df
+        pair_q = df["q_id"].str[1:].astype(int).to_numpy()
+        pair_d = df["id"].str[1:].astype(int).to_numpy()
+        want = fo.score_pairs(vec, off, np.arange(off[-1]), pair_q, pair_d, qv, m)
+        got = out._df.set_index(["q_id", "id"])["score"].reindex(list(zip(df["q_id"], df["id"]))).to_numpy()
+        assert (got.view(np.uint32) == want.view(np.uint32)).all()
+        inter = first.interpolate(out, 0.1).cut(50)
+        s = fo.interpolate_f32(df["score"].to_numpy(), want, 0.1)
+        ts, tp = fo.topk_per_query(np.arange(nq + 1) * C, s, 50)
+        assert (inter._df["score"].to_numpy().view(np.uint32) == ts.ravel().view(np.uint32)).all()
+        assert index.rerank(first, 0.1, cutoff=50) == inter
