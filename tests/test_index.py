@@ -67,8 +67,9 @@ def fill(index, which):
 def assert_same_vectors(vecs, ids, want_vecs, want_ids):
     """order-insensitive, like the reference helper (tests/test_index.py:667-683)."""
     assert len(ids) == len(want_ids) == len(vecs)
-    got = sorted(zip(ids, map(tuple, np.round(np.asarray(vecs, np.float64), 5))))
-    want = sorted(zip(want_ids, map(tuple, np.round(np.asarray(want_vecs, np.float64), 5))))
+    # the store keeps float32: the expected rows are the float32 roundings of the input
+    got = sorted(zip(ids, map(tuple, np.asarray(vecs, np.float32).tolist())))
+    want = sorted(zip(want_ids, map(tuple, np.asarray(want_vecs, np.float32).tolist())))
     assert got == want
 
 
