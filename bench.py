@@ -42,9 +42,20 @@ METRIC = "re-ranked (query,doc) pairs/sec, MAXP k=5000"
 DIM = 768
 MODE_MAXP = 2
 
+MODES = {"PASSAGE": 1, "MAXP": 2, "FIRSTP": 3, "AVEP": 4}
+
+# BASELINE.json configs; the default (and the driver's) workload is configs[2] = C3, the one
+# the metric is quoted on.  The others are selectable for profiling / DESIGN.md numbers.
 WORKLOADS = {
-    # name: (n_docs, mean passages/doc, queries, candidates/query, cut k)
-    "c3_msmarco_doc_maxp": dict(n_docs=3_200_000, mean_psg=6.25, nq=5193, cands=5000, k=5000),
+    "c1_passage_10k": dict(mode="PASSAGE", kind="f32", n_rows=10_000, nq=100, cands=1000, k=1000),
+    "c2_msmarco_passage": dict(mode="PASSAGE", kind="f32", n_rows=8_800_000, nq=6980, cands=1000, k=1000),
+    "c3_msmarco_doc_maxp": dict(mode="MAXP", kind="f32", n_docs=3_200_000, mean_psg=6.25, nq=5193,
+                                cands=5000, k=5000),
+    "c4_opq_avep": dict(mode="AVEP", kind="opq", n_docs=3_200_000, mean_psg=6.25, nq=5193, cands=5000,
+                        k=5000, M=96, Ks=256),
+    # per-GPU shard of 1.2M docs / 7.5M passages (60M passages at 8 GPUs), 12 500 queries per GPU
+    "c5_sharded_maxp": dict(mode="MAXP", kind="f32", n_docs=1_200_000, mean_psg=6.25, nq=12_500,
+                            cands=5000, k=1000, sharded=True),
 }
 
 
@@ -197,7 +208,7 @@ def run_reference(args, wl):
         return
     vals, times = [], []
     for step in range(args.warmup + args.steps):
-        v, dt, cores, sample, pairs = cpu_port_run(wl, args.alpha, q_per_core=8)
+        v, dt, cores, sample, pairs = cpu_port_run(wl, args.alpha, q_per_core=24)
         if step >= args.warmup:
             vals.append(v)
             times.append(dt)
@@ -217,11 +228,23 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def build_corpus(wl, scale, rank, world):
+    """Row counts per document of the (rank's part of the) synthetic corpus."""
+    if "n_docs" in wl:
+        n_docs = max(wl["cands"] * 2, int(wl["n_docs"] * scale))
+        if wl.get("sharded"):
+            n_docs *= world
+        cnt = doc_lengths(n_docs, wl["mean_psg"], seed=0)
+        return n_docs, cnt
+    return None, None
+
+
 def run_ffx(args, wl):
     import torch
     import torch.distributed as dist
 
     from fast_forward import _ffx
+    from fast_forward.sharded import ShardedReranker, plan_doc_shards
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -233,56 +256,100 @@ def run_ffx(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_docs = max(1000, int(wl["n_docs"] * args.scale))
-    nq = max(296, int(wl["nq"] * args.scale)) if args.scale < 1 else wl["nq"]
+    mode, sharded, pq = MODES[wl["mode"]], bool(wl.get("sharded")), wl["kind"] == "opq"
     cands, k = wl["cands"], wl["k"]
-    cnt = doc_lengths(n_docs, wl["mean_psg"], seed=0)
-    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
-    n_rows = int(off[-1])
+    nq = wl["nq"] if args.scale == 1 else max(296, int(wl["nq"] * args.scale))
+    if sharded:
+        nq *= world  # weak scaling: every rank scores ~nq*cands/world pairs of a world-times larger job
+    n_docs, cnt = build_corpus(wl, args.scale, rank, world)
+    if n_docs is not None:
+        off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        total_rows = int(off[-1])
+        pool = n_docs
+    else:
+        total_rows = max(cands * 2, int(wl["n_rows"] * args.scale))
+        off = None
+        pool = total_rows
+    doc_lo, doc_hi, row_lo, row_hi = 0, n_docs, 0, total_rows
+    if sharded:
+        bounds = plan_doc_shards(cnt, world)
+        doc_lo, doc_hi = int(bounds[rank]), int(bounds[rank + 1])
+        row_lo, row_hi = int(off[doc_lo]), int(off[doc_hi])
+    n_rows = row_hi - row_lo
+    width = wl["M"] if pq else DIM
 
-    # ---- index: synthetic N(0,1) fp32 rows generated on the device, staged into the store
+    # ---- index: synthetic rows generated on the device and staged into the store
     t_stage = time.perf_counter()
-    idx = _ffx.DeviceIndex(DIM, capacity=n_rows, device=local)
+    idx = _ffx.DeviceIndex(width, capacity=n_rows, row_kind=_ffx.ROWS_PQ_U8 if pq else _ffx.ROWS_F32,
+                           device=local)
     gen = torch.Generator(device=dev)
-    gen.manual_seed(1234)  # identical replicas on every rank
+    gen.manual_seed(1234 + (rank if sharded else 0))  # replicas are identical on every rank
     chunk = 1 << 20
     for r0 in range(0, n_rows, chunk):
         nr = min(chunk, n_rows - r0)
-        t = torch.randn((nr, DIM), device=dev, dtype=torch.float32, generator=gen)
+        if pq:
+            t = torch.randint(0, wl["Ks"], (nr, width), device=dev, dtype=torch.uint8, generator=gen)
+        else:
+            t = torch.randn((nr, DIM), device=dev, dtype=torch.float32, generator=gen)
         torch.cuda.synchronize()
         idx.stage_device(r0, nr, t.data_ptr())
         del t
-    idx.set_docs(off)
+    if off is not None:
+        idx.set_docs(off[doc_lo:doc_hi + 1] - row_lo)
+    if pq:
+        g_cpu = torch.Generator().manual_seed(7)
+        cw = torch.randn((wl["M"], wl["Ks"], DIM // wl["M"]), generator=g_cpu)
+        R = torch.linalg.qr(torch.randn((DIM, DIM), generator=g_cpu))[0]
+        idx.set_pq(cw.numpy(), R.numpy())
     torch.cuda.empty_cache()
     t_stage = time.perf_counter() - t_stage
 
-    # ---- queries of this rank: stratified distinct candidates, uniform over the corpus
-    gen.manual_seed(99 + rank)
+    # ---- queries: stratified distinct candidates, uniform over the corpus.  Query-DP ranks
+    # draw their own queries; shards all see the same ones.
+    gen.manual_seed(99 + (0 if sharded else rank))
     qv = torch.randn((nq, DIM), device=dev, dtype=torch.float32, generator=gen)
-    bucket = n_docs // cands
+    bucket = pool // cands
     if bucket < 1:
         raise RuntimeError("corpus smaller than the candidate list")
-    perm = torch.rand((nq, cands), device=dev, generator=gen).argsort(dim=1)
-    within = torch.randint(0, bucket, (nq, cands), device=dev, generator=gen)
-    cand = (perm * bucket + within).to(torch.int32).contiguous().view(-1)
-    del perm, within
+    cand_parts = []
+    for q0 in range(0, nq, 4096):  # bounded temporaries
+        qn = min(4096, nq - q0)
+        perm = torch.rand((qn, cands), device=dev, generator=gen).argsort(dim=1)
+        within = torch.randint(0, bucket, (qn, cands), device=dev, generator=gen)
+        cand_parts.append((perm * bucket + within).to(torch.int32))
+        del perm, within
+    cand = torch.cat(cand_parts).contiguous().view(-1)
+    del cand_parts
     lex = (torch.rand((nq * cands,), device=dev, generator=gen) * 20).contiguous()
     q_off = (torch.arange(nq + 1, device=dev, dtype=torch.int64) * cands).contiguous()
     topk_s = torch.empty((nq, k), device=dev, dtype=torch.float32)
     topk_p = torch.empty((nq, k), device=dev, dtype=torch.int32)
     n_pairs = nq * cands
-    d_cnt = torch.from_numpy(cnt).to(dev)
-    rows_touched = int(d_cnt[cand.long()].sum().item())
-    del d_cnt
-    # rows*D*4 + 16 B/pair (cand, lex, span) + per query (query vector + top-k out)
-    algo_bytes = rows_touched * DIM * 4 + n_pairs * 16 + nq * (DIM * 4 + k * 8)
+
+    # algorithmic bytes: row bytes of every pair this rank scores + 16 B/pair
+    # (candidate, lexical score, span) + per query (query vector + top-k out)
+    row_bytes = width * (1 if pq else 4)
+    if cnt is not None and mode != MODES["FIRSTP"]:
+        d_cnt = torch.from_numpy(cnt).to(dev)
+        c64 = cand.long()
+        mine = (c64 >= doc_lo) & (c64 < doc_hi)
+        rows_touched = int(d_cnt[c64[mine]].sum().item())
+        my_pairs = int(mine.sum().item())
+        del d_cnt, c64, mine
+    else:
+        rows_touched = my_pairs = n_pairs
+    algo_bytes = rows_touched * row_bytes + n_pairs * 8 + my_pairs * 8 + nq * (DIM * 4 + k * 8)
 
     stream = torch.cuda.current_stream()
+    reranker = ShardedReranker(idx, doc_lo, n_docs, row_lo, total_rows) if sharded else None
 
     def step():
-        idx.rerank_device(MODE_MAXP, qv.data_ptr(), nq, q_off.data_ptr(), cand.data_ptr(), lex.data_ptr(),
+        if sharded:
+            return reranker.rerank(mode, qv, q_off, cand, lex, args.alpha, k, cands)
+        idx.rerank_device(mode, qv.data_ptr(), nq, q_off.data_ptr(), cand.data_ptr(), lex.data_ptr(),
                           args.alpha, k, cands, 0, 0, topk_s.data_ptr(), topk_p.data_ptr(),
                           stream.cuda_stream)
+        return topk_s, topk_p
 
     def barrier():
         torch.cuda.synchronize()
@@ -290,15 +357,17 @@ def run_ffx(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        out_s, out_p = step()
     barrier()
+    idx.sync(stream.cuda_stream)
     clk_p, clk_path = clocks_start() if rank == 0 else (None, None)
     launches0 = _ffx.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record(stream)
     for i in range(args.steps):
-        step()
+        out_s, out_p = step()
         ev[i + 1].record(stream)
     barrier()
     launches = _ffx.launch_count() - launches0
@@ -306,76 +375,92 @@ def run_ffx(args, wl):
     total_ms = ev[0].elapsed_time(ev[-1])
     clocks = clocks_stop(clk_p, clk_path, local) if rank == 0 else None
 
-    # sanity on the timed output: ranked lists are sorted and are permutations of the block
-    s_host = topk_s[:4].cpu().numpy()
-    p_host = topk_p[:4].cpu().numpy()
+    # sanity on the timed output: ranked lists are sorted, positions distinct and in range
+    s_host = out_s[:4].cpu().numpy()
+    p_host = out_p[:4].cpu().numpy()
     assert (np.diff(s_host, axis=1) <= 0).all(), "top-k not sorted"
     assert all(len(set(r.tolist())) == k for r in p_host) and p_host.min() >= 0 and p_host.max() < cands
 
     # ---- e2e: host buffers through ffx_rerank_host (H2D + kernel + D2H inside the timed region)
-    h_q = _ffx.PinnedBuffer((nq, DIM), np.float32)
-    h_off = _ffx.PinnedBuffer((nq + 1,), np.int64)
-    h_cand = _ffx.PinnedBuffer((n_pairs,), np.int32)
-    h_lex = _ffx.PinnedBuffer((n_pairs,), np.float32)
-    h_ts = _ffx.PinnedBuffer((nq, k), np.float32)
-    h_tp = _ffx.PinnedBuffer((nq, k), np.int32)
-    h_q.array[:] = qv.cpu().numpy()
-    h_off.array[:] = q_off.cpu().numpy()
-    h_cand.array[:] = cand.cpu().numpy()
-    h_lex.array[:] = lex.cpu().numpy()
-    out = {"topk_score": h_ts.array, "topk_pos": h_tp.array}
+    e2e_s = h2d = d2h = None
+    if not sharded:
+        h_q = _ffx.PinnedBuffer((nq, DIM), np.float32)
+        h_off = _ffx.PinnedBuffer((nq + 1,), np.int64)
+        h_cand = _ffx.PinnedBuffer((n_pairs,), np.int32)
+        h_lex = _ffx.PinnedBuffer((n_pairs,), np.float32)
+        h_ts = _ffx.PinnedBuffer((nq, k), np.float32)
+        h_tp = _ffx.PinnedBuffer((nq, k), np.int32)
+        h_q.array[:] = qv.cpu().numpy()
+        h_off.array[:] = q_off.cpu().numpy()
+        h_cand.array[:] = cand.cpu().numpy()
+        h_lex.array[:] = lex.cpu().numpy()
+        out = {"topk_score": h_ts.array, "topk_pos": h_tp.array}
 
-    def e2e_step():
-        idx.rerank_host(MODE_MAXP, h_q.array, h_off.array, h_cand.array, h_lex.array, args.alpha, k,
-                        want_ff=False, want_int=False, out=out)
+        def e2e_step():
+            idx.rerank_host(mode, h_q.array, h_off.array, h_cand.array, h_lex.array, args.alpha, k,
+                            want_ff=False, want_int=False, out=out)
 
-    e2e_step()
-    assert (h_tp.array[:4] == p_host).all(), "host-buffer path disagrees with the device path"
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
         e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    h2d = h_q.array.nbytes + h_off.array.nbytes + h_cand.array.nbytes + h_lex.array.nbytes
-    d2h = h_ts.array.nbytes + h_tp.array.nbytes
+        assert (h_tp.array[:4] == p_host).all(), "host-buffer path disagrees with the device path"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        h2d = h_q.array.nbytes + h_off.array.nbytes + h_cand.array.nbytes + h_lex.array.nbytes
+        d2h = h_ts.array.nbytes + h_tp.array.nbytes
 
-    times = torch.tensor([total_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    times = torch.tensor([total_ms, (e2e_s or 0.0) * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = times.tolist()
 
     if rank == 0:
-        value = world * n_pairs * args.steps / (total_ms * 1e-3)
-        e2e_value = world * n_pairs * args.steps / (e2e_ms * 1e-3)
+        job_pairs = n_pairs if sharded else world * n_pairs  # shards split ONE job's pairs
+        value = job_pairs * args.steps / (total_ms * 1e-3)
         kern_ms = float(np.mean(per_step_ms))
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
         peak, peak_src = measured_peak()
         traffic = ncu_traffic()
+        kernel = ("ffx_adc_kernel (LUT in smem over uint8 codes) + ffx_topk_kernel" if pq else
+                  "ffx_score_kernel<2,12,%s> (gather-dot-%s-interpolate%s)" % (
+                      "true" if nq >= 296 else "false", wl["mode"], "-topk fused" if nq >= 296 else " ; ffx_topk_kernel"))
         line = {
-            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "metric": METRIC if args.workload == "c3_msmarco_doc_maxp" else
+            f"re-ranked (query,doc) pairs/sec, {wl['mode']} k={cands}",
+            "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 codes + f32 LUT" if pq else "f32",
+            "data": "synthetic",
             "config": {
                 "workload": args.workload if args.scale == 1 else f"{args.workload} (SCALED x{args.scale}: debug)",
-                "mode": "MAXP", "dim": DIM, "docs": n_docs, "passages": n_rows, "index_gb": n_rows * DIM * 4 / 1e9,
-                "queries_per_gpu": nq, "candidates_per_query": cands, "cut_k": k, "alpha": args.alpha,
-                "parallelism": f"query-dp{world} (replicated index, no data-path collective)",
-                "l2": "inputs larger than L2 (61 GB index, 499 GB touched per step)",
+                "mode": wl["mode"], "dim": DIM, "docs": n_docs, "passages": total_rows,
+                "index_gb_per_gpu": n_rows * row_bytes / 1e9,
+                "queries": nq if sharded else f"{nq} per GPU", "candidates_per_query": cands, "cut_k": k,
+                "alpha": args.alpha,
+                "parallelism": (f"doc-id-range shards x{world}: local fused top-k, one NCCL all-gather of "
+                                f"[nq,k] lists, ffx_merge_topk" if sharded else
+                                f"query-dp{world} (replicated index, no data-path collective)"),
+                "l2": "inputs larger than L2 (index %.1f GB/GPU, %.1f GB touched per step per GPU)" % (
+                    n_rows * row_bytes / 1e9, algo_bytes / 1e9),
                 "index_stage_s": round(t_stage, 2),
             },
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
+            "e2e": None if e2e_s is None else {
+                "value": world * n_pairs * args.steps / (e2e_ms * 1e-3), "unit": "pairs/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                         "kernel": "ffx_score_kernel<2,12,true> (fused gather-dot-MAXP-interpolate-topk)",
-                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_ms, "peak_source": peak_src,
-                         "frac_of_nominal_8TBs": achieved / 8000.0},
+                         "frac": achieved / peak,
+                         "traffic": traffic.get(args.workload) if traffic and args.scale == 1 else None,
+                         "kernel": kernel, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_ms,
+                         "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world == 1:
-            v, dt, cores, sample, _ = cpu_port_run(wl, args.alpha, q_per_core=16)
+        if pq:
+            line["roofline"]["lut_lookups_per_s"] = rows_touched * wl["M"] / (kern_ms * 1e-3)
+        if not args.no_cpu_baseline and world == 1 and args.workload == "c3_msmarco_doc_maxp":
+            v, dt, cores, sample, _ = cpu_port_run(wl, args.alpha, q_per_core=64)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
                                     "sample": sample, "seconds": round(dt, 2)}
         print(json.dumps(line), flush=True)
@@ -389,7 +474,7 @@ def main():
     args = parse()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args, WORKLOADS["c3_msmarco_doc_maxp"])
     else:
         run_ffx(args, wl)
 

@@ -96,6 +96,10 @@ struct ffx_index {
     int32_t *doc_rows = nullptr;
     int indirect = 0;
 
+    // doc-id-range shard of a larger corpus (ffx_index_set_shard); off = whole corpus
+    bool sharded = false;
+    int64_t doc_base = 0, global_docs = 0, row_base = 0, global_rows = 0;
+
     // PQ / OPQ
     int M = 0, Ks = 0, Ds = 0;
     float *codewords = nullptr;
@@ -527,6 +531,28 @@ int ffx_index_set_docs(ffx_index *idx, int64_t n_docs, const int64_t *doc_off,
     return FFX_OK;
 }
 
+int ffx_index_set_shard(ffx_index *idx, int64_t doc_base, int64_t global_docs, int64_t row_base,
+                        int64_t global_rows) {
+    if (!idx) return fail(FFX_ERR_INVALID, "ffx_index_set_shard: NULL index");
+    if (global_docs == 0 && global_rows == 0) {
+        idx->sharded = false;
+        return FFX_OK;
+    }
+    if (doc_base < 0 || row_base < 0 || global_docs > 0x7fffffffll || global_rows > 0xffffffffll ||
+        doc_base + idx->n_docs > global_docs || row_base + idx->num_rows > global_rows)
+        return fail(FFX_ERR_INVALID, "ffx_index_set_shard: shard [%lld,+%lld) docs / [%lld,+%lld) rows does "
+                    "not fit the corpus (%lld docs, %lld rows)", static_cast<long long>(doc_base),
+                    static_cast<long long>(idx->n_docs), static_cast<long long>(row_base),
+                    static_cast<long long>(idx->num_rows), static_cast<long long>(global_docs),
+                    static_cast<long long>(global_rows));
+    idx->sharded = true;
+    idx->doc_base = doc_base;
+    idx->global_docs = global_docs;
+    idx->row_base = row_base;
+    idx->global_rows = global_rows;
+    return FFX_OK;
+}
+
 int ffx_index_set_pq(ffx_index *idx, int M, int Ks, int Ds, const float *codewords, const float *R) {
     if (!idx || !codewords || M <= 0 || Ks <= 0 || Ds <= 0)
         return fail(FFX_ERR_INVALID, "ffx_index_set_pq: bad arguments");
@@ -585,14 +611,20 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
     const float alpha32 = static_cast<float>(alpha);
     const float beta32 = static_cast<float>(1.0 - alpha);
 
-    const uint32_t limit = static_cast<uint32_t>(mode == FFX_MODE_PASSAGE ? idx->num_rows : idx->n_docs);
+    const bool psg_mode = mode == FFX_MODE_PASSAGE;
+    const uint32_t count = static_cast<uint32_t>(psg_mode ? idx->num_rows : idx->n_docs);
+    const uint32_t base = idx->sharded ? static_cast<uint32_t>(psg_mode ? idx->row_base : idx->doc_base) : 0u;
+    const uint32_t limit = idx->sharded ? static_cast<uint32_t>(psg_mode ? idx->global_rows : idx->global_docs)
+                                        : count;
 
     // one CTA per query with the top-k fused needs enough queries to fill the machine
     const int64_t slots = static_cast<int64_t>(idx->sm_count) * 2;
     const bool fuse = will_fuse(idx, nq, k, cpad);
 
     // scratch plan: [scores n_total?][keys nq*cpad?][qeff nq*D?]
-    const bool need_scores = k > 0 && !fuse && !out_int;
+    // a separate top-k pass reads out_int when the caller asked for it; a shard must not (pairs
+    // of other shards stay untouched there), it ranks a scratch copy with NaN = "not mine"
+    const bool need_scores = k > 0 && !fuse && (!out_int || idx->sharded);
     const bool need_gkeys = k > 0 && !fuse && cpad > ffx::kMaxFusedCand;
     size_t off_scores = 0, off_keys = 0, off_qeff = 0, total = 0;
     int64_t n_total = 0;
@@ -612,7 +644,8 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
     }
     if (total) FFX_TRY(scratch_reserve(idx->work, total));
     char *work = static_cast<char *>(idx->work.p);
-    float *scores = out_int ? out_int : (need_scores ? reinterpret_cast<float *>(work + off_scores) : nullptr);
+    float *rank_scores = need_scores ? reinterpret_cast<float *>(work + off_scores) : nullptr;
+    const float *topk_src = rank_scores ? rank_scores : out_int;
 
     // tiles: split a query over several CTAs when there are few queries
     int tiles = 1, tile = static_cast<int>(std::max<int64_t>(max_cand, 1));
@@ -655,10 +688,13 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
             a.alpha = alpha32;
             a.beta = beta32;
             a.out_ff = out_ff;
-            a.out_int = scores;
+            a.out_int = out_int;
+            a.rank_scores = rank_scores;
             a.tiles_per_query = tiles;
             a.tile = tile;
             a.limit = limit;
+            a.base = base;
+            a.count = count;
             a.err = idx->err_flag;
             const size_t smem = static_cast<size_t>(idx->M) * idx->Ks * 4;
             FFX_CUDA(cudaFuncSetAttribute(ffx::ffx_adc_kernel,
@@ -683,13 +719,16 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
             a.beta = beta32;
             a.k = k;
             a.out_ff = out_ff;
-            a.out_int = fuse ? out_int : scores;
+            a.out_int = out_int;
+            a.rank_scores = rank_scores;
             a.topk_score = out_topk_score;
             a.topk_pos = out_topk_pos;
             a.tiles_per_query = tiles;
             a.tile = tile;
             a.cpad = cpad;
             a.limit = limit;
+            a.base = base;
+            a.count = count;
             a.err = idx->err_flag;
             if (fast) {
                 FFX_TRY(dispatch_score(idx->plan, a, fuse, static_cast<int>(nq * tiles),
@@ -706,7 +745,7 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
         }
     }
     if (k > 0 && !fuse)
-        FFX_TRY(launch_topk(scores, nullptr, 0.f, 0.f, nullptr, q_off, nq, k, cpad, idx->work, off_keys,
+        FFX_TRY(launch_topk(topk_src, nullptr, 0.f, 0.f, nullptr, q_off, nq, k, cpad, idx->work, off_keys,
                             out_topk_score, out_topk_pos, st));
     return FFX_OK;
 }

@@ -24,9 +24,9 @@ struct AdcArgs {
     const int32_t *cand;
     const float *lex;
     float alpha, beta;
-    float *out_ff, *out_int;
+    float *out_ff, *out_int, *rank_scores;
     int tiles_per_query, tile;
-    uint32_t limit;
+    uint32_t limit, base, count;
     int *err;
 };
 
@@ -69,14 +69,17 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_adc_kernel(const AdcArgs a) {
     for (int c = threadIdx.x; c < n_tile; c += kThreads) {
         const int64_t p = q_begin + c0 + c;
         const int32_t u = a.cand[p];
-        uint32_t start = 0, cnt = 0;
+        uint32_t start = 0, cnt = 0, loc = 0;
         if (!candidate_ok(u, a.limit, a.err, p)) {
             cnt = 0;
+        } else if (!candidate_mine(u, a.base, a.count, &loc)) {
+            if (a.rank_scores) a.rank_scores[p] = __int_as_float(0x7fc00000);
+            continue;
         } else if (a.mode == FFX_MODE_PASSAGE) {
-            start = static_cast<uint32_t>(u);
+            start = loc;
             cnt = 1;
         } else {
-            const uint2 sp = a.doc_span[u];
+            const uint2 sp = a.doc_span[loc];
             start = sp.x;
             cnt = a.mode == FFX_MODE_FIRSTP ? 1u : sp.y;
         }
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_adc_kernel(const AdcArgs a) {
         if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, a.lex[p]), __fmul_rn(a.beta, ff));
         if (a.out_ff) a.out_ff[p] = ff;
         if (a.out_int) a.out_int[p] = inter;
+        if (a.rank_scores) a.rank_scores[p] = inter;
     }
 }
 

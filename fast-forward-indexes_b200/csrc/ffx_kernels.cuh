@@ -38,12 +38,14 @@ struct ScoreArgs {
     float alpha, beta;        // fl32(alpha), fl32(1 - alpha)
     int k;
     float *out_ff, *out_int;  // [n] or nullptr
+    float *rank_scores;       // [n] or nullptr: input of a separate top-k pass (NaN = not ranked)
     float *topk_score;        // [nq, k]
     int32_t *topk_pos;
     int tiles_per_query;      // 1 when FUSE
     int tile;                 // candidates per tile
     int cpad;                 // FUSE: next pow2 >= max candidates per query
-    uint32_t limit;           // valid candidates are [0, limit): documents, or rows in PASSAGE mode
+    uint32_t limit;           // valid candidates are [0, limit): GLOBAL documents (rows in PASSAGE mode)
+    uint32_t base, count;     // this index holds candidates [base, base+count) of them (a shard)
     int *err;                 // set to 1 + (pair index & 0x3fffffff) when a candidate is out of range
 };
 
@@ -53,6 +55,14 @@ __device__ __forceinline__ bool candidate_ok(int32_t u, uint32_t limit, int *err
     if (static_cast<uint32_t>(u) < limit) return true;
     if (err) atomicCAS(err, 0, 1 + static_cast<int>(pair & 0x3fffffff));
     return false;
+}
+
+// Doc-id-range shards: candidates are global ordinals, a shard owns
+// [base, base+count).  A pair owned by another shard is skipped: no loads, no per-pair
+// outputs (the caller zero-fills them and sums across shards), no top-k key.
+__device__ __forceinline__ bool candidate_mine(int32_t u, uint32_t base, uint32_t count, uint32_t *local) {
+    *local = static_cast<uint32_t>(u) - base;
+    return *local < count;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -71,12 +81,12 @@ __device__ __forceinline__ float f4c(const float4 &v, int c) {
 }
 
 // Monotone key: larger score first, then smaller position first, when sorted DESCENDING.
-// -0.0 is folded onto +0.0 (pandas ties them); NaN sorts last.  Key 0 is "empty".
+// -0.0 is folded onto +0.0 (pandas ties them).  Key 0 is "empty" (also used for NaN).
 __device__ __forceinline__ unsigned long long topk_key(float s, uint32_t pos) {
+    if (s != s) return 0ull;  // NaN is not ranked (Ranking drops NaN rows, ranking.py:103)
     if (s == 0.f) s = 0.f;
     uint32_t u = __float_as_uint(s);
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    if (s != s) u = 1u;
     return (static_cast<unsigned long long>(u) << 32) | static_cast<uint32_t>(~pos);
 }
 __device__ __forceinline__ float key_score(unsigned long long key) {
@@ -110,7 +120,7 @@ __device__ inline void bitonic_sort_desc(unsigned long long *keys, int n) {
 __device__ __forceinline__ void write_topk(const unsigned long long *keys, int n_valid, int k,
                                            float *out_s, int32_t *out_p) {
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const bool ok = i < n_valid;
+        const bool ok = i < n_valid && keys[i] != 0ull;  // key 0 = empty slot (sorts last)
         out_s[i] = ok ? key_score(keys[i]) : -INFINITY;
         out_p[i] = ok ? key_pos(keys[i]) : -1;
     }
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_score_kernel(const ScoreArgs 
 
     if (threadIdx.x == 0) s_next = 0;
     if (FUSE) {
-        for (int i = n_query + threadIdx.x; i < a.cpad; i += kThreads) s_keys[i] = 0ull;
+        for (int i = threadIdx.x; i < a.cpad; i += kThreads) s_keys[i] = 0ull;
     }
 
     // this lane's slice of the query vector, gathered once from the original order
@@ -220,15 +230,21 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_score_kernel(const ScoreArgs 
         // lane j resolves candidate j of the batch: id -> (first row, count)
         uint32_t my_start = 0, my_cnt = 0;
         float my_lex = 0.f;
+        bool mine = false;
         if (lane < nb) {
             const int32_t u = __ldg(a.cand + my_pair);
+            uint32_t loc = 0;
             if (!candidate_ok(u, a.limit, a.err, my_pair)) {
+                mine = true;  // reported; scores as an empty document
+            } else if (!candidate_mine(u, a.base, a.count, &loc)) {
                 my_cnt = 0;
             } else if (a.mode == FFX_MODE_PASSAGE) {
-                my_start = static_cast<uint32_t>(u);
+                mine = true;
+                my_start = loc;
                 my_cnt = 1;
             } else {
-                const uint2 sp = __ldg(a.doc_span + u);
+                mine = true;
+                const uint2 sp = __ldg(a.doc_span + loc);
                 my_start = sp.x;
                 my_cnt = a.mode == FFX_MODE_FIRSTP ? 1u : sp.y;
             }
@@ -271,11 +287,13 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_score_kernel(const ScoreArgs 
         }
 
         // lane j now holds candidate j's score: coalesced epilogue
-        if (lane < nb) {
+        if (lane < nb && !mine && a.rank_scores) a.rank_scores[my_pair] = __int_as_float(0x7fc00000);
+        if (lane < nb && mine) {
             float inter = my_ff;
             if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, my_lex), __fmul_rn(a.beta, my_ff));
             if (a.out_ff) a.out_ff[my_pair] = my_ff;
             if (a.out_int) a.out_int[my_pair] = inter;
+            if (a.rank_scores) a.rank_scores[my_pair] = inter;
             if (FUSE) {
                 const uint32_t pos = static_cast<uint32_t>(c0 + base + lane);
                 s_keys[pos] = topk_key(inter, pos);
@@ -330,14 +348,17 @@ __global__ void __launch_bounds__(128) ffx_score_generic_kernel(const ScoreArgs 
     }
     const float *qv = a.qvecs + lo * a.dim;
     const int32_t u = a.cand[p];
-    uint32_t start = 0, cnt = 0;
+    uint32_t start = 0, cnt = 0, loc = 0;
     if (!candidate_ok(u, a.limit, a.err, p)) {
         cnt = 0;
+    } else if (!candidate_mine(u, a.base, a.count, &loc)) {
+        if (a.rank_scores) a.rank_scores[p] = __int_as_float(0x7fc00000);
+        return;
     } else if (a.mode == FFX_MODE_PASSAGE) {
-        start = static_cast<uint32_t>(u);
+        start = loc;
         cnt = 1;
     } else {
-        const uint2 sp = a.doc_span[u];
+        const uint2 sp = a.doc_span[loc];
         start = sp.x;
         cnt = a.mode == FFX_MODE_FIRSTP ? 1u : sp.y;
     }
@@ -356,6 +377,7 @@ __global__ void __launch_bounds__(128) ffx_score_generic_kernel(const ScoreArgs 
     if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, a.lex[p]), __fmul_rn(a.beta, ff));
     if (a.out_ff) a.out_ff[p] = ff;
     if (a.out_int) a.out_int[p] = inter;
+    if (a.rank_scores) a.rank_scores[p] = inter;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -36,6 +36,7 @@ SYMBOLS = {
     "ffx_index_dim": (_L, [_P]),
     "ffx_index_has_fast_path": (_I, [_P]),
     "ffx_index_set_docs": (_I, [_P, _L, _P, _P]),
+    "ffx_index_set_shard": (_I, [_P, _L, _L, _L, _L]),
     "ffx_index_set_pq": (_I, [_P, _I, _I, _I, _P, _P]),
     "ffx_rerank": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _L, _P, _P, _P, _P, _P]),
     "ffx_rerank_host": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _P, _P, _P, _P]),
@@ -192,6 +193,10 @@ class DeviceIndex:
         doc_off = _arr(doc_off, np.int64)
         doc_rows = None if doc_rows is None else _arr(doc_rows, np.int64)
         check(lib().ffx_index_set_docs(self.handle, len(doc_off) - 1, _ptr(doc_off), _ptr(doc_rows)))
+
+    def set_shard(self, doc_base=0, global_docs=0, row_base=0, global_rows=0):
+        check(lib().ffx_index_set_shard(self.handle, int(doc_base), int(global_docs), int(row_base),
+                                        int(global_rows)))
 
     def set_pq(self, codewords, R=None):
         codewords = _arr(codewords, np.float32)

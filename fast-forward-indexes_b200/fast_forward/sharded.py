@@ -1,0 +1,110 @@
+"""Doc-id-range sharded re-ranking across the GPUs of one box (BASELINE config 5).
+
+The reference has no counterpart: its index must fit one process (index/memory.py,
+index/disk.py).  Here a corpus larger than one GPU's HBM is cut into contiguous document
+ranges, one per rank (one process per GPU, `torch.distributed`, NCCL over NVLink).  Every rank
+receives the FULL integer-coded candidate lists (global document ordinals) and
+
+  1. scores the pairs whose document it owns — the kernel skips foreign pairs, so there is no
+     host-side bucketing and positions stay positions in the full candidate block,
+  2. interpolates and takes a LOCAL top-k per query (same fused kernel),
+  3. exchanges the `[nq, k]` (score, position) lists with ONE all-gather and merges them with
+     `ffx_merge_topk`.
+
+Exact: interpolation is per pair and the top-k of a union is the top-k of the per-shard
+top-ks.  Exchange volume is `world * nq * k * 8` bytes (C5, k=1000: 6.4 GB in total against
+9.6 TB of HBM traffic), so NVLink is never the bound.  When the semantic score of every pair
+is wanted instead, each rank writes only its own pairs into a zeroed buffer and one
+all-reduce(SUM) assembles the vector (`x + 0 == x` exactly).
+
+torch is plumbing here (device buffers, the process group); all compute is libffx.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from fast_forward import _ffx
+
+
+def plan_doc_shards(rows_per_doc: np.ndarray, world: int) -> np.ndarray:
+    """Contiguous document ranges with (nearly) equal row counts.
+
+    :return: int64 `[world + 1]` document boundaries; rank r owns docs [b[r], b[r+1])."""
+    rows_per_doc = np.asarray(rows_per_doc, dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(rows_per_doc)])
+    targets = cum[-1] * np.arange(1, world) / world
+    inner = np.searchsorted(cum, targets, side="left")
+    bounds = np.concatenate([[0], inner, [len(rows_per_doc)]]).astype(np.int64)
+    return np.maximum.accumulate(bounds)
+
+
+class ShardedReranker:
+    """One rank's shard (`index`, a `_ffx.DeviceIndex` holding documents
+    [doc_base, doc_base + n_local)) plus the exchange with the other ranks of `group`."""
+
+    def __init__(self, index, doc_base: int, global_docs: int, row_base: int = 0, global_rows: int = 0,
+                 group=None) -> None:
+        import torch.distributed as dist
+
+        self.index = index
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if index is not None:
+            index.set_shard(doc_base, global_docs, row_base, global_rows or row_base + len(index))
+
+    # -- the two compute steps (libffx); tests on CPU substitute them ------------------------
+    def _local_topk(self, mode, qvecs, q_off, cand, lex, alpha, k, max_cand, stream):
+        import torch
+
+        nq = qvecs.shape[0]
+        score = torch.empty((nq, k), dtype=torch.float32, device=qvecs.device)
+        pos = torch.empty((nq, k), dtype=torch.int32, device=qvecs.device)
+        self.index.rerank_device(mode, qvecs.data_ptr(), nq, q_off.data_ptr(), cand.data_ptr(),
+                                 lex.data_ptr() if lex is not None else 0, alpha, k, max_cand,
+                                 0, 0, score.data_ptr(), pos.data_ptr(), stream)
+        return score, pos
+
+    def _merge(self, all_score, all_pos, k, stream):
+        import torch
+
+        world, nq, _ = all_score.shape
+        score = torch.empty((nq, k), dtype=torch.float32, device=all_score.device)
+        pos = torch.empty((nq, k), dtype=torch.int32, device=all_score.device)
+        _ffx.merge_topk(all_score.device.index or 0, all_score.data_ptr(), all_pos.data_ptr(), world, nq, k,
+                        score.data_ptr(), pos.data_ptr(), stream)
+        return score, pos
+
+    # -- public ---------------------------------------------------------------------------------
+    def rerank(self, mode: int, qvecs, q_off, cand, lex, alpha: float, k: int, max_cand: int):
+        """Global per-query top-k `(score [nq,k], position [nq,k])` on every rank.  All inputs
+        are identical on all ranks: qvecs f32 [nq,D], q_off i64 [nq+1], cand i32 [n] (GLOBAL
+        ordinals), lex f32 [n] or None."""
+        import torch
+        import torch.distributed as dist
+
+        stream = torch.cuda.current_stream().cuda_stream if qvecs.is_cuda else 0
+        score, pos = self._local_topk(mode, qvecs, q_off, cand, lex, alpha, k, max_cand, stream)
+        if self.world == 1:
+            return score, pos
+        all_score = torch.empty((self.world,) + tuple(score.shape), dtype=score.dtype, device=score.device)
+        all_pos = torch.empty((self.world,) + tuple(pos.shape), dtype=pos.dtype, device=pos.device)
+        # slices of one contiguous [world, nq, k] buffer: NCCL gathers in place, gloo works too
+        dist.all_gather(list(all_score.unbind(0)), score.contiguous(), group=self.group)
+        dist.all_gather(list(all_pos.unbind(0)), pos.contiguous(), group=self.group)
+        return self._merge(all_score, all_pos, k, stream)
+
+    def scores(self, mode: int, qvecs, q_off, cand, max_cand: int):
+        """Semantic score of EVERY pair on every rank (plain `Index.__call__` over a sharded
+        corpus): own pairs into a zeroed buffer, then all-reduce(SUM)."""
+        import torch
+        import torch.distributed as dist
+
+        stream = torch.cuda.current_stream().cuda_stream if qvecs.is_cuda else 0
+        ff = torch.zeros(cand.shape[0], dtype=torch.float32, device=qvecs.device)
+        self.index.rerank_device(mode, qvecs.data_ptr(), qvecs.shape[0], q_off.data_ptr(), cand.data_ptr(),
+                                 0, 0.0, 0, max_cand, ff.data_ptr(), 0, 0, 0, stream)
+        if self.world > 1:
+            dist.all_reduce(ff, op=dist.ReduceOp.SUM, group=self.group)
+        return ff

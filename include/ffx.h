@@ -93,6 +93,17 @@ int ffx_index_has_fast_path(const ffx_index *idx);
 int ffx_index_set_docs(ffx_index *idx, int64_t n_docs, const int64_t *doc_off,
                        const int64_t *doc_rows);
 
+/* Declares this index to be one doc-id-range shard of a larger corpus (the
+ * reference has no sharding — a corpus must fit one process, index/memory.py).  Candidates
+ * passed to ffx_rerank are then GLOBAL ordinals: documents [doc_base, doc_base + #docs here) of
+ * `global_docs`, rows [row_base, row_base + #rows here) of `global_rows` in PASSAGE mode.  Pairs
+ * owned by another shard are skipped: their out_ff/out_int entries are left untouched (zero
+ * them and sum across shards) and they take no top-k slot; positions stay positions in the
+ * full candidate block, so per-shard lists merge with ffx_merge_topk.  global_docs ==
+ * global_rows == 0 switches sharding off.  Call after ffx_index_set_docs / staging. */
+int ffx_index_set_shard(ffx_index *idx, int64_t doc_base, int64_t global_docs, int64_t row_base,
+                        int64_t global_rows);
+
 /* Replaces `Quantizer.decode` on the scoring path (quantizer/base.py:123-132 ->
  * quantizer/nanopq.py:43-44,111-112): attaches nanopq-compatible codebooks
  * `codewords[M][Ks][Ds]` and, for OPQ, the rotation `R[D][D]` (NULL for plain PQ) to an
