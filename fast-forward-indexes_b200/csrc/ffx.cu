@@ -17,6 +17,7 @@
 #include "../../include/ffx.h"
 #include "ffx_adc.cuh"
 #include "ffx_kernels.cuh"
+#include "ffx_score_tma.cuh"
 #include "ffx_layout.h"
 
 namespace {
@@ -51,6 +52,16 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 constexpr int64_t kStageBytes = 32ll << 20;  // per pinned / device staging buffer
+constexpr size_t kSmemBudget = 227 * 1024 - 1024;  // opt-in shared memory per CTA on sm_100, minus static
+
+// Tuning / diagnostic knobs (ffx_set_option).  0 = automatic.
+struct Tuning {
+    int kernel = 0;      // 1: register-staged ffx_score_kernel, 2: TMA-staged ffx_score_tma_kernel
+    int tma_stages = 0;  // ring slots per warp
+    int tma_warps = 0;   // warps per CTA of the TMA-staged kernel (8..16)
+    int batch = 0;       // candidates a warp takes per grab
+};
+Tuning g_tune;
 
 struct Scratch {
     void *p = nullptr;
@@ -189,8 +200,92 @@ int launch_score(const ffx::ScoreArgs &a, bool fuse, int grid, size_t smem, cuda
     return FFX_OK;
 }
 
-int dispatch_score(const ffx_plan &p, const ffx::ScoreArgs &a, bool fuse, int grid, size_t smem,
+template <int CPL, int S>
+int launch_score_tma(const ffx::ScoreArgs &a, bool fuse, int grid, int warps, int ns, int batch,
+                     cudaStream_t st) {
+    const size_t smem = ffx::tma_smem_bytes(fuse ? a.cpad : 0, warps, ns, 32 * CPL * S * 4);
+    if (fuse) {
+        auto kern = ffx::ffx_score_tma_kernel<CPL, S, true>;
+        FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kern<<<grid, warps * 32, smem, st>>>(a, ns, batch);
+    } else {
+        auto kern = ffx::ffx_score_tma_kernel<CPL, S, false>;
+        FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kern<<<grid, warps * 32, smem, st>>>(a, ns, batch);
+    }
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
+// ---- launch planning for the fp32 lane-major path ------------------------------------------
+// TMA-staged kernel shapes (tools/sweep.py on B200): the register file
+// allows 16 warps per SM at ~122 registers, shared memory (227 KB) holds the row rings.
+//   fused, small key arrays : 2 CTAs/SM x 8 warps x >=3 ring slots (tails of one query overlap
+//                             the other CTA's stream)
+//   fused, 5000 candidates  : 1 CTA/SM x 14 warps x 4 slots (32 KB of scores leave 172 KB of ring)
+//   tiled (few queries)     : 4 warps per CTA, 4 CTAs/SM
+struct ScorePlan {
+    bool tma = false;
+    int warps = 8, ns = 0, batch = 16;
+};
+
+int ring_slots(int cpad_scores, int warps, int row_bytes, int ctas_per_sm) {
+    const size_t budget = kSmemBudget / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
+    const size_t fixed = ffx::tma_smem_bytes(cpad_scores, warps, 0, row_bytes);
+    if (fixed >= budget) return 0;
+    int ns = static_cast<int>((budget - fixed) / (static_cast<size_t>(warps) * (row_bytes + 8)));
+    ns = std::min(ns, 16);
+    // the fused top-k sorts cpad 64-bit keys inside the drained ring
+    if (static_cast<size_t>(ns) * warps * row_bytes < static_cast<size_t>(cpad_scores) * 8) return 0;
+    return ns;
+}
+
+ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes) {
+    ScorePlan p;
+    const bool one_row = mode == FFX_MODE_PASSAGE || mode == FFX_MODE_FIRSTP;
+    p.batch = g_tune.batch > 0 ? std::min(32, g_tune.batch) : (one_row ? 32 : 16);
+    if (g_tune.kernel == 1) return p;
+    const int keys = fuse ? cpad : 0;
+    if (g_tune.tma_warps > 0) {  // explicit shape (sweeps)
+        p.warps = g_tune.tma_warps;
+        p.ns = ring_slots(keys, p.warps, row_bytes, 1);
+    } else if (!fuse) {
+        p.warps = 4;
+        p.ns = std::min(4, ring_slots(0, 4, row_bytes, 4));
+    } else {
+        p.warps = 8;
+        p.ns = std::min(6, ring_slots(keys, 8, row_bytes, 2));
+        if (p.ns < 3) {
+            p.warps = 14;
+            p.ns = std::min(6, ring_slots(keys, 14, row_bytes, 1));
+        }
+        if (p.ns < 2) {
+            p.warps = 8;
+            p.ns = ring_slots(keys, 8, row_bytes, 1);
+        }
+    }
+    if (g_tune.tma_stages > 0) p.ns = std::min(p.ns, g_tune.tma_stages);
+    p.tma = p.ns >= 2;
+    return p;
+}
+
+int dispatch_score(const ffx_plan &p, const ScorePlan &sp, const ffx::ScoreArgs &a, bool fuse, int grid,
                    cudaStream_t st) {
+    if (sp.tma) {
+#define FFX_CASE(C, S_) \
+    if (p.cpl == C && p.steps == S_) return launch_score_tma<C, S_>(a, fuse, grid, sp.warps, sp.ns, sp.batch, st)
+        FFX_CASE(1, 12);
+        FFX_CASE(1, 16);
+        FFX_CASE(2, 10);
+        FFX_CASE(2, 12);
+        FFX_CASE(2, 14);
+        FFX_CASE(2, 16);
+        FFX_CASE(4, 12);
+        FFX_CASE(4, 16);
+#undef FFX_CASE
+    }
+    const size_t smem = fuse ? static_cast<size_t>(a.cpad) * 8 : 0;
 #define FFX_CASE(C, S_) \
     if (p.cpl == C && p.steps == S_) return launch_score<C, S_>(a, fuse, grid, smem, st)
     FFX_CASE(1, 12);
@@ -260,6 +355,17 @@ extern "C" {
 int ffx_abi_version(void) { return FFX_ABI_VERSION; }
 
 const char *ffx_last_error(void) { return g_err.c_str(); }
+
+int ffx_set_option(const char *name, int value) {
+    if (!name) return fail(FFX_ERR_INVALID, "ffx_set_option: NULL name");
+    const std::string key(name);
+    if (key == "kernel" && value >= 0 && value <= 2) g_tune.kernel = value;
+    else if (key == "tma_stages" && value >= 0 && value <= 16) g_tune.tma_stages = value;
+    else if (key == "batch" && value >= 0 && value <= 32) g_tune.batch = value;
+    else if (key == "tma_warps" && (value == 0 || (value >= 1 && value <= 16))) g_tune.tma_warps = value;
+    else return fail(FFX_ERR_INVALID, "ffx_set_option: unknown option or bad value (%s=%d)", name, value);
+    return FFX_OK;
+}
 
 int ffx_device_count(void) {
     int n = 0;
@@ -648,11 +754,15 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
     const float *topk_src = rank_scores ? rank_scores : out_int;
 
     // tiles: split a query over several CTAs when there are few queries
+    const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4) : ScorePlan{};
     int tiles = 1, tile = static_cast<int>(std::max<int64_t>(max_cand, 1));
     if (!fuse) {
+        // enough CTAs for ~2 waves at the plan's occupancy, but a tile keeps every warp of its
+        // CTA busy with at least one candidate batch
         const int64_t want = slots * 4;
+        const int64_t grain = (fast && sp.tma) ? static_cast<int64_t>(sp.warps) * sp.batch : 32;
         tiles = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((want + nq - 1) / nq,
-                                                                        (max_cand + 31) / 32)));
+                                                                        (max_cand + grain - 1) / grain)));
         tile = static_cast<int>((std::max<int64_t>(max_cand, 1) + tiles - 1) / tiles);
         tile = (tile + 31) & ~31;
         tiles = static_cast<int>((std::max<int64_t>(max_cand, 1) + tile - 1) / tile);
@@ -731,8 +841,7 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
             a.count = count;
             a.err = idx->err_flag;
             if (fast) {
-                FFX_TRY(dispatch_score(idx->plan, a, fuse, static_cast<int>(nq * tiles),
-                                       fuse ? static_cast<size_t>(cpad) * 8 : 0, st));
+                FFX_TRY(dispatch_score(idx->plan, sp, a, fuse, static_cast<int>(nq * tiles), st));
             } else {
                 // generic exact kernel: one thread per pair over the [0, nq*max_cand) bound;
                 // the kernel reads the true pair count from q_off[nq]

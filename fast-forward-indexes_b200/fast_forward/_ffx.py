@@ -24,6 +24,7 @@ SYMBOLS = {
     "ffx_abi_version": (_I, []),
     "ffx_last_error": (C.c_char_p, []),
     "ffx_device_count": (_I, []),
+    "ffx_set_option": (_I, [C.c_char_p, _I]),
     "ffx_host_alloc": (_I, [C.POINTER(_P), _L]),
     "ffx_host_free": (_I, [_P]),
     "ffx_index_create": (_I, [_I, _I, _L, _L, C.POINTER(_P)]),
@@ -85,6 +86,11 @@ def check(code: int) -> None:
 
 def device_count() -> int:
     return lib().ffx_device_count()
+
+
+def set_option(name: str, value: int) -> None:
+    """ffx_set_option: kernel / tma_stages / batch tuning knobs (0 = automatic)."""
+    check(lib().ffx_set_option(name.encode(), int(value)))
 
 
 def launch_count() -> int:

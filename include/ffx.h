@@ -58,6 +58,13 @@ const char *ffx_last_error(void);
 /* number of CUDA devices visible; 0 when there is none (then nothing else will work) */
 int ffx_device_count(void);
 
+/* Tuning / diagnostics (process-wide; 0 restores the automatic choice).  Not part of the
+ * reference contract — it has no kernels to tune.
+ *   "kernel"      1 = register-staged scoring kernel, 2 = TMA-staged (default when it fits)
+ *   "tma_stages"  ring slots per warp of the TMA-staged kernel (capped by shared memory)
+ *   "batch"       candidates a warp takes per grab (1..32) */
+int ffx_set_option(const char *name, int value);
+
 /* Pinned host memory for buffers that cross PCIe every call (candidate lists, query
  * vectors, outputs).  Plain malloc'ed buffers work too, just slower. */
 int ffx_host_alloc(void **out, int64_t bytes);

@@ -33,6 +33,15 @@ def ffx():
     return _ffx
 
 
+@pytest.fixture(params=["ldg", "tma"], autouse=True)
+def kernel_variant(request, ffx):
+    """Every test of this file runs against both scoring kernels: the register-staged
+    ffx_score_kernel and the TMA-staged ffx_score_tma_kernel (the default)."""
+    ffx.set_option("kernel", 1 if request.param == "ldg" else 2)
+    yield request.param
+    ffx.set_option("kernel", 0)
+
+
 def c_scores(oracle_c, vec, u_off, u_rows, pair_q, pair_u, qv, mode):
     vec = np.ascontiguousarray(vec, np.float32)
     qv = np.ascontiguousarray(qv, np.float32)
@@ -236,6 +245,38 @@ def test_fused_topk_path_many_queries(ffx, oracle_c, mode):
         # top-k only (no per-pair outputs) must give the same lists
         out2 = idx.rerank_host(m, qv, q_off, cand, lex, alpha, k, want_ff=False, want_int=False)
         assert (out2["topk_pos"] == tp).all() and (bits(out2["topk_score"]) == bits(ts)).all()
+    idx.close()
+
+
+@pytest.mark.parametrize("stages,batch", [(2, 5), (3, 32), (16, 1)])
+def test_tma_ring_and_batch_shapes(ffx, oracle_c, stages, batch):
+    """The ring depth and the candidate batch are tuning knobs: results must not depend on them."""
+    rng = np.random.default_rng(stages * 100 + batch)
+    off, rows, vec = make_corpus(rng, 1500, 40, 768, True)
+    idx = ffx.DeviceIndex(768, capacity=len(vec))
+    idx.stage(0, vec)
+    idx.set_docs(off)
+    nq = 300
+    qv = rng.standard_normal((nq, 768)).astype(np.float32)
+    ffx.set_option("kernel", 2)
+    ffx.set_option("tma_stages", stages)
+    ffx.set_option("batch", batch)
+    try:
+        for mode in (fo.MODE_MAXP, fo.MODE_AVEP, fo.MODE_FIRSTP, fo.MODE_PASSAGE):
+            pool = len(vec) if mode == fo.MODE_PASSAGE else 1500
+            q_off, cand, pair_q = make_pairs(rng, nq, pool, 0, 90)
+            lex = rng.uniform(0, 20, len(cand)).astype(np.float32)
+            u_off, u_rows = units_for_mode(off, rows, len(vec), mode)
+            ff = c_scores(oracle_c, vec, u_off, u_rows, pair_q, cand, qv, mode)
+            ts, tp = fo.topk_per_query(q_off, fo.interpolate_f32(lex, ff, 0.3), 20)
+            for sub in (nq, 7):  # fused and tiled launches
+                o = q_off[:sub + 1]
+                out = idx.rerank_host(mode, qv[:sub], o, cand[:o[-1]], lex[:o[-1]], 0.3, 20, want_ff=True)
+                assert (bits(out["ff"]) == bits(ff[:o[-1]])).all()
+                assert (out["topk_pos"] == tp[:sub]).all() and (bits(out["topk_score"]) == bits(ts[:sub])).all()
+    finally:
+        ffx.set_option("tma_stages", 0)
+        ffx.set_option("batch", 0)
     idx.close()
 
 
