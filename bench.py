@@ -424,7 +424,7 @@ def run_ffx(args, wl):
         peak, peak_src = measured_peak()
         traffic = ncu_traffic()
         kernel = ("ffx_adc_kernel (LUT in smem over uint8 codes) + ffx_topk_kernel" if pq else
-                  "ffx_score_kernel<2,12,%s> (gather-dot-%s-interpolate%s)" % (
+                  "ffx_score_tma_kernel<2,12,%s> (TMA-staged gather-dot-%s-interpolate%s)" % (
                       "true" if nq >= 296 else "false", wl["mode"], "-topk fused" if nq >= 296 else " ; ffx_topk_kernel"))
         line = {
             "metric": METRIC if args.workload == "c3_msmarco_doc_maxp" else

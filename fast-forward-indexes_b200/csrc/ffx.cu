@@ -218,6 +218,31 @@ int launch_score_tma(const ffx::ScoreArgs &a, bool fuse, int grid, int warps, in
     return FFX_OK;
 }
 
+template <int V16>
+int launch_adc_v(const ffx::AdcArgs &a, unsigned grid, size_t smem, cudaStream_t st) {
+    auto kern = ffx::ffx_adc_kernel<V16>;
+    FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, ffx::kThreads, smem, st>>>(a);
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
+int launch_adc(const ffx::AdcArgs &a, unsigned grid, size_t smem, cudaStream_t st) {
+    if (a.M % 16 == 0) {
+        switch (a.M / 16) {
+            case 1: return launch_adc_v<1>(a, grid, smem, st);
+            case 2: return launch_adc_v<2>(a, grid, smem, st);
+            case 3: return launch_adc_v<3>(a, grid, smem, st);
+            case 4: return launch_adc_v<4>(a, grid, smem, st);
+            case 6: return launch_adc_v<6>(a, grid, smem, st);
+            case 8: return launch_adc_v<8>(a, grid, smem, st);
+            default: break;
+        }
+    }
+    return launch_adc_v<0>(a, grid, smem, st);
+}
+
 // ---- launch planning for the fp32 lane-major path ------------------------------------------
 // TMA-staged kernel shapes (tools/sweep.py on B200): the register file
 // allows 16 warps per SM at ~122 registers, shared memory (227 KB) holds the row rings.
@@ -807,12 +832,7 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
             a.count = count;
             a.err = idx->err_flag;
             const size_t smem = static_cast<size_t>(idx->M) * idx->Ks * 4;
-            FFX_CUDA(cudaFuncSetAttribute(ffx::ffx_adc_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(smem)));
-            ffx::ffx_adc_kernel<<<static_cast<unsigned>(nq * tiles), ffx::kThreads, smem, st>>>(a);
-            g_launches++;
-            FFX_CUDA(cudaGetLastError());
+            FFX_TRY(launch_adc(a, static_cast<unsigned>(nq * tiles), smem, st));
         } else {
             ffx::ScoreArgs a{};
             a.vectors = static_cast<const float *>(idx->store);
