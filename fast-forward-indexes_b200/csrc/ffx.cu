@@ -16,6 +16,7 @@
 
 #include "../../include/ffx.h"
 #include "ffx_adc.cuh"
+#include "ffx_early_stop.cuh"
 #include "ffx_kernels.cuh"
 #include "ffx_score_tma.cuh"
 #include "ffx_layout.h"
@@ -369,6 +370,35 @@ int launch_topk(const float *scores, const float *lex, float alpha, float beta, 
         scores, lex, alpha, beta, q_off, k, cpad, gkeys, out_int, out_s, out_p);
     g_launches++;
     FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
+template <int CPL, int S>
+int launch_es(const ffx::ScoreArgs &a, const ffx::EsPlan &es, unsigned grid, size_t smem, cudaStream_t st) {
+    auto kern = ffx::ffx_score_es_kernel<CPL, S>;
+    FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, ffx::kThreads, smem, st>>>(a, es);
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
+// base.py:339-343,365-366: ascending, depths below the cutoff skipped, the walk ends at the first
+// depth that cannot add rows (a repeat)
+int plan_depths(const int32_t *depths, int n_depths, int cutoff, ffx::EsPlan *es) {
+    std::vector<int32_t> d(depths, depths + n_depths);
+    std::sort(d.begin(), d.end());
+    es->n_depths = 0;
+    es->cutoff = cutoff;
+    int prev = 0;
+    for (int32_t b : d) {
+        if (b < cutoff) continue;
+        if (b <= prev) break;
+        if (es->n_depths == ffx::kMaxEsDepths)
+            return fail(FFX_ERR_UNSUPPORTED, "ffx_rerank_early_stop: more than %d depths", ffx::kMaxEsDepths);
+        es->depths[es->n_depths++] = b;
+        prev = b;
+    }
     return FFX_OK;
 }
 
@@ -972,6 +1002,120 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
         }
     }
     return take_error(idx, idx->s_d2h);
+}
+
+int ffx_rerank_early_stop(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const int64_t *q_off,
+                          const int32_t *cand, const float *lex, double alpha, int cutoff,
+                          const int32_t *depths, int n_depths, int64_t max_cand, float *out_ff,
+                          float *out_int, int32_t *out_scored, void *stream) {
+    if (!idx) return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop: NULL index");
+    if (mode < FFX_MODE_PASSAGE || mode > FFX_MODE_AVEP)
+        return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop: unknown mode %d", mode);
+    if (nq < 0 || nq > 0x7fffffffll || max_cand < 0 || cutoff < 1 || n_depths < 0 || (n_depths > 0 && !depths))
+        return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop: bad sizes");
+    if (nq == 0) return FFX_OK;
+    if (!qvecs || !q_off || !out_scored || (max_cand > 0 && (!cand || !lex)))
+        return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop: NULL input");
+    if (idx->row_kind != FFX_ROWS_F32 || idx->plan.cpl == 0)
+        return fail(FFX_ERR_UNSUPPORTED, "ffx_rerank_early_stop: needs an fp32 index with a lane-major plan");
+    if (idx->sharded)
+        return fail(FFX_ERR_UNSUPPORTED, "ffx_rerank_early_stop: not defined on a doc-id-range shard");
+    if (mode != FFX_MODE_PASSAGE && idx->n_docs == 0 && max_cand > 0)
+        return fail(FFX_ERR_STATE, "ffx_rerank_early_stop: document modes need ffx_index_set_docs first");
+    const int cpad = next_pow2(std::max<int64_t>(max_cand, 1));
+    if (cpad > ffx::kMaxFusedCand)
+        return fail(FFX_ERR_UNSUPPORTED, "ffx_rerank_early_stop: more than %d candidates per query",
+                    ffx::kMaxFusedCand);
+    ffx::EsPlan es{};
+    FFX_TRY(plan_depths(depths, n_depths, cutoff, &es));
+    es.out_scored = out_scored;
+    FFX_TRY(bind(idx));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    ffx::ScoreArgs a{};
+    a.vectors = static_cast<const float *>(idx->store);
+    a.doc_span = idx->doc_span;
+    a.doc_rows = idx->doc_rows;
+    a.indirect = idx->indirect;
+    a.mode = mode;
+    a.dim = idx->dim;
+    a.qvecs = qvecs;
+    a.q_off = q_off;
+    a.cand = cand;
+    a.lex = lex;
+    a.alpha = static_cast<float>(alpha);
+    a.beta = static_cast<float>(1.0 - alpha);
+    a.out_ff = out_ff;
+    a.out_int = out_int;
+    a.tiles_per_query = 1;
+    a.cpad = cpad;
+    a.limit = a.count = static_cast<uint32_t>(mode == FFX_MODE_PASSAGE ? idx->num_rows : idx->n_docs);
+    a.err = idx->err_flag;
+    const size_t smem = static_cast<size_t>(cpad) * 8;
+    const ffx_plan &p = idx->plan;
+#define FFX_CASE(C, S_) \
+    if (p.cpl == C && p.steps == S_) return launch_es<C, S_>(a, es, static_cast<unsigned>(nq), smem, st)
+    FFX_CASE(1, 12);
+    FFX_CASE(1, 16);
+    FFX_CASE(2, 10);
+    FFX_CASE(2, 12);
+    FFX_CASE(2, 14);
+    FFX_CASE(2, 16);
+    FFX_CASE(4, 12);
+    FFX_CASE(4, 16);
+#undef FFX_CASE
+    return fail(FFX_ERR_UNSUPPORTED, "no lane-major kernel for plan (%d,%d)", p.cpl, p.steps);
+}
+
+int ffx_rerank_early_stop_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
+                               const int64_t *q_off, const int32_t *cand, const float *lex,
+                               double alpha, int cutoff, const int32_t *depths, int n_depths,
+                               float *out_ff, float *out_int, int32_t *out_scored) {
+    if (!idx) return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop_host: NULL index");
+    if (nq < 0) return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop_host: nq < 0");
+    if (nq == 0) return FFX_OK;
+    if (!qvecs || !q_off || q_off[0] != 0 || !out_scored)
+        return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop_host: bad input");
+    int64_t max_cand = 0;
+    for (int64_t q = 0; q < nq; q++) {
+        const int64_t c = q_off[q + 1] - q_off[q];
+        if (c < 0) return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop_host: q_off not monotone");
+        max_cand = std::max(max_cand, c);
+    }
+    const int64_t n = q_off[nq];
+    if (n > 0 && (!cand || !lex)) return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop_host: NULL candidates / scores");
+    FFX_TRY(bind(idx));
+    auto pad = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+    const size_t b_q = pad(static_cast<size_t>(nq) * idx->dim * 4), b_off = pad(static_cast<size_t>(nq + 1) * 8);
+    const size_t b_n = pad(static_cast<size_t>(n) * 4), b_s = pad(static_cast<size_t>(nq) * 4);
+    FFX_TRY(scratch_reserve(idx->hostio, b_q + b_off + 4 * b_n + b_s));
+    char *p = static_cast<char *>(idx->hostio.p);
+    auto take = [&](size_t b) { char *r = p; p += b; return r; };
+    float *d_q = reinterpret_cast<float *>(take(b_q));
+    int64_t *d_off = reinterpret_cast<int64_t *>(take(b_off));
+    int32_t *d_cand = reinterpret_cast<int32_t *>(take(b_n));
+    float *d_lex = reinterpret_cast<float *>(take(b_n));
+    float *d_ff = out_ff ? reinterpret_cast<float *>(take(b_n)) : nullptr;
+    float *d_int = out_int ? reinterpret_cast<float *>(take(b_n)) : nullptr;
+    int32_t *d_scored = reinterpret_cast<int32_t *>(take(b_s));
+    cudaStream_t st = idx->stream;
+    FFX_CUDA(cudaMemcpyAsync(d_q, qvecs, static_cast<size_t>(nq) * idx->dim * 4, cudaMemcpyHostToDevice, st));
+    FFX_CUDA(cudaMemcpyAsync(d_off, q_off, static_cast<size_t>(nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n > 0) {
+        FFX_CUDA(cudaMemcpyAsync(d_cand, cand, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));
+        FFX_CUDA(cudaMemcpyAsync(d_lex, lex, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));
+        // rows that are never scored read back as 0
+        if (d_ff) FFX_CUDA(cudaMemsetAsync(d_ff, 0, static_cast<size_t>(n) * 4, st));
+        if (d_int) FFX_CUDA(cudaMemsetAsync(d_int, 0, static_cast<size_t>(n) * 4, st));
+    }
+    FFX_TRY(ffx_rerank_early_stop(idx, mode, d_q, nq, d_off, d_cand, d_lex, alpha, cutoff, depths, n_depths,
+                                  max_cand, d_ff, d_int, d_scored, st));
+    if (n > 0) {
+        if (out_ff) FFX_CUDA(cudaMemcpyAsync(out_ff, d_ff, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, st));
+        if (out_int) FFX_CUDA(cudaMemcpyAsync(out_int, d_int, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, st));
+    }
+    FFX_CUDA(cudaMemcpyAsync(out_scored, d_scored, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, st));
+    return take_error(idx, st);
 }
 
 int ffx_index_sync(ffx_index *idx, void *stream) {

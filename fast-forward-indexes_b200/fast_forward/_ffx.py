@@ -41,6 +41,8 @@ SYMBOLS = {
     "ffx_index_set_pq": (_I, [_P, _I, _I, _I, _P, _P]),
     "ffx_rerank": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _L, _P, _P, _P, _P, _P]),
     "ffx_rerank_host": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _P, _P, _P, _P]),
+    "ffx_rerank_early_stop": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _P, _I, _L, _P, _P, _P, _P]),
+    "ffx_rerank_early_stop_host": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _P, _I, _P, _P, _P]),
     "ffx_index_sync": (_I, [_P, _P]),
     "ffx_interpolate_topk": (_I, [_P, _P, _P, _L, _P, _D, _I, _L, _P, _P, _P, _P]),
     "ffx_interpolate_topk_host": (_I, [_P, _P, _P, _L, _P, _D, _I, _P, _P, _P]),
@@ -238,6 +240,24 @@ class DeviceIndex:
         check(lib().ffx_rerank_host(self.handle, int(mode), _ptr(qvecs), nq, _ptr(q_off), _ptr(cand),
                                     _ptr(lex), float(alpha), int(k), _ptr(ff), _ptr(it), _ptr(ts),
                                     _ptr(tp)))
+        return out
+
+    def rerank_early_stop_host(self, mode, qvecs, q_off, cand, lex, alpha, cutoff, depths, want_int=False):
+        """ffx_rerank_early_stop_host: depth-interval scoring with the early-stopping criterion
+        evaluated on the device.  Returns ff [n] (0 where not scored), scored [nq] (rows scored
+        per query, a prefix of each block) and optionally int [n]."""
+        qvecs = _arr(qvecs, np.float32)
+        q_off = _arr(q_off, np.int64)
+        cand = _arr(cand, np.int32)
+        lex = _arr(lex, np.float32)
+        depths = _arr(list(depths), np.int32)
+        nq, n = len(q_off) - 1, len(cand)
+        out = {"ff": np.zeros(n, np.float32), "scored": np.zeros(nq, np.int32)}
+        if want_int:
+            out["int"] = np.zeros(n, np.float32)
+        check(lib().ffx_rerank_early_stop_host(self.handle, int(mode), _ptr(qvecs), nq, _ptr(q_off), _ptr(cand),
+                                               _ptr(lex), float(alpha), int(cutoff), _ptr(depths), len(depths),
+                                               _ptr(out["ff"]), _ptr(out.get("int")), _ptr(out["scored"])))
         return out
 
     def sync(self, stream=0):

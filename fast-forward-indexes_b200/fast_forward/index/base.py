@@ -281,22 +281,52 @@ class Index(abc.ABC):
         """Score in depth intervals and stop a query once its `cutoff`-th best interpolated
         score can no longer be beaten (index/base.py:316-387).  Only scored rows are returned.
 
-        `df` must be grouped by query with rows in rank order (what `__call__` passes)."""
+        `df` must hold each query's rows in rank order (what `__call__` passes).  On fp32
+        indexes with a lane-major plan the whole walk — every interval's scoring and the
+        stopping criterion between intervals — is ONE kernel launch with one CTA per query
+        (ffx_rerank_early_stop); other indexes (PQ codes, odd dimensions) walk the depths here
+        and score every interval with ffx_rerank."""
         n = len(df)
         q_no = df["q_no"].to_numpy(dtype=np.int64)
         if n and (np.diff(q_no) < 0).any():
             df = df.iloc[np.argsort(q_no, kind="stable")]
             q_no = df["q_no"].to_numpy(dtype=np.int64)
+        depths = [int(d) for d in depths]
+        if n == 0:
+            return df.assign(ff_score=np.zeros(0, np.float32))
         lex = df["score"].to_numpy(dtype=np.float32)
         present, start, count = np.unique(q_no, return_index=True, return_counts=True)
         depth_of_row = np.arange(n) - np.repeat(start, count)
         slot_of_row = np.repeat(np.arange(len(present)), count)
+
+        dev = self._device()
+        on_device = (dev.row_kind == _ffx.ROWS_F32 and dev.has_fast_path and int(count.max()) <= 16384
+                     and len({d for d in depths if d >= cutoff}) <= 32)
+        if on_device:
+            qv = np.ascontiguousarray(query_vectors, dtype=np.float32)[present]
+            codes, uniq = pd.factorize(df["id"].to_numpy())
+            cand = self._resolve(np.asarray(uniq, dtype=object), self.mode)[codes]
+            q_off = np.concatenate([[0], np.cumsum(count)]).astype(np.int64)
+            out = dev.rerank_early_stop_host(self.mode.value, qv, q_off, cand, lex, alpha, cutoff, depths)
+            ff, done_depth = out["ff"], out["scored"].astype(np.int64)
+            LOGGER.info("early stopping: %s of %s rows scored", int(done_depth.sum()), n)
+        else:
+            ff, done_depth = self._early_stopping_walk(df, query_vectors, cutoff, alpha, depths, lex, start,
+                                                       count, depth_of_row, slot_of_row)
+        scored = depth_of_row < done_depth[slot_of_row]
+        result = df.loc[scored].copy()
+        result["ff_score"] = ff[scored]
+        return result
+
+    def _early_stopping_walk(self, df, query_vectors, cutoff, alpha, depths, lex, start, count,
+                             depth_of_row, slot_of_row):
+        """Host-walked depths (index/base.py:339-385), one ffx_rerank launch per interval."""
+        n = len(df)
         ff = np.zeros(n, np.float32)
         inter = np.zeros(n, np.float32)
-        done_depth = np.zeros(len(present), np.int64)  # rows scored so far per query
-        active = np.ones(len(present), bool)
+        done_depth = np.zeros(len(start), np.int64)  # rows scored so far per query
+        active = np.ones(len(start), bool)
         a32, b32 = np.float32(alpha), np.float32(1 - alpha)
-
         lo = 0
         for hi in sorted(depths):
             if hi < cutoff:
@@ -304,9 +334,6 @@ class Index(abc.ABC):
             if lo > 0:
                 for s in np.flatnonzero(active):
                     b, e = start[s], start[s] + done_depth[s]
-                    if e == b:
-                        active[s] = False
-                        continue
                     kth = np.sort(inter[b:e])[::-1][:cutoff][-1]
                     bound = a32 * lex[e - 1] + b32 * ff[b:e].max()
                     active[s] = kth < bound
@@ -319,10 +346,7 @@ class Index(abc.ABC):
             inter[take] = a32 * lex[take] + b32 * ff[take]
             done_depth[active] = np.minimum(count[active], hi)
             lo = hi
-        scored = depth_of_row < done_depth[slot_of_row]
-        result = df.loc[scored].copy()
-        result["ff_score"] = ff[scored]
-        return result
+        return ff, done_depth
 
     def _query_vectors_for(self, src: pd.DataFrame):
         """Number the queries in order of appearance and encode each once (base.py:418-429)."""

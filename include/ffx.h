@@ -153,6 +153,32 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
                     int k, float *out_ff, float *out_int, float *out_topk_score,
                     int32_t *out_topk_pos);
 
+/* Replaces `Index._early_stopping` (index/base.py:316-387): scores every query's candidates in
+ * the depth intervals [0,d0), [d0,d1), ... and, before each interval after the first, stops a
+ * query once its `cutoff`-th best interpolated score so far is not below
+ * fl32(fl32(alpha)*lex[last scored row]) + fl32(fl32(1-alpha)*max ff so far)  (base.py:351-356).
+ * One launch, one CTA per query; a stopped query issues no further loads.
+ *
+ *   cand / lex   as ffx_rerank, each query's block in rank order (depth = position); lex required
+ *   depths       HOST array of n_depths depths in any order.  As in the reference they are taken
+ *                ascending, depths < cutoff are skipped (base.py:341-343) and the walk ends at the
+ *                first depth that adds no rows (a repeated depth; base.py:365-366)
+ *   out_ff / out_int [n]   written for the scored rows only (others untouched); may be NULL
+ *   out_scored [nq]        rows scored per query: always a prefix of the query's block
+ *
+ * fp32 lane-major indexes only, at most 16384 candidates per query and 32 distinct depths;
+ * anything else returns FFX_ERR_UNSUPPORTED (the host shell then walks the depths itself with
+ * ffx_rerank).  ffx_rerank_early_stop takes DEVICE pointers (except `depths`) and is
+ * asynchronous on `stream`; the _host variant takes host pointers and synchronises. */
+int ffx_rerank_early_stop(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const int64_t *q_off,
+                          const int32_t *cand, const float *lex, double alpha, int cutoff,
+                          const int32_t *depths, int n_depths, int64_t max_cand, float *out_ff,
+                          float *out_int, int32_t *out_scored, void *stream);
+int ffx_rerank_early_stop_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
+                               const int64_t *q_off, const int32_t *cand, const float *lex,
+                               double alpha, int cutoff, const int32_t *depths, int n_depths,
+                               float *out_ff, float *out_int, int32_t *out_scored);
+
 /* Synchronises `stream` and reports what the asynchronous launches on this index saw: the
  * kernels never dereference a candidate outside [0, #documents) (or [0, #rows) in PASSAGE
  * mode) — such a pair scores as an empty document and this call (like ffx_rerank_host)

@@ -206,6 +206,46 @@ def interpolate_f32(score_self: np.ndarray, score_other: np.ndarray, alpha: floa
         (b * score_other.astype(np.float32)).astype(np.float32)
 
 
+def early_stopping_depth(q_off: np.ndarray, lex: np.ndarray, ff: np.ndarray, alpha: float, cutoff: int,
+                         depths) -> np.ndarray:
+    """`Index._early_stopping` (index/base.py:316-387) on integer-coded pairs: how many rows of
+    every query's block (rows in rank order) the reference scores.
+
+    A row's `ff_score` does not depend on early stopping, so the walk is restated over the
+    full score vector `ff`: depths ascending, those below `cutoff` skipped (:341-343); from
+    the second interval on a query goes on only while the `cutoff`-th best interpolated score
+    so far (`nlargest(cutoff).iat[-1]`, the worst one when fewer rows were scored) is below
+    `alpha * score(last scored row) + (1 - alpha) * max(ff_score)` (:351-356; fp32 with N3
+    arithmetic under numpy 2 scalar promotion); the loop ends at the first interval that adds
+    no row for any query still going (:365-366).
+    """
+    q_off = np.asarray(q_off, dtype=np.int64)
+    lex = np.asarray(lex, dtype=np.float32)
+    ff = np.asarray(ff, dtype=np.float32)
+    a32, b32 = np.float32(alpha), np.float32(1 - alpha)
+    nq = len(q_off) - 1
+    size = np.diff(q_off)
+    done = np.zeros(nq, np.int64)
+    going = np.ones(nq, bool)
+    a = 0
+    for b in sorted(depths):
+        if b < cutoff:
+            continue
+        if a > 0:
+            for q in range(nq):
+                lo, e = q_off[q], q_off[q] + done[q]
+                inter = a32 * lex[lo:e] + b32 * ff[lo:e]
+                kth = np.sort(inter)[::-1][:cutoff][-1]
+                bound = a32 * lex[e - 1] + b32 * ff[lo:e].max()
+                going[q] = kth < bound
+        new_done = np.where(going, np.maximum(done, np.minimum(size, b)), done)
+        if a >= b or not (new_done > done).any():
+            break
+        done = new_done
+        a = b
+    return done
+
+
 def topk_per_query(q_off: np.ndarray, scores: np.ndarray, k: int):
     """ranking.py:115-117 + :285-291 on one query's block of pairs: stable sort by score
     DESC (ties keep position order), keep the first k.  Returns per query (scores, pos)

@@ -11,6 +11,8 @@ Outputs (committed):
                                   reference, every resulting frame recorded row by row
   tests/golden/ref_random.npz     seeded random fp32 cases: inputs + the reference's
   tests/golden/ref_random.json    Index.__call__ / interpolate / cut outputs per Mode
+  tests/golden/ref_es.npz/.json   seeded early-stopping cases (index/base.py:316-387): the
+                                  reference's `Index.__call__(early_stopping=...)` frames
 
 Scores are recorded as raw float32 bit patterns (uint32) so the comparison is bit-exact.
 """
@@ -182,6 +184,48 @@ def random_case(seed, dim, n_docs, max_psg, n_q, n_cand, alpha, cutoff, arrays, 
     meta[key] = case
 
 
+# ------------------------------------------------------------------ seeded early-stopping cases
+def es_case(seed, dim, n_docs, max_psg, n_q, n_cand, arrays, meta):
+    """`Index.__call__(early_stopping=...)` (index/base.py:316-387) on seeded random data:
+    first-stage scores fall off steeply with depth, so some queries stop at the first depth,
+    some later, some never.  Recorded: the reference's output frame per (mode, setting)."""
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(1, max_psg + 1, size=n_docs)
+    n_rows = int(counts.sum())
+    vectors = rng.standard_normal((n_rows, dim)).astype(np.float32)
+    doc_ids = [f"d{d}" for d, c in enumerate(counts) for _ in range(c)]
+    psg_ids = [f"p{i}" for i in range(n_rows)]
+    qvecs = rng.standard_normal((n_q, dim)).astype(np.float32)
+    queries = {f"q{i}": f"text {i}" for i in range(n_q)}
+    index = InMemoryIndex(TableEncoder({f"text {i}": qvecs[i] for i in range(n_q)}), init_size=n_rows)
+    index.add(vectors, doc_ids=doc_ids, psg_ids=psg_ids)
+    key = f"es{seed}"
+    arrays[f"{key}/vectors"] = vectors
+    arrays[f"{key}/qvecs"] = qvecs
+    case = {"dim": dim, "doc_ids": doc_ids, "psg_ids": psg_ids, "queries": queries, "modes": {}}
+    scale = float(np.sqrt(dim))
+    for mode in (Mode.MAXP, Mode.AVEP, Mode.FIRSTP, Mode.PASSAGE):
+        pool = psg_ids if mode == Mode.PASSAGE else sorted(set(doc_ids))
+        run = {}
+        for qi in range(n_q):
+            cands = rng.choice(len(pool), size=min(n_cand, len(pool)), replace=False)
+            # geometric fall-off, different steepness per query, on the scale of the dot products
+            steep = rng.uniform(0.55, 0.98)
+            lex = (6.0 * scale * steep ** np.arange(len(cands))).astype(np.float32)
+            run[f"q{qi}"] = {pool[c]: float(x) for c, x in zip(cands, lex)}
+        first = Ranking.from_run(run, queries=queries)
+        index.mode = mode
+        entry = {"first_stage": frame(first), "settings": []}
+        for cutoff, alpha, depths in ((3, 0.5, (5, 10, 20, 40)), (5, 0.2, (8, 16, 64)), (2, 0.8, (1, 4, 4, 30)),
+                                      (10, 0.5, (10, 12, 1000))):
+            res = index(first, early_stopping=cutoff, early_stopping_alpha=alpha, early_stopping_depths=depths)
+            entry["settings"].append({"cutoff": cutoff, "alpha": alpha, "depths": list(depths), "out": frame(res)})
+            per_q = res._df.groupby("q_id").size().to_dict()
+            print(key, mode.name, cutoff, alpha, depths, "rows scored per query:", per_q)
+        case["modes"][mode.name] = entry
+    meta[key] = case
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     with open(os.path.join(GOLDEN, "ref_kat.json"), "w") as f:
@@ -193,6 +237,12 @@ def main():
     random_case(14, 1024, 20, 4, 3, 15, 0.05, 4, arrays, meta)
     np.savez(os.path.join(GOLDEN, "ref_random.npz"), **arrays)
     with open(os.path.join(GOLDEN, "ref_random.json"), "w") as f:
+        json.dump(meta, f, indent=0)
+    arrays, meta = {}, {}
+    es_case(21, 768, 60, 5, 6, 45, arrays, meta)
+    es_case(22, 100, 40, 4, 4, 30, arrays, meta)  # non-uniform dim: host-walked depths
+    np.savez(os.path.join(GOLDEN, "ref_es.npz"), **arrays)
+    with open(os.path.join(GOLDEN, "ref_es.json"), "w") as f:
         json.dump(meta, f, indent=0)
     for fn in sorted(os.listdir(GOLDEN)):
         print(fn, os.path.getsize(os.path.join(GOLDEN, fn)))

@@ -54,6 +54,14 @@ def golden_random():
 
 
 @pytest.fixture(scope="session")
+def golden_es():
+    with open(os.path.join(GOLDEN, "ref_es.json")) as f:
+        meta = json.load(f)
+    arrays = np.load(os.path.join(GOLDEN, "ref_es.npz"))
+    return meta, arrays
+
+
+@pytest.fixture(scope="session")
 def oracle_c():
     """ctypes handle on the plain-C oracle (built on demand; test infrastructure)."""
     import ctypes

@@ -187,6 +187,37 @@ def test_early_stopping(api, golden_kat):
     same_frame(out, golden_kat["es/3_0.2_4-8-20"])
 
 
+@pytest.mark.parametrize("key", ["es21", "es22"])
+def test_early_stopping_random_golden(api, golden_es, key):
+    """Seeded early-stopping cases against the reference's frames: es21 (D=768) runs the whole
+    depth walk in one launch (ffx_rerank_early_stop), es22 (D=100) walks the depths on the host."""
+    from fast_forward import _ffx
+
+    meta, arrays = golden_es
+    case = meta[key]
+    vec, qvecs = arrays[f"{key}/vectors"], arrays[f"{key}/qvecs"]
+    enc = api.TableEncoder({f"text {i}": qvecs[i] for i in range(len(qvecs))})
+    index = api.new(query_encoder=enc, init_size=len(vec))
+    index.add(vec, doc_ids=case["doc_ids"], psg_ids=case["psg_ids"])
+    assert index._device().has_fast_path == (key == "es21")
+    for mode in api.Mode:
+        entry = case["modes"][mode.name]
+        fs = entry["first_stage"]
+        first = api.Ranking(pd.DataFrame({"q_id": fs["q_id"], "id": fs["id"], "score": fs["score"]}),
+                            queries=case["queries"])
+        index.mode = mode
+        for st in entry["settings"]:
+            before = _ffx.launch_count()
+            out = index(first, early_stopping=st["cutoff"], early_stopping_alpha=st["alpha"],
+                        early_stopping_depths=tuple(st["depths"]))
+            same_frame(out, st["out"])
+            if key == "es21":
+                assert _ffx.launch_count() - before == 1  # the whole walk is one kernel
+            # batches of queries walk independently
+            assert index(first, early_stopping=st["cutoff"], early_stopping_alpha=st["alpha"],
+                         early_stopping_depths=tuple(st["depths"]), batch_size=4) == out
+
+
 def test_iteration(api):
     for kw in ({"init_size": 2, "alloc_size": 2}, {"init_size": 5}):
         index = api.new(**kw)

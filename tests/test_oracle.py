@@ -197,3 +197,31 @@ def test_pq_port_consistency():
     lut = np.einsum("mkd,md->mk", opq.codewords, (q @ opq.R).reshape(4, 8))
     adc = lut[np.arange(4)[None, :], c2].sum(1)
     assert np.allclose(adc, opq.decode(c2) @ q, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("key", ["es21", "es22"])
+def test_early_stopping_golden(golden_es, key):
+    """`Index.__call__(early_stopping=...)` (index/base.py:316-387): rows scored per query and
+    their scores, against the frames the unmodified reference produced."""
+    meta, arrays = golden_es
+    case = meta[key]
+    vec, qvecs = arrays[f"{key}/vectors"], arrays[f"{key}/qvecs"]
+    index = fo.OracleIndex()
+    index.add(vec, doc_ids=case["doc_ids"], psg_ids=case["psg_ids"])
+    qv = {f"q{i}": qvecs[i] for i in range(len(qvecs))}
+    for mode_name, entry in case["modes"].items():
+        fs = entry["first_stage"]
+        ff = fo.call_index(index, fs["q_id"], fs["id"], qv, MODES[mode_name]).astype(np.float32)
+        # the first-stage frame is sorted (q_id DESC, score DESC): blocks are in rank order
+        q_ids = np.array(fs["q_id"])
+        starts = np.flatnonzero(np.concatenate([[True], q_ids[1:] != q_ids[:-1]]))
+        q_off = np.concatenate([starts, [len(q_ids)]])
+        lex = np.array(fs["score"], np.float32)
+        for st in entry["settings"]:
+            done = fo.early_stopping_depth(q_off, lex, ff, st["alpha"], st["cutoff"], st["depths"])
+            got = {}
+            for qi, b in enumerate(q_off[:-1]):
+                for r in range(b, b + done[qi]):
+                    got[(fs["q_id"][r], fs["id"][r])] = int(bits(ff[r:r + 1])[0])
+            want = {(q, i): b for q, i, b in zip(st["out"]["q_id"], st["out"]["id"], st["out"]["score_bits"])}
+            assert got == want, (mode_name, st["cutoff"], st["alpha"], st["depths"])
