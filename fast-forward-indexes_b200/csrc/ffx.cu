@@ -16,6 +16,8 @@
 
 #include "../../include/ffx.h"
 #include "ffx_adc.cuh"
+#include "ffx_adc_warp.cuh"
+#include "ffx_adc_xor.cuh"
 #include "ffx_early_stop.cuh"
 #include "ffx_kernels.cuh"
 #include "ffx_score_tma.cuh"
@@ -61,7 +63,11 @@ struct Tuning {
     int tma_stages = 0;  // ring slots per warp
     int tma_warps = 0;   // warps per CTA of the TMA-staged kernel (8..16)
     int batch = 0;       // candidates a warp takes per grab
+    int adc = 0;         // 1: ffx_adc_kernel, 2: warp-per-row, 3: XOR-swizzled thread-per-row; 0 = best the shape allows
 };
+
+// which ADC kernel scores this index: 3 = XOR-swizzled (M % 32 == 0), 2 = warp-per-row (M = 64..128), 1 = generic
+int adc_kind(const ffx_index *idx);
 Tuning g_tune;
 
 struct Scratch {
@@ -116,6 +122,8 @@ struct ffx_index {
     int M = 0, Ks = 0, Ds = 0;
     float *codewords = nullptr;
     float *R = nullptr;
+    float *cw_t = nullptr;  // [4][Ks][32][Ds] transposed codebooks of the warp-per-row ADC kernel (M = 64..128)
+    float *cw_x = nullptr;  // [M/32][Ks][32][Ds] codebooks in table order of the XOR-swizzled kernel (M = 32..128)
 
     // staging: pinned double buffer + device landing buffers (fp32 rows are permuted
     // from the landing buffer into the lane-major store)
@@ -136,6 +144,13 @@ struct ffx_index {
 };
 
 namespace {
+
+int adc_kind(const ffx_index *idx) {
+    if (g_tune.adc == 1) return 1;
+    if (idx->cw_x && g_tune.adc != 2) return 3;
+    if (idx->cw_t && g_tune.adc != 3) return 2;
+    return 1;
+}
 
 int bind(const ffx_index *idx) {
     FFX_CUDA(cudaSetDevice(idx->device));
@@ -329,8 +344,40 @@ int dispatch_score(const ffx_plan &p, const ScorePlan &sp, const ffx::ScoreArgs 
 // One CTA per query with the top-k fused into the scoring kernel: needs the lane-major fast
 // path, keys that fit shared memory, and enough queries to fill the machine.
 bool will_fuse(const ffx_index *idx, int64_t nq, int k, int cpad) {
-    return idx->row_kind == FFX_ROWS_F32 && idx->plan.cpl != 0 && k > 0 &&
-           cpad <= ffx::kMaxFusedCand && nq >= static_cast<int64_t>(idx->sm_count) * 2;
+    if (k <= 0 || cpad > ffx::kMaxFusedCand) return false;
+    if (idx->row_kind == FFX_ROWS_PQ_U8) {  // fused ADC kernels: one CTA per SM
+        const int kind = adc_kind(idx);
+        if (kind == 1 || nq < static_cast<int64_t>(idx->sm_count)) return false;
+        return (kind == 3 ? ffx::adc_xor_smem_bytes(idx->M, idx->Ks, cpad)
+                          : ffx::adc_warp_smem_bytes(idx->Ks, cpad)) <= kSmemBudget;
+    }
+    return idx->plan.cpl != 0 && nq >= static_cast<int64_t>(idx->sm_count) * 2;
+}
+
+template <int NC>
+int launch_adc_xor(const ffx::AdcWarpArgs &w, bool fuse, unsigned grid, size_t smem, cudaStream_t st) {
+    if (fuse) {
+        auto kern = ffx::ffx_adc_xor_kernel<NC, true>;
+        FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kern<<<grid, ffx::kAdcXorThreads, smem, st>>>(w);
+    } else {
+        auto kern = ffx::ffx_adc_xor_kernel<NC, false>;
+        FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kern<<<grid, ffx::kAdcXorThreads, smem, st>>>(w);
+    }
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
+template <bool FUSE, bool INDIRECT>
+int launch_adc_warp(const ffx::AdcWarpArgs &w, unsigned grid, size_t smem, cudaStream_t st) {
+    auto kern = ffx::ffx_adc_warp_kernel<FUSE, INDIRECT>;
+    FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, ffx::kAdcWarpThreads, smem, st>>>(w);
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
 }
 
 int take_error(ffx_index *idx, cudaStream_t st) {
@@ -417,6 +464,7 @@ int ffx_set_option(const char *name, int value) {
     if (key == "kernel" && value >= 0 && value <= 2) g_tune.kernel = value;
     else if (key == "tma_stages" && value >= 0 && value <= 16) g_tune.tma_stages = value;
     else if (key == "batch" && value >= 0 && value <= 32) g_tune.batch = value;
+    else if (key == "adc" && value >= 0 && value <= 3) g_tune.adc = value;
     else if (key == "tma_warps" && (value == 0 || (value >= 1 && value <= 16))) g_tune.tma_warps = value;
     else return fail(FFX_ERR_INVALID, "ffx_set_option: unknown option or bad value (%s=%d)", name, value);
     return FFX_OK;
@@ -510,6 +558,8 @@ int ffx_index_destroy(ffx_index *idx) {
     cudaFree(idx->doc_rows);
     cudaFree(idx->codewords);
     cudaFree(idx->R);
+    cudaFree(idx->cw_t);
+    cudaFree(idx->cw_x);
     cudaFree(idx->work.p);
     cudaFree(idx->hostio.p);
     cudaFree(idx->err_flag);
@@ -728,7 +778,9 @@ int ffx_index_set_pq(ffx_index *idx, int M, int Ks, int Ds, const float *codewor
     FFX_CUDA(cudaDeviceSynchronize());
     cudaFree(idx->codewords);
     cudaFree(idx->R);
-    idx->codewords = idx->R = nullptr;
+    cudaFree(idx->cw_t);
+    cudaFree(idx->cw_x);
+    idx->codewords = idx->R = idx->cw_t = idx->cw_x = nullptr;
     const size_t cw = static_cast<size_t>(M) * Ks * Ds * 4;
     FFX_CUDA(cudaMalloc(&idx->codewords, cw));
     FFX_CUDA(cudaMemcpy(idx->codewords, codewords, cw, cudaMemcpyHostToDevice));
@@ -740,6 +792,25 @@ int ffx_index_set_pq(ffx_index *idx, int M, int Ks, int Ds, const float *codewor
     idx->M = M;
     idx->Ks = Ks;
     idx->Ds = Ds;
+    // warp-per-row kernel with the transposed, conflict-free table: M = 64..128 in whole words
+    if (M % 4 == 0 && M / 4 >= 16 && M / 4 <= 32 && ffx::adc_warp_smem_bytes(Ks, 0) <= kSmemBudget) {
+        const size_t n = static_cast<size_t>(4) * Ks * 32 * Ds;
+        FFX_CUDA(cudaMalloc(&idx->cw_t, n * 4));
+        ffx::ffx_adc_transpose_codewords_kernel<<<permute_grid(static_cast<int64_t>(n), idx->sm_count), 256, 0,
+                                                  idx->stream>>>(idx->codewords, M, Ks, Ds, idx->cw_t);
+        g_launches++;
+        FFX_CUDA(cudaGetLastError());
+        FFX_CUDA(cudaStreamSynchronize(idx->stream));
+    }
+    if (M % 32 == 0 && M <= 128 && ffx::adc_xor_smem_bytes(M, Ks, 0) <= kSmemBudget) {
+        const size_t n = static_cast<size_t>(M) * Ks * Ds;
+        FFX_CUDA(cudaMalloc(&idx->cw_x, n * 4));
+        ffx::ffx_adc_xor_codewords_kernel<<<permute_grid(static_cast<int64_t>(n), idx->sm_count), 256, 0,
+                                            idx->stream>>>(idx->codewords, M, Ks, Ds, idx->cw_x);
+        g_launches++;
+        FFX_CUDA(cudaGetLastError());
+        FFX_CUDA(cudaStreamSynchronize(idx->stream));
+    }
     return FFX_OK;
 }
 
@@ -829,9 +900,15 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
             const float *qeff = qvecs;
             if (idx->R) {
                 float *qe = reinterpret_cast<float *>(work + off_qeff);
-                ffx::ffx_rotate_queries_kernel<<<static_cast<unsigned>(nq), 256,
-                                                 static_cast<size_t>(D) * 4, st>>>(
-                    qvecs, idx->R, static_cast<int>(D), qe);
+                const size_t rot_smem = static_cast<size_t>(D) * 8 * 4;
+                if (rot_smem <= 48 * 1024) {
+                    ffx::ffx_rotate_queries8_kernel<<<static_cast<unsigned>((nq + 7) / 8), 256, rot_smem, st>>>(
+                        qvecs, idx->R, static_cast<int>(D), nq, qe);
+                } else {
+                    ffx::ffx_rotate_queries_kernel<<<static_cast<unsigned>(nq), 256,
+                                                     static_cast<size_t>(D) * 4, st>>>(
+                        qvecs, idx->R, static_cast<int>(D), qe);
+                }
                 g_launches++;
                 FFX_CUDA(cudaGetLastError());
                 qeff = qe;
@@ -861,8 +938,42 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
             a.base = base;
             a.count = count;
             a.err = idx->err_flag;
-            const size_t smem = static_cast<size_t>(idx->M) * idx->Ks * 4;
-            FFX_TRY(launch_adc(a, static_cast<unsigned>(nq * tiles), smem, st));
+            const int kind = adc_kind(idx);
+            if (kind == 3) {
+                ffx::AdcWarpArgs w{};
+                w.base = a;
+                w.cw_t = idx->cw_x;
+                w.k = k;
+                w.cpad = cpad;
+                w.topk_score = out_topk_score;
+                w.topk_pos = out_topk_pos;
+                const size_t smem = ffx::adc_xor_smem_bytes(idx->M, idx->Ks, fuse ? cpad : 0);
+                const unsigned grid = static_cast<unsigned>(fuse ? nq : nq * tiles);
+                switch (idx->M / 32) {
+                    case 1: FFX_TRY(launch_adc_xor<1>(w, fuse, grid, smem, st)); break;
+                    case 2: FFX_TRY(launch_adc_xor<2>(w, fuse, grid, smem, st)); break;
+                    case 3: FFX_TRY(launch_adc_xor<3>(w, fuse, grid, smem, st)); break;
+                    default: FFX_TRY(launch_adc_xor<4>(w, fuse, grid, smem, st)); break;
+                }
+            } else if (kind == 2) {
+                ffx::AdcWarpArgs w{};
+                w.base = a;
+                w.cw_t = idx->cw_t;
+                w.k = k;
+                w.cpad = cpad;
+                w.topk_score = out_topk_score;
+                w.topk_pos = out_topk_pos;
+                const size_t smem = ffx::adc_warp_smem_bytes(idx->Ks, fuse ? cpad : 0);
+                const bool ind = idx->indirect && mode != FFX_MODE_PASSAGE;
+                const unsigned grid = static_cast<unsigned>(fuse ? nq : nq * tiles);
+                if (fuse && ind) FFX_TRY((launch_adc_warp<true, true>(w, grid, smem, st)));
+                else if (fuse) FFX_TRY((launch_adc_warp<true, false>(w, grid, smem, st)));
+                else if (ind) FFX_TRY((launch_adc_warp<false, true>(w, grid, smem, st)));
+                else FFX_TRY((launch_adc_warp<false, false>(w, grid, smem, st)));
+            } else {
+                const size_t smem = static_cast<size_t>(idx->M) * idx->Ks * 4;
+                FFX_TRY(launch_adc(a, static_cast<unsigned>(nq * tiles), smem, st));
+            }
         } else {
             ffx::ScoreArgs a{};
             a.vectors = static_cast<const float *>(idx->store);

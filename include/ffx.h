@@ -62,7 +62,11 @@ int ffx_device_count(void);
  * reference contract — it has no kernels to tune.
  *   "kernel"      1 = register-staged scoring kernel, 2 = TMA-staged (default when it fits)
  *   "tma_stages"  ring slots per warp of the TMA-staged kernel (capped by shared memory)
- *   "batch"       candidates a warp takes per grab (1..32) */
+ *   "batch"       candidates a warp takes per grab (1..32)
+ *   "tma_warps"   warps per CTA of the TMA-staged kernel
+ *   "adc"         1 = generic thread-per-row ADC kernel, 2 = warp-per-row with conflict-free tables
+ *                 (M = 64..128), 3 = XOR-swizzled thread-per-row (M % 32 == 0, M <= 128); a kernel the
+ *                 shape does not allow falls back to the next one */
 int ffx_set_option(const char *name, int value);
 
 /* Pinned host memory for buffers that cross PCIe every call (candidate lists, query

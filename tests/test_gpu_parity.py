@@ -364,16 +364,9 @@ def test_staging_larger_than_the_pinned_buffer(ffx):
 # ------------------------------------------------------------------------------------------
 # PQ / OPQ asymmetric distance
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rotate", [False, True])
-@pytest.mark.parametrize("M,Ks,Ds", [(96, 256, 8), (8, 16, 4), (12, 256, 3)])
-def test_adc_matches_decode_then_dot(ffx, M, Ks, Ds, rotate):
-    """quantizer/nanopq.py:43-44,111-112 + index/base.py:292-303.  ADC sums M LUT entries
-    instead of D products, so scores differ from decode-then-dot by reassociation only:
-    tolerance rtol 1e-5 (north_star) + atol 1e-5 * |q| * |d|."""
-    rng = np.random.default_rng(M + Ks)
+def adc_case(ffx, rng, M, Ks, Ds, rotate, contiguous, n_docs=500, max_psg=7):
     D = M * Ds
-    n_docs = 500
-    off, rows, _ = make_corpus(rng, n_docs, 7, 4, True)
+    off, rows, _ = make_corpus(rng, n_docs, max_psg, 4, contiguous)
     n_rows = int(off[-1])
     codes = rng.integers(0, Ks, (n_rows, M)).astype(np.uint8)
     cw = rng.standard_normal((M, Ks, Ds)).astype(np.float32)
@@ -381,17 +374,20 @@ def test_adc_matches_decode_then_dot(ffx, M, Ks, Ds, rotate):
     idx = ffx.DeviceIndex(M, capacity=n_rows, row_kind=ffx.ROWS_PQ_U8)
     idx.stage(0, codes)
     assert (idx.read_rows([0, n_rows - 1]) == codes[[0, n_rows - 1]]).all()
-    idx.set_docs(off)
+    idx.set_docs(off, None if contiguous else rows)
     idx.set_pq(cw, R)
-    nq = 6
-    qv = rng.standard_normal((nq, D)).astype(np.float32)
     dec = fo.pq_decode(codes, cw) if R is None else fo.opq_decode(codes, cw, R)
+    return idx, off, rows, n_rows, dec
+
+
+def check_adc(idx, rng, off, rows, n_rows, dec, qv, n_docs, lo, hi, k, modes=MODES):
     row_norm = np.linalg.norm(dec, axis=1)
-    for name, mode in MODES.items():
+    nq = len(qv)
+    for name, mode in modes.items():
         pool = n_rows if mode == fo.MODE_PASSAGE else n_docs
-        q_off, cand, pair_q = make_pairs(rng, nq, pool, 10, 200)
+        q_off, cand, pair_q = make_pairs(rng, nq, pool, lo, hi)
         lex = rng.uniform(0, 20, len(cand)).astype(np.float32)
-        out = idx.rerank_host(mode, qv, q_off, cand, lex, 0.2, 10, want_ff=True, want_int=True)
+        out = idx.rerank_host(mode, qv, q_off, cand, lex, 0.2, k, want_ff=True, want_int=True)
         u_off, u_rows = units_for_mode(off, rows, n_rows, mode)
         want = fo.score_pairs(dec.astype(np.float64), u_off, u_rows, pair_q, cand, qv.astype(np.float64), mode)
         scale = np.array([row_norm[u_rows[u_off[c]:u_off[c + 1]]].max() for c in cand]) * \
@@ -400,9 +396,51 @@ def test_adc_matches_decode_then_dot(ffx, M, Ks, Ds, rotate):
         assert (err <= 1e-5 * np.abs(want) + 1e-5 * scale).all(), name
         it = fo.interpolate_f32(lex, out["ff"], 0.2)
         assert (bits(out["int"]) == bits(it)).all()
-        ts, tp = fo.topk_per_query(q_off, it, 10)
-        assert (out["topk_pos"] == tp).all()
-    idx.close()
+        ts, tp = fo.topk_per_query(q_off, it, k)
+        assert (out["topk_pos"] == tp).all() and (bits(out["topk_score"]) == bits(ts)).all()
+        # top-k only: same lists without the per-pair outputs
+        out2 = idx.rerank_host(mode, qv, q_off, cand, lex, 0.2, k, want_ff=False, want_int=False)
+        assert (out2["topk_pos"] == tp).all() and (bits(out2["topk_score"]) == bits(ts)).all()
+
+
+@pytest.mark.parametrize("adc_kernel", [1, 2, 3])
+@pytest.mark.parametrize("rotate", [False, True])
+@pytest.mark.parametrize("M,Ks,Ds", [(96, 256, 8), (64, 256, 4), (128, 256, 2), (32, 50, 4), (80, 100, 3),
+                                     (8, 16, 4), (12, 256, 3)])
+def test_adc_matches_decode_then_dot(ffx, M, Ks, Ds, rotate, adc_kernel):
+    """quantizer/nanopq.py:43-44,111-112 + index/base.py:292-303.  ADC sums M LUT entries
+    instead of D products, so scores differ from decode-then-dot by reassociation only:
+    tolerance rtol 1e-5 (north_star) + atol 1e-5 * |q| * |d|.  All three ADC kernels: generic
+    thread-per-row (adc=1), warp-per-row with conflict-free tables for M = 64..128 (adc=2) and
+    XOR-swizzled thread-per-row for M % 32 == 0 (adc=3, the default where it applies)."""
+    ffx.set_option("adc", adc_kernel)
+    try:
+        rng = np.random.default_rng(M + Ks)
+        for contiguous in (True, False):
+            idx, off, rows, n_rows, dec = adc_case(ffx, rng, M, Ks, Ds, rotate, contiguous)
+            qv = rng.standard_normal((6, M * Ds)).astype(np.float32)
+            check_adc(idx, rng, off, rows, n_rows, dec, qv, 500, 10, 200, 10)
+            idx.close()
+    finally:
+        ffx.set_option("adc", 0)
+
+
+@pytest.mark.parametrize("adc_kernel", [2, 3])
+@pytest.mark.parametrize("M,Ks,Ds", [(96, 256, 8), (64, 64, 4)])
+def test_adc_fused_topk_many_queries(ffx, M, Ks, Ds, adc_kernel):
+    """nq >= #SMs switches the fast ADC kernels to their fused score+interpolate+top-k form
+    (one CTA per query, sort keys built over the dead tables); documents of up to 70 passages
+    cross the 32-row blocks of the kernels."""
+    ffx.set_option("adc", adc_kernel)
+    try:
+        rng = np.random.default_rng(M)
+        idx, off, rows, n_rows, dec = adc_case(ffx, rng, M, Ks, Ds, True, True, n_docs=700, max_psg=70)
+        qv = rng.standard_normal((200, M * Ds)).astype(np.float32)
+        check_adc(idx, rng, off, rows, n_rows, dec, qv, 700, 0, 300, 64,
+                  modes={"MAXP": fo.MODE_MAXP, "AVEP": fo.MODE_AVEP, "PASSAGE": fo.MODE_PASSAGE})
+        idx.close()
+    finally:
+        ffx.set_option("adc", 0)
 
 
 # ------------------------------------------------------------------------------------------
