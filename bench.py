@@ -423,7 +423,8 @@ def run_ffx(args, wl):
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
         peak, peak_src = measured_peak()
         traffic = ncu_traffic()
-        kernel = ("ffx_adc_kernel (LUT in smem over uint8 codes) + ffx_topk_kernel" if pq else
+        kernel = ("ffx_adc_xor_kernel<3,true> (TMA-staged codes, XOR-swizzled conflict-free LUT look-ups, "
+                  "AVEP-interpolate-topk fused; bound by shared-memory look-ups, not HBM)" if pq else
                   "ffx_score_tma_kernel<2,12,%s> (TMA-staged gather-dot-%s-interpolate%s)" % (
                       "true" if nq >= 296 else "false", wl["mode"], "-topk fused" if nq >= 296 else " ; ffx_topk_kernel"))
         line = {

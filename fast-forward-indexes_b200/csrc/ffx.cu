@@ -348,8 +348,10 @@ bool will_fuse(const ffx_index *idx, int64_t nq, int k, int cpad) {
     if (idx->row_kind == FFX_ROWS_PQ_U8) {  // fused ADC kernels: one CTA per SM
         const int kind = adc_kind(idx);
         if (kind == 1 || nq < static_cast<int64_t>(idx->sm_count)) return false;
-        return (kind == 3 ? ffx::adc_xor_smem_bytes(idx->M, idx->Ks, cpad)
-                          : ffx::adc_warp_smem_bytes(idx->Ks, cpad)) <= kSmemBudget;
+        if (kind == 3)  // sort keys overlay table + slots
+            return ffx::adc_xor_smem_bytes(idx->M, idx->Ks, cpad) <= kSmemBudget &&
+                   static_cast<size_t>(cpad) * 8 <= ffx::adc_xor_smem_bytes(idx->M, idx->Ks, 0) - 128;
+        return ffx::adc_warp_smem_bytes(idx->Ks, cpad) <= kSmemBudget;
     }
     return idx->plan.cpl != 0 && nq >= static_cast<int64_t>(idx->sm_count) * 2;
 }
@@ -400,7 +402,7 @@ cudaEvent_t event_at(ffx_index *idx, size_t i) {
     return idx->events[i];
 }
 
-int launch_topk(const float *scores, const float *lex, float alpha, float beta, float *out_int,
+int launch_topk(const float *scores, bool scores_rel, const float *lex, float alpha, float beta, float *out_int,
                 const int64_t *q_off, int64_t nq, int k, int cpad, Scratch &work, size_t work_off,
                 float *out_s, int32_t *out_p, cudaStream_t st) {
     unsigned long long *gkeys = nullptr;
@@ -414,7 +416,7 @@ int launch_topk(const float *scores, const float *lex, float alpha, float beta, 
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
     ffx::ffx_topk_kernel<<<static_cast<unsigned>(nq), ffx::kThreads, smem, st>>>(
-        scores, lex, alpha, beta, q_off, k, cpad, gkeys, out_int, out_s, out_p);
+        scores, scores_rel ? 1 : 0, lex, alpha, beta, q_off, k, cpad, gkeys, out_int, out_s, out_p);
     g_launches++;
     FFX_CUDA(cudaGetLastError());
     return FFX_OK;
@@ -815,10 +817,13 @@ int ffx_index_set_pq(ffx_index *idx, int M, int Ks, int Ds, const float *codewor
 }
 
 // ---- the hot path ----------------------------------------------------------------------
-int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const int64_t *q_off,
-               const int32_t *cand, const float *lex, double alpha, int k, int64_t max_cand,
-               float *out_ff, float *out_int, float *out_topk_score, int32_t *out_topk_pos,
-               void *stream) {
+// `qeff_buf` (device, [nq, D], optional): where the OPQ-rotated queries of this launch go.  The
+// default is the index's scratch, which launches on different streams would share — the
+// pipelined host path gives every query chunk its own slice instead.
+static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const int64_t *q_off,
+                       const int32_t *cand, const float *lex, double alpha, int k, int64_t max_cand,
+                       float *out_ff, float *out_int, float *out_topk_score, int32_t *out_topk_pos,
+                       void *stream, float *qeff_buf) {
     if (!idx) return fail(FFX_ERR_INVALID, "ffx_rerank: NULL index");
     if (mode < FFX_MODE_PASSAGE || mode > FFX_MODE_AVEP)
         return fail(FFX_ERR_INVALID, "ffx_rerank: unknown mode %d", mode);
@@ -870,14 +875,14 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
         off_keys = total;
         total += static_cast<size_t>(nq) * cpad * 8;
     }
-    if (pq && idx->R) {
+    if (pq && idx->R && !qeff_buf) {
         off_qeff = total;
         total += static_cast<size_t>(nq) * D * 4;
     }
     if (total) FFX_TRY(scratch_reserve(idx->work, total));
     char *work = static_cast<char *>(idx->work.p);
     float *rank_scores = need_scores ? reinterpret_cast<float *>(work + off_scores) : nullptr;
-    const float *topk_src = rank_scores ? rank_scores : out_int;
+    const float *topk_src = rank_scores ? rank_scores : out_int;  // input of a separate top-k pass
 
     // tiles: split a query over several CTAs when there are few queries
     const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4) : ScorePlan{};
@@ -899,7 +904,7 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
         if (pq) {
             const float *qeff = qvecs;
             if (idx->R) {
-                float *qe = reinterpret_cast<float *>(work + off_qeff);
+                float *qe = qeff_buf ? qeff_buf : reinterpret_cast<float *>(work + off_qeff);
                 const size_t rot_smem = static_cast<size_t>(D) * 8 * 4;
                 if (rot_smem <= 48 * 1024) {
                     ffx::ffx_rotate_queries8_kernel<<<static_cast<unsigned>((nq + 7) / 8), 256, rot_smem, st>>>(
@@ -1015,9 +1020,18 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
         }
     }
     if (k > 0 && !fuse)
-        FFX_TRY(launch_topk(topk_src, nullptr, 0.f, 0.f, nullptr, q_off, nq, k, cpad, idx->work, off_keys,
+        FFX_TRY(launch_topk(topk_src, rank_scores != nullptr, nullptr, 0.f, 0.f, nullptr, q_off, nq, k, cpad,
+                            idx->work, off_keys,
                             out_topk_score, out_topk_pos, st));
     return FFX_OK;
+}
+
+int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const int64_t *q_off,
+               const int32_t *cand, const float *lex, double alpha, int k, int64_t max_cand,
+               float *out_ff, float *out_int, float *out_topk_score, int32_t *out_topk_pos,
+               void *stream) {
+    return rerank_impl(idx, mode, qvecs, nq, q_off, cand, lex, alpha, k, max_cand, out_ff, out_int,
+                       out_topk_score, out_topk_pos, stream, nullptr);
 }
 
 int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
@@ -1046,12 +1060,14 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     auto pad = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
     const size_t b_q = pad(static_cast<size_t>(nq) * D * 4), b_off = pad(static_cast<size_t>(nq + 1) * 8);
     const size_t b_n = pad(static_cast<size_t>(n) * 4), b_k = pad(static_cast<size_t>(nq) * k * 4);
-    size_t total = b_q + b_off + b_n /*cand*/ + (lex ? b_n : 0) + (out_ff ? b_n : 0) +
+    const bool rotated = pq && idx->R;
+    size_t total = b_q + (rotated ? b_q : 0) + b_off + b_n /*cand*/ + (lex ? b_n : 0) + (out_ff ? b_n : 0) +
                    (out_int ? b_n : 0) + (k > 0 ? 2 * b_k : 0);
     FFX_TRY(scratch_reserve(idx->hostio, total));
     char *p = static_cast<char *>(idx->hostio.p);
     auto take = [&](size_t b) { char *r = p; p += b; return r; };
     float *d_q = reinterpret_cast<float *>(take(b_q));
+    float *d_qe = rotated ? reinterpret_cast<float *>(take(b_q)) : nullptr;  // OPQ-rotated queries, per chunk
     int64_t *d_off = reinterpret_cast<int64_t *>(take(b_off));
     int32_t *d_cand = reinterpret_cast<int32_t *>(take(b_n));
     float *d_lex = lex ? reinterpret_cast<float *>(take(b_n)) : nullptr;
@@ -1069,12 +1085,14 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     const int64_t wave = static_cast<int64_t>(idx->sm_count) * 2;
     int64_t chunk_q = nq;
     if (n >= (1 << 20) && nq >= 8 * wave && will_fuse(idx, 4 * wave, k, cpad)) chunk_q = 4 * wave;
-    const int64_t n_chunks = (nq + chunk_q - 1) / chunk_q;
+    // whole chunks only; the remainder rides with the last one (a tail of a few queries would
+    // fall below the fused kernel's query threshold)
+    const int64_t n_chunks = std::max<int64_t>(1, nq / chunk_q);
 
     FFX_CUDA(cudaMemcpyAsync(d_off, q_off, static_cast<size_t>(nq + 1) * 8, cudaMemcpyHostToDevice, idx->s_h2d));
     size_t ev = 0;
     for (int64_t c = 0; c < n_chunks; c++) {
-        const int64_t q0 = c * chunk_q, q1 = std::min(nq, q0 + chunk_q), cq = q1 - q0;
+        const int64_t q0 = c * chunk_q, q1 = c + 1 == n_chunks ? nq : q0 + chunk_q, cq = q1 - q0;
         const int64_t p0 = q_off[q0], np_ = q_off[q1] - p0;
         cudaStream_t comp = idx->s_comp[c & 1];
         FFX_CUDA(cudaMemcpyAsync(d_q + q0 * D, qvecs + q0 * D, static_cast<size_t>(cq) * D * 4,
@@ -1091,9 +1109,9 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
         FFX_CUDA(cudaStreamWaitEvent(comp, in_ready, 0));
         // q_off holds absolute pair offsets: pass the shifted offset pointer with the
         // unshifted per-pair arrays; per-query outputs are shifted to the chunk
-        FFX_TRY(ffx_rerank(idx, mode, d_q + q0 * D, cq, d_off + q0, d_cand, d_lex, alpha, k, max_cand,
-                           d_ff, d_int, d_ts ? d_ts + q0 * k : nullptr, d_tp ? d_tp + q0 * k : nullptr,
-                           comp));
+        FFX_TRY(rerank_impl(idx, mode, d_q + q0 * D, cq, d_off + q0, d_cand, d_lex, alpha, k, max_cand,
+                            d_ff, d_int, d_ts ? d_ts + q0 * k : nullptr, d_tp ? d_tp + q0 * k : nullptr,
+                            comp, d_qe ? d_qe + q0 * D : nullptr));
         cudaEvent_t out_ready = event_at(idx, ev++);
         FFX_CUDA(cudaEventRecord(out_ready, comp));
         FFX_CUDA(cudaStreamWaitEvent(idx->s_d2h, out_ready, 0));
@@ -1249,7 +1267,7 @@ int ffx_interpolate_topk(ffx_index *idx, const float *lex, const float *ff, int6
     const int cpad = next_pow2(std::max<int64_t>(max_cand, 1));
     if (cpad > ffx::kMaxFusedCand && k > 0)
         FFX_TRY(scratch_reserve(idx->work, static_cast<size_t>(nq) * cpad * 8));
-    return launch_topk(ff, lex, static_cast<float>(alpha), static_cast<float>(1.0 - alpha), out_int,
+    return launch_topk(ff, false, lex, static_cast<float>(alpha), static_cast<float>(1.0 - alpha), out_int,
                        q_off, nq, k, cpad, idx->work, 0, out_topk_score, out_topk_pos,
                        static_cast<cudaStream_t>(stream));
 }

@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_adc_kernel(const AdcArgs a) {
     const int c0 = t_idx * a.tile;
     const int n_tile = min(a.tile, n_query - c0);
     if (n_tile <= 0) return;
+    // the scratch scores of a separate top-k pass are indexed relative to the launch's first pair
+    float *rank = a.rank_scores ? a.rank_scores - a.q_off[0] : nullptr;
     if (threadIdx.x == 0) s_next = 0;
 
     // ---- per-query lookup table
@@ -176,9 +178,9 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_adc_kernel(const AdcArgs a) {
                 if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, __ldg(a.lex + p)), __fmul_rn(a.beta, ff));
                 if (a.out_ff) a.out_ff[p] = ff;
                 if (a.out_int) a.out_int[p] = inter;
-                if (a.rank_scores) a.rank_scores[p] = inter;
-            } else if (a.rank_scores) {
-                a.rank_scores[p] = __int_as_float(0x7fc00000);
+                if (rank) rank[p] = inter;
+            } else if (rank) {
+                rank[p] = __int_as_float(0x7fc00000);
             }
         }
     }

@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(kAdcWarpThreads, 1) ffx_adc_warp_kernel(const 
     const int c0 = t_idx * a.tile;
     const int n_tile = min(a.tile, n_query - c0);
     if (!FUSE && n_tile <= 0) return;
+    // the scratch scores of a separate top-k pass are indexed relative to the launch's first pair
+    float *rank = a.rank_scores ? a.rank_scores - a.q_off[0] : nullptr;
     if (threadIdx.x == 0) s_next = 0;
     if (FUSE) {
         for (int i = threadIdx.x; i < n_query; i += blockDim.x) s_scores[i] = __int_as_float(0x7fc00000);
@@ -276,10 +278,10 @@ __global__ void __launch_bounds__(kAdcWarpThreads, 1) ffx_adc_warp_kernel(const 
                 if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, __ldg(a.lex + p)), __fmul_rn(a.beta, ff));
                 if (a.out_ff) a.out_ff[p] = ff;
                 if (a.out_int) a.out_int[p] = inter;
-                if (a.rank_scores) a.rank_scores[p] = inter;
+                if (rank) rank[p] = inter;
                 if (FUSE) s_scores[c0 + base + lane] = inter;
-            } else if (a.rank_scores) {
-                a.rank_scores[p] = __int_as_float(0x7fc00000);
+            } else if (rank) {
+                rank[p] = __int_as_float(0x7fc00000);
             }
         }
     }
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(kAdcWarpThreads, 1) ffx_adc_warp_kernel(const 
         for (int i = threadIdx.x; i < w.cpad; i += blockDim.x)
             s_keys[i] = i < n_query ? topk_key(s_scores[i], static_cast<uint32_t>(i)) : 0ull;
         __syncthreads();
-        bitonic_sort_desc(s_keys, w.cpad);
+        block_sort_desc(s_keys, w.cpad);
         write_topk(s_keys, n_query, w.k, w.topk_score + q_idx * w.k, w.topk_pos + q_idx * w.k);
     }
 }

@@ -20,11 +20,25 @@
 // Rows of the 32 candidates a warp grabs are flattened (warp scan), lane r takes stream row r,
 // a segmented scan folds row scores into documents in row order and lane j pulls candidate j.
 //
-// Shapes: M % 32 == 0, M <= 128 (NC = M / 32 chunks); shared memory M * Ks * 4 bytes of table
-// (96 KB at M = 96, Ks = 256) + 4 B per candidate (FUSE).  1024 threads per CTA, one CTA per SM.
+// Code rows reach the SM through the bulk-copy engine: a thread reading its own row straight
+// from global memory touches 32 different lines per warp request (~24 L1 wavefronts each, the
+// first version spent a third of the L1 data pipe on that).  Instead every warp owns a
+// 32-row x M-byte slot buffer in shared memory; for each 32-row block of the stream the lanes
+// that own a document issue ONE cp.async.bulk per document (its rows are consecutive in the
+// store and in the stream), completion is counted on the warp's mbarrier, and lane t then reads
+// slot t with 32-bit loads in exactly the swizzled word order above — which is also bank-
+// conflict free for the slot stride (M = 96: bank = 8*((j3 - t) mod 4) + (w ^ (t >> 2))).
+// The next block's copies are issued as soon as the words are in registers, so they overlap the
+// look-ups.
+//
+// Shapes: M % 32 == 0, M <= 128 (NC = M / 32 chunks).  Shared memory: M * Ks * 4 bytes of table
+// (96 KB at M = 96, Ks = 256) + 32 * M bytes per warp of slots.  1024 threads per CTA, one CTA
+// per SM.  FUSE adds 4 B per candidate of scores and builds the sort keys over the dead table
+// and slots.
 // Bound: shared-memory look-ups (3 conflict-free LDS per row at M = 96) and instruction issue.
 #pragma once
 #include "ffx_adc_warp.cuh"
+#include "ffx_score_tma.cuh"
 
 namespace ffx {
 
@@ -44,27 +58,36 @@ __global__ void ffx_adc_xor_codewords_kernel(const float *cw, int M, int Ks, int
     }
 }
 
+// [table][slots: warps x 32 x M][mbarriers][FUSE: cpad interpolated scores]; the sort keys of the
+// fused top-k overlay table + slots once they are dead
 __host__ __device__ inline size_t adc_xor_smem_bytes(int M, int Ks, int cpad_scores) {
     const size_t lut = static_cast<size_t>(M) * Ks * 4;
-    const size_t keys = static_cast<size_t>(cpad_scores) * 8;  // sort keys overlay the dead table
-    return ((static_cast<size_t>(cpad_scores) * 4 + 127) & ~static_cast<size_t>(127)) + (lut > keys ? lut : keys);
+    const size_t rest = static_cast<size_t>(kAdcXorThreads / 32) * (32 * static_cast<size_t>(M) + 8);
+    return lut + rest + static_cast<size_t>(cpad_scores) * 4 + 128;
 }
 
-__device__ __forceinline__ uint4 ldg_u4(const void *p) {
-    return __ldg(reinterpret_cast<const uint4 *>(p));
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+    return r;
 }
 
 // AdcWarpArgs::cw_t holds cw_x here.
 template <int NC, bool FUSE>
 __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const AdcWarpArgs w) {
     const AdcArgs &a = w.base;
+    constexpr int M = NC * 32;
     extern __shared__ __align__(128) unsigned char adc_smem[];
-    float *s_scores = reinterpret_cast<float *>(adc_smem);  // [cpad] (FUSE), padded so the table stays 128-byte aligned
-    float *s_lut = reinterpret_cast<float *>(
-        adc_smem + (FUSE ? ((static_cast<size_t>(w.cpad) * 4 + 127) & ~static_cast<size_t>(127)) : 0));
+    float *s_lut = reinterpret_cast<float *>(adc_smem);  // 128-byte aligned (the XOR addressing relies on it)
     __shared__ int s_next;
 
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lut_bytes = static_cast<uint32_t>(M) * static_cast<uint32_t>(w.base.Ks) * 4u;
+    const uint32_t slots = smem_u32(adc_smem) + lut_bytes + static_cast<uint32_t>(warp) * (32u * M);
+    const uint32_t bars_off = lut_bytes + (kAdcXorThreads / 32) * (32u * M);
+    const uint32_t bar = smem_u32(adc_smem) + bars_off + static_cast<uint32_t>(warp) * 8u;
+    float *s_scores = reinterpret_cast<float *>(adc_smem + bars_off + (kAdcXorThreads / 32) * 8);  // [cpad] (FUSE)
     const int64_t q_idx = blockIdx.x / a.tiles_per_query;
     const int t_idx = blockIdx.x % a.tiles_per_query;
     const int64_t q_begin = a.q_off[q_idx];
@@ -72,12 +95,18 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
     const int c0 = t_idx * a.tile;
     const int n_tile = min(a.tile, n_query - c0);
     if (!FUSE && n_tile <= 0) return;
+    // the scratch scores of a separate top-k pass are indexed relative to the launch's first pair
+    float *rank = a.rank_scores ? a.rank_scores - a.q_off[0] : nullptr;
     if (threadIdx.x == 0) s_next = 0;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (FUSE) {
         for (int i = threadIdx.x; i < n_query; i += blockDim.x) s_scores[i] = __int_as_float(0x7fc00000);
     }
 
-    constexpr int M = NC * 32;
     // ---- per-query table: s_lut[(j3*Ks + c)*32 + b] = qeff[m*Ds..] . codewords[m][c],  m = 32*j3 + b
     {
         const float *qe = a.qeff + q_idx * (static_cast<int64_t>(M) * a.Ds);
@@ -112,14 +141,22 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
 #pragma unroll
     for (int k = 0; k < 4; k++) sel[k] = 0x80u << (8u * ((static_cast<uint32_t>(k) ^ t) & 3u));
     const uint32_t tab_bytes = static_cast<uint32_t>(a.Ks) * 128u;
-    uint32_t tab[NC];  // table j3 of this lane, low 7 bits = 4t (the table is 128-byte aligned)
+    uint32_t tab[1];  // table 0 of this lane, low 7 bits = 4t (the table is 128-byte aligned)
+    tab[0] = smem_u32(s_lut) | (t << 2);
+    // slot t of the warp's buffer; register position wi of chunk step j reads word
+    // 8*chunk(j) + (wi ^ (t >> 2)), chunk(j) = (j + rot) % NC with a per-lane rotation that keeps
+    // the 32-bit reads conflict free for every slot stride (NC = 2: rot = bit 1 of t, NC = 4: t & 3)
+    const uint32_t slot_x = (slots + t * M) | ((t >> 2) << 2);
+    const uint32_t rot = NC == 2 ? ((t >> 1) & 1u) : (NC == 4 ? (t & 3u) : 0u);
+    uint32_t tab_l[NC], chunk_off[NC];
 #pragma unroll
-    for (int j = 0; j < NC; j++)
-        tab[j] = (static_cast<uint32_t>(__cvta_generic_to_shared(s_lut)) + static_cast<uint32_t>(j) * tab_bytes) | (t << 2);
-    const uint32_t off_a = (t & 16u) ? 16u : 0u;  // which 16-byte half of a chunk lands in positions 0..3
-    const uint32_t off_b = 16u - off_a;
-    const bool sw1 = (t & 4u) != 0, sw2 = (t & 8u) != 0;
+    for (int j = 0; j < NC; j++) {
+        const uint32_t cj = (static_cast<uint32_t>(j) + rot) % NC;
+        chunk_off[j] = 32u * cj;
+        tab_l[j] = tab[0] + cj * tab_bytes;
+    }
     const bool indirect = a.indirect && a.mode != FFX_MODE_PASSAGE;
+    uint32_t phase = 0;  // parity of the warp's mbarrier
     const bool segmented = a.mode == FFX_MODE_MAXP || a.mode == FFX_MODE_AVEP;
     const bool is_max = a.mode == FFX_MODE_MAXP;
 
@@ -164,6 +201,23 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
         float acc = 0.f;  // lane j: running max / sum / first of candidate j
         bool acc_set = false;
 
+        // copies of stream rows [r0, r0+32) into the slots: one bulk copy per document piece
+        auto issue_block = [&](uint32_t r0) {
+            if (lane == 0) mbar_expect_tx(bar, min(32u, total - r0) * M);
+            const uint32_t lo = max(pre, r0), hi = min(pre + cnt, r0 + 32);
+            if (cnt > 0 && lo < hi) {
+                const uint32_t dst = slots + (lo - r0) * M;
+                const uint32_t first = start + (lo - pre);
+                if (!indirect) {
+                    bulk_g2s(dst, a.codes + static_cast<uint64_t>(first) * M, (hi - lo) * M, bar);
+                } else {
+                    for (uint32_t i = 0; i < hi - lo; i++)
+                        bulk_g2s(dst + i * M, a.codes + static_cast<uint64_t>(__ldg(a.doc_rows + first + i)) * M, M, bar);
+                }
+            }
+        };
+        if (total > 0) issue_block(0);
+
         for (uint32_t r0 = 0; r0 < total; r0 += 32) {
             const uint32_t g = r0 + t;  // this lane's row of the stream
             // owner of stream row g: first candidate whose inclusive count exceeds it
@@ -175,38 +229,36 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
             }
             c = min(c, 31);
             const uint32_t my_k = g - __shfl_sync(kFull, pre, c);  // position inside the document
-            const uint32_t c_start = __shfl_sync(kFull, start, c);
+
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            uint32_t wd[NC][8];
+            if (g < total) {
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+#pragma unroll
+                    for (int wi = 0; wi < 8; wi++) {
+                        const uint32_t addr = (slot_x ^ (static_cast<uint32_t>(wi) << 2)) +
+                                              ((NC == 2 || NC == 4) ? chunk_off[j] : 32u * j);
+                        wd[j][wi] = lds_u32(addr);
+                    }
+                }
+            }
+            __syncwarp();  // every lane holds its row in registers: the slots may be refilled
+            if (r0 + 32 < total) issue_block(r0 + 32);
 
             float s = 0.f;
             if (g < total) {
-                uint32_t row = c_start + my_k;
-                if (indirect) row = static_cast<uint32_t>(__ldg(a.doc_rows + row));
-                const uint8_t *code = a.codes + static_cast<uint64_t>(row) * M;
-                uint4 qa[NC], qb[NC];
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    qa[j] = ldg_u4(code + 32 * j + off_a);
-                    qb[j] = ldg_u4(code + 32 * j + off_b);
-                }
                 float acc4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int j = 0; j < NC; j++) {
-                    uint32_t wd[8] = {qa[j].x, qa[j].y, qa[j].z, qa[j].w, qb[j].x, qb[j].y, qb[j].z, qb[j].w};
-#pragma unroll
-                    for (int h = 0; h < 8; h += 4) {  // position i <- word i ^ ((t >> 2) & 3)
-                        const uint32_t x0 = sw1 ? wd[h + 1] : wd[h + 0], x1 = sw1 ? wd[h + 0] : wd[h + 1];
-                        const uint32_t x2 = sw1 ? wd[h + 3] : wd[h + 2], x3 = sw1 ? wd[h + 2] : wd[h + 3];
-                        wd[h + 0] = sw2 ? x2 : x0;
-                        wd[h + 1] = sw2 ? x3 : x1;
-                        wd[h + 2] = sw2 ? x0 : x2;
-                        wd[h + 3] = sw2 ? x1 : x3;
-                    }
+                    const uint32_t tj = (NC == 2 || NC == 4) ? tab_l[j] : tab[0] + static_cast<uint32_t>(j) * tab_bytes;
 #pragma unroll
                     for (int wi = 0; wi < 8; wi++) {
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             const uint32_t pos = static_cast<uint32_t>(4 * wi + k);
-                            acc4[k] += lds_f32(__dp4a(wd[wi], sel[k], tab[j] ^ (pos << 2)));
+                            acc4[k] += lds_f32(__dp4a(wd[j][wi], sel[k], tj ^ (pos << 2)));
                         }
                     }
                 }
@@ -241,22 +293,23 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
                 if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, __ldg(a.lex + p)), __fmul_rn(a.beta, ff));
                 if (a.out_ff) a.out_ff[p] = ff;
                 if (a.out_int) a.out_int[p] = inter;
-                if (a.rank_scores) a.rank_scores[p] = inter;
+                if (rank) rank[p] = inter;
                 if (FUSE) s_scores[c0 + base + lane] = inter;
-            } else if (a.rank_scores) {
-                a.rank_scores[p] = __int_as_float(0x7fc00000);
+            } else if (rank) {
+                rank[p] = __int_as_float(0x7fc00000);
             }
         }
     }
 
     if (FUSE) {
-        // the table is dead: build the 64-bit sort keys over it
+        // table and slots are dead (every issued copy has been waited for): build the 64-bit sort
+        // keys over them (NaN score = pair of another shard = not ranked)
         __syncthreads();
-        unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(s_lut);
+        unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(adc_smem);
         for (int i = threadIdx.x; i < w.cpad; i += blockDim.x)
             s_keys[i] = i < n_query ? topk_key(s_scores[i], static_cast<uint32_t>(i)) : 0ull;
         __syncthreads();
-        bitonic_sort_desc(s_keys, w.cpad);
+        block_sort_desc(s_keys, w.cpad);
         write_topk(s_keys, n_query, w.k, w.topk_score + q_idx * w.k, w.topk_pos + q_idx * w.k);
     }
 }

@@ -117,6 +117,77 @@ __device__ inline void bitonic_sort_desc(unsigned long long *keys, int n) {
     }
 }
 
+// Same result as bitonic_sort_desc, for n == E * blockDim.x keys (blockDim.x a multiple of 32):
+// every thread keeps E consecutive keys in registers.  Compare-exchange distances below E stay
+// inside a thread, distances up to 16*E go through warp shuffles, and only the distances that
+// cross warps use shared memory (as a striped exchange buffer: element i of thread t at
+// keys[i*T + t], conflict free).  For n = 8192, T = 1024 that is 15 shared-memory stages and 30
+// barriers instead of 91 of each; the fused ADC kernels, whose scoring is cheap, spent ~40 %
+// of their shared-memory traffic in the plain sort.
+template <int E>
+__device__ inline void bitonic_sort_desc_regs(unsigned long long *keys, int n) {
+    const int T = blockDim.x;
+    const int tid = threadIdx.x;
+    const int base = tid * E;
+    unsigned long long r[E];
+#pragma unroll
+    for (int i = 0; i < E; i++) r[i] = keys[base + i];
+    for (int k = 2; k <= n; k <<= 1) {
+        const bool desc_hi = (base & k) == 0;  // direction of this thread's keys when k >= 2E
+        for (int j = k >> 1; j >= 32 * E; j >>= 1) {  // partner in another warp, same lane
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < E; i++) keys[i * T + tid] = r[i];
+            __syncthreads();
+            const int ptid = tid ^ (j / E);
+            const bool take_max = ((base & j) == 0) == desc_hi;
+#pragma unroll
+            for (int i = 0; i < E; i++) {
+                const unsigned long long o = keys[i * T + ptid];
+                r[i] = take_max ? (o > r[i] ? o : r[i]) : (o < r[i] ? o : r[i]);
+            }
+        }
+        for (int j = min(k >> 1, 16 * E); j >= E; j >>= 1) {  // partner lane of the same warp
+            const int lm = j / E;
+            const bool take_max = ((base & j) == 0) == desc_hi;
+#pragma unroll
+            for (int i = 0; i < E; i++) {
+                const unsigned long long o = __shfl_xor_sync(kFull, r[i], lm);
+                r[i] = take_max ? (o > r[i] ? o : r[i]) : (o < r[i] ? o : r[i]);
+            }
+        }
+#pragma unroll
+        for (int jj = E / 2; jj >= 1; jj >>= 1) {  // inside the thread
+            if (jj <= (k >> 1)) {
+#pragma unroll
+                for (int i = 0; i < E; i++) {
+                    if ((i & jj) == 0) {
+                        const bool desc = ((base + i) & k) == 0;
+                        const unsigned long long a = r[i], b = r[i | jj];
+                        if ((a < b) == desc && a != b) {
+                            r[i] = b;
+                            r[i | jj] = a;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < E; i++) keys[base + i] = r[i];
+    __syncthreads();
+}
+
+// picks the register variant when the shape allows
+__device__ inline void block_sort_desc(unsigned long long *keys, int n) {
+    const int T = blockDim.x;
+    if ((T & 31) == 0 && n == 8 * T) bitonic_sort_desc_regs<8>(keys, n);
+    else if ((T & 31) == 0 && n == 4 * T) bitonic_sort_desc_regs<4>(keys, n);
+    else if ((T & 31) == 0 && n == 16 * T) bitonic_sort_desc_regs<16>(keys, n);
+    else bitonic_sort_desc(keys, n);
+}
+
 __device__ __forceinline__ void write_topk(const unsigned long long *keys, int n_valid, int k,
                                            float *out_s, int32_t *out_p) {
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
@@ -199,6 +270,8 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_score_kernel(const ScoreArgs 
     const int n_tile = min(a.tile, n_query - c0);
     if (!FUSE && n_tile <= 0) return;
 
+    // the scratch scores of a separate top-k pass are indexed relative to the launch's first pair
+    float *rank = a.rank_scores ? a.rank_scores - a.q_off[0] : nullptr;
     if (threadIdx.x == 0) s_next = 0;
     if (FUSE) {
         for (int i = threadIdx.x; i < a.cpad; i += kThreads) s_keys[i] = 0ull;
@@ -287,13 +360,13 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_score_kernel(const ScoreArgs 
         }
 
         // lane j now holds candidate j's score: coalesced epilogue
-        if (lane < nb && !mine && a.rank_scores) a.rank_scores[my_pair] = __int_as_float(0x7fc00000);
+        if (lane < nb && !mine && rank) rank[my_pair] = __int_as_float(0x7fc00000);
         if (lane < nb && mine) {
             float inter = my_ff;
             if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, my_lex), __fmul_rn(a.beta, my_ff));
             if (a.out_ff) a.out_ff[my_pair] = my_ff;
             if (a.out_int) a.out_int[my_pair] = inter;
-            if (a.rank_scores) a.rank_scores[my_pair] = inter;
+            if (rank) rank[my_pair] = inter;
             if (FUSE) {
                 const uint32_t pos = static_cast<uint32_t>(c0 + base + lane);
                 s_keys[pos] = topk_key(inter, pos);
@@ -352,7 +425,7 @@ __global__ void __launch_bounds__(128) ffx_score_generic_kernel(const ScoreArgs 
     if (!candidate_ok(u, a.limit, a.err, p)) {
         cnt = 0;
     } else if (!candidate_mine(u, a.base, a.count, &loc)) {
-        if (a.rank_scores) a.rank_scores[p] = __int_as_float(0x7fc00000);
+        if (a.rank_scores) a.rank_scores[p - a.q_off[0]] = __int_as_float(0x7fc00000);
         return;
     } else if (a.mode == FFX_MODE_PASSAGE) {
         start = loc;
@@ -377,7 +450,7 @@ __global__ void __launch_bounds__(128) ffx_score_generic_kernel(const ScoreArgs 
     if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, a.lex[p]), __fmul_rn(a.beta, ff));
     if (a.out_ff) a.out_ff[p] = ff;
     if (a.out_int) a.out_int[p] = inter;
-    if (a.rank_scores) a.rank_scores[p] = inter;
+    if (a.rank_scores) a.rank_scores[p - a.q_off[0]] = inter;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -386,7 +459,8 @@ __global__ void __launch_bounds__(128) ffx_score_generic_kernel(const ScoreArgs 
 // keys: shared memory when cpad <= kMaxFusedCand, else `gkeys + q*cpad` in global memory.
 // With `lex` the kernel first interpolates (ranking.py:319): s = fl(alpha*lex) + fl(beta*scores),
 // optionally storing s to out_int — `Ranking.interpolate` + `Ranking.cut` over existing scores.
-__global__ void __launch_bounds__(kThreads) ffx_topk_kernel(const float *scores, const float *lex,
+// `scores_rel` != 0: `scores` is a launch-local scratch vector whose element 0 is pair q_off[0].
+__global__ void __launch_bounds__(kThreads) ffx_topk_kernel(const float *scores, int scores_rel, const float *lex,
                                                             float alpha, float beta,
                                                             const int64_t *q_off, int k, int cpad,
                                                             unsigned long long *gkeys,
@@ -400,7 +474,7 @@ __global__ void __launch_bounds__(kThreads) ffx_topk_kernel(const float *scores,
     for (int i = threadIdx.x; i < cpad; i += blockDim.x) {
         unsigned long long key = 0ull;
         if (i < n) {
-            float s = scores[b + i];
+            float s = scores[b - (scores_rel ? q_off[0] : 0) + i];
             if (lex) {
                 s = __fadd_rn(__fmul_rn(alpha, lex[b + i]), __fmul_rn(beta, s));
                 if (out_int) out_int[b + i] = s;

@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
     off = (off + 15) & ~static_cast<size_t>(15);
     CandDesc *desc = reinterpret_cast<CandDesc *>(smem_raw + off) + warp * 64;  // [2][32]
 
+    // the scratch scores of a separate top-k pass are indexed relative to the launch's first pair
+    float *rank = a.rank_scores ? a.rank_scores - a.q_off[0] : nullptr;
     if (threadIdx.x == 0) s_next = 0;
     if (FUSE) {
         for (int i = threadIdx.x; i < n_query; i += blockDim.x) s_scores[i] = __int_as_float(0x7fc00000);
@@ -303,10 +305,10 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
                 if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, d.lex), __fmul_rn(a.beta, my_ff));
                 if (a.out_ff) a.out_ff[my_pair] = my_ff;
                 if (a.out_int) a.out_int[my_pair] = inter;
-                if (a.rank_scores) a.rank_scores[my_pair] = inter;
+                if (rank) rank[my_pair] = inter;
                 if (FUSE) s_scores[c0 + baseA + lane] = inter;
-            } else if (a.rank_scores) {
-                a.rank_scores[my_pair] = __int_as_float(0x7fc00000);
+            } else if (rank) {
+                rank[my_pair] = __int_as_float(0x7fc00000);
             }
         }
         __syncwarp();

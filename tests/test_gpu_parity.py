@@ -443,6 +443,63 @@ def test_adc_fused_topk_many_queries(ffx, M, Ks, Ds, adc_kernel):
         ffx.set_option("adc", 0)
 
 
+@pytest.mark.parametrize("adc_kernel", [2, 3])
+@pytest.mark.parametrize("lo,hi", [(4200, 5000), (2100, 4000)])
+def test_adc_fused_long_lists_use_the_register_sort(ffx, adc_kernel, lo, hi):
+    """Fused ADC kernels with thousands of candidates per query sort their keys with the
+    register / shuffle / shared-memory hybrid bitonic network (n = 4, 8 or 16 keys per thread).
+    Lexical ties are heavy (alpha close to 1), so the tie-by-position rule is exercised; the
+    ranked lists are checked against the oracle's ordering of the kernel's own scores."""
+    ffx.set_option("adc", adc_kernel)
+    try:
+        rng = np.random.default_rng(lo)
+        M, Ks, Ds = 64, 16, 2
+        idx, off, rows, n_rows, dec = adc_case(ffx, rng, M, Ks, Ds, False, True, n_docs=6000, max_psg=3)
+        nq = 150
+        qv = rng.standard_normal((nq, M * Ds)).astype(np.float32)
+        q_off, cand, pair_q = make_pairs(rng, nq, 6000, lo, hi)
+        lex = rng.integers(0, 6, len(cand)).astype(np.float32)
+        for alpha, k in ((0.999, int(np.diff(q_off).max())), (1.0, 1000), (0.1, 10)):
+            out = idx.rerank_host(fo.MODE_MAXP, qv, q_off, cand, lex, alpha, k, want_ff=True, want_int=True)
+            assert (bits(out["int"]) == bits(fo.interpolate_f32(lex, out["ff"], alpha))).all()
+            ts, tp = fo.topk_per_query(q_off, out["int"], k)
+            assert (out["topk_pos"] == tp).all() and (bits(out["topk_score"]) == bits(ts)).all()
+        idx.close()
+    finally:
+        ffx.set_option("adc", 0)
+
+
+def test_host_pipeline_matches_single_launch_opq(ffx):
+    """ffx_rerank_host cuts many queries into chunks that run on alternating streams; every
+    chunk must rotate its OPQ queries into its own buffer (a shared one is overwritten by the
+    next chunk's rotation while this chunk's tables are still being built).  All lists of the
+    pipelined host path are compared with one single launch over device buffers."""
+    import torch
+
+    rng = np.random.default_rng(77)
+    M, Ks, Ds = 32, 16, 2
+    idx, off, rows, n_rows, dec = adc_case(ffx, rng, M, Ks, Ds, True, True, n_docs=2000, max_psg=4)
+    nq, C, k = 2400, 450, 450
+    qv = rng.standard_normal((nq, M * Ds)).astype(np.float32)
+    cand = np.concatenate([rng.choice(2000, C, replace=False) for _ in range(nq)]).astype(np.int32)
+    q_off = np.arange(nq + 1, dtype=np.int64) * C
+    lex = rng.uniform(0, 20, nq * C).astype(np.float32)
+    host = idx.rerank_host(fo.MODE_AVEP, qv, q_off, cand, lex, 0.3, k, want_ff=True)
+    dev = torch.device("cuda", 0)
+    t = {n: torch.from_numpy(a).to(dev) for n, a in (("qv", qv), ("off", q_off), ("cand", cand), ("lex", lex))}
+    ff = torch.zeros(nq * C, device=dev)
+    ts = torch.empty((nq, k), device=dev)
+    tp = torch.empty((nq, k), device=dev, dtype=torch.int32)
+    torch.cuda.synchronize()
+    idx.rerank_device(fo.MODE_AVEP, t["qv"].data_ptr(), nq, t["off"].data_ptr(), t["cand"].data_ptr(),
+                      t["lex"].data_ptr(), 0.3, k, C, ff.data_ptr(), 0, ts.data_ptr(), tp.data_ptr())
+    idx.sync()
+    assert (bits(host["ff"]) == bits(ff.cpu().numpy())).all()
+    assert (host["topk_pos"] == tp.cpu().numpy()).all()
+    assert (bits(host["topk_score"]) == bits(ts.cpu().numpy())).all()
+    idx.close()
+
+
 # ------------------------------------------------------------------------------------------
 # shard merge (doc-id-range sharded corpora)
 # ------------------------------------------------------------------------------------------

@@ -1,0 +1,69 @@
+"""Stress the fused ADC path for run-to-run determinism: same inputs, repeated launches.
+Reports whether per-pair scores differ between launches (scoring race) and whether a launch's
+ranked lists disagree with the ordering of its own scores (sort race)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "fast-forward-indexes_b200"))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from fast_forward import _ffx  # noqa: E402
+
+nq = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+if len(sys.argv) > 4:
+    _ffx.set_option("adc", int(sys.argv[4]))
+dev = torch.device("cuda", 0)
+n_docs = 400_000
+cnt = bench.doc_lengths(n_docs, 6.25, seed=0)
+off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+n_rows = int(off[-1])
+M, Ks, D = 96, 256, 768
+idx = _ffx.DeviceIndex(M, capacity=n_rows, row_kind=_ffx.ROWS_PQ_U8)
+gen = torch.Generator(device=dev)
+gen.manual_seed(1)
+codes = torch.randint(0, Ks, (n_rows, M), device=dev, dtype=torch.uint8, generator=gen)
+torch.cuda.synchronize()
+idx.stage_device(0, n_rows, codes.data_ptr())
+idx.set_docs(off)
+g = torch.Generator().manual_seed(7)
+idx.set_pq(torch.randn((M, Ks, D // M), generator=g).numpy(), torch.linalg.qr(torch.randn((D, D), generator=g))[0].numpy())
+qv = torch.randn((nq, D), device=dev, generator=gen)
+bucket = n_docs // C
+perm = torch.rand((nq, C), device=dev, generator=gen).argsort(dim=1)
+cand = (perm * bucket + torch.randint(0, bucket, (nq, C), device=dev, generator=gen)).to(torch.int32).view(-1).contiguous()
+lex = (torch.rand((nq * C,), device=dev, generator=gen) * 20).contiguous()
+q_off = (torch.arange(nq + 1, device=dev, dtype=torch.int64) * C).contiguous()
+runs = []
+for r in range(reps):
+    it = torch.zeros(nq * C, device=dev)
+    ts = torch.empty((nq, C), device=dev)
+    tp = torch.empty((nq, C), device=dev, dtype=torch.int32)
+    torch.cuda.synchronize()
+    idx.rerank_device(4, qv.data_ptr(), nq, q_off.data_ptr(), cand.data_ptr(), lex.data_ptr(), 0.1, C, C,
+                      0, it.data_ptr(), ts.data_ptr(), tp.data_ptr())
+    idx.sync()
+    own = it.view(nq, C).gather(1, tp.long().clamp(min=0))
+    bad_sort = int((~torch.equal(own, ts)) or bool((ts[:, 1:] > ts[:, :-1]).any()))
+    perm_ok = bool((tp.long().sort(dim=1).values == torch.arange(C, device=dev)).all())
+    runs.append((it, ts, tp))
+    d_it = int((it != runs[0][0]).sum())
+    d_tp = int((tp != runs[0][2]).any(dim=1).sum())
+    print(f"run {r}: lists inconsistent with own scores: {bad_sort}, permutation ok: {perm_ok}, "
+          f"pairs differing from run 0: {d_it}, queries with different lists: {d_tp}", flush=True)
+
+# ---- pipelined host path (query chunks on alternating streams) vs the single device launch
+h = {"qv": qv.cpu().numpy(), "off": q_off.cpu().numpy(), "cand": cand.cpu().numpy(), "lex": lex.cpu().numpy()}
+ref_tp = runs[0][2].cpu().numpy()
+ref_ts = runs[0][1].cpu().numpy()
+for r in range(reps):
+    out = idx.rerank_host(4, h["qv"], h["off"], h["cand"], h["lex"], 0.1, C, want_ff=False, want_int=True)
+    bad = np.flatnonzero((out["topk_pos"] != ref_tp).any(axis=1))
+    d_it = np.flatnonzero(out["int"] != runs[0][0].cpu().numpy())
+    print(f"host run {r}: queries with different lists: {len(bad)} {bad[:12].tolist()}, pairs with different scores: "
+          f"{len(d_it)} first at pair {d_it[:3].tolist()} (queries {(d_it[:3] // C).tolist()})", flush=True)
