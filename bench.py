@@ -70,6 +70,9 @@ def parse():
                     help="shrink docs and queries (debug only; the line says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--alpha", type=float, default=0.1)
+    ap.add_argument("--emulate-shards", type=int, default=0,
+                    help="single GPU: hold shard 0 of this many doc-id-range shards and time the local step only "
+                         "(profiling the sharded kernel without the other GPUs; the line says so)")
     return ap.parse_args()
 
 
@@ -249,11 +252,14 @@ def run_ffx(args, wl):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    emulate = args.emulate_shards if world == 1 and wl.get("sharded") else 0
+    if emulate:
+        world = emulate  # sizes and shard plan of an `emulate`-GPU job; only rank 0's local work runs
     if _ffx.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: libffx has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not emulate:
         dist.init_process_group("nccl", device_id=dev)
 
     mode, sharded, pq = MODES[wl["mode"]], bool(wl.get("sharded")), wl["kind"] == "opq"
@@ -345,7 +351,7 @@ def run_ffx(args, wl):
 
     def step():
         if sharded:
-            return reranker.rerank(mode, qv, q_off, cand, lex, args.alpha, k, cands)
+            return reranker.rerank(mode, qv, q_off, cand, lex, args.alpha, k, cands, gather_result=False)
         idx.rerank_device(mode, qv.data_ptr(), nq, q_off.data_ptr(), cand.data_ptr(), lex.data_ptr(),
                           args.alpha, k, cands, 0, 0, topk_s.data_ptr(), topk_p.data_ptr(),
                           stream.cuda_stream)
@@ -353,7 +359,7 @@ def run_ffx(args, wl):
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
+        if world > 1 and not emulate:
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -378,8 +384,9 @@ def run_ffx(args, wl):
     # sanity on the timed output: ranked lists are sorted, positions distinct and in range
     s_host = out_s[:4].cpu().numpy()
     p_host = out_p[:4].cpu().numpy()
-    assert (np.diff(s_host, axis=1) <= 0).all(), "top-k not sorted"
-    assert all(len(set(r.tolist())) == k for r in p_host) and p_host.min() >= 0 and p_host.max() < cands
+    if not emulate:  # a lone shard's lists are padded with (-inf, -1)
+        assert (np.diff(s_host, axis=1) <= 0).all(), "top-k not sorted"
+        assert all(len(set(r.tolist())) == k for r in p_host) and p_host.min() >= 0 and p_host.max() < cands
 
     # ---- e2e: host buffers through ffx_rerank_host (H2D + kernel + D2H inside the timed region)
     e2e_s = h2d = d2h = None
@@ -412,7 +419,7 @@ def run_ffx(args, wl):
         d2h = h_ts.array.nbytes + h_tp.array.nbytes
 
     times = torch.tensor([total_ms, (e2e_s or 0.0) * 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
+    if world > 1 and not emulate:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = times.tolist()
 
@@ -435,13 +442,15 @@ def run_ffx(args, wl):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 codes + f32 LUT" if pq else "f32",
             "data": "synthetic",
             "config": {
-                "workload": args.workload if args.scale == 1 else f"{args.workload} (SCALED x{args.scale}: debug)",
+                "workload": (args.workload if args.scale == 1 else f"{args.workload} (SCALED x{args.scale}: debug)") +
+                (f" (EMULATED: local step of shard 0 of {emulate} on one GPU, no exchange; profiling only)"
+                 if emulate else ""),
                 "mode": wl["mode"], "dim": DIM, "docs": n_docs, "passages": total_rows,
                 "index_gb_per_gpu": n_rows * row_bytes / 1e9,
                 "queries": nq if sharded else f"{nq} per GPU", "candidates_per_query": cands, "cut_k": k,
                 "alpha": args.alpha,
-                "parallelism": (f"doc-id-range shards x{world}: local fused top-k, one NCCL all-gather of "
-                                f"[nq,k] lists, ffx_merge_topk" if sharded else
+                "parallelism": (f"doc-id-range shards x{world}: local fused top-k, one NCCL all-to-all of the "
+                                f"[nq,k] lists to the queries' owner ranks, ffx_merge_topk there" if sharded else
                                 f"query-dp{world} (replicated index, no data-path collective)"),
                 "l2": "inputs larger than L2 (index %.1f GB/GPU, %.1f GB touched per step per GPU)" % (
                     n_rows * row_bytes / 1e9, algo_bytes / 1e9),
@@ -465,7 +474,7 @@ def run_ffx(args, wl):
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
                                     "sample": sample, "seconds": round(dt, 2)}
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if world > 1 and not emulate:
         dist.barrier()
         dist.destroy_process_group()
     idx.close()

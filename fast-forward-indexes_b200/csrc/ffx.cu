@@ -282,10 +282,13 @@ int ring_slots(int cpad_scores, int warps, int row_bytes, int ctas_per_sm) {
     return ns;
 }
 
-ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes) {
+ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse) {
     ScorePlan p;
+    // candidates a warp publishes per batch: few rows per candidate (single-row modes, or a shard
+    // that owns only a fraction of the candidates) want the larger batch so that the row ring
+    // always has something to prefetch
     const bool one_row = mode == FFX_MODE_PASSAGE || mode == FFX_MODE_FIRSTP;
-    p.batch = g_tune.batch > 0 ? std::min(32, g_tune.batch) : (one_row ? 32 : 16);
+    p.batch = g_tune.batch > 0 ? std::min(32, g_tune.batch) : (one_row || sparse ? 32 : 16);
     if (g_tune.kernel == 1) return p;
     const int keys = fuse ? cpad : 0;
     if (g_tune.tma_warps > 0) {  // explicit shape (sweeps)
@@ -885,7 +888,7 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     const float *topk_src = rank_scores ? rank_scores : out_int;  // input of a separate top-k pass
 
     // tiles: split a query over several CTAs when there are few queries
-    const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4) : ScorePlan{};
+    const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4, idx->sharded) : ScorePlan{};
     int tiles = 1, tile = static_cast<int>(std::max<int64_t>(max_cand, 1));
     if (!fuse) {
         // enough CTAs for ~2 waves at the plan's occupancy, but a tile keeps every warp of its

@@ -290,11 +290,7 @@ __global__ void __launch_bounds__(kAdcWarpThreads, 1) ffx_adc_warp_kernel(const 
         // the tables are dead: build the 64-bit sort keys over them
         __syncthreads();
         unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(s_lut);
-        for (int i = threadIdx.x; i < w.cpad; i += blockDim.x)
-            s_keys[i] = i < n_query ? topk_key(s_scores[i], static_cast<uint32_t>(i)) : 0ull;
-        __syncthreads();
-        block_sort_desc(s_keys, w.cpad);
-        write_topk(s_keys, n_query, w.k, w.topk_score + q_idx * w.k, w.topk_pos + q_idx * w.k);
+        rank_scores_topk(s_scores, n_query, s_keys, w.k, w.topk_score + q_idx * w.k, w.topk_pos + q_idx * w.k);
     }
 }
 

@@ -306,11 +306,7 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
         // keys over them (NaN score = pair of another shard = not ranked)
         __syncthreads();
         unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(adc_smem);
-        for (int i = threadIdx.x; i < w.cpad; i += blockDim.x)
-            s_keys[i] = i < n_query ? topk_key(s_scores[i], static_cast<uint32_t>(i)) : 0ull;
-        __syncthreads();
-        block_sort_desc(s_keys, w.cpad);
-        write_topk(s_keys, n_query, w.k, w.topk_score + q_idx * w.k, w.topk_pos + q_idx * w.k);
+        rank_scores_topk(s_scores, n_query, s_keys, w.k, w.topk_score + q_idx * w.k, w.topk_pos + q_idx * w.k);
     }
 }
 

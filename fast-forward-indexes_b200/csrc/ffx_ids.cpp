@@ -1,0 +1,278 @@
+// ffx_ids.cpp — host-side id coding of libffx (plain C++17, no CUDA).
+//
+// The reference keeps two Python dicts per index (`_doc_id_to_idx: dict[str, list[int]]`,
+// `_psg_id_to_idx: dict[str, int]`, index/memory.py:46-47,84-95, rebuilt by an O(N) Python
+// loop in index/disk.py:408-417) and hashes every candidate id of every call again inside
+// pandas merges on string keys (index/base.py:291-298,314; index/util.py:29-41).  Here an id
+// dictionary is one open-addressing hash table over a byte arena; ids cross the ABI in Arrow
+// layout (int64 offsets into a UTF-8 byte buffer + optional validity bitmap), so a pandas /
+// pyarrow string column is looked up in place, without creating Python objects, on all host
+// cores.  What goes to the GPU afterwards is integers only.
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ffx.h"
+
+extern "C" int ffx_set_error_message(int code, const char *msg);  // ffx.cu: fills ffx_last_error
+
+struct ffx_dict {
+    // slot: high 32 bits = hash tag, low 32 bits = entry index + 1 (0 = empty)
+    std::vector<uint64_t> slots;
+    uint64_t mask = 0;
+    std::vector<int64_t> key_off{0};  // entry e occupies arena[key_off[e], key_off[e+1])
+    std::vector<char> arena;
+    std::vector<int64_t> values;
+};
+
+namespace {
+
+int fail(int code, const std::string &msg) { return ffx_set_error_message(code, msg.c_str()); }
+
+inline uint64_t mix(uint64_t h) {
+    h ^= h >> 32;
+    h *= 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+    return h;
+}
+
+inline uint64_t hash_bytes(const char *p, int64_t n) {
+    uint64_t h = 0x243F6A8885A308D3ull ^ (static_cast<uint64_t>(n) * 0xFF51AFD7ED558CCDull);
+    while (n >= 8) {
+        uint64_t w;
+        memcpy(&w, p, 8);
+        h = mix(h ^ w);
+        p += 8;
+        n -= 8;
+    }
+    if (n > 0) {
+        uint64_t w = 0;
+        memcpy(&w, p, static_cast<size_t>(n));
+        h = mix(h ^ w);
+    }
+    return mix(h);
+}
+
+inline bool is_valid(const uint8_t *validity, int64_t bit_offset, int64_t i) {
+    if (!validity) return true;
+    const int64_t b = bit_offset + i;
+    return (validity[b >> 3] >> (b & 7)) & 1;
+}
+
+// entry index of the key, or -1
+inline int64_t find(const ffx_dict *d, const char *p, int64_t n, uint64_t h) {
+    if (d->slots.empty()) return -1;
+    const uint64_t tag = h >> 32;
+    for (uint64_t s = h & d->mask;; s = (s + 1) & d->mask) {
+        const uint64_t slot = d->slots[s];
+        if (slot == 0) return -1;
+        if ((slot >> 32) == tag) {
+            const int64_t e = static_cast<int64_t>(slot & 0xffffffffu) - 1;
+            const int64_t b = d->key_off[static_cast<size_t>(e)];
+            if (d->key_off[static_cast<size_t>(e) + 1] - b == n && memcmp(d->arena.data() + b, p, static_cast<size_t>(n)) == 0)
+                return e;
+        }
+    }
+}
+
+void rehash(ffx_dict *d, uint64_t capacity) {
+    d->slots.assign(capacity, 0);
+    d->mask = capacity - 1;
+    const int64_t n = static_cast<int64_t>(d->values.size());
+    for (int64_t e = 0; e < n; e++) {
+        const int64_t b = d->key_off[static_cast<size_t>(e)];
+        const uint64_t h = hash_bytes(d->arena.data() + b, d->key_off[static_cast<size_t>(e) + 1] - b);
+        uint64_t s = h & d->mask;
+        while (d->slots[s] != 0) s = (s + 1) & d->mask;
+        d->slots[s] = ((h >> 32) << 32) | static_cast<uint64_t>(e + 1);
+    }
+}
+
+void reserve_for(ffx_dict *d, int64_t extra) {
+    const uint64_t need = static_cast<uint64_t>(d->values.size() + extra) * 2 + 16;
+    uint64_t cap = d->slots.empty() ? 1024 : d->slots.size();
+    while (cap < need) cap <<= 1;
+    if (cap != d->slots.size()) rehash(d, cap);
+}
+
+// appends the key; caller guarantees it is absent and that capacity is reserved
+inline int64_t put(ffx_dict *d, const char *p, int64_t n, uint64_t h, int64_t value) {
+    const int64_t e = static_cast<int64_t>(d->values.size());
+    d->arena.insert(d->arena.end(), p, p + n);
+    d->key_off.push_back(static_cast<int64_t>(d->arena.size()));
+    d->values.push_back(value);
+    uint64_t s = h & d->mask;
+    while (d->slots[s] != 0) s = (s + 1) & d->mask;
+    d->slots[s] = ((h >> 32) << 32) | static_cast<uint64_t>(e + 1);
+    return e;
+}
+
+int worker_count(int requested, int64_t n) {
+    int t = requested > 0 ? requested : static_cast<int>(std::thread::hardware_concurrency());
+    t = std::max(1, std::min(t, 64));
+    return static_cast<int>(std::min<int64_t>(t, std::max<int64_t>(1, n / 4096)));
+}
+
+template <class F>
+void parallel_ranges(int64_t n, int threads, F &&body) {
+    if (threads <= 1) {
+        body(0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const int64_t step = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) {
+        const int64_t lo = t * step, hi = std::min(n, lo + step);
+        if (lo >= hi) break;
+        pool.emplace_back([&body, lo, hi] { body(lo, hi); });
+    }
+    for (auto &th : pool) th.join();
+}
+
+bool bad_strings(const int64_t *offsets, const char *data, int64_t n) {
+    return n < 0 || (n > 0 && (!offsets || (!data && offsets[n] > offsets[0])));
+}
+
+}  // namespace
+
+extern "C" {
+
+int ffx_dict_create(ffx_dict **out) {
+    if (!out) return fail(FFX_ERR_INVALID, "ffx_dict_create: out is NULL");
+    *out = new ffx_dict();
+    return FFX_OK;
+}
+
+int ffx_dict_destroy(ffx_dict *d) {
+    delete d;
+    return FFX_OK;
+}
+
+int64_t ffx_dict_size(const ffx_dict *d) { return d ? static_cast<int64_t>(d->values.size()) : -1; }
+int64_t ffx_dict_key_bytes(const ffx_dict *d) { return d ? static_cast<int64_t>(d->arena.size()) : -1; }
+
+int ffx_dict_insert_ordinal(ffx_dict *d, const int64_t *offsets, const char *data, const uint8_t *validity,
+                            int64_t bit_offset, int64_t n, int64_t *out) {
+    if (!d || bad_strings(offsets, data, n)) return fail(FFX_ERR_INVALID, "ffx_dict_insert_ordinal: bad arguments");
+    if (static_cast<uint64_t>(d->values.size()) + static_cast<uint64_t>(n) > 0xfffffff0ull)
+        return fail(FFX_ERR_UNSUPPORTED, "ffx_dict_insert_ordinal: more than 2^32 keys");
+    reserve_for(d, n);
+    for (int64_t i = 0; i < n; i++) {
+        if (!is_valid(validity, bit_offset, i)) {
+            if (out) out[i] = -1;
+            continue;
+        }
+        const char *p = data + offsets[i];
+        const int64_t len = offsets[i + 1] - offsets[i];
+        const uint64_t h = hash_bytes(p, len);
+        int64_t e = find(d, p, len, h);
+        if (e < 0) e = put(d, p, len, h, static_cast<int64_t>(d->values.size()));
+        if (out) out[i] = d->values[static_cast<size_t>(e)];
+    }
+    return FFX_OK;
+}
+
+int ffx_dict_insert_unique(ffx_dict *d, const int64_t *offsets, const char *data, const uint8_t *validity,
+                           int64_t bit_offset, int64_t n, int64_t first_value, int dry_run, int64_t *first_dup) {
+    if (!d || bad_strings(offsets, data, n) || !first_dup)
+        return fail(FFX_ERR_INVALID, "ffx_dict_insert_unique: bad arguments");
+    *first_dup = -1;
+    if (static_cast<uint64_t>(d->values.size()) + static_cast<uint64_t>(n) > 0xfffffff0ull)
+        return fail(FFX_ERR_UNSUPPORTED, "ffx_dict_insert_unique: more than 2^32 keys");
+    // insert, remembering how to undo: a duplicate (against the dictionary or inside the batch)
+    // leaves the dictionary exactly as it was
+    const size_t keep_n = d->values.size(), keep_bytes = d->arena.size();
+    reserve_for(d, n);
+    for (int64_t i = 0; i < n; i++) {
+        if (!is_valid(validity, bit_offset, i)) continue;
+        const char *p = data + offsets[i];
+        const int64_t len = offsets[i + 1] - offsets[i];
+        const uint64_t h = hash_bytes(p, len);
+        if (find(d, p, len, h) >= 0) {
+            *first_dup = i;
+            break;
+        }
+        put(d, p, len, h, first_value + i);
+    }
+    if (*first_dup >= 0 || dry_run) {
+        if (d->values.size() != keep_n) {
+            d->values.resize(keep_n);
+            d->key_off.resize(keep_n + 1);
+            d->arena.resize(keep_bytes);
+            rehash(d, d->slots.size());
+        }
+        if (*first_dup >= 0) return fail(FFX_ERR_STATE, "ffx_dict_insert_unique: key already present");
+    }
+    return FFX_OK;
+}
+
+int ffx_dict_lookup(const ffx_dict *d, const int64_t *offsets, const char *data, const uint8_t *validity,
+                    int64_t bit_offset, int64_t n, int32_t *out, int64_t *first_missing, int n_threads) {
+    if (!d || bad_strings(offsets, data, n) || (n > 0 && !out))
+        return fail(FFX_ERR_INVALID, "ffx_dict_lookup: bad arguments");
+    std::atomic<int64_t> missing{INT64_MAX};
+    parallel_ranges(n, worker_count(n_threads, n), [&](int64_t lo, int64_t hi) {
+        constexpr int kBatch = 16;  // hash a batch, prefetch its slots, then probe
+        uint64_t hs[kBatch];
+        int64_t local_missing = INT64_MAX;
+        for (int64_t b = lo; b < hi; b += kBatch) {
+            const int m = static_cast<int>(std::min<int64_t>(kBatch, hi - b));
+            for (int j = 0; j < m; j++) {
+                const int64_t i = b + j;
+                hs[j] = hash_bytes(data + offsets[i], offsets[i + 1] - offsets[i]);
+                if (!d->slots.empty()) __builtin_prefetch(&d->slots[hs[j] & d->mask]);
+            }
+            for (int j = 0; j < m; j++) {
+                const int64_t i = b + j;
+                int64_t e = -1;
+                if (is_valid(validity, bit_offset, i))
+                    e = find(d, data + offsets[i], offsets[i + 1] - offsets[i], hs[j]);
+                if (e < 0) {
+                    out[i] = -1;
+                    local_missing = std::min(local_missing, i);
+                } else {
+                    out[i] = static_cast<int32_t>(static_cast<uint32_t>(d->values[static_cast<size_t>(e)]));
+                }
+            }
+        }
+        int64_t cur = missing.load();
+        while (local_missing < cur && !missing.compare_exchange_weak(cur, local_missing)) {
+        }
+    });
+    if (first_missing) *first_missing = missing.load() == INT64_MAX ? -1 : missing.load();
+    return FFX_OK;
+}
+
+int ffx_dict_export(const ffx_dict *d, int64_t *offsets, char *data, int64_t *values) {
+    if (!d || !offsets) return fail(FFX_ERR_INVALID, "ffx_dict_export: bad arguments");
+    memcpy(offsets, d->key_off.data(), d->key_off.size() * sizeof(int64_t));
+    if (data && !d->arena.empty()) memcpy(data, d->arena.data(), d->arena.size());
+    if (values && !d->values.empty()) memcpy(values, d->values.data(), d->values.size() * sizeof(int64_t));
+    return FFX_OK;
+}
+
+int ffx_csr_build(const int64_t *row_doc, int64_t n_rows, int64_t n_docs, int64_t *doc_off, int64_t *doc_rows) {
+    if (n_rows < 0 || n_docs < 0 || !doc_off || (n_rows > 0 && !row_doc))
+        return fail(FFX_ERR_INVALID, "ffx_csr_build: bad arguments");
+    std::fill(doc_off, doc_off + n_docs + 1, 0);
+    for (int64_t r = 0; r < n_rows; r++) {
+        const int64_t d = row_doc[r];
+        if (d >= n_docs) return fail(FFX_ERR_INVALID, "ffx_csr_build: document ordinal out of range");
+        if (d >= 0) doc_off[d + 1]++;
+    }
+    for (int64_t d = 0; d < n_docs; d++) doc_off[d + 1] += doc_off[d];
+    if (doc_rows) {
+        std::vector<int64_t> cursor(doc_off, doc_off + n_docs);
+        for (int64_t r = 0; r < n_rows; r++) {  // increasing r: rows of a document stay in insertion order
+            const int64_t d = row_doc[r];
+            if (d >= 0) doc_rows[cursor[static_cast<size_t>(d)]++] = r;
+        }
+    }
+    return FFX_OK;
+}
+
+}  // extern "C"

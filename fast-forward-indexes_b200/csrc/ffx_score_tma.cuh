@@ -336,11 +336,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
         // every row this CTA requested has been consumed, the ring is idle: build the sort keys
         // in it (NaN = pair of another shard or NaN score = not ranked)
         __syncthreads();
-        for (int i = threadIdx.x; i < a.cpad; i += blockDim.x)
-            s_keys[i] = i < n_query ? topk_key(s_scores[i], static_cast<uint32_t>(i)) : 0ull;
-        __syncthreads();
-        bitonic_sort_desc(s_keys, a.cpad);
-        write_topk(s_keys, n_query, a.k, a.topk_score + q_idx * a.k, a.topk_pos + q_idx * a.k);
+        rank_scores_topk(s_scores, n_query, s_keys, a.k, a.topk_score + q_idx * a.k, a.topk_pos + q_idx * a.k);
     }
 }
 

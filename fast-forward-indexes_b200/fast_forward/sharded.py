@@ -8,12 +8,16 @@ receives the FULL integer-coded candidate lists (global document ordinals) and
   1. scores the pairs whose document it owns — the kernel skips foreign pairs, so there is no
      host-side bucketing and positions stay positions in the full candidate block,
   2. interpolates and takes a LOCAL top-k per query (same fused kernel),
-  3. exchanges the `[nq, k]` (score, position) lists with ONE all-gather and merges them with
-     `ffx_merge_topk`.
+  3. exchanges the `[nq, k]` (score, position) lists with ONE all-to-all: every query has an
+     owner rank (contiguous query ranges), which receives that query's list from every shard
+     and merges them with `ffx_merge_topk`.  The merged lists stay with their owners
+     (`gather_result=False`, what a serving system wants) or are all-gathered so that every
+     rank holds the full result.
 
 Exact: interpolation is per pair and the top-k of a union is the top-k of the per-shard
-top-ks.  Exchange volume is `world * nq * k * 8` bytes (C5, k=1000: 6.4 GB in total against
-9.6 TB of HBM traffic), so NVLink is never the bound.  When the semantic score of every pair
+top-ks.  Each rank sends and receives `nq * k * 8` bytes (C5, k=1000, 8 GPUs: 0.8 GB per rank
+against 1.2 TB of HBM traffic per rank) and merges `nq / world` queries — an all-gather would
+move and merge `world` times as much.  When the semantic score of every pair
 is wanted instead, each rank writes only its own pairs into a zeroed buffer and one
 all-reduce(SUM) assembles the vector (`x + 0 == x` exactly).
 
@@ -76,11 +80,40 @@ class ShardedReranker:
                         score.data_ptr(), pos.data_ptr(), stream)
         return score, pos
 
+    # -- the exchange ---------------------------------------------------------------------------
+    def owner_bounds(self, nq: int) -> list[int]:
+        """Query q is merged on the rank r with bounds[r] <= q < bounds[r+1]."""
+        return [nq * r // self.world for r in range(self.world + 1)]
+
+    def _to_owners(self, local, bounds):
+        """`local` [nq, k] on every rank -> [world, mine, k]: slice [bounds[rank], bounds[rank+1])
+        of every rank's `local`.  One all-to-all on NCCL; gloo (CPU tests) has none, so one
+        gather per owner."""
+        import torch
+        import torch.distributed as dist
+
+        mine = bounds[self.rank + 1] - bounds[self.rank]
+        recv = torch.empty((self.world, mine) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_to_all_single(recv.view((self.world * mine,) + tuple(local.shape[1:])), local.contiguous(),
+                                   output_split_sizes=[mine] * self.world,
+                                   input_split_sizes=[bounds[r + 1] - bounds[r] for r in range(self.world)],
+                                   group=self.group)
+        else:
+            for r in range(self.world):
+                part = local[bounds[r]:bounds[r + 1]].contiguous()
+                dist.gather(part, list(recv.unbind(0)) if r == self.rank else None,
+                            dst=dist.get_global_rank(self.group, r) if self.group is not None else r,
+                            group=self.group)
+        return recv
+
     # -- public ---------------------------------------------------------------------------------
-    def rerank(self, mode: int, qvecs, q_off, cand, lex, alpha: float, k: int, max_cand: int):
-        """Global per-query top-k `(score [nq,k], position [nq,k])` on every rank.  All inputs
-        are identical on all ranks: qvecs f32 [nq,D], q_off i64 [nq+1], cand i32 [n] (GLOBAL
-        ordinals), lex f32 [n] or None."""
+    def rerank(self, mode: int, qvecs, q_off, cand, lex, alpha: float, k: int, max_cand: int,
+               gather_result: bool = True):
+        """Global per-query top-k `(score [nq,k], position [nq,k])`.  All inputs are identical on
+        all ranks: qvecs f32 [nq,D], q_off i64 [nq+1], cand i32 [n] (GLOBAL ordinals), lex f32 [n]
+        or None.  With `gather_result=False` every rank returns only the lists of the queries it
+        owns (`owner_bounds(nq)`), skipping the final all-gather."""
         import torch
         import torch.distributed as dist
 
@@ -88,12 +121,21 @@ class ShardedReranker:
         score, pos = self._local_topk(mode, qvecs, q_off, cand, lex, alpha, k, max_cand, stream)
         if self.world == 1:
             return score, pos
-        all_score = torch.empty((self.world,) + tuple(score.shape), dtype=score.dtype, device=score.device)
-        all_pos = torch.empty((self.world,) + tuple(pos.shape), dtype=pos.dtype, device=pos.device)
-        # slices of one contiguous [world, nq, k] buffer: NCCL gathers in place, gloo works too
-        dist.all_gather(list(all_score.unbind(0)), score.contiguous(), group=self.group)
-        dist.all_gather(list(all_pos.unbind(0)), pos.contiguous(), group=self.group)
-        return self._merge(all_score, all_pos, k, stream)
+        nq = score.shape[0]
+        bounds = self.owner_bounds(nq)
+        mine_s, mine_p = self._merge(self._to_owners(score, bounds), self._to_owners(pos, bounds), k, stream)
+        if not gather_result:
+            return mine_s, mine_p
+        # owners hold unequal slices when world does not divide nq: gather padded slices
+        cap = max(bounds[r + 1] - bounds[r] for r in range(self.world))
+        out = []
+        for part, fill in ((mine_s, float("-inf")), (mine_p, -1)):
+            padded = torch.full((cap, k), fill, dtype=part.dtype, device=part.device)
+            padded[:part.shape[0]] = part
+            everyone = torch.empty((self.world, cap, k), dtype=part.dtype, device=part.device)
+            dist.all_gather(list(everyone.unbind(0)), padded, group=self.group)
+            out.append(torch.cat([everyone[r, :bounds[r + 1] - bounds[r]] for r in range(self.world)]))
+        return out[0], out[1]
 
     def scores(self, mode: int, qvecs, q_off, cand, max_cand: int):
         """Semantic score of EVERY pair on every rank (plain `Index.__call__` over a sharded

@@ -106,7 +106,7 @@ def _gloo_worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.default_rng(3)  # same data on every rank
-    n_docs, nq, C, k, alpha = 200, 6, 50, 8, 0.25
+    n_docs, nq, C, k, alpha = 200, 7, 50, 8, 0.25  # 7 queries over 2 ranks: unequal owner slices
     cnt = rng.integers(1, 5, n_docs)
     off = np.concatenate([[0], np.cumsum(cnt)])
     vec = rng.standard_normal((off[-1], 16)).astype(np.float32)
@@ -149,6 +149,11 @@ def _gloo_worker(rank, world, port, out_dir):
     ff = fo.score_pairs(vec, off, np.arange(off[-1]), pair_q, cand, qv, fo.MODE_MAXP)
     ws, wp = fo.topk_per_query(q_off, fo.interpolate_f32(lex, ff, alpha), k)
     ok = (p.numpy() == wp).all() and (s.numpy().view(np.uint32) == ws.view(np.uint32)).all()
+    # owner-partitioned result: this rank's query slice only, no final all-gather
+    s2, p2 = sh.rerank(fo.MODE_MAXP, t(qv), t(q_off), t(cand), t(lex), alpha, k, C, gather_result=False)
+    b = sh.owner_bounds(nq)
+    ok = ok and b[0] == 0 and b[-1] == nq and (p2.numpy() == wp[b[rank]:b[rank + 1]]).all() and \
+        (s2.numpy().view(np.uint32) == ws[b[rank]:b[rank + 1]].view(np.uint32)).all()
     open(os.path.join(out_dir, f"rank{rank}.{'ok' if ok else 'bad'}"), "w").close()
     dist.destroy_process_group()
 
