@@ -34,6 +34,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: NCCL's own version / debug lines go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "fast-forward-indexes_b200")
 sys.path.insert(0, PKG)

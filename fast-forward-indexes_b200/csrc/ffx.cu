@@ -461,6 +461,9 @@ extern "C" {
 
 int ffx_abi_version(void) { return FFX_ABI_VERSION; }
 
+// used by the other translation units of the library (ffx_ids.cpp) to report through ffx_last_error
+int ffx_set_error_message(int code, const char *msg) { return fail(code, "%s", msg ? msg : ""); }
+
 const char *ffx_last_error(void) { return g_err.c_str(); }
 
 int ffx_set_option(const char *name, int value) {

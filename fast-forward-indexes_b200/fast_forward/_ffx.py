@@ -48,6 +48,15 @@ SYMBOLS = {
     "ffx_interpolate_topk_host": (_I, [_P, _P, _P, _L, _P, _D, _I, _P, _P, _P]),
     "ffx_merge_topk": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _P]),
     "ffx_launch_count": (_L, []),
+    "ffx_dict_create": (_I, [C.POINTER(_P)]),
+    "ffx_dict_destroy": (_I, [_P]),
+    "ffx_dict_size": (_L, [_P]),
+    "ffx_dict_key_bytes": (_L, [_P]),
+    "ffx_dict_insert_ordinal": (_I, [_P, _P, _P, _P, _L, _L, _P]),
+    "ffx_dict_insert_unique": (_I, [_P, _P, _P, _P, _L, _L, _L, _I, C.POINTER(_L)]),
+    "ffx_dict_lookup": (_I, [_P, _P, _P, _P, _L, _L, _P, C.POINTER(_L), _I]),
+    "ffx_dict_export": (_I, [_P, _P, _P, _P]),
+    "ffx_csr_build": (_I, [_P, _L, _L, _P, _P]),
 }
 
 _lib = None

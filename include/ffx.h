@@ -122,6 +122,42 @@ int ffx_index_set_shard(ffx_index *idx, int64_t doc_base, int64_t global_docs, i
 int ffx_index_set_pq(ffx_index *idx, int M, int Ks, int Ds, const float *codewords,
                      const float *R);
 
+/* ---- host-side id coding ------------------------------------------------------------- */
+/* Replaces the id dictionaries of the reference (`_doc_id_to_idx: dict[str, list[int]]`,
+ * `_psg_id_to_idx: dict[str, int]`, index/memory.py:46-47,84-95; rebuilt by an O(N) Python loop
+ * in index/disk.py:408-417) and the hashing of every candidate id of every call inside pandas
+ * merges on string keys (index/base.py:291-298,314; index/util.py:29-41).  Pure host code (no
+ * CUDA device needed).  Strings cross the ABI in Arrow layout: string i is
+ * data[offsets[i] .. offsets[i+1]) (UTF-8), `validity` is an optional bitmap (bit
+ * bit_offset + i, LSB first, NULL = all valid) — a pandas / pyarrow string column is coded in
+ * place, on all host cores, without creating Python objects. */
+typedef struct ffx_dict ffx_dict;
+int ffx_dict_create(ffx_dict **out);
+int ffx_dict_destroy(ffx_dict *d);
+int64_t ffx_dict_size(const ffx_dict *d);       /* number of keys */
+int64_t ffx_dict_key_bytes(const ffx_dict *d);  /* total length of all keys */
+/* Document ids (index/memory.py:86-88): a new key gets the next ordinal (= number of keys so
+ * far), a known key keeps its ordinal; out[i] = ordinal of string i, -1 for a null. */
+int ffx_dict_insert_ordinal(ffx_dict *d, const int64_t *offsets, const char *data, const uint8_t *validity,
+                            int64_t bit_offset, int64_t n, int64_t *out);
+/* Passage ids (index/memory.py:90-95): string i gets value first_value + i (its row number);
+ * nulls are skipped.  A key that already exists — in the dictionary or earlier in the batch —
+ * is an error: FFX_ERR_STATE, *first_dup = its index, and the dictionary is left unchanged
+ * ("Passage ID ... already exists").  dry_run != 0 only checks. */
+int ffx_dict_insert_unique(ffx_dict *d, const int64_t *offsets, const char *data, const uint8_t *validity,
+                           int64_t bit_offset, int64_t n, int64_t first_value, int dry_run, int64_t *first_dup);
+/* Replaces index/util.py:29-41 for a whole column: out[i] = value of string i (as the int32
+ * candidate ffx_rerank takes), -1 when absent or null; *first_missing = lowest such i or -1
+ * (the id IndexError names).  n_threads 0 = all host cores. */
+int ffx_dict_lookup(const ffx_dict *d, const int64_t *offsets, const char *data, const uint8_t *validity,
+                    int64_t bit_offset, int64_t n, int32_t *out, int64_t *first_missing, int n_threads);
+/* Keys in insertion order (Arrow layout; offsets[size+1], data[key_bytes]) and their values. */
+int ffx_dict_export(const ffx_dict *d, int64_t *offsets, char *data, int64_t *values);
+/* doc -> rows CSR from the per-row document ordinals (-1 = row without document id): counting
+ * sort, rows of a document in increasing (= insertion) order.  doc_off[n_docs+1]; doc_rows may
+ * be NULL to get the offsets only. */
+int ffx_csr_build(const int64_t *row_doc, int64_t n_rows, int64_t n_docs, int64_t *doc_off, int64_t *doc_rows);
+
 /* ---- the hot path ----------------------------------------------------------------- */
 /* Replaces, in one pass, `Index._compute_scores` (index/base.py:279-314) including
  * `_get_vectors` (index/memory.py:139-140), `Ranking.interpolate`'s arithmetic
