@@ -1,22 +1,29 @@
 """Host id maps + the HBM row store shared by the index back-ends.
 
-The id-mapping contract is the reference's (index/util.py:12-42, index/memory.py:84-95):
-`doc_rows[id]` lists a document's rows in insertion order, `psg_row[id]` is a passage's single
-row, an id that resolves to no row raises IndexError.  The maps stay on the host (id strings
-never cross the C ABI); what goes to the device is their integer form — a CSR
-document-ordinal -> rows table (ffx_index_set_docs) — plus the rows themselves.
+The id-mapping contract is the reference's (index/util.py:12-42, index/memory.py:84-95): a
+document id owns its rows in insertion order, a passage id owns exactly one row, an id that
+resolves to no row raises IndexError.  The maps live in two C++ dictionaries of libffx
+(`fast_forward._ids.IdDict`: document id -> document ordinal in order of first appearance,
+passage id -> row number) plus one integer per row (its document ordinal); id strings never
+cross to the device — what goes there is the integer form, a CSR document-ordinal -> rows table
+(ffx_index_set_docs), plus the rows themselves.
 """
 
 from __future__ import annotations
 
-import itertools
-from collections import defaultdict
 from collections.abc import Iterable, Sequence
 
 import numpy as np
-import pandas as pd
 
-from fast_forward import _ffx
+from fast_forward import _ffx, _ids
+
+
+def _take(keys, index: np.ndarray) -> list:
+    """keys[index] as a Python list, None where index < 0 (`keys`: pyarrow array or list)."""
+    if isinstance(keys, list):
+        return [None if i < 0 else keys[i] for i in index.tolist()]
+    picks = _ids.pa.array(np.where(index < 0, 0, index), mask=index < 0)
+    return keys.take(picks).to_pylist()
 
 
 class RowStore:
@@ -26,12 +33,13 @@ class RowStore:
         self.device = device
         self.dev: _ffx.DeviceIndex | None = None
         self.count = 0
-        self.doc_rows: dict[str, list[int]] = defaultdict(list)
-        self.psg_row: dict[str, int] = {}
+        self.docs = _ids.IdDict()   # document id -> ordinal (order of first appearance)
+        self.psgs = _ids.IdDict()   # passage id -> row
+        self._row_doc_parts: list[np.ndarray] = []  # document ordinal of every row (-1 = none)
         self._maps_stale = True
-        self._doc_lookup: pd.Index | None = None
-        self._psg_lookup: pd.Index | None = None
-        self._psg_rows: np.ndarray | None = None
+        self._doc_off: np.ndarray | None = None   # CSR ordinal -> rows (host copy, for _get_vectors)
+        self._doc_rows: np.ndarray | None = None
+        self._reverse = None  # (count, doc keys, psg keys, row -> psg key)
         self._pq_of: object | None = None  # quantizer whose tables are on the device
 
     # ---- properties -------------------------------------------------------------------
@@ -40,19 +48,26 @@ class RowStore:
         """Elements per stored row (vector dimension, or M for codes)."""
         return None if self.dev is None else self.dev.dim
 
-    def check_new_passages(self, psg_ids: Iterable[str | None]) -> None:
-        seen = set()
-        for p in psg_ids:
-            if p is None:
-                continue
-            if p in self.psg_row or p in seen:
-                raise RuntimeError(f"Passage ID {p} already exists.")
-            seen.add(p)
+    def doc_id_set(self) -> set[str]:
+        return set(self.docs.keys())
+
+    def psg_id_set(self) -> set[str]:
+        return set(self.psgs.keys())
+
+    def check_new_passages(self, psg_ids: Sequence[str | None]) -> None:
+        """RuntimeError if a passage id exists already or repeats in the batch (memory.py:93-94)."""
+        psg_ids = _ids.as_id_list(psg_ids)
+        dup = self.psgs.insert_unique(psg_ids, self.count, dry_run=True) if psg_ids else -1
+        if dup >= 0:
+            raise RuntimeError(f"Passage ID {psg_ids[dup]} already exists.")
 
     # ---- growth -------------------------------------------------------------------------
     def append(self, rows: np.ndarray, doc_ids, psg_ids, first_capacity: int, grow_by: int) -> None:
-        """Stage `rows` at the end of the store and record their ids."""
+        """Stage `rows` at the end of the store and record their ids (`None` for both id
+        arguments: a bulk loader names the rows afterwards with `adopt_id_columns`)."""
         n_new = rows.shape[0]
+        if psg_ids is not None:
+            self.check_new_passages(psg_ids)
         if self.dev is None:
             kind = _ffx.ROWS_PQ_U8 if rows.dtype == np.uint8 else _ffx.ROWS_F32
             self.dev = _ffx.DeviceIndex(rows.shape[1], capacity=max(first_capacity, n_new),
@@ -65,52 +80,70 @@ class RowStore:
             self.dev.reserve(max(self.dev.capacity + chunks * max(grow_by, 1),
                                  int(self.dev.capacity * 1.5)))
         self.dev.stage(self.count, rows)
-        for i, d in enumerate(doc_ids, self.count):
-            if d is not None:
-                self.doc_rows[d].append(i)
-        for i, p in enumerate(psg_ids, self.count):
-            if p is not None:
-                self.psg_row[p] = i
+        if doc_ids is not None or psg_ids is not None:
+            self.record_ids(doc_ids, psg_ids, self.count, n_new)
         self.count = need
         self._maps_stale = True
 
-    def record_ids(self, doc_ids: Sequence[str | None], psg_ids: Sequence[str | None], base: int) -> None:
-        """Register the ids of rows [base, base+len) (used by bulk loaders)."""
-        for i, d in enumerate(doc_ids, base):
-            if d is not None:
-                self.doc_rows[d].append(i)
-        for i, p in enumerate(psg_ids, base):
-            if p is not None:
-                self.psg_row[p] = i
+    def record_ids(self, doc_ids, psg_ids, base: int, n: int) -> None:
+        """Register the ids of rows [base, base+n); either sequence may hold None entries."""
+        if doc_ids is not None and len(doc_ids):
+            self._row_doc_parts.append(self.docs.insert_ordinal(doc_ids))
+        else:
+            self._row_doc_parts.append(np.full(n, -1, np.int64))
+        if psg_ids is not None and len(psg_ids):
+            psg_ids = _ids.as_id_list(psg_ids)
+            dup = self.psgs.insert_unique(psg_ids, base)
+            if dup >= 0:
+                raise RuntimeError(f"Passage ID {psg_ids[dup]} already exists.")
         self._maps_stale = True
 
+    def adopt_id_columns(self, doc_col, psg_col) -> None:
+        """Name all `count` rows at once from two id columns (None = no id): the vectorised
+        replacement for the O(N) Python loop of index/disk.py:408-417."""
+        self.docs, self.psgs, self._row_doc_parts = _ids.IdDict(), _ids.IdDict(), []
+        self.record_ids(doc_col, psg_col, 0, self.count)
+
     # ---- id mapping ---------------------------------------------------------------------
+    def _row_doc(self) -> np.ndarray:
+        if len(self._row_doc_parts) != 1:
+            merged = np.concatenate(self._row_doc_parts) if self._row_doc_parts else np.zeros(0, np.int64)
+            self._row_doc_parts = [merged]
+        return self._row_doc_parts[0]
+
     def _refresh(self) -> None:
         if not self._maps_stale:
             return
-        docs = self.doc_rows
-        self._doc_lookup = pd.Index(list(docs.keys()), dtype=object)
+        self._doc_off, self._doc_rows = _ids.csr_from_ordinals(self._row_doc(), len(self.docs))
         if self.dev is not None:
-            lengths = np.fromiter((len(v) for v in docs.values()), np.int64, len(docs))
-            off = np.zeros(len(docs) + 1, np.int64)
-            np.cumsum(lengths, out=off[1:])
-            flat = np.fromiter(itertools.chain.from_iterable(docs.values()), np.int64, int(off[-1]))
-            self.dev.set_docs(off, flat)
-        self._psg_lookup = pd.Index(list(self.psg_row.keys()), dtype=object)
-        self._psg_rows = np.fromiter(self.psg_row.values(), np.int64, len(self.psg_row))
+            self.dev.set_docs(self._doc_off, self._doc_rows)
         self._maps_stale = False
 
-    def resolve(self, ids: np.ndarray, passage_mode: bool) -> np.ndarray:
-        """Unique ids -> int32 document ordinals (or row numbers in PASSAGE mode)."""
+    def resolve(self, ids, passage_mode: bool) -> np.ndarray:
+        """An id column (one entry per pair, repeats welcome) -> int32 candidates for ffx_rerank:
+        document ordinals, or row numbers in PASSAGE mode.  IndexError names the first id that
+        is not in the index (index/util.py:38-39)."""
         self._refresh()
-        lookup = self._psg_lookup if passage_mode else self._doc_lookup
-        where = lookup.get_indexer(pd.Index(ids, dtype=object)) if len(ids) else np.zeros(0, np.int64)
-        missing = np.flatnonzero(where < 0)
-        if len(missing):
-            raise IndexError(f"ID {ids[missing[0]]} not found in the index.")
-        if passage_mode:
-            where = self._psg_rows[where]
-        return where.astype(np.int32)
+        codes, missing = (self.psgs if passage_mode else self.docs).lookup(ids)
+        if missing >= 0:
+            raise IndexError(f"ID {_ids.first_text(ids, missing)} not found in the index.")
+        return codes
+
+    def rows_for(self, ids: Iterable[str], mode_name: str) -> tuple[np.ndarray, list[str]]:
+        """index/util.py:12-42 (`get_indices`): the rows needed to score `ids` in the given mode
+        (all rows of a document, its first row, or a passage's row) and the owning id of each."""
+        ids = list(ids)
+        if not ids:
+            return np.zeros(0, np.int64), []
+        codes = self.resolve(ids, mode_name == "PASSAGE").astype(np.int64)
+        if mode_name == "PASSAGE":
+            return codes & 0xffffffff, ids
+        first = self._doc_off[codes]
+        if mode_name == "FIRSTP":
+            return self._doc_rows[first], ids
+        counts = self._doc_off[codes + 1] - first
+        within = np.arange(int(counts.sum())) - np.repeat(np.cumsum(counts) - counts, counts)
+        return self._doc_rows[np.repeat(first, counts) + within], np.repeat(np.asarray(ids, object), counts).tolist()
 
     # ---- device ---------------------------------------------------------------------------
     def device_index(self, quantizer=None) -> _ffx.DeviceIndex:
@@ -133,12 +166,11 @@ class RowStore:
 
     def id_columns(self, lo: int, hi: int):
         """(doc ids, passage ids) of rows [lo, hi), None where a row has no such id."""
-        if getattr(self, "_reverse_for", None) != self.count:
-            doc_of = np.full(self.count, None, dtype=object)
-            for d, rows in self.doc_rows.items():
-                doc_of[rows] = d
-            psg_of = np.full(self.count, None, dtype=object)
-            if self.psg_row:
-                psg_of[np.fromiter(self.psg_row.values(), np.int64, len(self.psg_row))] = list(self.psg_row.keys())
-            self._doc_of, self._psg_of, self._reverse_for = doc_of, psg_of, self.count
-        return self._doc_of[lo:hi].tolist(), self._psg_of[lo:hi].tolist()
+        if self._reverse is None or self._reverse[0] != self.count:
+            doc_keys, _ = self.docs.export()
+            psg_keys, psg_rows = self.psgs.export()
+            row_psg = np.full(self.count, -1, np.int64)
+            row_psg[psg_rows] = np.arange(len(psg_rows))
+            self._reverse = (self.count, doc_keys, psg_keys, row_psg)
+        _, doc_keys, psg_keys, row_psg = self._reverse
+        return _take(doc_keys, self._row_doc()[lo:hi]), _take(psg_keys, row_psg[lo:hi])

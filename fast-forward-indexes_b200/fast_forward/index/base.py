@@ -67,10 +67,8 @@ class _Origin:
         out = self.index._device().interpolate_topk_host(lex, self.ff, self.q_off, alpha, max_c,
                                                          want_int=False)
         rows, scores = _rows_from_topk(out["topk_pos"], out["topk_score"], self.q_off)
-        rows = _order_ties_by_id(rows, scores, df["id"].to_numpy(), self.q_off)
-        frame = df.iloc[rows].reset_index(drop=True)
-        frame["score"] = scores
-        return Ranking(frame, name=first.name, dtype=df.dtypes["score"], copy=False, is_sorted=True)
+        rows = _order_ties_by_id(rows, scores, df["id"], self.q_off)
+        return Ranking._reordered(first, rows, scores, name=first.name)
 
 
 def _rows_from_topk(pos: np.ndarray, score: np.ndarray, q_off: np.ndarray):
@@ -84,13 +82,18 @@ def _rows_from_topk(pos: np.ndarray, score: np.ndarray, q_off: np.ndarray):
 def _order_ties_by_id(rows, scores, ids, q_off):
     """The reference leaves equal interpolated scores of a query in ascending id order (its
     outer merge sorts the keys before the stable sort, ranking.py:312-326); the kernel orders
-    ties by position.  Re-order only the (rare) runs of equal scores."""
+    ties by position.  Re-order only the (rare) runs of equal scores.  `ids`: the id column
+    (Series or array) of the source frame."""
     if len(rows) < 2:
         return rows
-    q_of_row = np.searchsorted(q_off, rows, side="right") - 1
-    same = (scores[1:] == scores[:-1]) & (q_of_row[1:] == q_of_row[:-1])
+    same = scores[1:] == scores[:-1]
     if not same.any():
         return rows
+    q_of_row = np.searchsorted(q_off, rows, side="right") - 1
+    same &= q_of_row[1:] == q_of_row[:-1]
+    if not same.any():
+        return rows
+    ids = ids.to_numpy() if hasattr(ids, "to_numpy") else np.asarray(ids)
     rows = rows.copy()
     starts = np.flatnonzero(same & ~np.concatenate([[False], same[:-1]]))
     ends = np.flatnonzero(same & ~np.concatenate([same[1:], [False]])) + 2
@@ -212,9 +215,10 @@ class Index(abc.ABC):
         """The libffx index holding this index's rows in HBM, maps synchronised."""
 
     @abc.abstractmethod
-    def _resolve(self, ids: np.ndarray, mode: Mode) -> np.ndarray:
-        """Unique ids -> int32 candidates for ffx_rerank (document ordinals, or row numbers in
-        PASSAGE mode) with the semantics of index/util.py:29-41; IndexError if unknown."""
+    def _resolve(self, ids, mode: Mode) -> np.ndarray:
+        """An id column (Series / array, one entry per pair) -> int32 candidates for ffx_rerank
+        (document ordinals, or row numbers in PASSAGE mode) with the semantics of
+        index/util.py:29-41; IndexError names the first unknown id."""
 
     # ------------------------------------------------------------------ adding
     def add(self, vectors: np.ndarray, doc_ids: IDSequence | None = None,
@@ -245,8 +249,7 @@ class Index(abc.ABC):
         qv = np.ascontiguousarray(query_vectors, dtype=np.float32)
         if qv.ndim != 2 or (self.dim is not None and qv.shape[1] != self.dim):
             raise ValueError(f"Query vectors of shape {qv.shape} do not match index dimensionality {self.dim}.")
-        codes, uniq = pd.factorize(id_values)  # first-appearance order, like data["id"].unique()
-        cand = self._resolve(np.asarray(uniq, dtype=object), mode)[codes]
+        cand = self._resolve(id_values, mode)  # every pair's id, coded in C++ on all host cores
         q_off = np.zeros(qv.shape[0] + 1, np.int64)
         np.cumsum(np.bincount(q_no, minlength=qv.shape[0]), out=q_off[1:])
         out = self._device().rerank_host(mode.value, qv, q_off, cand, lex, alpha, k,
@@ -263,11 +266,11 @@ class Index(abc.ABC):
         if n == 0:
             return data.assign(ff_score=np.zeros(0, np.float32))
         q_no = data["q_no"].to_numpy(dtype=np.int64)
-        ids = data["id"].to_numpy()
+        ids = data["id"]
         order = None
         if (np.diff(q_no) < 0).any():
             order = np.argsort(q_no, kind="stable")
-            q_no, ids = q_no[order], ids[order]
+            q_no, ids = q_no[order], ids.iloc[order]
         out, _ = self._launch(self.mode, q_no, ids, query_vectors)
         ff = out["ff"]
         if order is not None:
@@ -304,8 +307,7 @@ class Index(abc.ABC):
                      and len({d for d in depths if d >= cutoff}) <= 32)
         if on_device:
             qv = np.ascontiguousarray(query_vectors, dtype=np.float32)[present]
-            codes, uniq = pd.factorize(df["id"].to_numpy())
-            cand = self._resolve(np.asarray(uniq, dtype=object), self.mode)[codes]
+            cand = self._resolve(df["id"], self.mode)
             q_off = np.concatenate([[0], np.cumsum(count)]).astype(np.int64)
             out = dev.rerank_early_stop_host(self.mode.value, qv, q_off, cand, lex, alpha, cutoff, depths)
             ff, done_depth = out["ff"], out["scored"].astype(np.int64)
@@ -381,7 +383,7 @@ class Index(abc.ABC):
         if early_stopping is None and grouped:
             # one launch per query batch: semantic scores AND the per-query order (ties keep
             # the incoming order, like the reference's stable sort), no pandas sort needed
-            ids = src["id"].to_numpy()
+            ids = src["id"]
             row_off = np.zeros(nq + 1, np.int64)
             np.cumsum(np.bincount(q_codes, minlength=nq), out=row_off[1:])
             ff = np.empty(len(src), np.float32)
@@ -390,7 +392,7 @@ class Index(abc.ABC):
                 hi = min(nq, lo + step)
                 r0, r1 = row_off[lo], row_off[hi]
                 widest = int(np.diff(row_off[lo:hi + 1]).max())
-                out, q_off = self._launch(self.mode, q_codes[r0:r1] - lo, ids[r0:r1],
+                out, q_off = self._launch(self.mode, q_codes[r0:r1] - lo, ids.iloc[r0:r1],
                                           query_vectors[lo:hi], k=widest)
                 ff[r0:r1] = out["ff"]
                 order.append(_rows_from_topk(out["topk_pos"], out["topk_score"], q_off)[0] + r0)
@@ -399,9 +401,7 @@ class Index(abc.ABC):
                 frame = src[["q_id", "id", "query"]].assign(score=ff)
                 return Ranking(frame, name="fast-forward", dtype=dtype, copy=False, is_sorted=False)
             rows = np.concatenate(order) if order else np.zeros(0, np.int64)
-            frame = src[["q_id", "id", "query"]].iloc[rows].reset_index(drop=True)
-            frame["score"] = ff[rows]
-            out_ranking = Ranking(frame, name="fast-forward", dtype=dtype, copy=False, is_sorted=True)
+            out_ranking = Ranking._reordered(ranking, rows, ff[rows].astype(dtype, copy=False), name="fast-forward")
             if dtype == np.float32:
                 out_ranking._origin = _Origin(self, src, row_off, ff)
             return out_ranking
@@ -439,16 +439,52 @@ class Index(abc.ABC):
         if nq == 0:
             return Ranking(src, name=ranking.name, dtype=np.float32, copy=True, is_sorted=True)
         counts = np.bincount(q_codes, minlength=nq)
-        k = int(counts.max()) if cutoff is None else int(min(cutoff, counts.max()))
-        out, q_off = self._launch(self.mode, q_codes, src["id"].to_numpy(), query_vectors,
-                                  lex=src["score"].to_numpy(), alpha=alpha, k=k, want_ff=False)
-        rows, scores = _rows_from_topk(out["topk_pos"], out["topk_score"], q_off)
-        # ties inside the kept lists come out in ascending id order like the reference; which of
-        # several candidates tied exactly AT a cut boundary survives is decided by position
-        rows = _order_ties_by_id(rows, scores, src["id"].to_numpy(), q_off)
-        frame = src.iloc[rows].reset_index(drop=True)
-        frame["score"] = scores
-        return Ranking(frame, name=ranking.name, dtype=src.dtypes["score"], copy=False, is_sorted=True)
+        widest = int(counts.max())
+        k = widest if cutoff is None else int(min(cutoff, widest))
+        # one slot more than the cut: it tells whether equal scores straddle the cut boundary
+        kk = min(k + 1, widest)
+        ids, lex = src["id"], src["score"].to_numpy()
+        out, q_off = self._launch(self.mode, q_codes, ids, query_vectors, lex=lex, alpha=alpha, k=kk, want_ff=False)
+        pos, score = out["topk_pos"], out["topk_score"]
+        straddle = np.zeros(0, np.int64)
+        if kk > k:
+            straddle = np.flatnonzero((pos[:, k] >= 0) & (score[:, k - 1] == score[:, k]))
+            pos, score = pos[:, :k], score[:, :k]
+        rows, scores = _rows_from_topk(pos, score, q_off)
+        # ties inside the kept lists come out in ascending id order like the reference
+        rows = _order_ties_by_id(rows, scores, ids, q_off)
+        if len(straddle):
+            # equal scores on both sides of the cut (float32 collisions; a handful of queries in
+            # millions of pairs): the reference keeps the smaller ids.  Rank those queries in
+            # full, order their ties by id and cut again.
+            rows, scores = self._recut_straddling(straddle, rows, scores, pos, q_off, q_codes, ids, lex,
+                                                  query_vectors, alpha, k)
+        return Ranking._reordered(ranking, rows, scores, name=ranking.name)
+
+    def _recut_straddling(self, queries, rows, scores, pos, q_off, q_codes, ids, lex, query_vectors, alpha, k):
+        """Exact cut for the queries whose k-th and (k+1)-th interpolated scores are equal."""
+        kept = (pos >= 0).sum(axis=1)
+        starts = np.concatenate([[0], np.cumsum(kept)])
+        take = np.concatenate([np.arange(q_off[q], q_off[q + 1]) for q in queries])
+        sub_q = np.repeat(np.arange(len(queries)), [q_off[q + 1] - q_off[q] for q in queries])
+        full, sub_off = self._launch(self.mode, sub_q, ids.iloc[take], query_vectors[queries], lex=lex[take],
+                                     alpha=alpha, k=int(np.diff(q_off)[queries].max()), want_ff=False)
+        sub_rows, sub_scores = _rows_from_topk(full["topk_pos"], full["topk_score"], sub_off)
+        sub_rows = _order_ties_by_id(sub_rows, sub_scores, ids.iloc[take].reset_index(drop=True), sub_off)
+        row_parts, score_parts, at = [], [], 0
+        done = 0
+        for j, q in enumerate(queries):
+            row_parts.append(rows[done:starts[q]])
+            score_parts.append(scores[done:starts[q]])
+            n_q = int(sub_off[j + 1] - sub_off[j])
+            sel = sub_rows[at:at + n_q][:k]
+            row_parts.append(take[sel])
+            score_parts.append(sub_scores[at:at + n_q][:k])
+            at += n_q
+            done = starts[q + 1]
+        row_parts.append(rows[done:])
+        score_parts.append(scores[done:])
+        return np.concatenate(row_parts), np.concatenate(score_parts)
 
     # ------------------------------------------------------------------ iteration
     def batch_iter(self, batch_size: int) -> Iterator[tuple[np.ndarray, IDSequence, IDSequence]]:

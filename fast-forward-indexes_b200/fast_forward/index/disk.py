@@ -15,7 +15,6 @@ from collections.abc import Iterable, Iterator
 from pathlib import Path
 
 import numpy as np
-import pandas as pd
 
 import fast_forward
 from fast_forward import _ffx
@@ -23,7 +22,6 @@ from fast_forward.encoder.base import Encoder
 from fast_forward.index._store import RowStore
 from fast_forward.index.base import IDSequence, Index, Mode
 from fast_forward.index.memory import InMemoryIndex
-from fast_forward.index.util import get_indices
 from fast_forward.quantizer import Quantizer
 
 LOGGER = logging.getLogger(__name__)
@@ -138,13 +136,13 @@ class OnDiskIndex(Index):
             return int(fp["vectors"].shape[1]) if "vectors" in fp else None
 
     def _get_doc_ids(self) -> set[str]:
-        return set(self._store.doc_rows.keys())
+        return self._store.doc_id_set()
 
     def _get_psg_ids(self) -> set[str]:
-        return set(self._store.psg_row.keys())
+        return self._store.psg_id_set()
 
     def _get_vectors(self, ids: Iterable[str]) -> tuple[np.ndarray, list[str]]:
-        rows, owners = get_indices(ids, self.mode, self._store.doc_rows, self._store.psg_row)
+        rows, owners = self._store.rows_for(ids, self.mode.name)
         return self._store.read(rows), owners
 
     def _batch_iter(self, batch_size: int) -> Iterator[tuple[np.ndarray, IDSequence, IDSequence]]:
@@ -157,7 +155,7 @@ class OnDiskIndex(Index):
     def _device(self) -> _ffx.DeviceIndex:
         return self._store.device_index(self.quantizer)
 
-    def _resolve(self, ids: np.ndarray, mode: Mode) -> np.ndarray:
+    def _resolve(self, ids, mode: Mode) -> np.ndarray:
         return self._store.resolve(ids, mode == Mode.PASSAGE)
 
     # ---- conversions ------------------------------------------------------------------------
@@ -208,20 +206,7 @@ class OnDiskIndex(Index):
                 block = fp["vectors"][lo:hi]
                 rows = np.ascontiguousarray(block) if index._quantizer is not None and block.dtype == np.uint8 \
                     else np.ascontiguousarray(block, dtype=np.float32)
-                index._store.append(rows, (), (), first_capacity=total, grow_by=step)
-            index._adopt_id_columns(_text_ids(fp["doc_ids"][:total]), _text_ids(fp["psg_ids"][:total]))
+                index._store.append(rows, None, None, first_capacity=total, grow_by=step)
+            # the O(N) Python loop of disk.py:408-417, as two calls into the C++ id dictionaries
+            index._store.adopt_id_columns(_text_ids(fp["doc_ids"][:total]), _text_ids(fp["psg_ids"][:total]))
         return index
-
-    def _adopt_id_columns(self, doc_col: np.ndarray, psg_col: np.ndarray) -> None:
-        """Vectorised replacement for the reference's O(N) Python loop (disk.py:408-417)."""
-        store = self._store
-        has_doc = np.flatnonzero(pd.notna(doc_col))
-        if len(has_doc):
-            codes, names = pd.factorize(doc_col[has_doc])
-            order = np.argsort(codes, kind="stable")  # rows of a document stay in file order
-            bounds = np.cumsum(np.bincount(codes, minlength=len(names)))[:-1]
-            for name, rows in zip(names, np.split(has_doc[order], bounds)):
-                store.doc_rows[name] = rows.tolist()
-        has_psg = np.flatnonzero(pd.notna(psg_col))
-        store.psg_row.update(zip(psg_col[has_psg].tolist(), has_psg.tolist()))
-        store._maps_stale = True

@@ -13,7 +13,6 @@ from fast_forward import _ffx
 from fast_forward.encoder.base import Encoder
 from fast_forward.index._store import RowStore
 from fast_forward.index.base import IDSequence, Index, Mode
-from fast_forward.index.util import get_indices
 from fast_forward.quantizer import Quantizer
 
 LOGGER = logging.getLogger(__name__)
@@ -41,16 +40,15 @@ class InMemoryIndex(Index):
         return self._store.width
 
     def _get_doc_ids(self) -> set[str]:
-        return set(self._store.doc_rows.keys())
+        return self._store.doc_id_set()
 
     def _get_psg_ids(self) -> set[str]:
-        return set(self._store.psg_row.keys())
+        return self._store.psg_id_set()
 
     def _add(self, vectors: np.ndarray, doc_ids: IDSequence, psg_ids: IDSequence) -> None:
         """Stage rows into HBM.  Vectors are stored as float32 (codes as uint8): integer or
         float64 input is converted, unlike the reference which keeps the first chunk's dtype
         (index/memory.py:79-82)."""
-        self._store.check_new_passages(psg_ids)
         if self.quantizer is not None:
             if vectors.dtype != np.uint8:
                 raise RuntimeError("Only uint8 codes (Ks <= 256) can be stored on the device.")
@@ -63,7 +61,7 @@ class InMemoryIndex(Index):
         """Kept for API compatibility: the device store is always one contiguous array."""
 
     def _get_vectors(self, ids: Iterable[str]) -> tuple[np.ndarray, list[str]]:
-        rows, owners = get_indices(ids, self.mode, self._store.doc_rows, self._store.psg_row)
+        rows, owners = self._store.rows_for(ids, self.mode.name)
         return self._store.read(rows), owners
 
     def _batch_iter(self, batch_size: int) -> Iterator[tuple[np.ndarray, IDSequence, IDSequence]]:
@@ -76,5 +74,5 @@ class InMemoryIndex(Index):
     def _device(self) -> _ffx.DeviceIndex:
         return self._store.device_index(self.quantizer)
 
-    def _resolve(self, ids: np.ndarray, mode: Mode) -> np.ndarray:
+    def _resolve(self, ids, mode: Mode) -> np.ndarray:
         return self._store.resolve(ids, mode == Mode.PASSAGE)

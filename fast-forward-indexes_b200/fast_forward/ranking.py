@@ -92,6 +92,23 @@ class Ranking:
         self._q_ids = set(pd.unique(frame["q_id"]))
         self._df = frame if queries is None else _with_queries(frame, queries)
 
+    @classmethod
+    def _reordered(cls, source: "Ranking", rows: np.ndarray, scores: np.ndarray, name: str | None) -> "Ranking":
+        """Rows `rows` of `source` (a selection without repeats, already in ranking order: query
+        blocks in frame order, scores descending inside a block) with new scores.  The checks of
+        `__init__` would only re-derive what holds by construction — keys of a valid ranking
+        stay unique under row selection, dtypes are kept, the order is the kernel's — so the
+        frame is adopted as is (at 26 M rows `duplicated()` alone costs more than the GPU pass).
+        NaN scores never get here: the kernel does not rank them."""
+        out = cls.__new__(cls)
+        out.name = name
+        out._origin = None
+        frame = source._df.iloc[rows].reset_index(drop=True)
+        frame["score"] = scores
+        out._df = frame
+        out._q_ids = set(pd.unique(frame["q_id"])) if len(rows) != len(source._df) else set(source._q_ids)
+        return out
+
     # ------------------------------------------------------------------ container protocol
     @property
     def has_queries(self) -> bool:

@@ -59,7 +59,7 @@ def test_create_score_reload(api, tmp_path, golden_kat):
     for mode in (api.Mode.MAXP, api.Mode.AVEP, api.Mode.FIRSTP):
         loaded = api.OnDiskIndex.load(path, api.ones, mode=mode)
         assert len(loaded) == 5 and loaded.doc_ids == set(DOC) and loaded.psg_ids == set(PSG)
-        assert loaded._store.doc_rows["d0"] == [0, 1]
+        assert loaded._store.rows_for(["d0"], "MAXP")[0].tolist() == [0, 1]
         got = loaded(rank)
         assert got._df["score"].tolist() == golden_kat[f"full/{mode.name}"]["score"]
         assert got._df["id"].tolist() == golden_kat[f"full/{mode.name}"]["id"]
@@ -86,7 +86,8 @@ def test_partial_ids_and_id_length(api, tmp_path):
     assert len(index) == 7
     loaded = api.OnDiskIndex.load(tmp_path / "p.h5")
     assert loaded.doc_ids == set(DOC) and loaded.psg_ids == set(PSG[:3])
-    assert loaded._store.doc_rows["d0"] == [5, 6] and loaded._store.psg_row["p2"] == 2
+    assert loaded._store.rows_for(["d0"], "MAXP")[0].tolist() == [5, 6]
+    assert loaded._store.rows_for(["p2"], "PASSAGE")[0].tolist() == [2]
     docs, psgs = zip(*[(d, p) for _, d, p in loaded])
     assert list(docs) == [None, None, "d1", "d2", "d3", "d0", "d0"]
     assert list(psgs) == ["p0", "p1", "p2", None, None, None, None]
