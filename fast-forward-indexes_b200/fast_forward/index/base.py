@@ -83,7 +83,7 @@ def _order_ties_by_id(rows, scores, ids, q_off):
     """The reference leaves equal interpolated scores of a query in ascending id order (its
     outer merge sorts the keys before the stable sort, ranking.py:312-326); the kernel orders
     ties by position.  Re-order only the (rare) runs of equal scores.  `ids`: the id column
-    (Series or array) of the source frame."""
+    (Series or array) of the source frame; only the ids inside tie runs are materialised."""
     if len(rows) < 2:
         return rows
     same = scores[1:] == scores[:-1]
@@ -93,14 +93,26 @@ def _order_ties_by_id(rows, scores, ids, q_off):
     same &= q_of_row[1:] == q_of_row[:-1]
     if not same.any():
         return rows
-    ids = ids.to_numpy() if hasattr(ids, "to_numpy") else np.asarray(ids)
     rows = rows.copy()
     starts = np.flatnonzero(same & ~np.concatenate([[False], same[:-1]]))
     ends = np.flatnonzero(same & ~np.concatenate([same[1:], [False]])) + 2
+    in_runs = np.concatenate([np.arange(s, e) for s, e in zip(starts, ends)])
+    picked = ids.iloc[rows[in_runs]] if hasattr(ids, "iloc") else np.asarray(ids)[rows[in_runs]]
+    names = np.asarray(picked, dtype=object).astype(str)
+    at = 0
     for s, e in zip(starts, ends):
         run = rows[s:e]
-        rows[s:e] = run[np.argsort(ids[run].astype(str), kind="stable")]
+        rows[s:e] = run[np.argsort(names[at:at + (e - s)], kind="stable")]
+        at += e - s
     return rows
+
+
+def _number_queries(q_ids: pd.Series):
+    """`q_no` per row in order of first appearance + the first row of every query
+    (index/base.py:418-422)."""
+    q_codes, _ = pd.factorize(q_ids)
+    first_row = np.unique(q_codes, return_index=True)[1]
+    return q_codes.astype(np.int64), first_row
 
 
 class Index(abc.ABC):
@@ -352,10 +364,9 @@ class Index(abc.ABC):
 
     def _query_vectors_for(self, src: pd.DataFrame):
         """Number the queries in order of appearance and encode each once (base.py:418-429)."""
-        q_codes, q_names = pd.factorize(src["q_id"])
-        first_row = np.unique(q_codes, return_index=True)[1]
-        vectors = self.encode_queries(list(src["query"].to_numpy()[first_row]))
-        return q_codes.astype(np.int64), len(q_names), vectors
+        q_codes, first_row = _number_queries(src["q_id"])
+        vectors = self.encode_queries(src["query"].iloc[first_row].tolist())
+        return q_codes, len(first_row), vectors
 
     def __call__(self, ranking: Ranking, early_stopping: int | None = None,
                  early_stopping_alpha: float | None = None,

@@ -71,3 +71,12 @@ print(json.dumps({"docs": n_docs, "passages": n_rows, "pairs": nq * C, "cutoff":
                   "pairs_per_s": {k: round(nq * C / v) for k, v in times.items()},
                   "fused_equals_three_call": bool(fused == three),
                   "kernel_launches": _ffx.launch_count()}))
+if os.environ.get("FFX_PROFILE"):
+    import cProfile
+    import pstats
+
+    pr = cProfile.Profile()
+    pr.enable()
+    index.rerank(ranking, alpha, cutoff)
+    pr.disable()
+    pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(28)
