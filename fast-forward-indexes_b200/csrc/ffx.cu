@@ -19,6 +19,7 @@
 #include "ffx_adc_warp.cuh"
 #include "ffx_adc_xor.cuh"
 #include "ffx_early_stop.cuh"
+#include "ffx_pq_build.cuh"
 #include "ffx_kernels.cuh"
 #include "ffx_score_tma.cuh"
 #include "ffx_layout.h"
@@ -1251,6 +1252,129 @@ int ffx_rerank_early_stop_host(ffx_index *idx, int mode, const float *qvecs, int
     }
     FFX_CUDA(cudaMemcpyAsync(out_scored, d_scored, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, st));
     return take_error(idx, st);
+}
+
+// ---- product-quantizer build side --------------------------------------------------------
+extern "C++" {
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+template <int DS>
+int launch_pq_assign(const float *vecs, int64_t n, int M, int Ks, int Ds, const float *cw, uint8_t *codes,
+                     int sm_count) {
+    const size_t smem = static_cast<size_t>(Ks) * Ds * 4;
+    auto kern = ffx::ffx_pq_assign_kernel<DS>;
+    FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int64_t tiles = std::min<int64_t>((n + ffx::kPqThreads - 1) / ffx::kPqThreads,
+                                            std::max<int64_t>(1, static_cast<int64_t>(sm_count) * 16 / M));
+    kern<<<dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(M)), ffx::kPqThreads, smem>>>(vecs, n, M, Ks, Ds,
+                                                                                                  cw, codes);
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
+template <int DS>
+int launch_pq_lloyd(const float *vecs, int64_t n, int M, int Ks, int Ds, const float *cw, double *sums,
+                    unsigned long long *counts) {
+    const size_t smem = static_cast<size_t>(Ks) * Ds * 8 + static_cast<size_t>(Ks) * 4;
+    auto kern = ffx::ffx_pq_lloyd_kernel<DS>;
+    FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int rows_per_cta = 4096;
+    kern<<<dim3(static_cast<unsigned>((n + rows_per_cta - 1) / rows_per_cta), static_cast<unsigned>(M)),
+           ffx::kPqThreads, smem>>>(vecs, n, M, Ks, Ds, cw, sums, counts, rows_per_cta);
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
+#define FFX_PQ_DISPATCH(fn, ...)                      \
+    switch (Ds) {                                     \
+        case 4: return fn<4>(__VA_ARGS__);            \
+        case 8: return fn<8>(__VA_ARGS__);            \
+        case 16: return fn<16>(__VA_ARGS__);          \
+        case 32: return fn<32>(__VA_ARGS__);          \
+        default: return fn<0>(__VA_ARGS__);           \
+    }
+
+int pq_assign(const float *vecs, int64_t n, int M, int Ks, int Ds, const float *cw, uint8_t *codes, int sm_count) {
+    FFX_PQ_DISPATCH(launch_pq_assign, vecs, n, M, Ks, Ds, cw, codes, sm_count)
+}
+int pq_lloyd(const float *vecs, int64_t n, int M, int Ks, int Ds, const float *cw, double *sums,
+             unsigned long long *counts) {
+    FFX_PQ_DISPATCH(launch_pq_lloyd, vecs, n, M, Ks, Ds, cw, sums, counts)
+}
+
+int pq_check(const char *who, int device, const float *vecs, int64_t n, int M, int Ks, int Ds, const void *cw,
+             size_t smem, int *sm_count) {
+    if (!vecs || !cw || n < 0 || M <= 0 || Ks <= 0 || Ds <= 0) return fail(FFX_ERR_INVALID, "%s: bad arguments", who);
+    if (Ks > 256) return fail(FFX_ERR_UNSUPPORTED, "%s: Ks=%d > 256 (uint8 codes)", who, Ks);
+    if (smem > kSmemBudget) return fail(FFX_ERR_UNSUPPORTED, "%s: a %d x %d codebook exceeds shared memory", who, Ks, Ds);
+    const int n_dev = ffx_device_count();
+    if (n_dev <= 0) return fail(FFX_ERR_CUDA, "no CUDA device (ffx has no CPU path)");
+    if (device < 0 || device >= n_dev) return fail(FFX_ERR_INVALID, "%s: device %d of %d", who, device, n_dev);
+    FFX_CUDA(cudaSetDevice(device));
+    cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device);
+    return FFX_OK;
+}
+
+}  // namespace
+}  // extern "C++"
+
+int ffx_pq_encode(int device, const float *vecs, int64_t n, int M, int Ks, int Ds, const float *codewords,
+                  uint8_t *codes) {
+    int sm_count = 148;
+    FFX_TRY(pq_check("ffx_pq_encode", device, vecs, n, M, Ks, Ds, codewords, static_cast<size_t>(Ks) * Ds * 4, &sm_count));
+    if (n == 0) return FFX_OK;
+    if (!codes) return fail(FFX_ERR_INVALID, "ffx_pq_encode: codes is NULL");
+    const size_t D = static_cast<size_t>(M) * Ds;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n, (256ll << 20) / static_cast<int64_t>(D * 4)));
+    DevBuf d_vec, d_codes, d_cw;
+    FFX_CUDA(cudaMalloc(&d_vec.p, static_cast<size_t>(chunk) * D * 4));
+    FFX_CUDA(cudaMalloc(&d_codes.p, static_cast<size_t>(chunk) * M));
+    FFX_CUDA(cudaMalloc(&d_cw.p, static_cast<size_t>(M) * Ks * Ds * 4));
+    FFX_CUDA(cudaMemcpy(d_cw.p, codewords, static_cast<size_t>(M) * Ks * Ds * 4, cudaMemcpyHostToDevice));
+    for (int64_t r = 0; r < n; r += chunk) {
+        const int64_t nr = std::min(chunk, n - r);
+        FFX_CUDA(cudaMemcpy(d_vec.p, vecs + static_cast<size_t>(r) * D, static_cast<size_t>(nr) * D * 4, cudaMemcpyHostToDevice));
+        FFX_TRY(pq_assign(static_cast<const float *>(d_vec.p), nr, M, Ks, Ds, static_cast<const float *>(d_cw.p),
+                          static_cast<uint8_t *>(d_codes.p), sm_count));
+        FFX_CUDA(cudaMemcpy(codes + static_cast<size_t>(r) * M, d_codes.p, static_cast<size_t>(nr) * M, cudaMemcpyDeviceToHost));
+    }
+    return FFX_OK;
+}
+
+int ffx_pq_kmeans(int device, const float *vecs, int64_t n, int M, int Ks, int Ds, float *codewords, int iters) {
+    int sm_count = 148;
+    FFX_TRY(pq_check("ffx_pq_kmeans", device, vecs, n, M, Ks, Ds, codewords,
+                     static_cast<size_t>(Ks) * Ds * 8 + static_cast<size_t>(Ks) * 4, &sm_count));
+    if (iters < 0) return fail(FFX_ERR_INVALID, "ffx_pq_kmeans: iters < 0");
+    if (n == 0 || iters == 0) return FFX_OK;
+    const size_t D = static_cast<size_t>(M) * Ds, n_cw = static_cast<size_t>(M) * Ks * Ds;
+    DevBuf d_vec, d_cw, d_sum, d_cnt;
+    FFX_CUDA(cudaMalloc(&d_vec.p, static_cast<size_t>(n) * D * 4));  // the training set stays resident
+    FFX_CUDA(cudaMalloc(&d_cw.p, n_cw * 4));
+    FFX_CUDA(cudaMalloc(&d_sum.p, n_cw * 8));
+    FFX_CUDA(cudaMalloc(&d_cnt.p, static_cast<size_t>(M) * Ks * 8));
+    FFX_CUDA(cudaMemcpy(d_vec.p, vecs, static_cast<size_t>(n) * D * 4, cudaMemcpyHostToDevice));
+    FFX_CUDA(cudaMemcpy(d_cw.p, codewords, n_cw * 4, cudaMemcpyHostToDevice));
+    for (int it = 0; it < iters; it++) {
+        FFX_CUDA(cudaMemsetAsync(d_sum.p, 0, n_cw * 8));
+        FFX_CUDA(cudaMemsetAsync(d_cnt.p, 0, static_cast<size_t>(M) * Ks * 8));
+        FFX_TRY(pq_lloyd(static_cast<const float *>(d_vec.p), n, M, Ks, Ds, static_cast<const float *>(d_cw.p),
+                         static_cast<double *>(d_sum.p), static_cast<unsigned long long *>(d_cnt.p)));
+        ffx::ffx_pq_means_kernel<<<permute_grid(static_cast<int64_t>(n_cw), sm_count), 256>>>(
+            static_cast<float *>(d_cw.p), static_cast<const double *>(d_sum.p),
+            static_cast<const unsigned long long *>(d_cnt.p), static_cast<int64_t>(n_cw), Ds);
+        g_launches++;
+        FFX_CUDA(cudaGetLastError());
+    }
+    FFX_CUDA(cudaMemcpy(codewords, d_cw.p, n_cw * 4, cudaMemcpyDeviceToHost));
+    return FFX_OK;
 }
 
 int ffx_index_sync(ffx_index *idx, void *stream) {

@@ -48,6 +48,8 @@ SYMBOLS = {
     "ffx_interpolate_topk_host": (_I, [_P, _P, _P, _L, _P, _D, _I, _P, _P, _P]),
     "ffx_merge_topk": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _P]),
     "ffx_launch_count": (_L, []),
+    "ffx_pq_encode": (_I, [_I, _P, _L, _I, _I, _I, _P, _P]),
+    "ffx_pq_kmeans": (_I, [_I, _P, _L, _I, _I, _I, _P, _I]),
     "ffx_dict_create": (_I, [C.POINTER(_P)]),
     "ffx_dict_destroy": (_I, [_P]),
     "ffx_dict_size": (_L, [_P]),
@@ -297,6 +299,29 @@ class DeviceIndex:
                                vp(cand_ptr), vp(lex_ptr), float(alpha), int(k), int(max_cand),
                                vp(out_ff_ptr), vp(out_int_ptr), vp(topk_score_ptr), vp(topk_pos_ptr),
                                vp(stream)))
+
+
+def pq_encode(vecs, codewords, device: int = 0) -> np.ndarray:
+    """ffx_pq_encode: nearest codeword per subspace on the GPU; uint8 codes [n, M]."""
+    vecs = _arr(vecs, np.float32)
+    codewords = _arr(codewords, np.float32)
+    M, Ks, Ds = codewords.shape
+    if vecs.ndim != 2 or vecs.shape[1] != M * Ds:
+        raise ValueError(f"expected vectors of shape [n, {M * Ds}], got {vecs.shape}")
+    codes = np.empty((vecs.shape[0], M), np.uint8)
+    check(lib().ffx_pq_encode(int(device), _ptr(vecs), vecs.shape[0], M, Ks, Ds, _ptr(codewords), _ptr(codes)))
+    return codes
+
+
+def pq_kmeans(vecs, init_codewords, iters: int, device: int = 0) -> np.ndarray:
+    """ffx_pq_kmeans: `iters` Lloyd rounds per subspace on the GPU from `init_codewords` [M, Ks, Ds]."""
+    vecs = _arr(vecs, np.float32)
+    codewords = np.array(init_codewords, dtype=np.float32, order="C", copy=True)
+    M, Ks, Ds = codewords.shape
+    if vecs.ndim != 2 or vecs.shape[1] != M * Ds:
+        raise ValueError(f"expected vectors of shape [n, {M * Ds}], got {vecs.shape}")
+    check(lib().ffx_pq_kmeans(int(device), _ptr(vecs), vecs.shape[0], M, Ks, Ds, _ptr(codewords), int(iters)))
+    return codewords
 
 
 def merge_topk(device, shard_scores_ptr, shard_pos_ptr, n_shards, nq, k, out_score_ptr, out_pos_ptr,

@@ -219,6 +219,20 @@ int ffx_rerank_early_stop_host(ffx_index *idx, int mode, const float *qvecs, int
                                double alpha, int cutoff, const int32_t *depths, int n_depths,
                                float *out_ff, float *out_int, int32_t *out_scored);
 
+/* ---- product-quantizer build side ------------------------------------------------------ */
+/* Replace what the reference delegates to nanopq 0.2.1 / scipy on the host.  Host pointers;
+ * synchronous; need a CUDA device.  Ks <= 256 (uint8 codes).
+ * ffx_pq_encode: nanopq `PQ.encode` (quantizer/nanopq.py:41,109 -> scipy.cluster.vq.vq per
+ *   subspace): codes[i, m] = argmin_k |vecs[i, m*Ds:(m+1)*Ds] - codewords[m, k]|^2, ties to the
+ *   lower k.  `vecs` are already rotated for OPQ.
+ * ffx_pq_kmeans: the Lloyd iterations of nanopq `PQ.fit` (quantizer/nanopq.py:30,98 ->
+ *   scipy.cluster.vq.kmeans2 per subspace): `iters` rounds of assign + mean from the initial
+ *   `codewords` (in/out, [M, Ks, Ds]); a codeword without members keeps its value
+ *   (kmeans2 missing="warn").  The training set must fit the device. */
+int ffx_pq_encode(int device, const float *vecs, int64_t n, int M, int Ks, int Ds, const float *codewords,
+                  uint8_t *codes);
+int ffx_pq_kmeans(int device, const float *vecs, int64_t n, int M, int Ks, int Ds, float *codewords, int iters);
+
 /* Synchronises `stream` and reports what the asynchronous launches on this index saw: the
  * kernels never dereference a candidate outside [0, #documents) (or [0, #rows) in PASSAGE
  * mode) — such a pair scores as an empty document and this call (like ffx_rerank_host)
