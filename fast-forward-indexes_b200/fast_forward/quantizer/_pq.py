@@ -5,7 +5,14 @@ is not a dependency here.  This module keeps nanopq's state layout — `codeword
 float32, rotation `R[D, D]`, code dtype by `Ks` — and its algorithm (per-subspace k-means,
 nearest-codeword encoding, OPQ = alternating PQ fit / orthogonal Procrustes), so index files
 and serialised quantizers are interchangeable with the reference.  Training and encoding are
-offline index-build steps and run on the host; scoring never decodes (see ffx_adc.cuh).
+offline index-build steps; scoring never decodes (see ffx_adc_xor.cuh).
+
+By default they run on the host (scipy), like the reference.  With `device=<cuda ordinal>` the
+two expensive pieces — the Lloyd iterations of `fit` and the nearest-codeword search of
+`encode` — run on the GPU instead (libffx `ffx_pq_kmeans` / `ffx_pq_encode`,
+csrc/ffx_pq_build.cuh): same algorithm and same initial centroids (the `minit="points"` draws
+of kmeans2 are repeated on the host), direct fp32 distances.  That is an explicit choice, not a
+fallback: with `device` set and no CUDA device the calls raise.
 """
 
 from __future__ import annotations
@@ -21,12 +28,14 @@ def code_dtype_for(Ks: int) -> type:
 class Codebook:
     """M subspaces x Ks codewords; optional learned rotation (OPQ)."""
 
-    def __init__(self, M: int, Ks: int, metric: str, verbose: bool, rotated: bool) -> None:
+    def __init__(self, M: int, Ks: int, metric: str, verbose: bool, rotated: bool,
+                 device: int | None = None) -> None:
         if not 0 < Ks <= 1 << 32:
             raise ValueError("Ks out of range")
         if metric not in ("l2", "dot"):
             raise ValueError("metric must be 'l2' or 'dot'")
         self.M, self.Ks, self.metric, self.verbose, self.rotated = M, Ks, metric, verbose, rotated
+        self.device = device
         self.Ds: int | None = None
         self.codewords: np.ndarray | None = None
         self.R: np.ndarray | None = None
@@ -42,12 +51,27 @@ class Codebook:
 
     def _fit_pq(self, vecs: np.ndarray, iters: int, seed: int, minit: str) -> np.ndarray:
         np.random.seed(seed)  # kmeans2(minit="points") draws from the global generator
+        if self.device is not None:
+            if minit != "points":
+                raise ValueError("device k-means supports minit='points' (the nanopq default) only")
+            if self.Ks > 256:
+                raise ValueError("device k-means needs Ks <= 256")
+            from fast_forward import _ffx
+
+            # the draws kmeans2 would make: Ks distinct training points per subspace, in order
+            init = np.stack([sub[np.random.mtrand._rand.choice(vecs.shape[0], size=self.Ks, replace=False)]
+                             for _, sub in self._split(vecs)]).astype(np.float32)
+            return _ffx.pq_kmeans(vecs, init, iters, self.device)
         words = np.zeros((self.M, self.Ks, self.Ds), np.float32)
         for m, sub in self._split(vecs):
             words[m], _ = kmeans2(sub, self.Ks, iter=iters, minit=minit)
         return words
 
     def _assign(self, vecs: np.ndarray, words: np.ndarray) -> np.ndarray:
+        if self.device is not None and self.Ks <= 256:
+            from fast_forward import _ffx
+
+            return _ffx.pq_encode(vecs, words, self.device)
         codes = np.empty((vecs.shape[0], self.M), self.code_dtype)
         for m, sub in self._split(vecs):
             codes[:, m], _ = vq(sub, words[m])

@@ -19,10 +19,13 @@ from fast_forward.quantizer.base import Quantizer, QuantizerAttributes, Quantize
 class _CodebookQuantizer(Quantizer):
     _ROTATED = False
 
-    def __init__(self, M: int, Ks: int, metric: str = "dot", verbose: bool = False) -> None:
+    def __init__(self, M: int, Ks: int, metric: str = "dot", verbose: bool = False,
+                 device: int | None = None) -> None:
         """:param M: number of subspaces. :param Ks: codewords per subspace.
-        :param metric: "dot" or "l2". :param verbose: kept for API compatibility."""
-        self._book = Codebook(M=M, Ks=Ks, metric=metric, verbose=verbose, rotated=self._ROTATED)
+        :param metric: "dot" or "l2". :param verbose: kept for API compatibility.
+        :param device: CUDA ordinal to run `fit`'s k-means and `encode` on (not in the reference;
+            None = on the host with scipy, like the reference)."""
+        self._book = Codebook(M=M, Ks=Ks, metric=metric, verbose=verbose, rotated=self._ROTATED, device=device)
         super().__init__()
 
     def _fit(self, vectors: np.ndarray, **kwargs: Any) -> None:
