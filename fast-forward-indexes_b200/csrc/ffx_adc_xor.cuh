@@ -66,6 +66,19 @@ __host__ __device__ inline size_t adc_xor_smem_bytes(int M, int Ks, int cpad_sco
     return lut + rest + static_cast<size_t>(cpad_scores) * 4 + 128;
 }
 
+// acc += (a, b) as one packed fp32x2 add (sm_100)
+__device__ __forceinline__ void add_f32x2(float2 &acc, float a, float b) {
+    asm("{\n\t"
+        ".reg .b64 va, vb;\n\t"
+        "mov.b64 va, {%0, %1};\n\t"
+        "mov.b64 vb, {%2, %3};\n\t"
+        "add.rn.f32x2 va, va, vb;\n\t"
+        "mov.b64 {%0, %1}, va;\n\t"
+        "}"
+        : "+f"(acc.x), "+f"(acc.y)
+        : "f"(a), "f"(b));
+}
+
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t r;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
@@ -220,15 +233,13 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
 
         for (uint32_t r0 = 0; r0 < total; r0 += 32) {
             const uint32_t g = r0 + t;  // this lane's row of the stream
-            // owner of stream row g: first candidate whose inclusive count exceeds it
-            int c = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const uint32_t v = __shfl_sync(kFull, incl, c + step - 1);
-                if (v <= g) c += step;
-            }
-            c = min(c, 31);
-            const uint32_t my_k = g - __shfl_sync(kFull, pre, c);  // position inside the document
+            // rows of the same document to the left of this lane inside the block: distance to the
+            // nearest document start at or below lane t (bit i of `heads` = a document starts at
+            // block row i), or t when the document began in an earlier block
+            const bool starts_here = cnt > 0 && pre >= r0 && pre < r0 + 32;
+            const uint32_t heads = __reduce_or_sync(kFull, starts_here ? 1u << (pre - r0) : 0u);
+            const uint32_t below = heads & (0xffffffffu >> (31u - t));
+            const uint32_t dist = below ? t - (31u - static_cast<uint32_t>(__clz(below))) : t;
 
             mbar_wait(bar, phase);
             phase ^= 1u;
@@ -249,26 +260,27 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
 
             float s = 0.f;
             if (g < total) {
-                float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+                float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < NC; j++) {
                     const uint32_t tj = (NC == 2 || NC == 4) ? tab_l[j] : tab[0] + static_cast<uint32_t>(j) * tab_bytes;
 #pragma unroll
                     for (int wi = 0; wi < 8; wi++) {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const uint32_t pos = static_cast<uint32_t>(4 * wi + k);
-                            acc4[k] += lds_f32(__dp4a(wd[j][wi], sel[k], tj ^ (pos << 2)));
-                        }
+                        const uint32_t pos = static_cast<uint32_t>(4 * wi);
+                        const float v0 = lds_f32(__dp4a(wd[j][wi], sel[0], tj ^ ((pos + 0u) << 2)));
+                        const float v1 = lds_f32(__dp4a(wd[j][wi], sel[1], tj ^ ((pos + 1u) << 2)));
+                        const float v2 = lds_f32(__dp4a(wd[j][wi], sel[2], tj ^ ((pos + 2u) << 2)));
+                        const float v3 = lds_f32(__dp4a(wd[j][wi], sel[3], tj ^ ((pos + 3u) << 2)));
+                        add_f32x2(acc01, v0, v1);
+                        add_f32x2(acc23, v2, v3);
                     }
                 }
-                s = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+                s = (acc01.x + acc01.y) + (acc23.x + acc23.y);
             }
 
             // fold rows into documents (segmented inclusive scan in row order), then lane j pulls
             // candidate j's partial from the lane of its last row in this block
             if (segmented) {
-                const uint32_t dist = min(my_k, t);  // same-document rows to the left
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const float v = __shfl_up_sync(kFull, s, d);
