@@ -271,6 +271,15 @@ class DeviceIndex:
                                                _ptr(out["ff"]), _ptr(out.get("int")), _ptr(out["scored"])))
         return out
 
+    def rerank_early_stop_device(self, mode, qvecs_ptr, nq, q_off_ptr, cand_ptr, lex_ptr, alpha, cutoff, depths,
+                                 max_cand, out_ff_ptr, out_int_ptr, scored_ptr, stream=0):
+        """ffx_rerank_early_stop on raw device pointers (`depths` is a host sequence); asynchronous."""
+        vp = lambda x: C.c_void_p(x) if x else None  # noqa: E731
+        depths = _arr(list(depths), np.int32)
+        check(lib().ffx_rerank_early_stop(self.handle, int(mode), vp(qvecs_ptr), int(nq), vp(q_off_ptr), vp(cand_ptr),
+                                          vp(lex_ptr), float(alpha), int(cutoff), _ptr(depths), len(depths),
+                                          int(max_cand), vp(out_ff_ptr), vp(out_int_ptr), vp(scored_ptr), vp(stream)))
+
     def sync(self, stream=0):
         """ffx_index_sync: wait for `stream`, raise if a kernel saw an out-of-range candidate."""
         check(lib().ffx_index_sync(self.handle, C.c_void_p(stream) if stream else None))
