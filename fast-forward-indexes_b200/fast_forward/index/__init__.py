@@ -1,7 +1,12 @@
-"""Indexes (reference: src/fast_forward/index/__init__.py)."""
+"""Index back-ends of the drop-in package.
 
-from fast_forward.index.base import Index, Mode
-from fast_forward.index.disk import OnDiskIndex
-from fast_forward.index.memory import InMemoryIndex
+`InMemoryIndex` keeps its rows in the GPU's HBM, `OnDiskIndex` persists them in the reference's
+HDF5 layout and serves them from HBM as well; both score through libffx (`Index.__call__`,
+`Index.rerank`).  `Mode` selects how a document's passages are reduced.
+"""
 
-__all__ = ["Index", "Mode", "OnDiskIndex", "InMemoryIndex"]
+from .base import Index, Mode
+from .memory import InMemoryIndex
+from .disk import OnDiskIndex
+
+__all__ = ("Mode", "Index", "InMemoryIndex", "OnDiskIndex")

@@ -1,6 +1,13 @@
-"""Quantizers (reference: src/fast_forward/quantizer/__init__.py)."""
+"""Quantizers of the drop-in package.
 
-from fast_forward.quantizer.base import Quantizer
-from fast_forward.quantizer.nanopq import NanoOPQ, NanoPQ
+`Quantizer` is the abstract contract (fit / encode / decode / serialize); `NanoPQ` and `NanoOPQ`
+keep nanopq's state layout so stored quantizers stay interchangeable with the reference.  On
+the scoring path codes are never decoded: a quantized index is scored by the asymmetric-distance
+kernels of libffx straight from the uint8 codes.  `device=` moves k-means and encoding of the
+build side to the GPU.
+"""
 
-__all__ = ["Quantizer", "NanoPQ", "NanoOPQ"]
+from .base import Quantizer
+from .nanopq import NanoOPQ, NanoPQ
+
+__all__ = ("NanoOPQ", "NanoPQ", "Quantizer")
