@@ -863,7 +863,8 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
 
     // one CTA per query with the top-k fused needs enough queries to fill the machine
     const int64_t slots = static_cast<int64_t>(idx->sm_count) * 2;
-    const bool fuse = will_fuse(idx, nq, k, cpad);
+    // nothing to score (every list empty): the separate top-k pass still writes the (-inf, -1) padding
+    const bool fuse = max_cand > 0 && will_fuse(idx, nq, k, cpad);
 
     // scratch plan: [scores n_total?][keys nq*cpad?][qeff nq*D?]
     // a separate top-k pass reads out_int when the caller asked for it; a shard must not (pairs

@@ -79,7 +79,8 @@ struct AdcWarpArgs {
 __host__ __device__ inline size_t adc_warp_smem_bytes(int Ks, int cpad_scores) {
     const size_t lut = static_cast<size_t>(4) * Ks * 128;
     const size_t keys = static_cast<size_t>(cpad_scores) * 8;  // sort keys overlay the dead tables
-    return static_cast<size_t>(cpad_scores) * 4 + (lut > keys ? lut : keys);
+    // the score region is padded so that the tables (and the 64-bit keys built over them) stay aligned
+    return ((static_cast<size_t>(cpad_scores) * 4 + 127) & ~static_cast<size_t>(127)) + (lut > keys ? lut : keys);
 }
 
 template <bool FUSE, bool INDIRECT>
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(kAdcWarpThreads, 1) ffx_adc_warp_kernel(const 
     const AdcArgs &a = w.base;
     extern __shared__ __align__(128) unsigned char adc_smem[];
     float *s_scores = reinterpret_cast<float *>(adc_smem);  // [cpad] (FUSE)
-    float *s_lut = reinterpret_cast<float *>(adc_smem + (FUSE ? static_cast<size_t>(w.cpad) * 4 : 0));
+    float *s_lut = reinterpret_cast<float *>(
+        adc_smem + (FUSE ? ((static_cast<size_t>(w.cpad) * 4 + 127) & ~static_cast<size_t>(127)) : 0));
     __shared__ int s_next;
 
     const int lane = threadIdx.x & 31;
