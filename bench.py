@@ -73,6 +73,8 @@ def parse():
                     help="shrink docs and queries (debug only; the line says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--alpha", type=float, default=0.1)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="sharded workloads: fused peer-memory exchange in the kernel epilogue, or an NCCL all-to-all")
     ap.add_argument("--emulate-shards", type=int, default=0,
                     help="single GPU: hold shard 0 of this many doc-id-range shards and time the local step only "
                          "(profiling the sharded kernel without the other GPUs; the line says so)")
@@ -350,7 +352,8 @@ def run_ffx(args, wl):
     algo_bytes = rows_touched * row_bytes + n_pairs * 8 + my_pairs * 8 + nq * (DIM * 4 + k * 8)
 
     stream = torch.cuda.current_stream()
-    reranker = ShardedReranker(idx, doc_lo, n_docs, row_lo, total_rows) if sharded else None
+    p2p = sharded and world > 1 and not emulate and args.exchange == "p2p"
+    reranker = ShardedReranker(idx, doc_lo, n_docs, row_lo, total_rows, p2p=p2p) if sharded else None
 
     def step():
         if sharded:
@@ -452,8 +455,11 @@ def run_ffx(args, wl):
                 "index_gb_per_gpu": n_rows * row_bytes / 1e9,
                 "queries": nq if sharded else f"{nq} per GPU", "candidates_per_query": cands, "cut_k": k,
                 "alpha": args.alpha,
-                "parallelism": (f"doc-id-range shards x{world}: local fused top-k, one NCCL all-to-all of the "
-                                f"[nq,k] lists to the queries' owner ranks, ffx_merge_topk there" if sharded else
+                "parallelism": ((f"doc-id-range shards x{world}: fused score+top-k kernel whose epilogue stores each "
+                                 f"query's [k] list into its owner rank's buffer over NVLink peer memory, device "
+                                 f"barrier, ffx_merge_topk at the owner" if p2p else
+                                 f"doc-id-range shards x{world}: local fused top-k, one NCCL all-to-all of the "
+                                 f"[nq,k] lists to the queries' owner ranks, ffx_merge_topk there") if sharded else
                                 f"query-dp{world} (replicated index, no data-path collective)"),
                 "l2": "inputs larger than L2 (index %.1f GB/GPU, %.1f GB touched per step per GPU)" % (
                     n_rows * row_bytes / 1e9, algo_bytes / 1e9),

@@ -136,6 +136,16 @@ struct ffx_index {
     Scratch work;     // kernel scratch of ffx_rerank (scores / keys / rotated queries)
     Scratch hostio;   // device mirrors of ffx_rerank_host's host buffers
 
+    // scatter plan (ffx_index_set_topk_scatter): host copy + device arrays refreshed, stream
+    // ordered, by the next launch when the plan changed
+    int sc_world = 0, sc_rank = 0;
+    int64_t sc_stride = 0;
+    bool sc_dirty = false;
+    std::vector<int64_t> sc_bounds_h;
+    std::vector<void *> sc_score_h, sc_pos_h;
+    int64_t *sc_bounds = nullptr;
+    void **sc_score = nullptr, **sc_pos = nullptr;
+
     int *err_flag = nullptr;   // device: first out-of-range candidate seen by a kernel (0 = none)
     int *err_host = nullptr;   // pinned mirror
 
@@ -569,6 +579,9 @@ int ffx_index_destroy(ffx_index *idx) {
     cudaFree(idx->R);
     cudaFree(idx->cw_t);
     cudaFree(idx->cw_x);
+    cudaFree(idx->sc_bounds);
+    cudaFree(idx->sc_score);
+    cudaFree(idx->sc_pos);
     cudaFree(idx->work.p);
     cudaFree(idx->hostio.p);
     cudaFree(idx->err_flag);
@@ -773,6 +786,36 @@ int ffx_index_set_shard(ffx_index *idx, int64_t doc_base, int64_t global_docs, i
     return FFX_OK;
 }
 
+int ffx_index_set_topk_scatter(ffx_index *idx, int world, int rank, int64_t stride, const int64_t *bounds,
+                               void *const *peer_score, void *const *peer_pos) {
+    constexpr int kMaxWorld = 64;
+    if (!idx) return fail(FFX_ERR_INVALID, "ffx_index_set_topk_scatter: NULL index");
+    if (world == 0) {
+        idx->sc_world = 0;
+        return FFX_OK;
+    }
+    if (world < 0 || world > kMaxWorld || rank < 0 || rank >= world || stride <= 0 || !bounds || !peer_score ||
+        !peer_pos)
+        return fail(FFX_ERR_INVALID, "ffx_index_set_topk_scatter: bad arguments");
+    for (int o = 0; o < world; o++)
+        if (bounds[o + 1] < bounds[o] || bounds[o + 1] - bounds[o] > stride || !peer_score[o] || !peer_pos[o])
+            return fail(FFX_ERR_INVALID, "ffx_index_set_topk_scatter: bad bounds / buffers for owner %d", o);
+    FFX_TRY(bind(idx));
+    if (!idx->sc_bounds) {
+        FFX_CUDA(cudaMalloc(&idx->sc_bounds, (kMaxWorld + 1) * sizeof(int64_t)));
+        FFX_CUDA(cudaMalloc(&idx->sc_score, kMaxWorld * sizeof(void *)));
+        FFX_CUDA(cudaMalloc(&idx->sc_pos, kMaxWorld * sizeof(void *)));
+    }
+    idx->sc_bounds_h.assign(bounds, bounds + world + 1);
+    idx->sc_score_h.assign(peer_score, peer_score + world);
+    idx->sc_pos_h.assign(peer_pos, peer_pos + world);
+    idx->sc_world = world;
+    idx->sc_rank = rank;
+    idx->sc_stride = stride;
+    idx->sc_dirty = true;
+    return FFX_OK;
+}
+
 int ffx_index_set_pq(ffx_index *idx, int M, int Ks, int Ds, const float *codewords, const float *R) {
     if (!idx || !codewords || M <= 0 || Ks <= 0 || Ds <= 0)
         return fail(FFX_ERR_INVALID, "ffx_index_set_pq: bad arguments");
@@ -839,7 +882,7 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     if (nq == 0) return FFX_OK;
     if (!qvecs || !q_off || (!cand && max_cand > 0))
         return fail(FFX_ERR_INVALID, "ffx_rerank: NULL input");
-    if (k > 0 && (!out_topk_score || !out_topk_pos))
+    if (k > 0 && (!out_topk_score || !out_topk_pos) && idx->sc_world == 0)
         return fail(FFX_ERR_INVALID, "ffx_rerank: k > 0 needs top-k outputs");
     if (mode != FFX_MODE_PASSAGE && idx->n_docs == 0 && max_cand > 0)
         return fail(FFX_ERR_STATE, "ffx_rerank: document modes need ffx_index_set_docs first");
@@ -1014,6 +1057,29 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
             a.base = base;
             a.count = count;
             a.err = idx->err_flag;
+            if (idx->sc_world) {
+                // the fused exchange lives in the epilogue of the fused TMA-staged kernel only
+                if (!(fast && fuse && sp.tma))
+                    return fail(FFX_ERR_UNSUPPORTED, "ffx_rerank: a scatter plan needs the fused fp32 kernel "
+                                "(lane-major dimension, k > 0, >= 2 queries per SM, <= %d candidates per query)",
+                                ffx::kMaxFusedCand);
+                if (idx->sc_dirty) {  // pageable sources: the calls return once the data is staged
+                    const size_t w = static_cast<size_t>(idx->sc_world);
+                    FFX_CUDA(cudaMemcpyAsync(idx->sc_bounds, idx->sc_bounds_h.data(), (w + 1) * sizeof(int64_t),
+                                             cudaMemcpyHostToDevice, st));
+                    FFX_CUDA(cudaMemcpyAsync(idx->sc_score, idx->sc_score_h.data(), w * sizeof(void *),
+                                             cudaMemcpyHostToDevice, st));
+                    FFX_CUDA(cudaMemcpyAsync(idx->sc_pos, idx->sc_pos_h.data(), w * sizeof(void *),
+                                             cudaMemcpyHostToDevice, st));
+                    idx->sc_dirty = false;
+                }
+                a.sc_world = idx->sc_world;
+                a.sc_rank = idx->sc_rank;
+                a.sc_stride = idx->sc_stride;
+                a.sc_bounds = idx->sc_bounds;
+                a.sc_score = reinterpret_cast<float *const *>(idx->sc_score);
+                a.sc_pos = reinterpret_cast<int32_t *const *>(idx->sc_pos);
+            }
             if (fast) {
                 FFX_TRY(dispatch_score(idx->plan, sp, a, fuse, static_cast<int>(nq * tiles), st));
             } else {

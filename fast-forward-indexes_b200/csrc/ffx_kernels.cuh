@@ -47,7 +47,28 @@ struct ScoreArgs {
     uint32_t limit;           // valid candidates are [0, limit): GLOBAL documents (rows in PASSAGE mode)
     uint32_t base, count;     // this index holds candidates [base, base+count) of them (a shard)
     int *err;                 // set to 1 + (pair index & 0x3fffffff) when a candidate is out of range
+    // scatter plan of a sharded corpus (ffx_index_set_topk_scatter): query q's top-k list goes to
+    // its owner rank's receive buffer over peer memory instead of topk_score / topk_pos
+    int sc_world, sc_rank;
+    int64_t sc_stride;              // queries per (owner, shard) block of a receive buffer
+    const int64_t *sc_bounds;       // [sc_world + 1] owner o merges queries [bounds[o], bounds[o+1])
+    float *const *sc_score;         // [sc_world] receive buffers [world][stride][k], peer pointers
+    int32_t *const *sc_pos;
 };
+
+// where query q's ranked list is written: locally, or into the owner's receive buffer
+__device__ __forceinline__ void topk_destination(const ScoreArgs &a, int64_t q, float **out_s, int32_t **out_p) {
+    if (a.sc_world == 0) {
+        *out_s = a.topk_score + q * a.k;
+        *out_p = a.topk_pos + q * a.k;
+        return;
+    }
+    int o = 0;
+    while (o + 1 < a.sc_world && q >= a.sc_bounds[o + 1]) o++;
+    const int64_t slot = (static_cast<int64_t>(a.sc_rank) * a.sc_stride + (q - a.sc_bounds[o])) * a.k;
+    *out_s = a.sc_score[o] + slot;
+    *out_p = a.sc_pos[o] + slot;
+}
 
 // An out-of-range candidate is never dereferenced: it scores as an empty document and is
 // reported through the index's error flag (checked by the host at the next sync).

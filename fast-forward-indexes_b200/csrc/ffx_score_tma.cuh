@@ -336,7 +336,11 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
         // every row this CTA requested has been consumed, the ring is idle: build the sort keys
         // in it (NaN = pair of another shard or NaN score = not ranked)
         __syncthreads();
-        rank_scores_topk(s_scores, n_query, s_keys, a.k, a.topk_score + q_idx * a.k, a.topk_pos + q_idx * a.k);
+        float *out_s;
+        int32_t *out_p;
+        topk_destination(a, q_idx, &out_s, &out_p);
+        rank_scores_topk(s_scores, n_query, s_keys, a.k, out_s, out_p);
+        if (a.sc_world) __threadfence_system();  // peer stores: visible to the owner once the kernel ends
     }
 }
 

@@ -39,6 +39,7 @@ SYMBOLS = {
     "ffx_index_set_docs": (_I, [_P, _L, _P, _P]),
     "ffx_index_set_shard": (_I, [_P, _L, _L, _L, _L]),
     "ffx_index_set_pq": (_I, [_P, _I, _I, _I, _P, _P]),
+    "ffx_index_set_topk_scatter": (_I, [_P, _I, _I, _L, _P, _P, _P]),
     "ffx_rerank": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _L, _P, _P, _P, _P, _P]),
     "ffx_rerank_host": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _P, _P, _P, _P]),
     "ffx_rerank_early_stop": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _P, _I, _L, _P, _P, _P, _P]),
@@ -216,6 +217,17 @@ class DeviceIndex:
     def set_shard(self, doc_base=0, global_docs=0, row_base=0, global_rows=0):
         check(lib().ffx_index_set_shard(self.handle, int(doc_base), int(global_docs), int(row_base),
                                         int(global_rows)))
+
+    def set_topk_scatter(self, world=0, rank=0, stride=0, bounds=None, peer_score=None, peer_pos=None):
+        """ffx_index_set_topk_scatter: peer receive buffers (lists of device pointers, one per
+        owner rank) the fused kernel writes its top-k lists into; world=0 removes the plan."""
+        if not world:
+            check(lib().ffx_index_set_topk_scatter(self.handle, 0, 0, 0, None, None, None))
+            return
+        b = _arr(bounds, np.int64)
+        ps = (C.c_void_p * world)(*[int(x) for x in peer_score])
+        pp = (C.c_void_p * world)(*[int(x) for x in peer_pos])
+        check(lib().ffx_index_set_topk_scatter(self.handle, int(world), int(rank), int(stride), _ptr(b), ps, pp))
 
     def set_pq(self, codewords, R=None):
         codewords = _arr(codewords, np.float32)

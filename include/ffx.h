@@ -115,6 +115,20 @@ int ffx_index_set_docs(ffx_index *idx, int64_t n_docs, const int64_t *doc_off,
 int ffx_index_set_shard(ffx_index *idx, int64_t doc_base, int64_t global_docs, int64_t row_base,
                         int64_t global_rows);
 
+/* Fused exchange of a doc-id-range sharded corpus (the reference has no counterpart).
+ * With a scatter plan the fused scoring kernel writes every query's top-k list in its epilogue
+ * straight into the receive buffer of the query's OWNER rank, over NVLink peer memory (plain
+ * stores to a peer-mapped pointer), instead of into out_topk_* — compute and exchange are one
+ * kernel, no all-to-all.  Owner o merges queries [bounds[o], bounds[o+1]) (host array
+ * [world + 1]); peer_score[o] / peer_pos[o] are owner o's receive buffers as device pointers
+ * valid on THIS device, laid out [world][stride][k] (stride >= every owner's query count); this
+ * index writes block `rank` of each.  The caller synchronises the ranks (a device-side barrier
+ * on the launching stream) before merging block-wise with ffx_merge_topk, and alternates two
+ * buffer sets between calls.  Only the fused fp32 kernel carries the plan: ffx_rerank returns
+ * FFX_ERR_UNSUPPORTED otherwise.  world = 0 removes the plan. */
+int ffx_index_set_topk_scatter(ffx_index *idx, int world, int rank, int64_t stride, const int64_t *bounds,
+                               void *const *peer_score, void *const *peer_pos);
+
 /* Replaces `Quantizer.decode` on the scoring path (quantizer/base.py:123-132 ->
  * quantizer/nanopq.py:43-44,111-112): attaches nanopq-compatible codebooks
  * `codewords[M][Ks][Ds]` and, for OPQ, the rotation `R[D][D]` (NULL for plain PQ) to an

@@ -164,3 +164,22 @@ def test_exchange_plumbing_gloo_world2(tmp_path):
     port = _free_port()
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["rank0.ok", "rank1.ok"]
+
+
+@pytest.mark.gpu
+def test_fused_peer_memory_exchange_on_two_gpus():
+    """`ShardedReranker(p2p=True)`: the scoring kernel's epilogue stores the top-k lists into the
+    owner rank's buffer over peer memory.  Needs two GPUs (skipped on a one-GPU box): compared
+    with the NCCL all-to-all path and with an unsharded index by tools/p2p_check.py."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+                          os.path.join(root, "tools", "p2p_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "identical=True" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
