@@ -168,6 +168,14 @@ class ShardedReranker:
         stream = torch.cuda.current_stream().cuda_stream if qvecs.is_cuda else 0
         nq = qvecs.shape[0]
         bounds = self.owner_bounds(nq)
+        if self.world > 1 and self.p2p and self._p2p_sets is None:
+            try:  # collective set-up: it fails on every rank or on none
+                self._p2p_buffers(nq, k, qvecs.device)
+            except Exception as e:  # no peer access between the GPUs: say so, use NCCL
+                import warnings
+
+                warnings.warn(f"symmetric memory unavailable ({e}); exchanging the top-k lists with NCCL all-to-all")
+                self.p2p = False
         if self.world > 1 and self.p2p:
             mine_s, mine_p = self._rerank_p2p(mode, qvecs, q_off, cand, lex, alpha, k, max_cand, stream)
         else:
