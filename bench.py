@@ -34,8 +34,25 @@ import time
 
 import numpy as np
 
-# stdout carries exactly one JSON line: NCCL's own version / debug lines go to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line: everything libraries print there (NCCL's version
+# banner, ...) is sent to stderr at the file-descriptor level; emit() writes to the real stdout
+_REAL_STDOUT = None
+
+
+def _claim_stdout() -> None:
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    if _REAL_STDOUT is None:
+        print(json.dumps(line), flush=True)
+    else:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "fast-forward-indexes_b200")
@@ -233,7 +250,7 @@ def run_reference(args, wl):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def build_corpus(wl, scale, rank, world):
@@ -482,7 +499,7 @@ def run_ffx(args, wl):
             v, dt, cores, sample, _ = cpu_port_run(wl, args.alpha, q_per_core=64)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
                                     "sample": sample, "seconds": round(dt, 2)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1 and not emulate:
         dist.barrier()
         dist.destroy_process_group()
@@ -490,6 +507,7 @@ def run_ffx(args, wl):
 
 
 def main():
+    _claim_stdout()
     args = parse()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
