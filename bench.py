@@ -56,7 +56,7 @@ def emit(line: dict) -> None:
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "fast-forward-indexes_b200")
-sys.path.insert(0, PKG)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")  # the unmodified reference, pip-installed offline
 
 METRIC = "re-ranked (query,doc) pairs/sec, MAXP k=5000"
 DIM = 768
@@ -90,6 +90,8 @@ def parse():
                     help="shrink docs and queries (debug only; the line says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--alpha", type=float, default=0.1)
+    ap.add_argument("--cpu-budget", default="short", choices=["short", "long"],
+                    help="--impl reference: queries per core and step (short: a few seconds per step)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="sharded workloads: fused peer-memory exchange in the kernel epilogue, or an NCCL all-to-all")
     ap.add_argument("--emulate-shards", type=int, default=0,
@@ -227,13 +229,120 @@ def ncu_traffic():
 
 
 # ------------------------------------------------------------------------------------------
+# CPU baseline, preferred form: the UNMODIFIED reference package from baseline/_ref
+# ------------------------------------------------------------------------------------------
+def reference_installed() -> bool:
+    return os.path.isdir(os.path.join(REF_DIR, "fast_forward"))
+
+
+def _import_reference():
+    """`import fast_forward` from baseline/_ref.  Its two dependencies that are not in the image
+    (h5py: only OnDiskIndex needs it; nanopq: only the quantizers) are stubbed with empty modules —
+    the path timed here (InMemoryIndex fp32 -> Index.__call__ -> Ranking.interpolate -> cut)
+    touches neither."""
+    import types
+
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    for name in ("h5py", "nanopq"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except ImportError:
+                stub = types.ModuleType(name)
+                stub.File = None  # index/disk.py:138 names h5py.File in an annotation at import time
+                sys.modules[name] = stub
+    import fast_forward
+
+    assert os.path.abspath(fast_forward.__file__).startswith(os.path.abspath(REF_DIR)), fast_forward.__file__
+    return fast_forward
+
+
+def _ref_worker(args):
+    """One process: the reference's own three calls over its share of the queries."""
+    import pandas as pd
+
+    q_lo, q_hi, cands, k, alpha, batch = args
+    ff = _import_reference()
+    from fast_forward.encoder import LambdaEncoder
+    from fast_forward.index import InMemoryIndex, Mode
+
+    qv, cand, lex = _CPU["qv"], _CPU["cand"], _CPU["lex"]
+    if "index" not in _CPU:  # built once per worker process (outside the timed region: see the warm-up)
+        table = {f"text {i}": qv[i] for i in range(len(qv))}
+        index = InMemoryIndex(LambdaEncoder(lambda q: table[q]), mode=Mode.MAXP, init_size=len(_CPU["vec"]))
+        index.add(_CPU["vec"], doc_ids=_CPU["doc_ids"])
+        _CPU["index"] = index
+    if q_hi <= q_lo:
+        return 0.0
+    index = _CPU["index"]
+    rows = slice(q_lo * cands, q_hi * cands)
+    frame = pd.DataFrame({"q_id": np.repeat([f"q{i}" for i in range(q_lo, q_hi)], cands),
+                          "id": [f"D{d}" for d in cand[rows]], "score": lex[rows]})
+    first = ff.Ranking(frame, queries={f"q{i}": f"text {i}" for i in range(q_lo, q_hi)})
+    t0 = time.perf_counter()
+    out = first.interpolate(index(first, batch_size=batch), alpha).cut(k)
+    dt = time.perf_counter() - t0
+    assert len(out._df) == (q_hi - q_lo) * min(k, cands)
+    return dt
+
+
+def cpu_reference_run(wl, alpha, q_per_core=5, cores=None):
+    """Times the unmodified reference (`Index.__call__` + `Ranking.interpolate` + `Ranking.cut`,
+    index/base.py:389-469, ranking.py:293-326,279-291) on `cores` processes x `q_per_core`
+    queries of the workload's shape over a scaled-down in-memory index.  `batch_size=2` keeps
+    its three [pairs*passages, 768] temporaries near 300 MB per process (index/base.py:445-459)."""
+    import multiprocessing as mp
+
+    cores = min(cores or os.cpu_count() or 1, 64)
+    n_docs = 10_000
+    cnt = doc_lengths(n_docs, wl["mean_psg"], seed=1)
+    rng = np.random.default_rng(2)
+    n_rows = int(cnt.sum())
+    _CPU["vec"] = rng.standard_normal((n_rows, DIM), dtype=np.float32)
+    _CPU["doc_ids"] = np.repeat([f"D{d}" for d in range(n_docs)], cnt).tolist()
+    nq = cores * q_per_core
+    cands = wl["cands"]
+    _CPU["qv"] = rng.standard_normal((nq, DIM), dtype=np.float32)
+    _CPU["cand"] = np.concatenate([rng.choice(n_docs, cands, replace=False) for _ in range(nq)])
+    _CPU["lex"] = rng.uniform(0, 20, nq * cands).astype(np.float32)
+    if q_per_core % 2 == 0:
+        q_per_core_batch = 3  # the reference crashes on an empty trailing batch (batch_size | #queries)
+    else:
+        q_per_core_batch = 2
+    jobs = [(c * q_per_core, (c + 1) * q_per_core, cands, wl["k"], alpha, q_per_core_batch) for c in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_ref_worker, [(0, 0, cands, wl["k"], alpha, 2)] * cores, chunksize=1)  # import + build the index
+        # every process times its own three calls (the first-stage Ranking is built before the
+        # clock starts); the processes run side by side, the slowest one is the step
+        dt = max(pool.map(_ref_worker, jobs, chunksize=1))
+    pairs = nq * cands
+    sample = (f"{nq} queries x {cands} candidates MAXP over a {n_docs}-doc / {n_rows}-passage 768-d fp32 "
+              f"InMemoryIndex, the UNMODIFIED reference package (baseline/_ref): Index.__call__(batch_size="
+              f"{q_per_core_batch}) + Ranking.interpolate + Ranking.cut, {cores} processes x {q_per_core} queries")
+    _CPU.clear()
+    return pairs / dt, dt, cores, sample, pairs
+
+
+def cpu_baseline_run(wl, alpha, budget="long"):
+    """(value, seconds, cores, sample, kind): the reference itself when baseline/_ref travelled
+    with the repo, else the numpy port of oracle/."""
+    if reference_installed():
+        v, dt, cores, sample, _ = cpu_reference_run(wl, alpha, q_per_core=9 if budget == "long" else 5)
+        return v, dt, cores, sample, "reference"
+    v, dt, cores, sample, _ = cpu_port_run(wl, alpha, q_per_core=64 if budget == "long" else 24)
+    return v, dt, cores, sample, "port"
+
+
+# ------------------------------------------------------------------------------------------
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     vals, times = [], []
     for step in range(args.warmup + args.steps):
-        v, dt, cores, sample, pairs = cpu_port_run(wl, args.alpha, q_per_core=24)
+        v, dt, cores, sample, kind = cpu_baseline_run(wl, args.alpha, budget=args.cpu_budget)
         if step >= args.warmup:
             vals.append(v)
             times.append(dt)
@@ -246,11 +355,26 @@ def run_reference(args, wl):
         "config": {"workload": args.workload, "mode": "MAXP", "dim": DIM, "candidates_per_query": wl["cands"],
                    "cut_k": wl["k"], "alpha": args.alpha,
                    "note": "each step = a bounded sample of the workload on the host cores"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def cpu_baseline_subprocess(args):
+    """The CPU baseline runs in its own interpreter: the reference package has the same import
+    name (`fast_forward`) as the drop-in this process has loaded."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--alpha", str(args.alpha), "--cpu-budget", "long"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    for ln in out.stdout.splitlines():
+        if ln.startswith("{"):
+            base = json.loads(ln)["cpu_baseline"]
+            base["seconds"] = round(json.loads(ln)["ms_per_step"] / 1e3, 2)
+            return base
+    raise RuntimeError("cpu baseline failed: " + out.stderr[-2000:])
 
 
 def build_corpus(wl, scale, rank, world):
@@ -268,6 +392,7 @@ def run_ffx(args, wl):
     import torch
     import torch.distributed as dist
 
+    sys.path.insert(0, PKG)
     from fast_forward import _ffx
     from fast_forward.sharded import ShardedReranker, plan_doc_shards
 
@@ -496,9 +621,7 @@ def run_ffx(args, wl):
         if pq:
             line["roofline"]["lut_lookups_per_s"] = rows_touched * wl["M"] / (kern_ms * 1e-3)
         if not args.no_cpu_baseline and world == 1 and args.workload == "c3_msmarco_doc_maxp":
-            v, dt, cores, sample, _ = cpu_port_run(wl, args.alpha, q_per_core=64)
-            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                    "sample": sample, "seconds": round(dt, 2)}
+            line["cpu_baseline"] = cpu_baseline_subprocess(args)
         emit(line)
     if world > 1 and not emulate:
         dist.barrier()
