@@ -27,13 +27,20 @@ qvecs = data["qvecs"]
 queries = {f"q{i}": f"text {i}" for i in range(len(qvecs))}
 table = {f"text {i}": qvecs[i] for i in range(len(qvecs))}
 index = InMemoryIndex(LambdaEncoder(lambda q: table[q]), init_size=len(data["vectors"]))
-index.add(data["vectors"], doc_ids=data["doc_ids"].tolist(), psg_ids=[f"p{i}" for i in range(len(data["vectors"]))])
+split = int(data["split"]) if "split" in data else len(data["vectors"])
+psg_ids = [f"p{i}" for i in range(len(data["vectors"]))]
+# two add() calls: rows after `split` extend earlier documents (their rows are not contiguous)
+index.add(data["vectors"][:split], doc_ids=data["doc_ids"][:split].tolist(), psg_ids=psg_ids[:split])
+if split < len(psg_ids):
+    index.add(data["vectors"][split:], doc_ids=data["doc_ids"][split:].tolist(), psg_ids=psg_ids[split:])
+score_dtype = np.dtype(str(data["score_dtype"])) if "score_dtype" in data else np.dtype(np.float32)
+batch_size = int(data["batch_size"]) if "batch_size" in data and int(data["batch_size"]) > 0 else None
 
 
 def frame(r):
     df = r._df
-    return {"q_id": df["q_id"].tolist(), "id": df["id"].tolist(),
-            "score_bits": df["score"].to_numpy().astype(np.float32).view(np.uint32).tolist()}
+    return {"q_id": df["q_id"].tolist(), "id": df["id"].tolist(), "dtype": str(df["score"].dtype),
+            "score_bits": df["score"].to_numpy().astype(np.float64).view(np.uint64).tolist()}
 
 
 out = {}
@@ -41,9 +48,9 @@ alpha, cutoff = float(data["alpha"]), int(data["cutoff"])
 for mode in (Mode.MAXP, Mode.AVEP, Mode.FIRSTP, Mode.PASSAGE):
     key = "psg" if mode == Mode.PASSAGE else "doc"
     first = ff.Ranking(pd.DataFrame({"q_id": data[f"{key}_q_id"], "id": data[f"{key}_id"], "score": data[f"{key}_score"]}),
-                       queries=queries)
+                       queries=queries, dtype=score_dtype)
     index.mode = mode
-    scored = index(first)
+    scored = index(first, batch_size=batch_size)
     inter = first.interpolate(scored, alpha)
     es = index(first, early_stopping=int(data["es_cutoff"]), early_stopping_alpha=float(data["es_alpha"]),
                early_stopping_depths=tuple(int(d) for d in data["es_depths"]))
