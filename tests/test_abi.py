@@ -62,3 +62,27 @@ def test_bad_arguments_are_rejected_before_cuda(ffx):
     assert lib.ffx_merge_topk(0, None, None, 1, 1, 1, None, None, None) == -1
     assert lib.ffx_index_destroy(None) == 0
     assert lib.ffx_index_num_rows(None) == -1
+
+
+def test_header_is_plain_c():
+    """include/ffx.h is the C ABI: it must compile as C99 on its own (no C++, no torch types)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    header = os.path.join(ROOT, "include", "ffx.h")
+    out = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", header],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+
+
+def test_host_side_id_coding_needs_no_gpu(ffx):
+    """The ffx_dict_* entry points are pure host code: they work in this (GPU-less) container."""
+    import ctypes as C
+
+    h = C.c_void_p()
+    assert ffx.lib().ffx_dict_create(C.byref(h)) == 0
+    assert ffx.lib().ffx_dict_size(h) == 0
+    assert ffx.lib().ffx_dict_destroy(h) == 0
