@@ -325,7 +325,7 @@ int ring_slots(int cpad_scores, int warps, int row_bytes, int ctas_per_sm) {
     return ns;
 }
 
-ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse) {
+ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, bool few_pairs) {
     ScorePlan p;
     // candidates a warp publishes per batch: few rows per candidate (single-row modes, or a shard
     // that owns only a fraction of the candidates) want the larger batch so that the row ring
@@ -337,6 +337,12 @@ ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse) 
     if (g_tune.tma_warps > 0) {  // explicit shape (sweeps)
         p.warps = g_tune.tma_warps;
         p.ns = ring_slots(keys, p.warps, row_bytes, 1);
+    } else if (!fuse && few_pairs) {
+        // a handful of queries (serving latency): small CTAs and small batches give enough tiles to
+        // put rows in flight on every SM
+        p.warps = 2;
+        p.batch = g_tune.batch > 0 ? p.batch : 8;
+        p.ns = std::min(8, ring_slots(0, 2, row_bytes, 4));
     } else if (!fuse) {
         p.warps = 4;
         p.ns = std::min(4, ring_slots(0, 4, row_bytes, 4));
@@ -461,7 +467,9 @@ int launch_topk(const float *scores, bool scores_rel, const float *lex, float al
         FFX_CUDA(cudaFuncSetAttribute(ffx::ffx_topk_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-    ffx::ffx_topk_kernel<<<static_cast<unsigned>(nq), ffx::kThreads, smem, st>>>(
+    // 8 keys per thread where possible: the register / shuffle sort applies from 2048 keys up
+    const int threads = std::max(256, std::min(1024, cpad / 8));
+    ffx::ffx_topk_kernel<<<static_cast<unsigned>(nq), threads, smem, st>>>(
         scores, scores_rel ? 1 : 0, lex, alpha, beta, q_off, k, cpad, gkeys, out_int, out_s, out_p);
     g_launches++;
     FFX_CUDA(cudaGetLastError());
@@ -973,7 +981,8 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     const float *topk_src = rank_scores ? rank_scores : out_int;  // input of a separate top-k pass
 
     // tiles: split a query over several CTAs when there are few queries
-    const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4, idx->sharded) : ScorePlan{};
+    const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4, idx->sharded,
+                                                     nq * max_cand < static_cast<int64_t>(idx->sm_count) * 8 * 64) : ScorePlan{};
     int tiles = 1, tile = static_cast<int>(std::max<int64_t>(max_cand, 1));
     if (!fuse) {
         // enough CTAs for ~2 waves at the plan's occupancy, but a tile keeps every warp of its

@@ -224,15 +224,16 @@ __device__ __forceinline__ void write_topk(const unsigned long long *keys, int n
 // their count and writes the k best.  A shard that owns 1/8 of the candidates therefore sorts
 // 1024 keys per query instead of 8192 (the sort was ~20 % of such a shard's time).
 // All threads of the CTA must call it; `keys` must hold next_pow2(n) entries.
-__device__ inline void rank_scores_topk(const float *scores, int n, unsigned long long *keys, int k,
-                                        float *out_s, int32_t *out_p) {
+template <class ScoreAt>
+__device__ inline void rank_topk(ScoreAt score_at, int n, unsigned long long *keys, int k, float *out_s,
+                                 int32_t *out_p) {
     __shared__ int s_ranked;
     if (threadIdx.x == 0) s_ranked = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     for (int i0 = (threadIdx.x & ~31); i0 < n; i0 += blockDim.x) {  // whole warps stay in the loop
         const int i = i0 + lane;
-        const unsigned long long key = i < n ? topk_key(scores[i], static_cast<uint32_t>(i)) : 0ull;
+        const unsigned long long key = i < n ? topk_key(score_at(i), static_cast<uint32_t>(i)) : 0ull;
         const unsigned ranked = __ballot_sync(kFull, key != 0ull);
         int base = 0;
         if (lane == 0 && ranked) base = atomicAdd(&s_ranked, __popc(ranked));
@@ -247,6 +248,11 @@ __device__ inline void rank_scores_topk(const float *scores, int n, unsigned lon
     __syncthreads();
     block_sort_desc(keys, mpad);
     write_topk(keys, m, k, out_s, out_p);
+}
+
+__device__ inline void rank_scores_topk(const float *scores, int n, unsigned long long *keys, int k,
+                                        float *out_s, int32_t *out_p) {
+    rank_topk([scores](int i) { return scores[i]; }, n, keys, k, out_s, out_p);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -512,33 +518,31 @@ __global__ void __launch_bounds__(128) ffx_score_generic_kernel(const ScoreArgs 
 // With `lex` the kernel first interpolates (ranking.py:319): s = fl(alpha*lex) + fl(beta*scores),
 // optionally storing s to out_int — `Ranking.interpolate` + `Ranking.cut` over existing scores.
 // `scores_rel` != 0: `scores` is a launch-local scratch vector whose element 0 is pair q_off[0].
-__global__ void __launch_bounds__(kThreads) ffx_topk_kernel(const float *scores, int scores_rel, const float *lex,
-                                                            float alpha, float beta,
-                                                            const int64_t *q_off, int k, int cpad,
-                                                            unsigned long long *gkeys,
-                                                            float *out_int, float *out_s,
-                                                            int32_t *out_p) {
+__global__ void __launch_bounds__(1024) ffx_topk_kernel(const float *scores, int scores_rel, const float *lex,
+                                                        float alpha, float beta,
+                                                        const int64_t *q_off, int k, int cpad,
+                                                        unsigned long long *gkeys,
+                                                        float *out_int, float *out_s,
+                                                        int32_t *out_p) {
     extern __shared__ unsigned long long s_keys[];
     const int64_t q = blockIdx.x;
     const int64_t b = q_off[q];
     const int n = static_cast<int>(q_off[q + 1] - b);
+    const float *sc = scores + (b - (scores_rel ? q_off[0] : 0));
     unsigned long long *keys = gkeys ? gkeys + q * cpad : s_keys;
-    for (int i = threadIdx.x; i < cpad; i += blockDim.x) {
-        unsigned long long key = 0ull;
-        if (i < n) {
-            float s = scores[b - (scores_rel ? q_off[0] : 0) + i];
-            if (lex) {
-                s = __fadd_rn(__fmul_rn(alpha, lex[b + i]), __fmul_rn(beta, s));
-                if (out_int) out_int[b + i] = s;
-            }
-            key = topk_key(s, static_cast<uint32_t>(i));
+    auto score_at = [=](int i) {
+        float s = sc[i];
+        if (lex) {
+            s = __fadd_rn(__fmul_rn(alpha, lex[b + i]), __fmul_rn(beta, s));
+            if (out_int) out_int[b + i] = s;
         }
-        if (k > 0) keys[i] = key;
-    }
-    __syncthreads();
+        return s;
+    };
     if (k > 0) {
-        bitonic_sort_desc(keys, cpad);
-        write_topk(keys, n, k, out_s + q * k, out_p + q * k);
+        // only the ranked pairs are sorted (NaN = pair of another shard / NaN score)
+        rank_topk(score_at, n, keys, k, out_s + q * k, out_p + q * k);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) score_at(i);
     }
 }
 
