@@ -404,6 +404,8 @@ def run_ffx(args, wl):
         world = emulate  # sizes and shard plan of an `emulate`-GPU job; only rank 0's local work runs
     if _ffx.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: libffx has no CPU path")
+    if os.environ.get("FFX_CHUNK_WAVES"):
+        _ffx.set_option("chunk_waves", int(os.environ["FFX_CHUNK_WAVES"]))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1 and not emulate:

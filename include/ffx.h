@@ -64,6 +64,7 @@ int ffx_device_count(void);
  *   "tma_stages"  ring slots per warp of the TMA-staged kernel (capped by shared memory)
  *   "batch"       candidates a warp takes per grab (1..32)
  *   "tma_warps"   warps per CTA of the TMA-staged kernel
+ *   "chunk_waves" ffx_rerank_host: queries per pipelined chunk, in units of 2 x #SMs (default 1)
  *   "adc"         1 = generic thread-per-row ADC kernel, 2 = warp-per-row with conflict-free tables
  *                 (M = 64..128), 3 = XOR-swizzled thread-per-row (M % 32 == 0, M <= 128); a kernel the
  *                 shape does not allow falls back to the next one */
