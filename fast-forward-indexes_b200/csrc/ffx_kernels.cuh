@@ -224,6 +224,89 @@ __device__ __forceinline__ void write_topk(const unsigned long long *keys, int n
 // their count and writes the k best.  A shard that owns 1/8 of the candidates therefore sorts
 // 1024 keys per query instead of 8192 (the sort was ~20 % of such a shard's time).
 // All threads of the CTA must call it; `keys` must hold next_pow2(n) entries.
+// keys[0, m): distinct non-zero keys.  Moves the kk = min(k, m) largest to keys[0, kk) (in their
+// original relative order) without sorting: MSB-first radix select of the kk-th largest key in
+// 8-bit digits (histogram in shared memory, at most 8 passes, usually 3-4: it stops as soon as
+// the bucket of the kk-th key is wholly selected), then a stable in-place compaction.  For
+// k << m this replaces a bitonic sort of next_pow2(m) keys by one of next_pow2(k).
+__device__ inline void select_largest_keys(unsigned long long *keys, int m, int kk) {
+    __shared__ int s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_rem, s_done, s_base;
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        s_prefix = 0ull;
+        s_rem = kk;
+        s_done = 0;
+    }
+    int shift = 56;
+    for (; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += T) s_hist[i] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        for (int i = tid; i < m; i += T) {
+            const unsigned long long key = keys[i];
+            if (shift == 56 || (key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (tid < 32) {  // lane l owns digits 8l .. 8l+7; find the digit holding the s_rem-th largest
+            const int rem = s_rem;
+            int c[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                c[j] = s_hist[8 * lane + j];
+                tot += c[j];
+            }
+            int incl = tot;  // keys in the digits of lanes >= lane
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_down_sync(kFull, incl, d);
+                if (lane + d < 32) incl += v;
+            }
+            int acc = incl - tot;  // keys in strictly higher lanes
+            if (acc < rem && rem <= incl) {
+#pragma unroll
+                for (int j = 7; j >= 0; j--) {
+                    if (acc + c[j] >= rem) {
+                        s_prefix = (prefix << 8) | static_cast<unsigned long long>(8 * lane + j);
+                        s_rem = rem - acc;
+                        s_done = (c[j] == rem - acc) ? 1 : 0;  // the whole bucket is selected
+                        break;
+                    }
+                    acc += c[j];
+                }
+            }
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+    if (shift < 0) shift = 0;
+    const unsigned long long threshold = s_prefix << shift;  // smallest selected key (or a lower bound of it)
+    // stable in-place compaction, one block of T keys at a time (writes never pass the reads)
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    __shared__ int s_warp_cnt[32];
+    for (int i0 = 0; i0 < m; i0 += T) {
+        const int i = i0 + tid;
+        const unsigned long long key = i < m ? keys[i] : 0ull;
+        const bool keep = key >= threshold && key != 0ull;
+        const unsigned mask = __ballot_sync(kFull, keep);
+        if (lane == 0) s_warp_cnt[tid >> 5] = __popc(mask);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < (tid >> 5); w++) before += s_warp_cnt[w];
+        const int base = s_base;
+        if (keep) keys[base + before + __popc(mask & ((1u << lane) - 1u))] = key;
+        __syncthreads();
+        if (tid == 0) {
+            int total = 0;
+            for (int w = 0; w < (T + 31) / 32; w++) total += s_warp_cnt[w];
+            s_base = base + total;
+        }
+        __syncthreads();
+    }
+}
+
 template <class ScoreAt>
 __device__ inline void rank_topk(ScoreAt score_at, int n, unsigned long long *keys, int k, float *out_s,
                                  int32_t *out_p) {
@@ -241,7 +324,11 @@ __device__ inline void rank_topk(ScoreAt score_at, int n, unsigned long long *ke
         if (key != 0ull) keys[base + __popc(ranked & ((1u << lane) - 1u))] = key;
     }
     __syncthreads();
-    const int m = s_ranked;
+    int m = s_ranked;
+    if (m >= 1024 && k <= m / 4) {  // a short list out of many: select first, sort only the survivors
+        select_largest_keys(keys, m, k);
+        m = k;
+    }
     int mpad = 1;
     while (mpad < m) mpad <<= 1;
     for (int i = m + threadIdx.x; i < mpad; i += blockDim.x) keys[i] = 0ull;

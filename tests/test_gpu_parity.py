@@ -361,6 +361,31 @@ def test_staging_larger_than_the_pinned_buffer(ffx):
     idx.close()
 
 
+@pytest.mark.parametrize("nq", [4, 320])
+def test_short_lists_out_of_long_candidate_lists(ffx, oracle_c, nq):
+    """k << candidates takes the radix-select path (select_largest_keys: the k-th largest key by
+    8-bit digits, stable compaction, then a sort of only next_pow2(k) keys) — in the fused
+    kernel's epilogue (nq = 320) and in ffx_topk_kernel (nq = 4).  Coarse lexical scores with
+    alpha = 1 make thousands of exactly equal scores: the cut must fall by position."""
+    rng = np.random.default_rng(nq)
+    off, rows, vec = make_corpus(rng, 6000, 3, 384, True)
+    idx = ffx.DeviceIndex(384, capacity=len(vec))
+    idx.stage(0, vec)
+    idx.set_docs(off)
+    qv = rng.standard_normal((nq, 384)).astype(np.float32)
+    q_off, cand, pair_q = make_pairs(rng, nq, 6000, 1100, 5000)
+    ff = c_scores(oracle_c, vec, off, rows, pair_q, cand, qv, fo.MODE_MAXP)
+    for alpha, lex in ((1.0, rng.integers(0, 5, len(cand)).astype(np.float32)),
+                       (0.3, rng.uniform(0, 20, len(cand)).astype(np.float32))):
+        it = fo.interpolate_f32(lex, ff, alpha)
+        for k in (1, 7, 100, 256, 275):
+            out = idx.rerank_host(fo.MODE_MAXP, qv, q_off, cand, lex, alpha, k, want_ff=False, want_int=False)
+            ts, tp = fo.topk_per_query(q_off, it, k)
+            assert (out["topk_pos"] == tp).all(), (alpha, k)
+            assert (bits(out["topk_score"]) == bits(ts)).all(), (alpha, k)
+    idx.close()
+
+
 # ------------------------------------------------------------------------------------------
 # PQ / OPQ asymmetric distance
 # ------------------------------------------------------------------------------------------
