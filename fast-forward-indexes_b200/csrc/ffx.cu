@@ -333,8 +333,19 @@ ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, 
     // always has something to prefetch
     const bool one_row = mode == FFX_MODE_PASSAGE || mode == FFX_MODE_FIRSTP;
     p.batch = g_tune.batch > 0 ? std::min(32, g_tune.batch) : (one_row || sparse ? 32 : 16);
-    if (g_tune.kernel == 1) return p;
     const int keys = fuse ? cpad : 0;
+    if (ffx::tma_streams_query(row_bytes)) {
+        // 10-16 KB rows (D >= 2560): only the TMA-staged kernel exists; few warps, each with at least
+        // two row slots, fill shared memory next to the query vector and the scores
+        for (p.warps = 8; p.warps >= 2; p.warps -= 2) {
+            p.ns = std::min(4, ring_slots(keys, p.warps, row_bytes, 1));
+            if (p.ns >= 2) break;
+        }
+        if (g_tune.tma_stages > 0) p.ns = std::min(p.ns, std::max(2, g_tune.tma_stages));
+        p.tma = p.ns >= 2;
+        return p;
+    }
+    if (g_tune.kernel == 1) return p;
     if (g_tune.tma_warps > 0) {  // explicit shape (sweeps)
         p.warps = g_tune.tma_warps;
         p.ns = ring_slots(keys, p.warps, row_bytes, 1);
@@ -377,6 +388,10 @@ int dispatch_score(const ffx_plan &p, const ScorePlan &sp, const ffx::ScoreArgs 
         FFX_CASE(2, 16);
         FFX_CASE(4, 12);
         FFX_CASE(4, 16);
+        FFX_CASE(8, 10);
+        FFX_CASE(8, 12);
+        FFX_CASE(8, 14);
+        FFX_CASE(8, 16);
 #undef FFX_CASE
     }
     const size_t smem = fuse ? static_cast<size_t>(a.cpad) * 8 : 0;

@@ -30,6 +30,9 @@ static inline ffx_plan ffx_plan_for_dim(int64_t dim) {
     static const struct { int dim, cpl, steps; } table[] = {
         {384, 1, 12}, {512, 1, 16}, {640, 2, 10}, {768, 2, 12},
         {896, 2, 14}, {1024, 2, 16}, {1536, 4, 12}, {2048, 4, 16},
+        // 32 leaves of 8*S elements, one whole leaf per lane: the row is streamed against a
+        // shared-memory copy of the query vector (ffx_score_tma.cuh, kStream)
+        {2560, 8, 10}, {3072, 8, 12}, {3584, 8, 14}, {4096, 8, 16},
     };
     for (unsigned i = 0; i < sizeof(table) / sizeof(table[0]); i++)
         if (table[i].dim == dim) return ffx_plan{table[i].cpl, table[i].steps};

@@ -64,10 +64,41 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 
 // Dynamic shared memory of one CTA: [FUSE: cpad interpolated scores][ring][mbarriers][descriptors].
 // The 64-bit sort keys of the fused top-k are built inside the ring once it has drained.
+// Rows of more than 64 elements per lane (D >= 2560) do not fit the register file next to the
+// query vector: the query is kept in shared memory too (one more row-sized region).
+__host__ __device__ inline bool tma_streams_query(int row_bytes) { return row_bytes > 32 * 64 * 4; }
+
 __host__ __device__ inline size_t tma_smem_bytes(int cpad_scores, int warps, int ns, int row_bytes) {
     size_t keys = (static_cast<size_t>(cpad_scores) * 4 + 127) & ~static_cast<size_t>(127);
-    return keys + static_cast<size_t>(warps) * ns * row_bytes + static_cast<size_t>(warps) * ns * 8 +
+    return keys + (tma_streams_query(row_bytes) ? static_cast<size_t>(row_bytes) : 0) +
+           static_cast<size_t>(warps) * ns * row_bytes + static_cast<size_t>(warps) * ns * 8 +
            static_cast<size_t>(warps) * 2 * 32 * sizeof(CandDesc) + 128;
+}
+
+// One row against the query, both in shared memory in lane-major order: lane l owns one whole
+// numpy leaf (CPL = 8 accumulators of S terms); same products, same chains, same combine order
+// as lane_chain_sum, with 8 live accumulators instead of 2 x 8*S registers.
+template <int CPL, int S>
+__device__ __forceinline__ float lane_chain_sum_streamed(uint32_t q_addr, uint32_t row_addr) {
+    constexpr int NV4 = CPL * S / 4;
+    float acc[CPL];
+#pragma unroll
+    for (int i = 0; i < NV4; i++) {
+        const float4 q = lds_f4(q_addr + i * 512);
+        const float4 v = lds_f4(row_addr + i * 512);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int m = 4 * i + c, ch = m % CPL;
+            const float prod = __fmul_rn(f4c(q, c), f4c(v, c));
+            acc[ch] = (m / CPL == 0) ? prod : __fadd_rn(acc[ch], prod);
+        }
+    }
+#pragma unroll
+    for (int w = 1; w < CPL; w <<= 1) {
+#pragma unroll
+        for (int ch = 0; ch < CPL; ch += 2 * w) acc[ch] = __fadd_rn(acc[ch], acc[ch + w]);
+    }
+    return acc[0];
 }
 
 template <int CPL, int S, bool FUSE>
@@ -77,6 +108,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
     constexpr int NV4 = EPL / 4;
     constexpr uint32_t ROWB = 32u * EPL * 4u;
     constexpr bool kPairRows = EPL <= 32;  // two rows of registers per lane only while they fit
+    constexpr bool kStream = EPL > 64;     // query vector in shared memory, rows streamed against it
     static_assert(EPL % 4 == 0, "lane slice must be whole float4s");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -96,6 +128,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
     // ---- carve shared memory: [scores][ring][mbarriers][descriptors]
     float *s_scores = reinterpret_cast<float *>(smem_raw);
     size_t off = FUSE ? ((static_cast<size_t>(a.cpad) * 4 + 127) & ~static_cast<size_t>(127)) : 0;
+    float *s_q = reinterpret_cast<float *>(smem_raw + off);  // kStream: the query vector, lane-major
+    if (kStream) off += ROWB;
     unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem_raw + off);  // = ring, after the drain
     const uint32_t ring = smem_u32(smem_raw + off) + static_cast<uint32_t>(warp) * ns * ROWB;
     off += static_cast<size_t>(n_warps) * ns * ROWB;
@@ -116,16 +150,20 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
 
-    // this lane's slice of the query vector (registers, lane-major order)
-    float q[EPL];
-    {
-        const float *qv = a.qvecs + q_idx * (32 * EPL);
+    // this lane's slice of the query vector: registers (lane-major order), or — long rows — a
+    // lane-major copy of the whole vector in shared memory
+    float q[kStream ? 1 : EPL];
+    const float *qv = a.qvecs + q_idx * (32 * EPL);
+    if (kStream) {
+        for (int k = threadIdx.x; k < 32 * EPL; k += blockDim.x) s_q[k] = __ldg(qv + ffx_orig_index(CPL, S, k));
+    } else {
 #pragma unroll
-        for (int m = 0; m < EPL; m++) {
+        for (int m = 0; m < (kStream ? 1 : EPL); m++) {
             const int g = lane * CPL + (m % CPL);
             q[m] = __ldg(qv + (g >> 3) * (8 * S) + 8 * (m / CPL) + (g & 7));
         }
     }
+    const uint32_t q_addr = smem_u32(s_q) + lane * 16;
     __syncthreads();
 
     const char *rows_base = reinterpret_cast<const char *>(a.vectors);
@@ -268,19 +306,25 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
                 const bool two = kPairRows && ck + 1 < cnt;  // warp-uniform
                 const int s0 = c_stage;
                 const int s1 = s0 + 1 == ns ? 0 : s0 + 1;
-                float4 v0[NV4], v1[NV4];
-                mbar_wait(bars + s0 * 8, (c_phase >> s0) & 1u);
-                const uint32_t src0 = ring + s0 * ROWB + lane * 16;
+                float sa, sb = 0.f;
+                if constexpr (kStream) {
+                    mbar_wait(bars + s0 * 8, (c_phase >> s0) & 1u);
+                    sa = lane_chain_sum_streamed<CPL, S>(q_addr, ring + s0 * ROWB + lane * 16);
+                } else {
+                    float4 v0[NV4], v1[NV4];
+                    mbar_wait(bars + s0 * 8, (c_phase >> s0) & 1u);
+                    const uint32_t src0 = ring + s0 * ROWB + lane * 16;
 #pragma unroll
-                for (int i = 0; i < NV4; i++) v0[i] = lds_f4(src0 + i * 512);
-                if (two) {
-                    mbar_wait(bars + s1 * 8, (c_phase >> s1) & 1u);
-                    const uint32_t src1 = ring + s1 * ROWB + lane * 16;
+                    for (int i = 0; i < NV4; i++) v0[i] = lds_f4(src0 + i * 512);
+                    if (two) {
+                        mbar_wait(bars + s1 * 8, (c_phase >> s1) & 1u);
+                        const uint32_t src1 = ring + s1 * ROWB + lane * 16;
 #pragma unroll
-                    for (int i = 0; i < NV4; i++) v1[i] = lds_f4(src1 + i * 512);
+                        for (int i = 0; i < NV4; i++) v1[i] = lds_f4(src1 + i * 512);
+                    }
+                    sa = lane_chain_sum<CPL, S>(q, v0);
+                    sb = two ? lane_chain_sum<CPL, S>(q, v1) : 0.f;
                 }
-                float sa = lane_chain_sum<CPL, S>(q, v0);
-                float sb = two ? lane_chain_sum<CPL, S>(q, v1) : 0.f;
                 sa = warp_tree_sum(sa);
                 if (two) sb = warp_tree_sum(sb);
                 // every lane holds the rows' values in registers now: the slots may be refilled

@@ -321,10 +321,16 @@ class Index(abc.ABC):
             qv = np.ascontiguousarray(query_vectors, dtype=np.float32)[present]
             cand = self._resolve(df["id"], self.mode)
             q_off = np.concatenate([[0], np.cumsum(count)]).astype(np.int64)
-            out = dev.rerank_early_stop_host(self.mode.value, qv, q_off, cand, lex, alpha, cutoff, depths)
-            ff, done_depth = out["ff"], out["scored"].astype(np.int64)
-            LOGGER.info("early stopping: %s of %s rows scored", int(done_depth.sum()), n)
-        else:
+            try:
+                out = dev.rerank_early_stop_host(self.mode.value, qv, q_off, cand, lex, alpha, cutoff, depths)
+            except _ffx.FFXError as e:
+                if e.code != -5:  # FFX_ERR_UNSUPPORTED: e.g. D >= 2560 has no one-launch walk
+                    raise
+                on_device = False
+            else:
+                ff, done_depth = out["ff"], out["scored"].astype(np.int64)
+                LOGGER.info("early stopping: %s of %s rows scored", int(done_depth.sum()), n)
+        if not on_device:
             ff, done_depth = self._early_stopping_walk(df, query_vectors, cutoff, alpha, depths, lex, start,
                                                        count, depth_of_row, slot_of_row)
         scored = depth_of_row < done_depth[slot_of_row]

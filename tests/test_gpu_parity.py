@@ -174,7 +174,7 @@ def test_reference_known_answers(ffx, golden_kat):
 # ------------------------------------------------------------------------------------------
 # seeded random problems against the oracle
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dim", [768, 384, 512, 640, 896, 1024, 1536, 2048, 100, 5, 130])
+@pytest.mark.parametrize("dim", [768, 384, 512, 640, 896, 1024, 1536, 2048, 2560, 3072, 3584, 4096, 100, 5, 130])
 @pytest.mark.parametrize("contiguous", [True, False])
 def test_scores_bit_exact_all_modes(ffx, oracle_c, dim, contiguous):
     rng = np.random.default_rng(dim * 2 + contiguous)
@@ -245,6 +245,32 @@ def test_fused_topk_path_many_queries(ffx, oracle_c, mode):
         # top-k only (no per-pair outputs) must give the same lists
         out2 = idx.rerank_host(m, qv, q_off, cand, lex, alpha, k, want_ff=False, want_int=False)
         assert (out2["topk_pos"] == tp).all() and (bits(out2["topk_score"]) == bits(ts)).all()
+    idx.close()
+
+
+@pytest.mark.parametrize("dim", [2560, 3072, 3584, 4096])
+def test_long_rows_fused_path(ffx, oracle_c, dim):
+    """D >= 2560: 10-16 KB rows streamed from the TMA ring against a shared-memory copy of the
+    query vector (one numpy leaf per lane), in the fused one-CTA-per-query form."""
+    rng = np.random.default_rng(dim)
+    off, rows, vec = make_corpus(rng, 300, 6, dim, True)
+    idx = ffx.DeviceIndex(dim, capacity=len(vec))
+    idx.stage(0, vec)
+    assert (idx.read_rows([0, len(vec) - 1]) == vec[[0, len(vec) - 1]]).all()
+    idx.set_docs(off)
+    nq = 310
+    qv = rng.standard_normal((nq, dim)).astype(np.float32)
+    for mode in (fo.MODE_MAXP, fo.MODE_AVEP, fo.MODE_PASSAGE):
+        pool = len(vec) if mode == fo.MODE_PASSAGE else 300
+        q_off, cand, pair_q = make_pairs(rng, nq, pool, 0, 90)
+        lex = (rng.integers(0, 8, len(cand)) * 4).astype(np.float32)
+        u_off, u_rows = units_for_mode(off, rows, len(vec), mode)
+        ff = c_scores(oracle_c, vec, u_off, u_rows, pair_q, cand, qv, mode)
+        out = idx.rerank_host(mode, qv, q_off, cand, lex, 0.2, 20, want_ff=True, want_int=True)
+        it = fo.interpolate_f32(lex, ff, 0.2)
+        ts, tp = fo.topk_per_query(q_off, it, 20)
+        assert (bits(out["ff"]) == bits(ff)).all()
+        assert (out["topk_pos"] == tp).all() and (bits(out["topk_score"]) == bits(ts)).all()
     idx.close()
 
 
@@ -332,7 +358,7 @@ def test_large_candidate_lists_use_global_keys(ffx, oracle_c):
 # ------------------------------------------------------------------------------------------
 # storage
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dim", [768, 100, 2048])
+@pytest.mark.parametrize("dim", [768, 100, 2048, 3072])
 def test_stage_read_roundtrip_and_growth(ffx, dim):
     rng = np.random.default_rng(dim)
     vec = rng.standard_normal((5000, dim)).astype(np.float32)
