@@ -106,7 +106,7 @@ struct ffx_index {
     int64_t dim = 0;
     int64_t capacity = 0;
     int64_t num_rows = 0;
-    ffx_plan plan{0, 0};
+    ffx_plan plan{0, 0, 32};
     size_t row_bytes = 0;
     void *store = nullptr;
     int sm_count = 148;
@@ -234,7 +234,7 @@ int launch_to_store(ffx_index *idx, int64_t row0, int64_t nrows, const void *src
         ffx::ffx_permute_rows_kernel<<<permute_grid(nrows * idx->dim, idx->sm_count), 256, 0,
                                        idx->stream>>>(
             reinterpret_cast<float *>(dst), static_cast<const float *>(src_dev), nrows,
-            static_cast<int>(idx->dim), idx->plan.cpl, idx->plan.steps, 1, nullptr);
+            static_cast<int>(idx->dim), idx->plan.cpl, idx->plan.steps, idx->plan.lanes, 1, nullptr);
         g_launches++;
         FFX_CUDA(cudaGetLastError());
     } else {
@@ -260,16 +260,16 @@ int launch_score(const ffx::ScoreArgs &a, bool fuse, int grid, size_t smem, cuda
     return FFX_OK;
 }
 
-template <int CPL, int S>
+template <int CPL, int S, int LPR = 32>
 int launch_score_tma(const ffx::ScoreArgs &a, bool fuse, int grid, int warps, int ns, int batch,
                      cudaStream_t st) {
-    const size_t smem = ffx::tma_smem_bytes(fuse ? a.cpad : 0, warps, ns, 32 * CPL * S * 4);
+    const size_t smem = ffx::tma_smem_bytes(fuse ? a.cpad : 0, warps, ns, LPR * CPL * S * 4);
     if (fuse) {
-        auto kern = ffx::ffx_score_tma_kernel<CPL, S, true>;
+        auto kern = ffx::ffx_score_tma_kernel<CPL, S, true, LPR>;
         FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         kern<<<grid, warps * 32, smem, st>>>(a, ns, batch);
     } else {
-        auto kern = ffx::ffx_score_tma_kernel<CPL, S, false>;
+        auto kern = ffx::ffx_score_tma_kernel<CPL, S, false, LPR>;
         FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         kern<<<grid, warps * 32, smem, st>>>(a, ns, batch);
     }
@@ -326,7 +326,7 @@ int ring_slots(int cpad_scores, int warps, int row_bytes, int ctas_per_sm) {
     return ns;
 }
 
-ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, bool few_pairs) {
+ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, bool few_pairs, bool short_rows) {
     ScorePlan p;
     // candidates a warp publishes per batch: few rows per candidate (single-row modes, or a shard
     // that owns only a fraction of the candidates) want the larger batch so that the row ring
@@ -343,6 +343,16 @@ ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, 
         }
         if (g_tune.tma_stages > 0) p.ns = std::min(p.ns, std::max(2, g_tune.tma_stages));
         p.tma = p.ns >= 2;
+        return p;
+    }
+    if (short_rows) {
+        // 256-1024 byte rows (D <= 256), 2 or 4 per warp step: deep rings keep enough bytes in flight
+        p.warps = fuse ? 8 : (few_pairs ? 2 : 4);
+        if (!fuse && few_pairs && g_tune.batch <= 0) p.batch = 8;
+        p.ns = std::min(16, ring_slots(keys, p.warps, row_bytes, fuse ? 2 : 4));
+        if (p.ns < 4) p.ns = std::min(16, ring_slots(keys, p.warps, row_bytes, 1));
+        if (g_tune.tma_stages > 0) p.ns = std::min(p.ns, std::max(4, g_tune.tma_stages));
+        p.tma = p.ns >= 4;
         return p;
     }
     if (g_tune.kernel == 1) return p;
@@ -379,7 +389,8 @@ int dispatch_score(const ffx_plan &p, const ScorePlan &sp, const ffx::ScoreArgs 
                    cudaStream_t st) {
     if (sp.tma) {
 #define FFX_CASE(C, S_) \
-    if (p.cpl == C && p.steps == S_) return launch_score_tma<C, S_>(a, fuse, grid, sp.warps, sp.ns, sp.batch, st)
+    if (p.lanes == 32 && p.cpl == C && p.steps == S_) \
+        return launch_score_tma<C, S_>(a, fuse, grid, sp.warps, sp.ns, sp.batch, st)
         FFX_CASE(1, 12);
         FFX_CASE(1, 16);
         FFX_CASE(2, 10);
@@ -393,10 +404,18 @@ int dispatch_score(const ffx_plan &p, const ScorePlan &sp, const ffx::ScoreArgs 
         FFX_CASE(8, 14);
         FFX_CASE(8, 16);
 #undef FFX_CASE
+#define FFX_CASE(S_, L) \
+    if (p.lanes == L && p.steps == S_) return launch_score_tma<1, S_, L>(a, fuse, grid, sp.warps, sp.ns, sp.batch, st)
+        FFX_CASE(8, 8);
+        FFX_CASE(12, 8);
+        FFX_CASE(16, 8);
+        FFX_CASE(12, 16);
+        FFX_CASE(16, 16);
+#undef FFX_CASE
     }
     const size_t smem = fuse ? static_cast<size_t>(a.cpad) * 8 : 0;
 #define FFX_CASE(C, S_) \
-    if (p.cpl == C && p.steps == S_) return launch_score<C, S_>(a, fuse, grid, smem, st)
+    if (p.lanes == 32 && p.cpl == C && p.steps == S_) return launch_score<C, S_>(a, fuse, grid, smem, st)
     FFX_CASE(1, 12);
     FFX_CASE(1, 16);
     FFX_CASE(2, 10);
@@ -745,7 +764,7 @@ int ffx_index_read_rows(ffx_index *idx, const int64_t *rows, int64_t n, void *ou
             ffx::ffx_permute_rows_kernel<<<permute_grid(nr * idx->dim, idx->sm_count), 256, 0,
                                            idx->stream>>>(
                 reinterpret_cast<float *>(d_out), static_cast<const float *>(idx->store), nr,
-                static_cast<int>(idx->dim), idx->plan.cpl, idx->plan.steps, 0, d_rows);
+                static_cast<int>(idx->dim), idx->plan.cpl, idx->plan.steps, idx->plan.lanes, 0, d_rows);
         } else {
             ffx::ffx_gather_bytes_kernel<<<permute_grid(nr * idx->dim, idx->sm_count), 256, 0,
                                            idx->stream>>>(
@@ -999,7 +1018,8 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
 
     // tiles: split a query over several CTAs when there are few queries
     const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4, idx->sharded,
-                                                     nq * max_cand < static_cast<int64_t>(idx->sm_count) * 8 * 64) : ScorePlan{};
+                                                     nq * max_cand < static_cast<int64_t>(idx->sm_count) * 8 * 64,
+                                                     idx->plan.lanes != 32) : ScorePlan{};
     int tiles = 1, tile = static_cast<int>(std::max<int64_t>(max_cand, 1));
     if (!fuse) {
         // enough CTAs for ~2 waves at the plan's occupancy, but a tile keeps every warp of its
@@ -1325,7 +1345,7 @@ int ffx_rerank_early_stop(ffx_index *idx, int mode, const float *qvecs, int64_t 
     const size_t smem = static_cast<size_t>(cpad) * 8;
     const ffx_plan &p = idx->plan;
 #define FFX_CASE(C, S_) \
-    if (p.cpl == C && p.steps == S_) return launch_es<C, S_>(a, es, static_cast<unsigned>(nq), smem, st)
+    if (p.lanes == 32 && p.cpl == C && p.steps == S_) return launch_es<C, S_>(a, es, static_cast<unsigned>(nq), smem, st)
     FFX_CASE(1, 12);
     FFX_CASE(1, 16);
     FFX_CASE(2, 10);

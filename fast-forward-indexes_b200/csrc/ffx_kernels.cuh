@@ -668,13 +668,13 @@ __global__ void __launch_bounds__(kThreads) ffx_merge_topk_kernel(const float *s
 // to_store != 0: dst(store row, staged k) = src(row, orig(k)); else the inverse.
 // `rows` (optional) lists the store rows to read when gathering back.
 __global__ void ffx_permute_rows_kernel(float *dst, const float *src, int64_t nrows, int dim,
-                                        int cpl, int steps, int to_store, const int64_t *rows) {
+                                        int cpl, int steps, int lanes, int to_store, const int64_t *rows) {
     const int64_t total = nrows * dim;
     for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
          t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t r = t / dim;
         const int k = static_cast<int>(t % dim);
-        const int e = cpl ? ffx_orig_index(cpl, steps, k) : k;
+        const int e = cpl ? ffx_orig_index(cpl, steps, k, lanes) : k;
         if (to_store) {
             dst[r * dim + k] = src[r * dim + e];
         } else {

@@ -23,28 +23,32 @@
 struct ffx_plan {
     int cpl;    // chains per lane (1, 2, 4, 8); 0 = no fast plan (identity layout)
     int steps;  // S: terms per chain
+    int lanes;  // lanes that share one row: 32, or 16 / 8 for short rows (several rows per warp step)
 };
 
-// D = 32 * cpl * steps.  Only shapes whose numpy tree is uniform qualify.
+// D = lanes * cpl * steps.  Only shapes whose numpy tree is uniform qualify.
 static inline ffx_plan ffx_plan_for_dim(int64_t dim) {
-    static const struct { int dim, cpl, steps; } table[] = {
-        {384, 1, 12}, {512, 1, 16}, {640, 2, 10}, {768, 2, 12},
-        {896, 2, 14}, {1024, 2, 16}, {1536, 4, 12}, {2048, 4, 16},
+    static const struct { int dim, cpl, steps, lanes; } table[] = {
+        {384, 1, 12, 32}, {512, 1, 16, 32}, {640, 2, 10, 32}, {768, 2, 12, 32},
+        {896, 2, 14, 32}, {1024, 2, 16, 32}, {1536, 4, 12, 32}, {2048, 4, 16, 32},
         // 32 leaves of 8*S elements, one whole leaf per lane: the row is streamed against a
         // shared-memory copy of the query vector (ffx_score_tma.cuh, kStream)
-        {2560, 8, 10}, {3072, 8, 12}, {3584, 8, 14}, {4096, 8, 16},
+        {2560, 8, 10, 32}, {3072, 8, 12, 32}, {3584, 8, 14, 32}, {4096, 8, 16, 32},
+        // short rows: one leaf (8 chains) or two (16 chains) — a quarter / half warp per row
+        {64, 1, 8, 8}, {96, 1, 12, 8}, {128, 1, 16, 8}, {192, 1, 12, 16}, {256, 1, 16, 16},
     };
     for (unsigned i = 0; i < sizeof(table) / sizeof(table[0]); i++)
-        if (table[i].dim == dim) return ffx_plan{table[i].cpl, table[i].steps};
-    return ffx_plan{0, 0};
+        if (table[i].dim == dim) return ffx_plan{table[i].cpl, table[i].steps, table[i].lanes};
+    return ffx_plan{0, 0, 32};
 }
 
-// staged float offset k inside a row  ->  original element index
-FFX_HD static inline int ffx_orig_index(int cpl, int steps, int k) {
-    const int i = k >> 7;          // which float4 of the lane
-    const int l = (k & 127) >> 2;  // lane
+// staged float offset k inside a row  ->  original element index.  The i-th float4 of lane l
+// (of the `lanes` lanes sharing the row) sits at float offset (i*lanes + l)*4.
+FFX_HD static inline int ffx_orig_index(int cpl, int steps, int k, int lanes = 32) {
+    const int i = k / (4 * lanes);        // which float4 of the lane
+    const int l = (k % (4 * lanes)) >> 2; // lane
     const int c = k & 3;
-    const int m = 4 * i + c;       // lane-local element
+    const int m = 4 * i + c;              // lane-local element
     const int s = m / cpl, ch = m % cpl;
     const int g = l * cpl + ch;
     return (g >> 3) * (8 * steps) + 8 * s + (g & 7);

@@ -101,15 +101,19 @@ __device__ __forceinline__ float lane_chain_sum_streamed(uint32_t q_addr, uint32
     return acc[0];
 }
 
-template <int CPL, int S, bool FUSE>
+// LPR = lanes that share one row: 32, or 16 / 8 for short rows (D <= 256), where 2 / 4 rows of a
+// document are consumed per warp step, one per lane group.
+template <int CPL, int S, bool FUSE, int LPR = 32>
 __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const ScoreArgs a, const int ns,
                                                                         const int batch) {
     constexpr int EPL = CPL * S;
     constexpr int NV4 = EPL / 4;
-    constexpr uint32_t ROWB = 32u * EPL * 4u;
-    constexpr bool kPairRows = EPL <= 32;  // two rows of registers per lane only while they fit
-    constexpr bool kStream = EPL > 64;     // query vector in shared memory, rows streamed against it
+    constexpr uint32_t ROWB = static_cast<uint32_t>(LPR) * EPL * 4u;
+    constexpr int RPS = 32 / LPR;                        // rows per warp step (short rows)
+    constexpr bool kPairRows = LPR == 32 && EPL <= 32;   // two rows of registers per lane only while they fit
+    constexpr bool kStream = EPL > 64;                   // query vector in shared memory, rows streamed against it
     static_assert(EPL % 4 == 0, "lane slice must be whole float4s");
+    static_assert(LPR == 32 || CPL == 1, "short rows: one chain per lane");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_next;
@@ -153,13 +157,13 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
     // this lane's slice of the query vector: registers (lane-major order), or — long rows — a
     // lane-major copy of the whole vector in shared memory
     float q[kStream ? 1 : EPL];
-    const float *qv = a.qvecs + q_idx * (32 * EPL);
+    const float *qv = a.qvecs + q_idx * (LPR * EPL);
     if (kStream) {
         for (int k = threadIdx.x; k < 32 * EPL; k += blockDim.x) s_q[k] = __ldg(qv + ffx_orig_index(CPL, S, k));
     } else {
 #pragma unroll
         for (int m = 0; m < (kStream ? 1 : EPL); m++) {
-            const int g = lane * CPL + (m % CPL);
+            const int g = (lane % LPR) * CPL + (m % CPL);
             q[m] = __ldg(qv + (g >> 3) * (8 * S) + 8 * (m / CPL) + (g & 7));
         }
     }
@@ -301,6 +305,39 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
             DocReduce red;
             red.init();
             for (uint32_t ck = 0; ck < cnt;) {
+                if constexpr (LPR < 32) {
+                    // short rows: lane group g takes row ck + g of the document from ring slot
+                    // c_stage + g; the butterfly stays inside the group
+                    top_up();
+                    const int nr = static_cast<int>(min(static_cast<uint32_t>(RPS), cnt - ck));  // warp-uniform
+                    const int grp = lane / LPR, sub = lane % LPR;
+                    int sg = c_stage + grp;
+                    if (sg >= ns) sg -= ns;
+                    float part = 0.f;
+                    if (grp < nr) {
+                        float4 v[NV4];
+                        mbar_wait(bars + sg * 8, (c_phase >> sg) & 1u);
+                        const uint32_t src = ring + sg * ROWB + sub * 16;
+#pragma unroll
+                        for (int i = 0; i < NV4; i++) v[i] = lds_f4(src + i * (LPR * 16));
+                        part = lane_chain_sum<CPL, S>(q, v);
+                    }
+#pragma unroll
+                    for (int o = 1; o < LPR; o <<= 1) part = __fadd_rn(part, __shfl_xor_sync(kFull, part, o));
+                    part = __fadd_rn(0.f, part);
+                    __syncwarp();  // the rows are in registers: the slots may be refilled
+                    for (int g = 0; g < nr; g++) {
+                        int slot = c_stage + g;
+                        if (slot >= ns) slot -= ns;
+                        c_phase ^= 1u << slot;
+                        red.add(__shfl_sync(kFull, part, g * LPR), ck + g == 0, a.mode);
+                    }
+                    c_stage += nr;
+                    if (c_stage >= ns) c_stage -= ns;
+                    inflight -= nr;
+                    ck += nr;
+                    continue;
+                }
                 // two rows of the document per step: their multiply/reduce chains interleave
                 top_up();
                 const bool two = kPairRows && ck + 1 < cnt;  // warp-uniform

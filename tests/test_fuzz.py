@@ -12,7 +12,7 @@ from test_gpu_parity import bits, c_scores, make_corpus, units_for_mode
 
 pytestmark = pytest.mark.gpu
 
-DIMS = [768, 384, 1024, 512, 3072, 4096, 100, 33, 8]
+DIMS = [768, 384, 1024, 512, 3072, 4096, 256, 128, 192, 64, 100, 33, 8]
 
 
 @pytest.fixture(scope="module")

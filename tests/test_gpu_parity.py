@@ -174,7 +174,8 @@ def test_reference_known_answers(ffx, golden_kat):
 # ------------------------------------------------------------------------------------------
 # seeded random problems against the oracle
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dim", [768, 384, 512, 640, 896, 1024, 1536, 2048, 2560, 3072, 3584, 4096, 100, 5, 130])
+@pytest.mark.parametrize("dim", [768, 384, 512, 640, 896, 1024, 1536, 2048, 2560, 3072, 3584, 4096, 64, 96, 128, 192,
+                                 256, 100, 5, 130])
 @pytest.mark.parametrize("contiguous", [True, False])
 def test_scores_bit_exact_all_modes(ffx, oracle_c, dim, contiguous):
     rng = np.random.default_rng(dim * 2 + contiguous)
@@ -248,10 +249,11 @@ def test_fused_topk_path_many_queries(ffx, oracle_c, mode):
     idx.close()
 
 
-@pytest.mark.parametrize("dim", [2560, 3072, 3584, 4096])
-def test_long_rows_fused_path(ffx, oracle_c, dim):
+@pytest.mark.parametrize("dim", [2560, 3072, 3584, 4096, 64, 96, 128, 192, 256])
+def test_long_and_short_rows_fused_path(ffx, oracle_c, dim):
     """D >= 2560: 10-16 KB rows streamed from the TMA ring against a shared-memory copy of the
-    query vector (one numpy leaf per lane), in the fused one-CTA-per-query form."""
+    query vector (one numpy leaf per lane); D <= 256: a quarter / half warp per row, 4 / 2 rows
+    per warp step.  Both in the fused one-CTA-per-query form."""
     rng = np.random.default_rng(dim)
     off, rows, vec = make_corpus(rng, 300, 6, dim, True)
     idx = ffx.DeviceIndex(dim, capacity=len(vec))
@@ -358,7 +360,7 @@ def test_large_candidate_lists_use_global_keys(ffx, oracle_c):
 # ------------------------------------------------------------------------------------------
 # storage
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dim", [768, 100, 2048, 3072])
+@pytest.mark.parametrize("dim", [768, 100, 2048, 3072, 128, 256])
 def test_stage_read_roundtrip_and_growth(ffx, dim):
     rng = np.random.default_rng(dim)
     vec = rng.standard_normal((5000, dim)).astype(np.float32)
