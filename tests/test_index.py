@@ -218,6 +218,37 @@ def test_early_stopping_random_golden(api, golden_es, key):
                          early_stopping_depths=tuple(st["depths"]), batch_size=4) == out
 
 
+@pytest.mark.parametrize("dim", [128, 3072])
+def test_early_stopping_falls_back_to_the_host_walk(api, dim):
+    """Dimensions whose rows are scored by the TMA-staged kernel only (short and long rows) have
+    no one-launch depth walk: ffx_rerank_early_stop answers FFX_ERR_UNSUPPORTED and the shell
+    walks the depths itself — same rows, same scores as the oracle's restatement predicts from
+    the full scores."""
+    rng = np.random.default_rng(dim)
+    n_docs, nq, C = 300, 12, 120
+    vec = rng.standard_normal((n_docs, dim)).astype(np.float32)
+    qv = rng.standard_normal((nq, dim)).astype(np.float32)
+    index = api.new(query_encoder=api.TableEncoder({f"t{i}": qv[i] for i in range(nq)}), mode=api.Mode.PASSAGE)
+    index.add(vec, psg_ids=[f"p{i}" for i in range(n_docs)])
+    steep = rng.uniform(0.93, 0.999, nq)  # first-stage scores fall off at a different rate per query
+    rows = [{"q_id": f"q{q:02d}", "query": f"t{q}", "id": f"p{int(p)}",
+             "score": float(np.float32(3.0 * np.sqrt(dim)) * np.float32(steep[q]) ** r)}
+            for q in range(nq) for r, p in enumerate(rng.choice(n_docs, C, replace=False))]
+    first = api.Ranking(pd.DataFrame(rows))
+    full = index(first)
+    es = index(first, early_stopping=5, early_stopping_alpha=0.5, early_stopping_depths=(10, 30, 120))
+    src = first._df
+    ff_of = {(q, i): s for q, i, s in zip(full._df["q_id"], full._df["id"], full._df["score"])}
+    ff = np.array([ff_of[(q, i)] for q, i in zip(src["q_id"], src["id"])], np.float32)
+    q_off = np.arange(nq + 1) * C
+    want = fo.early_stopping_depth(q_off, src["score"].to_numpy(), ff, 0.5, 5, (10, 30, 120))
+    assert 1 < len(set(want.tolist()))  # queries stop at different depths
+    got = es._df.groupby("q_id").size()
+    assert [int(got[q]) for q in pd.unique(src["q_id"])] == want.tolist()
+    es_of = {(q, i): s for q, i, s in zip(es._df["q_id"], es._df["id"], es._df["score"])}
+    assert all(ff_of[key] == s for key, s in es_of.items())
+
+
 def test_iteration(api):
     for kw in ({"init_size": 2, "alloc_size": 2}, {"init_size": 5}):
         index = api.new(**kw)
