@@ -343,7 +343,6 @@ class Index(abc.ABC):
         """Host-walked depths (index/base.py:339-385), one ffx_rerank launch per interval."""
         n = len(df)
         ff = np.zeros(n, np.float32)
-        inter = np.zeros(n, np.float32)
         done_depth = np.zeros(len(start), np.int64)  # rows scored so far per query
         active = np.ones(len(start), bool)
         a32, b32 = np.float32(alpha), np.float32(1 - alpha)
@@ -351,19 +350,25 @@ class Index(abc.ABC):
         for hi in sorted(depths):
             if hi < cutoff:
                 continue
-            if lo > 0:
-                for s in np.flatnonzero(active):
-                    b, e = start[s], start[s] + done_depth[s]
-                    kth = np.sort(inter[b:e])[::-1][:cutoff][-1]
-                    bound = a32 * lex[e - 1] + b32 * ff[b:e].max()
-                    active[s] = kth < bound
+            if lo > 0 and active.any():
+                # the stopping criterion of every query still going, in one ffx_interpolate_topk call
+                # over the rows scored so far: cutoff-th best interpolated score (the worst one when
+                # fewer rows were scored) against alpha*lex[last] + (1-alpha)*max ff  (base.py:351-356)
+                going = np.flatnonzero(active)
+                sizes = done_depth[going]
+                sub_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+                rows = np.repeat(start[going] - sub_off[:-1], sizes) + np.arange(sub_off[-1])
+                top = self._device().interpolate_topk_host(lex[rows], ff[rows], sub_off, alpha, cutoff,
+                                                           want_int=False)["topk_score"]
+                kth = top[np.arange(len(going)), np.minimum(cutoff, sizes) - 1]
+                bound = a32 * lex[start[going] + sizes - 1] + b32 * np.maximum.reduceat(ff[rows], sub_off[:-1])
+                active[going] = kth < bound
             LOGGER.info("depth %s: %s queries left", hi, int(active.sum()))
             take = active[slot_of_row] & (depth_of_row >= lo) & (depth_of_row < hi)
             if not take.any():
                 break
             chunk = self._compute_scores(df.loc[take, ["id", "q_no"]], query_vectors)
             ff[take] = chunk["ff_score"].to_numpy()
-            inter[take] = a32 * lex[take] + b32 * ff[take]
             done_depth[active] = np.minimum(count[active], hi)
             lo = hi
         return ff, done_depth
