@@ -317,9 +317,9 @@ class Index(abc.ABC):
         dev = self._device()
         on_device = (dev.row_kind == _ffx.ROWS_F32 and dev.has_fast_path and int(count.max()) <= 16384
                      and len({d for d in depths if d >= cutoff}) <= 32)
+        qv = np.ascontiguousarray(query_vectors, dtype=np.float32)[present]
+        cand = self._resolve(df["id"], self.mode)  # every id coded once, whatever the number of depths
         if on_device:
-            qv = np.ascontiguousarray(query_vectors, dtype=np.float32)[present]
-            cand = self._resolve(df["id"], self.mode)
             q_off = np.concatenate([[0], np.cumsum(count)]).astype(np.int64)
             try:
                 out = dev.rerank_early_stop_host(self.mode.value, qv, q_off, cand, lex, alpha, cutoff, depths)
@@ -331,17 +331,17 @@ class Index(abc.ABC):
                 ff, done_depth = out["ff"], out["scored"].astype(np.int64)
                 LOGGER.info("early stopping: %s of %s rows scored", int(done_depth.sum()), n)
         if not on_device:
-            ff, done_depth = self._early_stopping_walk(df, query_vectors, cutoff, alpha, depths, lex, start,
-                                                       count, depth_of_row, slot_of_row)
+            ff, done_depth = self._early_stopping_walk(qv, cand, cutoff, alpha, depths, lex, start, count,
+                                                       depth_of_row, slot_of_row)
         scored = depth_of_row < done_depth[slot_of_row]
         result = df.loc[scored].copy()
         result["ff_score"] = ff[scored]
         return result
 
-    def _early_stopping_walk(self, df, query_vectors, cutoff, alpha, depths, lex, start, count,
-                             depth_of_row, slot_of_row):
-        """Host-walked depths (index/base.py:339-385), one ffx_rerank launch per interval."""
-        n = len(df)
+    def _early_stopping_walk(self, qv, cand, cutoff, alpha, depths, lex, start, count, depth_of_row, slot_of_row):
+        """Host-walked depths (index/base.py:339-385) over integer-coded pairs: per interval one
+        ffx_rerank launch for the scores and one ffx_interpolate_topk launch for the criterion."""
+        n = len(cand)
         ff = np.zeros(n, np.float32)
         done_depth = np.zeros(len(start), np.int64)  # rows scored so far per query
         active = np.ones(len(start), bool)
@@ -367,8 +367,10 @@ class Index(abc.ABC):
             take = active[slot_of_row] & (depth_of_row >= lo) & (depth_of_row < hi)
             if not take.any():
                 break
-            chunk = self._compute_scores(df.loc[take, ["id", "q_no"]], query_vectors)
-            ff[take] = chunk["ff_score"].to_numpy()
+            taken = np.flatnonzero(take)
+            part_off = np.concatenate([[0], np.cumsum(np.bincount(slot_of_row[taken], minlength=len(start)))])
+            ff[taken] = self._device().rerank_host(self.mode.value, qv, part_off.astype(np.int64), cand[taken],
+                                                   want_ff=True)["ff"]
             done_depth[active] = np.minimum(count[active], hi)
             lo = hi
         return ff, done_depth
