@@ -137,6 +137,7 @@ struct ffx_index {
     bool stage_pending = false;  // host rows copied out, device side of the staging still in flight
 
     Scratch work;     // kernel scratch of ffx_rerank (scores / keys / rotated queries)
+    Scratch es_work;  // state of the multi-launch early-stopping walk
     Scratch hostio;   // device mirrors of ffx_rerank_host's host buffers
 
     // scatter plan (ffx_index_set_topk_scatter): host copy + device arrays refreshed, stream
@@ -659,6 +660,7 @@ int ffx_index_destroy(ffx_index *idx) {
     cudaFree(idx->sc_score);
     cudaFree(idx->sc_pos);
     cudaFree(idx->work.p);
+    cudaFree(idx->es_work.p);
     cudaFree(idx->hostio.p);
     cudaFree(idx->err_flag);
     if (idx->err_host) cudaFreeHost(idx->err_host);
@@ -1294,6 +1296,66 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     return take_error(idx, idx->s_d2h);
 }
 
+// The walk as a stream-ordered sequence of launches per depth (ffx_early_stop.cuh), for the index
+// kinds the one-launch kernel does not cover.  Scores come from the index's ordinary kernels.
+static int early_stop_walk(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const int64_t *q_off,
+                           const int32_t *cand, const float *lex, double alpha, const ffx::EsPlan &es,
+                           int64_t max_cand, float *out_ff, float *out_int, int32_t *out_scored, cudaStream_t st) {
+    auto pad = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+    const size_t n_bound = static_cast<size_t>(nq) * static_cast<size_t>(max_cand);
+    const size_t b_q = pad(static_cast<size_t>(nq) * 4), b_off = pad(static_cast<size_t>(nq + 1) * 8), b_n = pad(n_bound * 4);
+    FFX_TRY(scratch_reserve(idx->es_work, 3 * b_q + b_off + 2 * b_n + (out_ff ? 0 : b_n) + (out_int ? 0 : b_n)));
+    char *p = static_cast<char *>(idx->es_work.p);
+    auto take = [&](size_t b) { char *r = p; p += b; return r; };
+    ffx::EsWalk w{};
+    w.q_off = q_off;
+    w.cand = cand;
+    w.lex = lex;
+    w.alpha = static_cast<float>(alpha);
+    w.beta = static_cast<float>(1.0 - alpha);
+    w.cutoff = es.cutoff;
+    w.done = reinterpret_cast<int32_t *>(take(b_q));
+    w.active = reinterpret_cast<int32_t *>(take(b_q));
+    w.take = reinterpret_cast<int32_t *>(take(b_q));
+    w.part_off = reinterpret_cast<int64_t *>(take(b_off));
+    w.cand_sub = reinterpret_cast<int32_t *>(take(b_n));
+    w.ff_sub = reinterpret_cast<float *>(take(b_n));
+    w.ff = out_ff ? out_ff : reinterpret_cast<float *>(take(b_n));
+    w.inter = out_int ? out_int : reinterpret_cast<float *>(take(b_n));
+    const unsigned per_query = static_cast<unsigned>(nq);
+    const unsigned flat = static_cast<unsigned>(std::min<int64_t>((nq + 255) / 256, 1 << 16));
+    ffx::es_init_kernel<<<flat, 256, 0, st>>>(w, nq);
+    g_launches++;
+    int prev = 0;
+    for (int d = 0; d < es.n_depths; d++) {
+        const int depth = es.depths[d];
+        if (prev >= max_cand) break;  // every block is exhausted
+        if (d > 0) {
+            const size_t smem = static_cast<size_t>(next_pow2(std::min<int64_t>(prev, max_cand))) * 4;
+            if (smem > 48 * 1024)
+                FFX_CUDA(cudaFuncSetAttribute(ffx::es_criterion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(smem)));
+            ffx::es_criterion_kernel<<<per_query, 256, smem, st>>>(w);
+            g_launches++;
+        }
+        ffx::es_plan_kernel<<<1, 1024, 0, st>>>(w, nq, depth);
+        ffx::es_gather_kernel<<<per_query, 128, 0, st>>>(w);
+        g_launches += 2;
+        FFX_CUDA(cudaGetLastError());
+        const int64_t window = std::min<int64_t>(max_cand, depth) - std::min<int64_t>(max_cand, prev);
+        FFX_TRY(rerank_impl(idx, mode, qvecs, nq, w.part_off, w.cand_sub, nullptr, 0.0, 0, std::max<int64_t>(window, 1),
+                            w.ff_sub, nullptr, nullptr, nullptr, st, nullptr));
+        ffx::es_scatter_kernel<<<per_query, 128, 0, st>>>(w);
+        g_launches++;
+        FFX_CUDA(cudaGetLastError());
+        prev = depth;
+    }
+    ffx::es_finish_kernel<<<flat, 256, 0, st>>>(w, nq, out_scored);
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
 int ffx_rerank_early_stop(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const int64_t *q_off,
                           const int32_t *cand, const float *lex, double alpha, int cutoff,
                           const int32_t *depths, int n_depths, int64_t max_cand, float *out_ff,
@@ -1306,8 +1368,8 @@ int ffx_rerank_early_stop(ffx_index *idx, int mode, const float *qvecs, int64_t 
     if (nq == 0) return FFX_OK;
     if (!qvecs || !q_off || !out_scored || (max_cand > 0 && (!cand || !lex)))
         return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop: NULL input");
-    if (idx->row_kind != FFX_ROWS_F32 || idx->plan.cpl == 0)
-        return fail(FFX_ERR_UNSUPPORTED, "ffx_rerank_early_stop: needs an fp32 index with a lane-major plan");
+    if (idx->row_kind == FFX_ROWS_PQ_U8 && !idx->codewords)
+        return fail(FFX_ERR_STATE, "ffx_rerank_early_stop: PQ index without codebooks (ffx_index_set_pq)");
     if (idx->sharded)
         return fail(FFX_ERR_UNSUPPORTED, "ffx_rerank_early_stop: not defined on a doc-id-range shard");
     if (mode != FFX_MODE_PASSAGE && idx->n_docs == 0 && max_cand > 0)
@@ -1321,6 +1383,13 @@ int ffx_rerank_early_stop(ffx_index *idx, int mode, const float *qvecs, int64_t 
     es.out_scored = out_scored;
     FFX_TRY(bind(idx));
     FFX_TRY(settle(idx));
+    // one launch for the register-staged lane-major dimensions; every other index kind walks the
+    // depths as a stream-ordered sequence of launches
+    const bool one_launch = idx->row_kind == FFX_ROWS_F32 && idx->plan.cpl != 0 && idx->plan.cpl <= 4 &&
+                            idx->plan.lanes == 32;
+    if (!one_launch)
+        return early_stop_walk(idx, mode, qvecs, nq, q_off, cand, lex, alpha, es, max_cand, out_ff, out_int,
+                               out_scored, static_cast<cudaStream_t>(stream));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     ffx::ScoreArgs a{};
@@ -1377,7 +1446,8 @@ int ffx_rerank_early_stop_host(ffx_index *idx, int mode, const float *qvecs, int
     if (n > 0 && (!cand || !lex)) return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop_host: NULL candidates / scores");
     FFX_TRY(bind(idx));
     auto pad = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
-    const size_t b_q = pad(static_cast<size_t>(nq) * idx->dim * 4), b_off = pad(static_cast<size_t>(nq + 1) * 8);
+    const int64_t D = idx->row_kind == FFX_ROWS_PQ_U8 ? static_cast<int64_t>(idx->M) * idx->Ds : idx->dim;
+    const size_t b_q = pad(static_cast<size_t>(nq) * D * 4), b_off = pad(static_cast<size_t>(nq + 1) * 8);
     const size_t b_n = pad(static_cast<size_t>(n) * 4), b_s = pad(static_cast<size_t>(nq) * 4);
     FFX_TRY(scratch_reserve(idx->hostio, b_q + b_off + 4 * b_n + b_s));
     char *p = static_cast<char *>(idx->hostio.p);
@@ -1390,7 +1460,7 @@ int ffx_rerank_early_stop_host(ffx_index *idx, int mode, const float *qvecs, int
     float *d_int = out_int ? reinterpret_cast<float *>(take(b_n)) : nullptr;
     int32_t *d_scored = reinterpret_cast<int32_t *>(take(b_s));
     cudaStream_t st = idx->stream;
-    FFX_CUDA(cudaMemcpyAsync(d_q, qvecs, static_cast<size_t>(nq) * idx->dim * 4, cudaMemcpyHostToDevice, st));
+    FFX_CUDA(cudaMemcpyAsync(d_q, qvecs, static_cast<size_t>(nq) * D * 4, cudaMemcpyHostToDevice, st));
     FFX_CUDA(cudaMemcpyAsync(d_off, q_off, static_cast<size_t>(nq + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n > 0) {
         FFX_CUDA(cudaMemcpyAsync(d_cand, cand, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));

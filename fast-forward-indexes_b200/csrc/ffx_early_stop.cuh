@@ -197,4 +197,129 @@ __global__ void __launch_bounds__(kThreads, 2) ffx_score_es_kernel(const ScoreAr
     if (threadIdx.x == 0) es.out_scored[q_idx] = done;
 }
 
+// ---------------------------------------------------------------------------------------
+// Early stopping for every other index kind (PQ / OPQ codes, dimensions that exist in the
+// TMA-staged kernel only, dimensions without a lane-major plan): the same walk as a short
+// sequence of launches per depth, all on the device and stream ordered — no host round trip
+// decides anything.  Per depth: es_criterion (who goes on) -> es_plan (compact pair offsets)
+// -> es_gather (compact candidate list) -> the index's ordinary scoring kernel over the compact
+// list -> es_scatter (scores back to their pairs, interpolation, progress).
+// ---------------------------------------------------------------------------------------
+struct EsWalk {
+    const int64_t *q_off;  // [nq+1] the full candidate blocks
+    const int32_t *cand;   // [n]
+    const float *lex;      // [n]
+    float alpha, beta;
+    int cutoff;
+    int32_t *done;         // [nq] rows scored so far
+    int32_t *active;       // [nq]
+    int32_t *take;         // [nq] rows to score at this depth
+    int64_t *part_off;     // [nq+1] offsets of the compact list
+    int32_t *cand_sub;     // compact candidates
+    float *ff_sub;         // their scores
+    float *ff, *inter;     // [n] scores by pair (the caller's out_ff / out_int or scratch)
+};
+
+__global__ void es_init_kernel(EsWalk w, int64_t nq) {
+    for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < nq;
+         q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        w.done[q] = 0;
+        w.active[q] = 1;
+    }
+}
+
+// One CTA per query: the stopping criterion over the rows scored so far (index/base.py:351-356).
+// Dynamic shared memory: next_pow2(max rows scored) 32-bit keys.
+__global__ void __launch_bounds__(256) es_criterion_kernel(EsWalk w) {
+    extern __shared__ uint32_t s_sort32[];
+    __shared__ float s_wmax[8];
+    const int64_t q = blockIdx.x;
+    const int done = w.done[q];
+    if (!w.active[q] || done == 0) {  // CTA-uniform
+        if (threadIdx.x == 0 && done == 0) w.active[q] = 0;  // a query without rows never restarts
+        return;
+    }
+    const int64_t b = w.q_off[q];
+    int np2 = 1;
+    while (np2 < done) np2 <<= 1;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        s_sort32[i] = i < done ? score_key32(w.inter[b + i]) : 0u;
+        if (i < done) mx = fmaxf(mx, w.ff[b + i]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, off));
+    if ((threadIdx.x & 31) == 0) s_wmax[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    bitonic_sort_desc_u32(s_sort32, np2);
+    if (threadIdx.x == 0) {
+        float max_ff = s_wmax[0];
+        for (int i = 1; i < 8; i++) max_ff = fmaxf(max_ff, s_wmax[i]);
+        const float kth = key32_score(s_sort32[min(w.cutoff, done) - 1]);
+        const float bound = __fadd_rn(__fmul_rn(w.alpha, w.lex[b + done - 1]), __fmul_rn(w.beta, max_ff));
+        w.active[q] = kth < bound ? 1 : 0;
+    }
+}
+
+// take[q] and the exclusive scan part_off[] — one CTA, chunked (nq is at most a few 10^5)
+__global__ void __launch_bounds__(1024) es_plan_kernel(EsWalk w, int64_t nq, int depth) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t q0 = 0; q0 < nq; q0 += blockDim.x) {
+        const int64_t q = q0 + threadIdx.x;
+        long long t = 0;
+        if (q < nq) {
+            const int count = static_cast<int>(w.q_off[q + 1] - w.q_off[q]);
+            t = w.active[q] ? max(0, min(depth, count) - w.done[q]) : 0;
+            w.take[q] = static_cast<int32_t>(t);
+        }
+        long long incl = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long v = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        long long before = s_carry;
+        for (int x = 0; x < warp; x++) before += s_warp[x];
+        if (q < nq) w.part_off[q] = before + incl - t;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) w.part_off[nq] = s_carry;
+}
+
+// one CTA per query: compact candidate list of this depth
+__global__ void es_gather_kernel(EsWalk w) {
+    const int64_t q = blockIdx.x;
+    const int t = w.take[q];
+    const int64_t src = w.q_off[q] + w.done[q], dst = w.part_off[q];
+    for (int i = threadIdx.x; i < t; i += blockDim.x) w.cand_sub[dst + i] = w.cand[src + i];
+}
+
+// one CTA per query: scores back to their pairs, interpolation, progress
+__global__ void es_scatter_kernel(EsWalk w) {
+    const int64_t q = blockIdx.x;
+    const int t = w.take[q];
+    const int64_t dst = w.q_off[q] + w.done[q], src = w.part_off[q];
+    for (int i = threadIdx.x; i < t; i += blockDim.x) {
+        const float f = w.ff_sub[src + i];
+        w.ff[dst + i] = f;
+        w.inter[dst + i] = __fadd_rn(__fmul_rn(w.alpha, w.lex[dst + i]), __fmul_rn(w.beta, f));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) w.done[q] += t;
+}
+
+__global__ void es_finish_kernel(EsWalk w, int64_t nq, int32_t *out_scored) {
+    for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < nq;
+         q += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        out_scored[q] = w.done[q];
+}
+
 }  // namespace ffx

@@ -296,11 +296,12 @@ class Index(abc.ABC):
         """Score in depth intervals and stop a query once its `cutoff`-th best interpolated
         score can no longer be beaten (index/base.py:316-387).  Only scored rows are returned.
 
-        `df` must hold each query's rows in rank order (what `__call__` passes).  On fp32
-        indexes with a lane-major plan the whole walk — every interval's scoring and the
-        stopping criterion between intervals — is ONE kernel launch with one CTA per query
-        (ffx_rerank_early_stop); other indexes (PQ codes, odd dimensions) walk the depths here
-        and score every interval with ffx_rerank."""
+        `df` must hold each query's rows in rank order (what `__call__` passes).  The whole
+        walk — every interval's scoring and the stopping criterion between intervals — runs on
+        the device (ffx_rerank_early_stop: one kernel launch with one CTA per query on fp32
+        indexes of the common dimensions, a stream-ordered sequence of launches per depth on PQ
+        indexes and the other dimensions); only beyond its limits (more than 16384 candidates per
+        query or 32 depths) are the depths walked here."""
         n = len(df)
         q_no = df["q_no"].to_numpy(dtype=np.int64)
         if n and (np.diff(q_no) < 0).any():
@@ -315,8 +316,7 @@ class Index(abc.ABC):
         slot_of_row = np.repeat(np.arange(len(present)), count)
 
         dev = self._device()
-        on_device = (dev.row_kind == _ffx.ROWS_F32 and dev.has_fast_path and int(count.max()) <= 16384
-                     and len({d for d in depths if d >= cutoff}) <= 32)
+        on_device = int(count.max()) <= 16384 and len({d for d in depths if d >= cutoff}) <= 32
         qv = np.ascontiguousarray(query_vectors, dtype=np.float32)[present]
         cand = self._resolve(df["id"], self.mode)  # every id coded once, whatever the number of depths
         if on_device:
@@ -324,7 +324,7 @@ class Index(abc.ABC):
             try:
                 out = dev.rerank_early_stop_host(self.mode.value, qv, q_off, cand, lex, alpha, cutoff, depths)
             except _ffx.FFXError as e:
-                if e.code != -5:  # FFX_ERR_UNSUPPORTED: e.g. D >= 2560 has no one-launch walk
+                if e.code != -5:  # FFX_ERR_UNSUPPORTED: beyond the device walk's limits
                     raise
                 on_device = False
             else:

@@ -221,9 +221,12 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
  *   out_ff / out_int [n]   written for the scored rows only (others untouched); may be NULL
  *   out_scored [nq]        rows scored per query: always a prefix of the query's block
  *
- * fp32 lane-major indexes only, at most 16384 candidates per query and 32 distinct depths;
- * anything else returns FFX_ERR_UNSUPPORTED (the host shell then walks the depths itself with
- * ffx_rerank).  ffx_rerank_early_stop takes DEVICE pointers (except `depths`) and is
+ * One launch, one CTA per query, on fp32 indexes of the register-staged lane-major dimensions
+ * (384 ... 2048); every other index kind (PQ / OPQ codes, the other dimensions) walks the depths
+ * as a stream-ordered sequence of launches per depth — criterion, compaction of the pairs still
+ * to score, the index's ordinary scoring kernel, scatter — with no host round trip in between.
+ * At most 16384 candidates per query and 32 distinct depths, not on a shard: anything else returns
+ * FFX_ERR_UNSUPPORTED (the host shell then walks the depths itself with ffx_rerank).  ffx_rerank_early_stop takes DEVICE pointers (except `depths`) and is
  * asynchronous on `stream`; the _host variant takes host pointers and synchronises. */
 int ffx_rerank_early_stop(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const int64_t *q_off,
                           const int32_t *cand, const float *lex, double alpha, int cutoff,

@@ -71,15 +71,7 @@ def test_early_stop_matches_oracle(ffx, oracle_c, dim, contiguous, mode):
 
 def test_early_stop_limits(ffx):
     rng = np.random.default_rng(0)
-    vec = rng.standard_normal((64, 100)).astype(np.float32)  # D=100: no lane-major plan
-    idx = ffx.DeviceIndex(100, capacity=64)
-    idx.stage(0, vec)
     q_off = np.array([0, 10], np.int64)
-    args = (fo.MODE_PASSAGE, vec[:1], q_off, np.arange(10, dtype=np.int32), np.ones(10, np.float32), 0.5)
-    with pytest.raises(ffx.FFXError) as e:
-        idx.rerank_early_stop_host(*args, 2, (2, 4))
-    assert e.value.code == -5  # FFX_ERR_UNSUPPORTED: the host shell walks the depths instead
-    idx.close()
     idx = ffx.DeviceIndex(768, capacity=64)
     idx.stage(0, rng.standard_normal((64, 768)).astype(np.float32))
     qv = rng.standard_normal((1, 768)).astype(np.float32)
@@ -94,4 +86,58 @@ def test_early_stop_limits(ffx):
     bad[4] = 64
     with pytest.raises(ffx.FFXError):  # out-of-range candidate is reported, never dereferenced
         idx.rerank_early_stop_host(fo.MODE_PASSAGE, qv, q_off, bad, np.ones(10, np.float32), 0.5, 2, (10,))
+    idx.close()
+
+
+@pytest.mark.parametrize("kind", ["dim100", "dim128", "dim3072", "pq96", "pq8"])
+@pytest.mark.parametrize("mode", ["MAXP", "AVEP", "PASSAGE"])
+def test_device_walk_for_the_other_index_kinds(ffx, oracle_c, kind, mode):
+    """Indexes the one-launch kernel does not cover (dimensions without a lane-major plan, short
+    and long rows, PQ / OPQ codes) walk the depths as a stream-ordered sequence of launches on
+    the device.  Checked against the oracle's restatement applied to the scores the index itself
+    produces without early stopping (so that the PQ case does not depend on ADC rounding)."""
+    rng = np.random.default_rng(len(kind) * 7 + len(mode))
+    m = MODES[mode]
+    n_docs = 500
+    off, rows, _ = make_corpus(rng, n_docs, 5, 4, True)
+    n_rows = int(off[-1])
+    if kind.startswith("pq"):
+        M, Ks, Ds = int(kind[2:]), 32, 4
+        D = M * Ds
+        idx = ffx.DeviceIndex(M, capacity=n_rows, row_kind=ffx.ROWS_PQ_U8)
+        idx.stage(0, rng.integers(0, Ks, (n_rows, M)).astype(np.uint8))
+        idx.set_docs(off)
+        idx.set_pq(rng.standard_normal((M, Ks, Ds)).astype(np.float32),
+                   np.linalg.qr(rng.standard_normal((D, D)))[0].astype(np.float32))
+    else:
+        D = int(kind[3:])
+        idx = ffx.DeviceIndex(D, capacity=n_rows)
+        idx.stage(0, rng.standard_normal((n_rows, D)).astype(np.float32))
+        idx.set_docs(off)
+    nq = 90
+    pool = n_rows if m == fo.MODE_PASSAGE else n_docs
+    qv = rng.standard_normal((nq, D)).astype(np.float32)
+    q_off, cand, pair_q = make_pairs(rng, nq, pool, 1, 300)
+    lex = falling_lex(rng, q_off, float(np.sqrt(D)))
+    full = idx.rerank_host(m, qv, q_off, cand, want_ff=True)["ff"]  # no early stopping
+    sizes = np.diff(q_off)
+    stops = set()
+    for cutoff, alpha, depths in ((5, 0.5, (5, 20, 60, 150, 300)), (3, 0.8, (10, 10, 200)), (10, 0.2, (4, 50, 120))):
+        out = idx.rerank_early_stop_host(m, qv, q_off, cand, lex, alpha, cutoff, depths, want_int=True)
+        scored = (np.arange(len(cand)) - np.repeat(q_off[:-1], sizes)) < np.repeat(out["scored"], sizes)
+        if kind == "pq96":
+            # the XOR-swizzled ADC kernel sums a row's table entries in an order that depends on the
+            # lane that scores it, and the compact lists of the walk move pairs to other lanes: scores
+            # agree to reassociation, and the walk must be the oracle's walk over ITS OWN scores
+            assert np.allclose(out["ff"][scored], full[scored], rtol=1e-4, atol=1e-3)
+            seen_scores = np.where(scored, out["ff"], full)
+        else:
+            assert (bits(out["ff"][scored]) == bits(full[scored])).all()
+            seen_scores = full
+        want = fo.early_stopping_depth(q_off, lex, seen_scores, alpha, cutoff, depths)
+        assert (out["scored"] == want).all(), (cutoff, alpha, depths)
+        assert (out["ff"][~scored] == 0).all()
+        assert (bits(out["int"][scored]) == bits(fo.interpolate_f32(lex, seen_scores, alpha)[scored])).all()
+        stops.update((want / sizes).round(2).tolist())
+    assert len(stops) > 2
     idx.close()
