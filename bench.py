@@ -328,10 +328,11 @@ def cpu_reference_run(wl, alpha, q_per_core=5, cores=None):
 def cpu_baseline_run(wl, alpha, budget="long"):
     """(value, seconds, cores, sample, kind): the reference itself when baseline/_ref travelled
     with the repo, else the numpy port of oracle/."""
-    if reference_installed():
-        v, dt, cores, sample, _ = cpu_reference_run(wl, alpha, q_per_core=9 if budget == "long" else 5)
+    force = int(os.environ.get("FFX_CPU_Q_PER_CORE", "0"))  # tests shrink the sample
+    if reference_installed() and os.environ.get("FFX_CPU_BASELINE", "") != "port":
+        v, dt, cores, sample, _ = cpu_reference_run(wl, alpha, q_per_core=force or (9 if budget == "long" else 5))
         return v, dt, cores, sample, "reference"
-    v, dt, cores, sample, _ = cpu_port_run(wl, alpha, q_per_core=64 if budget == "long" else 24)
+    v, dt, cores, sample, _ = cpu_port_run(wl, alpha, q_per_core=force or (64 if budget == "long" else 24))
     return v, dt, cores, sample, "port"
 
 
