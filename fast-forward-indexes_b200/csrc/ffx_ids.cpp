@@ -111,6 +111,38 @@ inline int64_t put(ffx_dict *d, const char *p, int64_t n, uint64_t h, int64_t va
     return e;
 }
 
+// Building a dictionary is one dependent cache miss per key (the home slot of its hash).  The
+// hashes are therefore computed kAhead keys early and their slots prefetched, which keeps that
+// many misses in flight; valid while the table is not resized (callers reserve first).
+struct HashAhead {
+    static const int kAhead = 16;
+    const ffx_dict *d;
+    const int64_t *offsets;
+    const char *data;
+    const uint8_t *validity;
+    int64_t bit_offset, n;
+    uint64_t ring[kAhead];
+    HashAhead(const ffx_dict *d_, const int64_t *o, const char *p, const uint8_t *v, int64_t b, int64_t n_)
+        : d(d_), offsets(o), data(p), validity(v), bit_offset(b), n(n_) {
+        for (int64_t i = 0; i < std::min<int64_t>(kAhead, n); i++) prime(i);
+    }
+    void prime(int64_t i) {
+        if (!is_valid(validity, bit_offset, i)) return;
+        const uint64_t h = hash_bytes(data + offsets[i], offsets[i + 1] - offsets[i]);
+        ring[i % kAhead] = h;
+        __builtin_prefetch(&d->slots[h & d->mask], 1);
+    }
+    // hash of key i (valid keys only); primes key i + kAhead
+    uint64_t take(int64_t i) {
+        const uint64_t h = ring[i % kAhead];
+        if (i + kAhead < n) prime(i + kAhead);
+        return h;
+    }
+    void skip(int64_t i) {
+        if (i + kAhead < n) prime(i + kAhead);
+    }
+};
+
 int worker_count(int requested, int64_t n) {
     int t = requested > 0 ? requested : static_cast<int>(std::thread::hardware_concurrency());
     t = std::max(1, std::min(t, 64));
@@ -161,14 +193,21 @@ int ffx_dict_insert_ordinal(ffx_dict *d, const int64_t *offsets, const char *dat
     if (static_cast<uint64_t>(d->values.size()) + static_cast<uint64_t>(n) > 0xfffffff0ull)
         return fail(FFX_ERR_UNSUPPORTED, "ffx_dict_insert_ordinal: more than 2^32 keys");
     reserve_for(d, n);
+    if (n > 0) {  // at most n new keys of offsets[n] - offsets[0] bytes: no regrowth inside the loop
+        d->values.reserve(d->values.size() + static_cast<size_t>(n));
+        d->key_off.reserve(d->key_off.size() + static_cast<size_t>(n));
+        d->arena.reserve(d->arena.size() + static_cast<size_t>(offsets[n] - offsets[0]));
+    }
+    HashAhead hashes(d, offsets, data, validity, bit_offset, n);
     for (int64_t i = 0; i < n; i++) {
         if (!is_valid(validity, bit_offset, i)) {
             if (out) out[i] = -1;
+            hashes.skip(i);
             continue;
         }
         const char *p = data + offsets[i];
         const int64_t len = offsets[i + 1] - offsets[i];
-        const uint64_t h = hash_bytes(p, len);
+        const uint64_t h = hashes.take(i);
         int64_t e = find(d, p, len, h);
         if (e < 0) e = put(d, p, len, h, static_cast<int64_t>(d->values.size()));
         if (out) out[i] = d->values[static_cast<size_t>(e)];
@@ -187,11 +226,20 @@ int ffx_dict_insert_unique(ffx_dict *d, const int64_t *offsets, const char *data
     // leaves the dictionary exactly as it was
     const size_t keep_n = d->values.size(), keep_bytes = d->arena.size();
     reserve_for(d, n);
+    if (n > 0) {  // at most n new keys of offsets[n] - offsets[0] bytes: no regrowth inside the loop
+        d->values.reserve(d->values.size() + static_cast<size_t>(n));
+        d->key_off.reserve(d->key_off.size() + static_cast<size_t>(n));
+        d->arena.reserve(d->arena.size() + static_cast<size_t>(offsets[n] - offsets[0]));
+    }
+    HashAhead hashes(d, offsets, data, validity, bit_offset, n);
     for (int64_t i = 0; i < n; i++) {
-        if (!is_valid(validity, bit_offset, i)) continue;
+        if (!is_valid(validity, bit_offset, i)) {
+            hashes.skip(i);
+            continue;
+        }
         const char *p = data + offsets[i];
         const int64_t len = offsets[i + 1] - offsets[i];
-        const uint64_t h = hash_bytes(p, len);
+        const uint64_t h = hashes.take(i);
         if (find(d, p, len, h) >= 0) {
             *first_dup = i;
             break;

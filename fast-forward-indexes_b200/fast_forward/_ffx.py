@@ -49,6 +49,15 @@ SYMBOLS = {
     "ffx_interpolate_topk_host": (_I, [_P, _P, _P, _L, _P, _D, _I, _P, _P, _P]),
     "ffx_merge_topk": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _P]),
     "ffx_launch_count": (_L, []),
+    "ffx_h5_open": (_I, [C.c_char_p, C.POINTER(_P)]),
+    "ffx_h5_close": (None, [_P]),
+    "ffx_h5_kind": (_I, [_P, C.c_char_p, C.POINTER(_I)]),
+    "ffx_h5_list": (_I, [_P, C.c_char_p, _P, _L, C.POINTER(_L)]),
+    "ffx_h5_attr_names": (_I, [_P, C.c_char_p, _P, _L, C.POINTER(_L)]),
+    "ffx_h5_dataset_info": (_I, [_P, C.c_char_p, _P]),
+    "ffx_h5_read_rows": (_I, [_P, C.c_char_p, _L, _L, _P]),
+    "ffx_h5_row_span": (_I, [_P, C.c_char_p, _L, C.POINTER(_P), C.POINTER(_L)]),
+    "ffx_h5_attr_read": (_I, [_P, C.c_char_p, C.c_char_p, _P, _P, _L, C.POINTER(_L)]),
     "ffx_pq_encode": (_I, [_I, _P, _L, _I, _I, _I, _P, _P]),
     "ffx_pq_kmeans": (_I, [_I, _P, _L, _I, _I, _I, _P, _I]),
     "ffx_dict_create": (_I, [C.POINTER(_P)]),

@@ -5,7 +5,13 @@ The HDF5 file keeps the reference's layout (root attrs `num_vectors`, `ff_versio
 bytes with "" = absent; group `quantizer/{meta,attributes,data}`), so files are
 interchangeable.  The difference is the read path: instead of fancy-indexing the file on
 every call, the rows are staged ONCE — HDF5 chunk by chunk through the pinned double buffer —
-into an HBM row store, and all scoring runs there.  Needs `h5py` (an ImportError says so).
+into an HBM row store, and all scoring runs there.
+
+`load` (and everything a loaded index does afterwards except `add`) reads the file with the
+library's own HDF5 reader (`fast_forward._h5`, csrc/ffx_h5.cpp): the file is mapped, every chunk
+of `vectors` is handed to the staging buffers as a pointer into the mapping, and the two id
+columns are coded by the C++ dictionaries straight from their fixed-width bytes.  Creating a
+file and adding to it writes through `h5py` (an ImportError says so when it is missing).
 """
 
 from __future__ import annotations
@@ -17,7 +23,7 @@ from pathlib import Path
 import numpy as np
 
 import fast_forward
-from fast_forward import _ffx
+from fast_forward import _ffx, _h5
 from fast_forward.encoder.base import Encoder
 from fast_forward.index._store import RowStore
 from fast_forward.index.base import IDSequence, Index, Mode
@@ -35,11 +41,26 @@ def _h5py():
     return h5py
 
 
-def _text_ids(raw: np.ndarray) -> np.ndarray:
-    """Fixed-width bytes -> object array of str, None where the stored id is empty."""
-    out = np.char.decode(np.asarray(raw, dtype="S"), "utf-8").astype(object)
-    out[out == ""] = None
-    return out
+def _text_ids(raw: np.ndarray):
+    """A column of fixed-width byte ids (b"" = no id, disk.py:414-417) as an Arrow string array
+    with nulls, built from the bytes without creating one Python object per id; without
+    pyarrow, an object array of `str | None`."""
+    raw = np.ascontiguousarray(raw, dtype=f"S{max(np.asarray(raw).dtype.itemsize, 1)}")
+    try:
+        import pyarrow as pa
+    except ImportError:  # pragma: no cover - depends on the environment
+        out = np.char.decode(raw, "utf-8").astype(object)
+        out[out == ""] = None
+        return out
+    n, width = len(raw), raw.dtype.itemsize
+    lengths = np.char.str_len(raw).astype(np.int64)
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(lengths, out=offsets[1:])
+    data = raw.view(np.uint8).reshape(n, width)[np.arange(width) < lengths[:, None]]
+    present = lengths > 0
+    buffers = [pa.py_buffer(np.packbits(present, bitorder="little")), pa.py_buffer(offsets),
+               pa.py_buffer(np.ascontiguousarray(data) if len(data) else np.zeros(1, np.uint8))]
+    return pa.Array.from_buffers(pa.large_string(), n, buffers, null_count=int(n - present.sum()))
 
 
 class OnDiskIndex(Index):
@@ -128,12 +149,10 @@ class OnDiskIndex(Index):
 
     # ---- Index contract -------------------------------------------------------------------
     def _get_num_vectors(self) -> int:
-        with _h5py().File(self._index_file, "r") as fp:
-            return int(fp.attrs["num_vectors"])
+        return self._store.count  # == the file's `num_vectors`: this object is its only writer
 
     def _get_internal_dim(self) -> int | None:
-        with _h5py().File(self._index_file, "r") as fp:
-            return int(fp["vectors"].shape[1]) if "vectors" in fp else None
+        return self._store.width
 
     def _get_doc_ids(self) -> set[str]:
         return self._store.doc_id_set()
@@ -182,31 +201,27 @@ class OnDiskIndex(Index):
         index._memory_mapped = memory_mapped
         index._max_indexing_size = max_indexing_size
 
-        with _h5py().File(index_file, "r") as fp:
+        with _h5.H5File(index_file) as fp:
             if "quantizer" in fp:
                 index._quantizer = Quantizer.deserialize(
-                    dict(fp["quantizer/meta"].attrs), dict(fp["quantizer/attributes"].attrs),
-                    {k: v[:] for k, v in fp["quantizer/data"].items()})
-            total = int(fp.attrs["num_vectors"])
-            if "vectors" in fp:
-                chunks = fp["vectors"].chunks
-                index._chunk_size = int(chunks[0]) if chunks else 2**16
-                index._init_size = index._chunk_size
-                index._max_id_length = int(fp["doc_ids"].dtype.itemsize)
-            else:
-                index._chunk_size = index._init_size = 2**16
-                index._max_id_length = 8
+                    fp.attrs("quantizer/meta"), fp.attrs("quantizer/attributes"),
+                    {k: fp.read(f"quantizer/data/{k}") for k in fp.keys("quantizer/data")})
+            total = int(fp.attr("/", "num_vectors"))
+            index._chunk_size = index._init_size = 2**16
+            index._max_id_length = 8
+            if "vectors" not in fp:
+                return index
+            meta = fp.info("vectors")
+            index._chunk_size = index._init_size = meta["chunk_rows"] or 2**16
+            index._max_id_length = fp.info("doc_ids")["dtype"].itemsize
             if total == 0:
                 return index
 
-            # one HDF5 chunk (a contiguous byte range of the file) per staging step
-            step = index._chunk_size
-            for lo in range(0, total, step):
-                hi = min(lo + step, total)
-                block = fp["vectors"][lo:hi]
-                rows = np.ascontiguousarray(block) if index._quantizer is not None and block.dtype == np.uint8 \
-                    else np.ascontiguousarray(block, dtype=np.float32)
-                index._store.append(rows, None, None, first_capacity=total, grow_by=step)
+            # one HDF5 chunk (a contiguous byte range of the file) per staging step, read in place
+            codes = index._quantizer is not None and meta["dtype"] == np.uint8
+            for _, block in fp.spans("vectors", 0, total):
+                rows = block if codes or block.dtype == np.float32 else block.astype(np.float32)
+                index._store.append(rows, None, None, first_capacity=total, grow_by=index._chunk_size)
             # the O(N) Python loop of disk.py:408-417, as two calls into the C++ id dictionaries
-            index._store.adopt_id_columns(_text_ids(fp["doc_ids"][:total]), _text_ids(fp["psg_ids"][:total]))
+            index._store.adopt_id_columns(_text_ids(fp.read("doc_ids", 0, total)), _text_ids(fp.read("psg_ids", 0, total)))
         return index

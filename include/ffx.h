@@ -280,6 +280,44 @@ int ffx_merge_topk(int device, const float *shard_scores, const int32_t *shard_p
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t ffx_launch_count(void);
 
+/* ---- index files: the HDF5 layout OnDiskIndex writes, read without libhdf5 / h5py --------
+ * Replaces the h5py reads of OnDiskIndex.load (index/disk.py:355-418), to_memory
+ * (:177-205) and _get_vectors / _get_mmap_indexer (:94-121,309-336) as a staging source: the
+ * file is mapped read-only and its structures (superblock, object headers, symbol-table
+ * groups, v1 chunk B-trees, attributes, global heap) are walked in place.  Supported is what
+ * such files contain (layout written by _create_ds, :138-165: uncompressed, chunks spanning
+ * whole rows); compression, libver='latest' chunk indexes and dense attribute / link storage
+ * return FFX_ERR_UNSUPPORTED.  Host only: no device is needed.  A handle is not thread-safe.
+ * `path` arguments are '/'-separated object names ("vectors", "quantizer/data/codewords"). */
+typedef struct ffx_h5 ffx_h5;
+int ffx_h5_open(const char *file_name, ffx_h5 **out);
+void ffx_h5_close(ffx_h5 *f);
+/* *kind = 0 (no such object), 1 (group) or 2 (dataset)  — `"vectors" in fp`, disk.py:392 */
+int ffx_h5_kind(ffx_h5 *f, const char *path, int *kind);
+/* Member names of a group / attribute names of an object, each followed by '\n'.  Writes at
+ * most `cap` bytes; *needed = the full length (call again with a larger buffer). */
+int ffx_h5_list(ffx_h5 *f, const char *path, char *buf, int64_t cap, int64_t *needed);
+int ffx_h5_attr_names(ffx_h5 *f, const char *path, char *buf, int64_t cap, int64_t *needed);
+/* info[16] = { type class (0 integer, 1 float, 3 fixed-width string, 8 enum), element bytes,
+ * signed, rank, dims[8], layout (0 compact, 1 contiguous, 2 chunked), chunk rows (axis 0),
+ * bytes per row (= per index of axis 0), 0 }.  fp["vectors"].shape/.dtype/.chunks. */
+int ffx_h5_dataset_info(ffx_h5 *f, const char *path, int64_t *info);
+/* Copies rows [row0, row0 + nrows) of axis 0, row-major, little-endian as stored, into `dst`
+ * (nrows * bytes-per-row bytes).  Chunks that were never written read as zeros. */
+int ffx_h5_read_rows(ffx_h5 *f, const char *path, int64_t row0, int64_t nrows, void *dst);
+/* The longest run of rows starting at row0 that is contiguous in the file: *rows points INTO
+ * the mapping (valid until ffx_h5_close; NULL if that chunk was never written), *nrows is
+ * its length.  One HDF5 chunk = one contiguous byte range = one ffx_index_stage_rows call
+ * (the reference's memory-mapped read path, disk.py:94-121, as a staging source). */
+int ffx_h5_row_span(ffx_h5 *f, const char *path, int64_t row0, const void **rows, int64_t *nrows);
+/* One attribute: info[13] = { type class (0 integer, 1 float, 3 string, 8 enum), element
+ * bytes, signed, rank, element count, dims[8] }; value bytes into buf (numbers raw
+ * little-endian; strings — fixed or variable length — as their characters, several strings
+ * separated by NUL), at most `cap` bytes, *needed = full length.  fp.attrs["num_vectors"],
+ * dict(fp["quantizer/meta"].attrs) (disk.py:380-391). */
+int ffx_h5_attr_read(ffx_h5 *f, const char *path, const char *name, int64_t *info, void *buf,
+                     int64_t cap, int64_t *needed);
+
 #ifdef __cplusplus
 }
 #endif

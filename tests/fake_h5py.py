@@ -1,22 +1,27 @@
 """TEST INFRASTRUCTURE — a tiny stand-in for the subset of h5py that `OnDiskIndex` uses.
 
-Neither h5py nor libhdf5 is installed in the build image or on the GPU box, so the real
-HDF5 path of `fast_forward.index.disk` cannot run there.  This module keeps a "file" as a
-pickled tree of groups / datasets / attributes at the given path and mimics the h5py calls
-made by disk.py (File as a context manager, attrs, create_dataset with maxshape/chunks,
-resize, slice and increasing-list indexing, fixed-width byte strings, groups, `in`, `del`).
+Neither h5py nor libhdf5 is installed in the build image or on the GPU box, so the write
+side of `fast_forward.index.disk` (which needs h5py) cannot run there.  This module mimics the
+h5py calls made by disk.py (File as a context manager, attrs, create_dataset with
+maxshape/chunks, resize, slice and increasing-list indexing, fixed-width byte strings, groups,
+`in`, `del`) on an in-memory tree, and persists that tree as genuine HDF5 bytes: written by
+tests/h5_writer.py on close, re-read through the product's own native reader
+(`fast_forward._h5.H5File`) on open.  So every OnDiskIndex test crosses the real file format,
+and `OnDiskIndex.load` reads these files exactly as it would read h5py's.
 tests/test_disk.py installs it as `h5py` only when the real package is missing.
 """
 
 import os
-import pickle
 
 import numpy as np
+
+import h5_writer
 
 
 class Dataset:
     def __init__(self, data, maxshape=None, chunks=None):
         self._a = data
+        self.attrs = {}
         self.maxshape = maxshape
         self.chunks = chunks if chunks is not True else (min(len(data), 1024) or 1,) + data.shape[1:]
 
@@ -98,16 +103,45 @@ class File(Group):
         super().__init__()
         self._path, self._mode = str(path), mode
         if mode in ("r", "a") and os.path.exists(self._path):
-            with open(self._path, "rb") as f:
-                self.attrs, self._items = pickle.load(f)
+            from fast_forward._h5 import H5File
+
+            with H5File(self._path) as src:
+                self._adopt(src, "/", self)
         elif mode == "r":
             raise FileNotFoundError(path)
+
+    @classmethod
+    def _adopt(cls, src, path, node):
+        node.attrs = src.attrs(path)
+        for name in src.keys(path):
+            child = path.rstrip("/") + "/" + name
+            if src.kind(child) == 2:
+                meta = src.info(child)
+                chunked = meta["chunk_rows"] is not None
+                ds = Dataset(src.read(child), (None,) + meta["shape"][1:] if chunked else None,
+                             (meta["chunk_rows"],) + meta["shape"][1:] if chunked else None)
+                ds.attrs = src.attrs(child)
+                node._items[name] = ds
+            else:
+                node._items[name] = Group()
+                cls._adopt(src, child, node._items[name])
+
+    def _tree(self, node):
+        out = h5_writer.Group()
+        out.attrs = dict(node.attrs)
+        for name, child in node._items.items():
+            if isinstance(child, Dataset):
+                ds = h5_writer.Dataset(child._a, child.chunks if child.maxshape is not None else None, child.maxshape)
+                ds.attrs = dict(getattr(child, "attrs", {}))
+                out.children[name] = ds
+            else:
+                out.children[name] = self._tree(child)
+        return out
 
     def __enter__(self):
         return self
 
     def __exit__(self, *exc):
         if self._mode != "r" and exc[0] is None:
-            with open(self._path, "wb") as f:
-                pickle.dump((self.attrs, self._items), f)
+            h5_writer.write_hdf5(self._tree(self), self._path)
         return False
