@@ -49,6 +49,8 @@ SYMBOLS = {
     "ffx_interpolate_topk_host": (_I, [_P, _P, _P, _L, _P, _D, _I, _P, _P, _P]),
     "ffx_merge_topk": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _P]),
     "ffx_launch_count": (_L, []),
+    "ffx_first_repeat": (_I, [_P, _L, C.POINTER(_L)]),
+    "ffx_ranking_order": (_I, [_P, _P, _L, _P, _I]),
     "ffx_h5_open": (_I, [C.c_char_p, C.POINTER(_P)]),
     "ffx_h5_close": (None, [_P]),
     "ffx_h5_kind": (_I, [_P, C.c_char_p, C.POINTER(_I)]),

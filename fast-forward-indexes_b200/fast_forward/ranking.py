@@ -54,6 +54,63 @@ def _minmax(df: pd.DataFrame) -> pd.DataFrame:
     return out
 
 
+_CODED_FROM = 50_000  # rows from which the integer-coded constructor path pays off
+
+
+def _coded_frame(df: pd.DataFrame, is_sorted: bool) -> pd.DataFrame | None:
+    """The frame `Ranking.__init__` builds (ranking.py:95-117: duplicate check, NaN rows dropped,
+    q_id DESC / score DESC stable order), computed on integer codes by libffx's host routines
+    instead of pandas' `duplicated` + `sort_values` over two string columns: ids are coded by
+    the C++ dictionary, pairs are checked as int64 keys, the order is one radix sort.  Returns
+    None (the caller then takes the pandas route, with identical results) unless both id
+    columns already are strings without nulls and the scores are floats."""
+    from fast_forward import _ffx, _ids
+
+    q_col, id_col, s_col = df["q_id"], df["id"], df["score"]
+    if not (pd.api.types.is_string_dtype(q_col.dtype) and pd.api.types.is_string_dtype(id_col.dtype)
+            and q_col.dtype != object and id_col.dtype != object and s_col.dtype.kind == "f"):
+        return None
+    if len(df) == 0 or q_col.isna().any() or id_col.isna().any():
+        return None
+    import ctypes as C
+
+    n = len(df)
+    q_code, q_keys = pd.factorize(q_col)
+    id_code = _ids.IdDict().insert_ordinal(id_col)
+    pair = q_code.astype(np.int64) * (int(id_code.max()) + 1) + id_code
+    first = C.c_int64(-1)
+    _ffx.check(_ffx.lib().ffx_first_repeat(C.c_void_p(pair.ctypes.data), n, C.byref(first)))
+    if first.value >= 0:
+        raise ValueError("Only one score per query-document/passage pair is allowed.")
+
+    keep = ["q_id", "id", "score"] + (["query"] if "query" in df.columns else [])
+    score = np.ascontiguousarray(s_col.to_numpy(), dtype=np.float32)  # cast first, then order (ranking.py:107-117)
+    alive = ~np.isnan(score)
+    if "query" in df.columns:
+        alive &= ~df["query"].isna().to_numpy()
+    rows = None if alive.all() else np.flatnonzero(alive)  # rows that survive dropna, in frame order
+    if not is_sorted:
+        # rank of every distinct q_id in DEscending string order, then one stable radix sort
+        q_rank_of = np.empty(len(q_keys), np.int32)
+        q_rank_of[np.argsort(np.asarray(q_keys, dtype=object), kind="stable")[::-1]] = np.arange(len(q_keys), dtype=np.int32)
+        q_rank = q_rank_of[q_code]
+        kept_score = score
+        if rows is not None:
+            q_rank, kept_score = q_rank[rows], score[rows]
+        order = np.empty(len(q_rank), np.int64)
+        _ffx.check(_ffx.lib().ffx_ranking_order(C.c_void_p(q_rank.ctypes.data), C.c_void_p(kept_score.ctypes.data),
+                                                len(q_rank), C.c_void_p(order.ctypes.data), 0))
+        rows = order if rows is None else rows[order]
+    if rows is None:
+        frame = df.loc[:, keep].copy()
+    else:
+        frame = df.loc[:, keep].take(rows)
+        score = score[rows]
+    frame["score"] = score
+    frame.reset_index(drop=True, inplace=True)
+    return frame
+
+
 class Ranking:
     """Rankings of documents/passages w.r.t. queries."""
 
@@ -73,6 +130,13 @@ class Ranking:
         """
         self.name = name
         self._origin = None  # set by Index.__call__ (device-side provenance)
+
+        if len(df) >= _CODED_FROM and np.dtype(dtype) == np.float32:
+            frame = _coded_frame(df, is_sorted)
+            if frame is not None:
+                self._q_ids = set(pd.unique(frame["q_id"]))
+                self._df = frame if queries is None else _with_queries(frame, queries)
+                return
 
         if df.duplicated(subset=_KEYS).any():
             raise ValueError("Only one score per query-document/passage pair is allowed.")

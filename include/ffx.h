@@ -173,6 +173,16 @@ int ffx_dict_export(const ffx_dict *d, int64_t *offsets, char *data, int64_t *va
  * be NULL to get the offsets only. */
 int ffx_csr_build(const int64_t *row_doc, int64_t n_rows, int64_t n_docs, int64_t *doc_off, int64_t *doc_rows);
 
+/* ---- Ranking.__init__ on integer codes (host; ranking.py:67-121) ---------------------- */
+/* The duplicate-pair check (ranking.py:95-98) over keys = q_code * n_ids + id_code:
+ * *first = index of the first key that equals an earlier one, -1 if all are distinct. */
+int ffx_first_repeat(const int64_t *keys, int64_t n, int64_t *first);
+/* The frame order of ranking.py:115-117 — q_id descending (q_rank[i] = position of row i's
+ * q_id among the distinct q_ids sorted descending), then score descending, ties in incoming
+ * order (pandas' lexsort is stable; -0.0 ties with +0.0; NaN sorts after every number):
+ * order[j] = the row that comes j-th.  A radix sort on all host cores (n_threads 0). */
+int ffx_ranking_order(const int32_t *q_rank, const float *score, int64_t n, int64_t *order, int n_threads);
+
 /* ---- the hot path ----------------------------------------------------------------- */
 /* Replaces, in one pass, `Index._compute_scores` (index/base.py:279-314) including
  * `_get_vectors` (index/memory.py:139-140), `Ranking.interpolate`'s arithmetic
