@@ -1,7 +1,7 @@
-"""Encoders.  Only the pieces the re-ranking path needs: the `Encoder` interface,
-`LambdaEncoder` (reference: src/fast_forward/encoder/__init__.py:32-44) and `TableEncoder`
-for precomputed query vectors.  The HF transformer presets of the reference
-(encoder/transformer.py) are out of scope: wrap any model in a `LambdaEncoder`."""
+"""Encoders: the `Encoder` interface, `LambdaEncoder` (reference:
+src/fast_forward/encoder/__init__.py:32-44), `TableEncoder` for precomputed query vectors, and
+the Transformer presets of encoder/transformer.py (resolved on first use, so importing the
+package does not import torch / transformers)."""
 
 from __future__ import annotations
 
@@ -11,7 +11,18 @@ import numpy as np
 
 from fast_forward.encoder.base import Encoder
 
-__all__ = ["Encoder", "LambdaEncoder", "TableEncoder"]
+_TRANSFORMER_PRESETS = ("TransformerEncoder", "TCTColBERTQueryEncoder", "TCTColBERTDocumentEncoder",
+                        "TASBEncoder", "ContrieverEncoder", "BGEEncoder")
+
+__all__ = ["Encoder", "LambdaEncoder", "TableEncoder", *_TRANSFORMER_PRESETS]
+
+
+def __getattr__(name: str):
+    if name in _TRANSFORMER_PRESETS:
+        from fast_forward.encoder import transformer
+
+        return getattr(transformer, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
 
 class LambdaEncoder(Encoder):
