@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
         // keys over them (NaN score = pair of another shard = not ranked)
         __syncthreads();
         unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(adc_smem);
-        rank_scores_topk(s_scores, n_query, s_keys, w.k, w.topk_score + q_idx * w.k, w.topk_pos + q_idx * w.k);
+        rank_scores_topk<8>(s_scores, n_query, s_keys, w.k, w.topk_score + q_idx * w.k, w.topk_pos + q_idx * w.k,
+                            bars_off);  // table + slots
     }
 }
 

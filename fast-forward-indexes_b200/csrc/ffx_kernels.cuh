@@ -307,10 +307,113 @@ __device__ inline void select_largest_keys(unsigned long long *keys, int m, int 
     }
 }
 
-template <class ScoreAt>
+// Stable LSD radix sort of keys[0, n) by their UPPER 32 bits (the score part of topk_key),
+// descending, 8-bit digits, 4 passes; keys whose upper halves are equal keep their incoming
+// order.  With the keys laid out by candidate position that is exactly the descending order of
+// the full 64-bit keys, at a cost linear in n: ~1 k instructions per thread for 5000 keys on
+// 1024 threads, where the bitonic network on the next power of two (8192) spends ~9 k.
+// Warp w owns keys [w*E*32, (w+1)*E*32), E = ceil(n / T) <= EMAX, and takes them 32 at a time in
+// index order: rank inside the warp = keys of the same digit in earlier rounds (the warp's
+// shared-memory counter) + same-digit lanes below (match.any).  One block scan over the
+// (digit, warp) counters turns them into destinations.  Keys travel through registers, so one
+// buffer suffices.  `hist`: (T/32)*512 + 128 bytes of shared memory.  Requires n < 65536.
+template <int EMAX>
+__device__ inline void block_radix_sort_desc_hi32(unsigned long long *keys, int n, unsigned short *hist) {
+    const int T = blockDim.x, W = T >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int E = (n + T - 1) / T;
+    const int wbase = warp * E * 32;
+    unsigned short *wh = hist + warp * 256;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned int *s_warp_total = reinterpret_cast<unsigned int *>(hist + W * 256);  // [32], behind the counters
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 32 + 8 * pass;
+        unsigned long long kreg[EMAX];
+        unsigned short rk[EMAX];
+        for (int i = lane; i < 128; i += 32) reinterpret_cast<unsigned int *>(wh)[i] = 0u;
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < EMAX; r++) {
+            if (r < E) {  // warp-uniform
+                const int idx = wbase + r * 32 + lane;
+                const bool valid = idx < n;
+                kreg[r] = valid ? keys[idx] : 0ull;
+                const unsigned dig = 255u - static_cast<unsigned>((kreg[r] >> shift) & 255ull);
+                const unsigned peers = __match_any_sync(kFull, valid ? dig : 256u + lane);
+                const unsigned before = valid ? wh[dig] : 0u;
+                rk[r] = static_cast<unsigned short>(before + __popc(peers & lt));
+                __syncwarp();
+                if (valid && (peers & lt) == 0u) wh[dig] = static_cast<unsigned short>(before + __popc(peers));
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the W*256 counters in (digit, warp) order: 8 consecutive ones per thread
+        unsigned cnt[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int seq = tid * 8 + j;
+            cnt[j] = hist[(seq % W) * 256 + seq / W];
+            sum += cnt[j];
+        }
+        unsigned incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp_total[warp] = incl;
+        __syncthreads();
+        unsigned offset = incl - sum;
+        for (int w = 0; w < warp; w++) offset += s_warp_total[w];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int seq = tid * 8 + j;
+            hist[(seq % W) * 256 + seq / W] = static_cast<unsigned short>(offset);
+            offset += cnt[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < EMAX; r++) {
+            if (r < E) {
+                const int idx = wbase + r * 32 + lane;
+                if (idx < n) {
+                    const unsigned dig = 255u - static_cast<unsigned>((kreg[r] >> shift) & 255ull);
+                    keys[wh[dig] + rk[r]] = kreg[r];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// RADIX_E > 0 enables the radix sort for lists whose every pair is ranked (no other-shard / NaN
+// entries), from 2048 keys up, when k is not small enough for the select path, the CTA has at
+// most RADIX_E keys per thread and `key_bytes` (the shared memory available at `keys`; 0 =
+// unknown / global memory) also holds the counters.
+template <int RADIX_E = 0, class ScoreAt>
 __device__ inline void rank_topk(ScoreAt score_at, int n, unsigned long long *keys, int k, float *out_s,
-                                 int32_t *out_p) {
+                                 int32_t *out_p, size_t key_bytes = 0) {
     __shared__ int s_ranked;
+    if constexpr (RADIX_E > 0) {
+        const int T = blockDim.x;
+        const size_t hist_off = (static_cast<size_t>(n) * 8 + 15) & ~static_cast<size_t>(15);
+        if (n >= 2048 && n < 65536 && k > n / 4 && (T & 31) == 0 && (n + T - 1) / T <= RADIX_E &&
+            hist_off + static_cast<size_t>(T >> 5) * 512 + 128 <= key_bytes) {
+            int all = 1;
+            for (int i = threadIdx.x; i < n; i += T) {
+                const unsigned long long key = topk_key(score_at(i), static_cast<uint32_t>(i));
+                keys[i] = key;
+                all &= key != 0ull;
+            }
+            if (__syncthreads_and(all)) {
+                block_radix_sort_desc_hi32<RADIX_E>(
+                    keys, n, reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(keys) + hist_off));
+                write_topk(keys, n, k, out_s, out_p);
+                return;
+            }
+        }
+    }
     if (threadIdx.x == 0) s_ranked = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -337,9 +440,10 @@ __device__ inline void rank_topk(ScoreAt score_at, int n, unsigned long long *ke
     write_topk(keys, m, k, out_s, out_p);
 }
 
+template <int RADIX_E = 0>
 __device__ inline void rank_scores_topk(const float *scores, int n, unsigned long long *keys, int k,
-                                        float *out_s, int32_t *out_p) {
-    rank_topk([scores](int i) { return scores[i]; }, n, keys, k, out_s, out_p);
+                                        float *out_s, int32_t *out_p, size_t key_bytes = 0) {
+    rank_topk<RADIX_E>([scores](int i) { return scores[i]; }, n, keys, k, out_s, out_p, key_bytes);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -627,7 +731,7 @@ __global__ void __launch_bounds__(1024) ffx_topk_kernel(const float *scores, int
     };
     if (k > 0) {
         // only the ranked pairs are sorted (NaN = pair of another shard / NaN score)
-        rank_topk(score_at, n, keys, k, out_s + q * k, out_p + q * k);
+        rank_topk<8>(score_at, n, keys, k, out_s + q * k, out_p + q * k, gkeys ? 0 : static_cast<size_t>(cpad) * 8);
     } else {
         for (int i = threadIdx.x; i < n; i += blockDim.x) score_at(i);
     }

@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
         float *out_s;
         int32_t *out_p;
         topk_destination(a, q_idx, &out_s, &out_p);
-        rank_scores_topk(s_scores, n_query, s_keys, a.k, out_s, out_p);
+        rank_scores_topk<16>(s_scores, n_query, s_keys, a.k, out_s, out_p,
+                             static_cast<size_t>(n_warps) * ns * ROWB);  // the drained ring
         if (a.sc_world) __threadfence_system();  // peer stores: visible to the owner once the kernel ends
     }
 }

@@ -522,6 +522,36 @@ def test_adc_fused_long_lists_use_the_register_sort(ffx, adc_kernel, lo, hi):
         ffx.set_option("adc", 0)
 
 
+@pytest.mark.parametrize("lo,hi", [(2048, 2400), (4700, 5000), (5900, 6145), (7000, 8192), (9000, 12000)])
+def test_long_lists_sorted_by_the_radix_epilogue(ffx, oracle_c, lo, hi):
+    """Lists of >= 2048 candidates whose every pair is ranked, with k above a quarter of the list,
+    are ordered by the stable LSD radix sort on the score half of the keys (fused fp32 kernel
+    and the stand-alone top-k kernel); lists that leave no room for its counters, longer than
+    its keys-per-thread limit, or with k small, keep the bitonic / select paths.  Heavy ties
+    (8 distinct lexical scores, alpha = 1) pin the tie-by-position rule; -0.0 and +0.0 tie."""
+    rng = np.random.default_rng(lo)
+    off, rows, vec = make_corpus(rng, 13000, 2, 384, True)
+    idx = ffx.DeviceIndex(384, capacity=len(vec))
+    idx.stage(0, vec)
+    idx.set_docs(off)
+    nq = 300
+    qv = rng.standard_normal((nq, 384)).astype(np.float32)
+    q_off, cand, pair_q = make_pairs(rng, nq, 13000, lo, hi)
+    lex = (rng.integers(0, 8, len(cand)) * 0.5).astype(np.float32)
+    lex[rng.integers(0, len(lex), 500)] = -0.0
+    u_off, u_rows = units_for_mode(off, rows, len(vec), fo.MODE_MAXP)
+    ff = c_scores(oracle_c, vec, u_off, u_rows, pair_q, cand, qv, fo.MODE_MAXP)
+    longest = int(np.diff(q_off).max())
+    for alpha, k in ((1.0, longest), (0.3, longest), (1.0, longest // 2), (0.3, 100)):
+        it = fo.interpolate_f32(lex, ff, alpha)
+        ts, tp = fo.topk_per_query(q_off, it, k)
+        out = idx.rerank_host(fo.MODE_MAXP, qv, q_off, cand, lex, alpha, k, want_ff=False, want_int=False)
+        assert (out["topk_pos"] == tp).all() and (bits(out["topk_score"]) == bits(ts)).all()
+        alone = idx.interpolate_topk_host(lex, ff, q_off, alpha, k)
+        assert (alone["topk_pos"] == tp).all() and (bits(alone["topk_score"]) == bits(ts)).all()
+    idx.close()
+
+
 def test_host_pipeline_matches_single_launch_opq(ffx):
     """ffx_rerank_host cuts many queries into chunks that run on alternating streams; every
     chunk must rotate its OPQ queries into its own buffer (a shared one is overwritten by the
