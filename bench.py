@@ -559,6 +559,18 @@ def run_ffx(args, wl):
                             want_ff=False, want_int=False, out=out)
 
         e2e_step()
+        if not (h_tp.array[:4] == p_host).all():  # say where before failing
+            for q in range(4):
+                d = np.flatnonzero(h_tp.array[q] != p_host[q])
+                if len(d):
+                    r = int(d[0])
+                    print(f"query {q}: {len(d)} ranks differ, first at {r}: host pos/score "
+                          f"{h_tp.array[q, r:r + 4].tolist()} {h_ts.array[q, r:r + 4].tolist()} device "
+                          f"{p_host[q, r:r + 4].tolist()} {s_host[q, r:r + 4].tolist()}", file=sys.stderr)
+                    for pos in (int(h_tp.array[q, r]), int(p_host[q, r])):
+                        rh, rd = np.flatnonzero(h_tp.array[q] == pos), np.flatnonzero(p_host[q] == pos)
+                        print(f"   pos {pos}: host rank {rh.tolist()} score {h_ts.array[q, rh].tolist()}; "
+                              f"device rank {rd.tolist()} score {s_host[q, rd].tolist()}", file=sys.stderr)
         assert (h_tp.array[:4] == p_host).all(), "host-buffer path disagrees with the device path"
         barrier()
         t0 = time.perf_counter()

@@ -255,7 +255,12 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
                     }
                 }
             }
-            __syncwarp();  // every lane holds its row in registers: the slots may be refilled
+            // The slots are refilled by the bulk-copy engine (async proxy) while the words above were
+            // read through the generic proxy and have not been consumed yet: without a cross-proxy
+            // fence a copy can land before a queued ld.shared has executed (seen as ~1 wrong row in
+            // 10^6 when the LSU queue is deep).  Fence, then let the warp agree that all reads are done.
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
             if (r0 + 32 < total) issue_block(r0 + 32);
 
             float s = 0.f;

@@ -395,7 +395,10 @@ template <int RADIX_E = 0, class ScoreAt>
 __device__ inline void rank_topk(ScoreAt score_at, int n, unsigned long long *keys, int k, float *out_s,
                                  int32_t *out_p, size_t key_bytes = 0) {
     __shared__ int s_ranked;
-    if constexpr (RADIX_E > 0) {
+#ifndef FFX_NO_RADIX
+#define FFX_NO_RADIX 0
+#endif
+    if constexpr (RADIX_E > 0 && !FFX_NO_RADIX) {
         const int T = blockDim.x;
         const size_t hist_off = (static_cast<size_t>(n) * 8 + 15) & ~static_cast<size_t>(15);
         if (n >= 2048 && n < 65536 && k > n / 4 && (T & 31) == 0 && (n + T - 1) / T <= RADIX_E &&

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libffx.so")
+LIB_PATH = os.environ.get("FFX_LIB") or os.path.join(_HERE, "lib", "libffx.so")  # FFX_LIB: an alternative build (A/B measurements)
 
 ROWS_F32, ROWS_PQ_U8 = 0, 1
 MODE_PASSAGE, MODE_MAXP, MODE_FIRSTP, MODE_AVEP = 1, 2, 3, 4

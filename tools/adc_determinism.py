@@ -67,3 +67,17 @@ for r in range(reps):
     d_it = np.flatnonzero(out["int"] != runs[0][0].cpu().numpy())
     print(f"host run {r}: queries with different lists: {len(bad)} {bad[:12].tolist()}, pairs with different scores: "
           f"{len(d_it)} first at pair {d_it[:3].tolist()} (queries {(d_it[:3] // C).tolist()})", flush=True)
+
+# ---- the same without per-pair outputs (what bench.py times): lists only
+for r in range(reps):
+    ts = torch.empty((nq, C), device=dev)
+    tp = torch.empty((nq, C), device=dev, dtype=torch.int32)
+    idx.rerank_device(4, qv.data_ptr(), nq, q_off.data_ptr(), cand.data_ptr(), lex.data_ptr(), 0.1, C, C,
+                      0, 0, ts.data_ptr(), tp.data_ptr())
+    idx.sync()
+    bad = np.flatnonzero((tp.cpu().numpy() != ref_tp).any(axis=1))
+    out = idx.rerank_host(4, h["qv"], h["off"], h["cand"], h["lex"], 0.1, C, want_ff=False, want_int=False)
+    badh = np.flatnonzero((out["topk_pos"] != ref_tp).any(axis=1))
+    perm_ok = bool((np.sort(out["topk_pos"], axis=1) == np.arange(C)).all())
+    print(f"lists-only run {r}: device launch: queries with different lists {len(bad)} {bad[:8].tolist()}; "
+          f"host path: {len(badh)} {badh[:8].tolist()} (permutation ok: {perm_ok})", flush=True)
