@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
         const int per_table = a.Ks * 32;
         const bool vec4 = (a.Ds & 3) == 0 && (reinterpret_cast<uintptr_t>(qe) & 15) == 0;
         for (int e = threadIdx.x; e < total; e += blockDim.x) {
-            const int m = 32 * (e / per_table) + (e & 31);
+            // e / per_table without an integer division: at most NC = 4 tables
+            const int j3 = (e >= per_table) + (e >= 2 * per_table) + (e >= 3 * per_table);
+            const int m = 32 * j3 + (e & 31);
             const float *cw = w.cw_t + static_cast<size_t>(e) * a.Ds;
             const float *qm = qe + m * a.Ds;
             float acc = 0.f;

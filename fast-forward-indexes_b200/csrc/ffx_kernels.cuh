@@ -349,12 +349,17 @@ __device__ inline void block_radix_sort_desc_hi32(unsigned long long *keys, int 
         }
         __syncthreads();
         // exclusive scan of the W*256 counters in (digit, warp) order: 8 consecutive ones per thread
+        // sequence number seq = digit * W + warp  <->  hist[warp * 256 + digit]; stepped, not divided
         unsigned cnt[8], sum = 0;
+        const int dig0 = (tid * 8) / W, w0 = (tid * 8) % W;
+        {
+            int dig = dig0, w = w0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int seq = tid * 8 + j;
-            cnt[j] = hist[(seq % W) * 256 + seq / W];
-            sum += cnt[j];
+            for (int j = 0; j < 8; j++) {
+                cnt[j] = hist[w * 256 + dig];
+                sum += cnt[j];
+                if (++w == W) w = 0, dig++;
+            }
         }
         unsigned incl = sum;
 #pragma unroll
@@ -366,11 +371,14 @@ __device__ inline void block_radix_sort_desc_hi32(unsigned long long *keys, int 
         __syncthreads();
         unsigned offset = incl - sum;
         for (int w = 0; w < warp; w++) offset += s_warp_total[w];
+        {
+            int dig = dig0, w = w0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int seq = tid * 8 + j;
-            hist[(seq % W) * 256 + seq / W] = static_cast<unsigned short>(offset);
-            offset += cnt[j];
+            for (int j = 0; j < 8; j++) {
+                hist[w * 256 + dig] = static_cast<unsigned short>(offset);
+                offset += cnt[j];
+                if (++w == W) w = 0, dig++;
+            }
         }
         __syncthreads();
 #pragma unroll

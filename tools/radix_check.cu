@@ -56,7 +56,8 @@ int main() {
         bad += run<8>(256, 2048, 600, distinct);
         bad += run<16>(448, 5000, 600, distinct);
         bad += run<16>(256, 4096, 600, distinct);
-        bad += run<16>(1024, 3000, 600, distinct);
+        bad += run<16>(512, 6000, 400, distinct);
+        bad += run<8>(1024, 3000, 600, distinct);
     }
     return bad ? 1 : 0;
 }
