@@ -74,7 +74,10 @@ struct Space {
     uint64_t count() const {
         if (null_space) return 0;
         uint64_t n = 1;
-        for (int i = 0; i < rank; i++) n *= dims[i];
+        for (int i = 0; i < rank; i++) {
+            if (dims[i] != 0 && n > ~uint64_t(0) / dims[i]) throw std::runtime_error("dataspace extent overflows 64 bits");
+            n *= dims[i];
+        }
         return n;
     }
 };
@@ -135,6 +138,11 @@ uint64_t le(const uint8_t *p, int n) {
     uint64_t v = 0;
     for (int i = n - 1; i >= 0; i--) v = (v << 8) | p[i];
     return v;
+}
+
+uint64_t mul_checked(uint64_t a, uint64_t b) {  // sizes come from the file: never let them wrap
+    if (a != 0 && b > UNDEF / a) throw std::runtime_error("size in an HDF5 structure overflows 64 bits");
+    return a * b;
 }
 
 uint64_t le_addr(const uint8_t *p, int n) {  // all-ones of any width = the undefined address
@@ -411,7 +419,7 @@ void walk_chunk_tree(const ffx_h5 &f, uint64_t node, Dataset &d, int depth) {
         if (row % d.chunk[0]) throw std::runtime_error("chunk offset is not a multiple of the chunk shape");
         const uint64_t ci = row / d.chunk[0];
         if (ci >= d.chunk_addr.size()) continue;  // beyond the current extent (dataset was shrunk)
-        if (nbytes != d.chunk[0] * d.row_bytes) throw Unsupported("chunk with a filtered (compressed) size");
+        if (nbytes != mul_checked(d.chunk[0], d.row_bytes)) throw Unsupported("chunk with a filtered (compressed) size");
         f.addr(child, nbytes);
         d.chunk_addr[ci] = child;
     }
@@ -436,14 +444,14 @@ Dataset &dataset_of(ffx_h5 &f, Object &o, const std::string &path) {
     if (!layout || !have_type || !have_space) throw std::runtime_error("dataset header lacks datatype, dataspace or layout");
     if (d.type.vlen_string) throw Unsupported("dataset of variable-length strings");
     d.row_bytes = d.type.size;
-    for (int i = 1; i < d.space.rank; i++) d.row_bytes *= d.space.dims[i];
+    for (int i = 1; i < d.space.rank; i++) d.row_bytes = mul_checked(d.row_bytes, d.space.dims[i]);
     const uint8_t *p = f.at(layout->off, layout->len);
     if (layout->len < 2) throw std::runtime_error("short layout message");
     if (p[0] != 3 && !(p[0] == 4 && p[1] != 2))
         throw Unsupported(p[0] == 4 ? "layout version 4 chunk index (file written with libver='latest')"
                                     : "data layout message version " + std::to_string(p[0]));
     d.layout = p[1];
-    const uint64_t total = d.space.count() * d.type.size;
+    const uint64_t total = mul_checked(d.space.count(), d.type.size);
     if (d.layout == 0) {
         const uint64_t n = le(f.at(layout->off + 2, 2), 2);
         if (n < total || 4 + n > layout->len) throw std::runtime_error("compact dataset smaller than its dataspace");
@@ -485,6 +493,7 @@ void copy_rows(const ffx_h5 &f, const Dataset &d, uint64_t row0, uint64_t n, uin
             return;
         }
         const uint8_t *src = d.layout == 0 ? f.at(d.addr, d.bytes) : f.addr(d.addr, d.bytes);
+        if (mul_checked(row0 + n, d.row_bytes) > d.bytes) throw std::runtime_error("rows outside the stored data");
         memcpy(dst, src + row0 * d.row_bytes, n * d.row_bytes);
         return;
     }
@@ -731,7 +740,7 @@ int ffx_h5_read_rows(ffx_h5 *f, const char *path, int64_t row0, int64_t nrows, v
         const uint64_t rows = d.space.rank ? d.space.dims[0] : 1;
         if ((uint64_t)row0 + (uint64_t)nrows > rows) throw std::runtime_error("rows outside the dataset");
         if (d.space.null_space || nrows == 0) return (int)FFX_OK;
-        const uint64_t bytes = (uint64_t)nrows * d.row_bytes;
+        const uint64_t bytes = mul_checked((uint64_t)nrows, d.row_bytes);
         unsigned workers = bytes >= (32u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
         if (workers <= 1) {
             copy_rows(*f, d, row0, nrows, (uint8_t *)dst);
@@ -776,8 +785,10 @@ int ffx_h5_row_span(ffx_h5 *f, const char *path, int64_t row0, const void **rows
                 *rows = f->addr(d.chunk_addr[ci], d.chunk[0] * d.row_bytes) + in * d.row_bytes;
         } else {
             *nrows = (int64_t)(total - row0);
-            if (d.addr != UNDEF)
+            if (d.addr != UNDEF) {
+                if (mul_checked(total, d.row_bytes) > d.bytes) throw std::runtime_error("rows outside the stored data");
                 *rows = (d.layout == 0 ? f->at(d.addr, d.bytes) : f->addr(d.addr, d.bytes)) + row0 * d.row_bytes;
+            }
         }
         return FFX_OK;
     });

@@ -202,10 +202,18 @@ def test_damaged_files_are_errors_not_faults(h5, tmp_path):
             opens(raw[:cut], f"cut{cut}.h5")
     # random corruption of the metadata must never crash the process; data bytes may change silently
     flips = np.random.default_rng(7)
-    for trial in range(300):
+    meta_from = max(i for i in range(len(raw) - 4) if raw[i:i + 4] in (b"TREE", b"HEAP", b"SNOD")) - 4096
+    for trial in range(1500):
         data = bytearray(raw)
-        for pos in flips.integers(0, len(raw), 6):
-            data[pos] ^= 1 << int(flips.integers(0, 8))
+        # two thirds of the trials hit the structures (B-trees, heaps, headers sit behind the
+        # chunk data in these files; the superblock in front), the rest anywhere
+        where = (flips.integers(0, len(raw), 6) if trial % 3 == 0 else
+                 np.concatenate([flips.integers(max(meta_from, 0), len(raw), 5), flips.integers(0, 96, 1)]))
+        for pos in where:
+            if trial % 2:
+                data[pos] ^= 1 << int(flips.integers(0, 8))
+            else:
+                data[pos] = int(flips.integers(0, 256))
         try:
             opens(bytes(data), "flip.h5")
         except (h5.FFXError, ValueError, MemoryError):  # reported, or a datatype numpy cannot express
