@@ -45,6 +45,18 @@ class Codebook:
         return code_dtype_for(self.Ks)
 
     # ---- plain PQ pieces ----------------------------------------------------------
+    def __eq__(self, other: object) -> bool:
+        """Same configuration and the same trained tables (what nanopq's `PQ.__eq__` compares)."""
+        if not isinstance(other, Codebook):
+            return NotImplemented
+        same = (self.M, self.Ks, self.metric, self.verbose, self.rotated, self.Ds) == \
+               (other.M, other.Ks, other.metric, other.verbose, other.rotated, other.Ds)
+        for mine, theirs in ((self.codewords, other.codewords), (self.R, other.R)):
+            same = same and (mine is None) == (theirs is None) and (mine is None or np.array_equal(mine, theirs))
+        return bool(same)
+
+    __hash__ = None
+
     def _split(self, vecs: np.ndarray):
         for m in range(self.M):
             yield m, vecs[:, m * self.Ds:(m + 1) * self.Ds]

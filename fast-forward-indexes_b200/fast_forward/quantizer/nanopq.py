@@ -76,8 +76,11 @@ class _CodebookQuantizer(Quantizer):
 class NanoPQ(_CodebookQuantizer):
     """Product quantizer (nanopq.PQ semantics)."""
 
+    _pq = property(lambda self: self._book)  # the attribute name of quantizer/nanopq.py:26
+
 
 class NanoOPQ(_CodebookQuantizer):
     """Optimised product quantizer: learned rotation + PQ (nanopq.OPQ semantics)."""
 
     _ROTATED = True
+    _opq = property(lambda self: self._book)  # the attribute name of quantizer/nanopq.py:94
