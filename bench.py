@@ -73,6 +73,10 @@ WORKLOADS = {
                                 cands=5000, k=5000),
     "c4_opq_avep": dict(mode="AVEP", kind="opq", n_docs=3_200_000, mean_psg=6.25, nq=5193, cands=5000,
                         k=5000, M=96, Ks=256),
+    # SURVEY 8d's skewed variant (reported, not the headline): Zipf-like document popularity inside
+    # every candidate stratum, so that popular documents recur across queries and hit in L2
+    "c3_zipf_doc_maxp": dict(mode="MAXP", kind="f32", n_docs=3_200_000, mean_psg=6.25, nq=5193,
+                             cands=5000, k=5000, popularity="zipf"),
     # per-GPU shard of 1.2M docs / 7.5M passages (60M passages at 8 GPUs), 12 500 queries per GPU
     "c5_sharded_maxp": dict(mode="MAXP", kind="f32", n_docs=1_200_000, mean_psg=6.25, nq=12_500,
                             cands=5000, k=1000, sharded=True),
@@ -471,7 +475,11 @@ def run_ffx(args, wl):
     for q0 in range(0, nq, 4096):  # bounded temporaries
         qn = min(4096, nq - q0)
         perm = torch.rand((qn, cands), device=dev, generator=gen).argsort(dim=1)
-        within = torch.randint(0, bucket, (qn, cands), device=dev, generator=gen)
+        if wl.get("popularity") == "zipf":  # P(rank r inside the stratum) ~ 1/r: log-uniform draw
+            u = torch.rand((qn, cands), device=dev, generator=gen)
+            within = (torch.exp(u * float(np.log(bucket))) - 1.0).long().clamp_(0, bucket - 1)
+        else:
+            within = torch.randint(0, bucket, (qn, cands), device=dev, generator=gen)
         cand_parts.append((perm * bucket + within).to(torch.int32))
         del perm, within
     cand = torch.cat(cand_parts).contiguous().view(-1)
