@@ -11,7 +11,8 @@ into an HBM row store, and all scoring runs there.
 library's own HDF5 reader (`fast_forward._h5`, csrc/ffx_h5.cpp): the file is mapped, every chunk
 of `vectors` is handed to the staging buffers as a pointer into the mapping, and the two id
 columns are coded by the C++ dictionaries straight from their fixed-width bytes.  Creating a
-file and adding to it writes through `h5py` (an ImportError says so when it is missing).
+file and adding to it writes through `h5py` when it is installed, else through the package's
+own writer of the same layout (`fast_forward._h5_write`).
 """
 
 from __future__ import annotations
@@ -23,7 +24,7 @@ from pathlib import Path
 import numpy as np
 
 import fast_forward
-from fast_forward import _ffx, _h5
+from fast_forward import _ffx, _h5, _h5_write
 from fast_forward.encoder.base import Encoder
 from fast_forward.index._store import RowStore
 from fast_forward.index.base import IDSequence, Index, Mode
@@ -34,10 +35,11 @@ LOGGER = logging.getLogger(__name__)
 
 
 def _h5py():
+    """The h5py module, or None when it is not installed (the native writer is used then)."""
     try:
         import h5py
-    except ImportError as e:  # pragma: no cover - depends on the environment
-        raise ImportError("OnDiskIndex reads and writes HDF5 files and needs the `h5py` package.") from e
+    except ImportError:
+        return None
     return h5py
 
 
@@ -86,16 +88,25 @@ class OnDiskIndex(Index):
         self._memory_mapped = memory_mapped
         self._max_indexing_size = max_indexing_size
         LOGGER.debug("creating file %s", self._index_file)
-        with _h5py().File(self._index_file, "w") as fp:
-            fp.attrs["num_vectors"] = 0
-            fp.attrs["ff_version"] = fast_forward.__version__
+        h5py = _h5py()
+        if h5py is None:
+            _h5_write.IndexFile.create(self._index_file, fast_forward.__version__).close()
+        else:
+            with h5py.File(self._index_file, "w") as fp:
+                fp.attrs["num_vectors"] = 0
+                fp.attrs["ff_version"] = fast_forward.__version__
         super().__init__(query_encoder=query_encoder, quantizer=quantizer, mode=mode,
                          encoder_batch_size=encoder_batch_size)
 
     # ---- persistence ----------------------------------------------------------------------
     def _on_quantizer_set(self) -> None:
         meta, attributes, data = self.quantizer.serialize()
-        with _h5py().File(self._index_file, "a") as fp:
+        h5py = _h5py()
+        if h5py is None:
+            with _h5_write.IndexFile.open_existing(self._index_file) as out:
+                out.set_quantizer(meta, attributes, data)
+            return
+        with h5py.File(self._index_file, "a") as fp:
             if "quantizer" in fp:
                 del fp["quantizer"]
             fp.create_group("quantizer/meta").attrs.update(meta)
@@ -120,8 +131,35 @@ class OnDiskIndex(Index):
                 raise RuntimeError(f"Passage ID {p} is longer than the maximum ({psg_width} characters).")
         self._store.check_new_passages(psg_ids)
 
+    def _grown(self, have: int, extra: int) -> int:
+        """Capacity after growing in whole HDF5 chunks (disk.py:268-276)."""
+        return max(int((have + extra) / self._chunk_size + 0.5) * self._chunk_size, have + extra)
+
+    def _add_native(self, vectors: np.ndarray, doc_ids: IDSequence, psg_ids: IDSequence) -> None:
+        """`_add` through the package's own HDF5 writer (no h5py)."""
+        with _h5_write.IndexFile.open_existing(self._index_file) as out:
+            if not out.datasets:
+                out.create_datasets(vectors.shape[-1], vectors.dtype, self._init_size, self._chunk_size,
+                                    self._max_id_length)
+            self._validate_ids(doc_ids, psg_ids, out.datasets["doc_ids"].dtype.itemsize,
+                               out.datasets["psg_ids"].dtype.itemsize)
+            have, extra = out.num_vectors, vectors.shape[0]
+            if extra > out.capacity - have:
+                LOGGER.debug("resizing index from %s to %s", out.capacity, self._grown(have, extra))
+                out.resize(self._grown(have, extra))
+            for name, ids in (("doc_ids", doc_ids), ("psg_ids", psg_ids)):
+                out.write_at(name, [have + i for i, v in enumerate(ids) if v is not None],
+                             [v for v in ids if v is not None])
+            out.write_rows("vectors", have, vectors)
+            out.set_num_vectors(have + extra)  # bumped last: the file stays consistent
+
     def _add(self, vectors: np.ndarray, doc_ids: IDSequence, psg_ids: IDSequence) -> None:
-        with _h5py().File(self._index_file, "a") as fp:
+        h5py = _h5py()
+        if h5py is None:
+            self._add_native(vectors, doc_ids, psg_ids)
+            self._stage_added(vectors, doc_ids, psg_ids)
+            return
+        with h5py.File(self._index_file, "a") as fp:
             if "vectors" not in fp:
                 self._create_datasets(fp, vectors.shape[-1], vectors.dtype)
             self._validate_ids(doc_ids, psg_ids, fp["doc_ids"].dtype.itemsize, fp["psg_ids"].dtype.itemsize)
@@ -129,9 +167,7 @@ class OnDiskIndex(Index):
             have = int(fp.attrs["num_vectors"])
             extra = vectors.shape[0]
             if extra > fp["vectors"].shape[0] - have:
-                # grow in whole HDF5 chunks (disk.py:268-276)
-                grown = int((have + extra) / self._chunk_size + 0.5) * self._chunk_size
-                grown = max(grown, have + extra)
+                grown = self._grown(have, extra)
                 LOGGER.debug("resizing index from %s to %s", fp["vectors"].shape[0], grown)
                 for name in ("vectors", "doc_ids", "psg_ids"):
                     fp[name].resize(grown, axis=0)
@@ -142,7 +178,9 @@ class OnDiskIndex(Index):
                     fp[name][where] = [v for v in ids if v is not None]
             fp["vectors"][have:have + extra] = vectors
             fp.attrs["num_vectors"] = have + extra  # bumped last: the file stays consistent
+        self._stage_added(vectors, doc_ids, psg_ids)
 
+    def _stage_added(self, vectors: np.ndarray, doc_ids: IDSequence, psg_ids: IDSequence) -> None:
         rows = np.ascontiguousarray(vectors) if vectors.dtype == np.uint8 and self.quantizer is not None \
             else np.ascontiguousarray(vectors, dtype=np.float32)
         self._store.append(rows, doc_ids, psg_ids, self._init_size, self._chunk_size)

@@ -17,6 +17,18 @@ except ImportError:
 
     sys.modules["h5py"] = fake_h5py
 
+@pytest.fixture(params=["h5py", "native-writer"], autouse=True)
+def writer(request, monkeypatch):
+    """Every test runs twice: writing through h5py (the real package, or tests/fake_h5py.py
+    persisting HDF5 bytes) and through the package's own writer (`fast_forward._h5_write`, what
+    `OnDiskIndex` uses when h5py is not installed).  Reading is always the native reader."""
+    if request.param == "native-writer":
+        import fast_forward.index.disk as disk
+
+        monkeypatch.setattr(disk, "_h5py", lambda: None)
+    return request.param
+
+
 DOC = ["d0", "d0", "d1", "d2", "d3"]
 PSG = ["p0", "p1", "p2", "p3", "p4"]
 V = np.tril(np.ones((5, 5), dtype=np.float32))

@@ -238,3 +238,63 @@ def test_unsupported_features_say_so(h5, tmp_path):
     with h5.H5File(bad) as fp:
         with pytest.raises(h5.FFXError, match="filter pipeline"):
             fp.read("vectors")
+
+
+def test_native_writer_grows_reopens_and_reads_back(h5, tmp_path):
+    """`fast_forward._h5_write.IndexFile` (OnDiskIndex's writer when h5py is missing) against the
+    native reader: many small adds (two B-tree levels with 4-row chunks), capacity growth in whole
+    chunks, ids with gaps, re-opening between adds, the quantizer group with every attribute type
+    `Quantizer.serialize` produces, replacing the quantizer, and refusing foreign files."""
+    from fast_forward import _h5_write as hw2
+
+    rng = np.random.default_rng(9)
+    path = tmp_path / "native.h5"
+    hw2.IndexFile.create(path, "0.8.0").close()
+    with h5.H5File(path) as fp:
+        assert fp.attrs("/") == {"num_vectors": 0, "ff_version": "0.8.0", "ffx_writer": 1} and fp.keys() == []
+    dim, chunk = 6, 4
+    vec = rng.standard_normal((1000, dim)).astype(np.float32)
+    docs = [None if i % 5 == 2 else f"d{i // 3}" for i in range(1000)]
+    psgs = [None if i % 7 == 3 else f"p{i}" for i in range(1000)]
+    have = 0
+    for step in (1, 3, 4, 9, 200, 83, 700):
+        with hw2.IndexFile.open_existing(path) as out:
+            if not out.datasets:
+                out.create_datasets(dim, np.float32, 8, chunk, 8)
+            assert out.num_vectors == have
+            if have + step > out.capacity:
+                out.resize(-(-(have + step) // chunk) * chunk)
+            for name, ids in (("doc_ids", docs), ("psg_ids", psgs)):
+                part = ids[have:have + step]
+                out.write_at(name, [have + i for i, v in enumerate(part) if v is not None], [v for v in part if v is not None])
+            out.write_rows("vectors", have, vec[have:have + step])
+            out.set_num_vectors(have + step)
+        have += step
+        with h5.H5File(path) as fp:
+            assert fp.attr("/", "num_vectors") == have and fp.info("vectors")["chunk_rows"] == chunk
+            assert (fp.read("vectors", 0, have) == vec[:have]).all()
+            got_docs = [b.decode() or None for b in fp.read("doc_ids", 0, have)]
+            got_psgs = [b.decode() or None for b in fp.read("psg_ids", 0, have)]
+            assert got_docs == docs[:have] and got_psgs == psgs[:have]
+            assert fp.info("vectors")["shape"][0] >= have and fp.info("vectors")["shape"][0] % chunk == 0
+    cw = rng.standard_normal((2, 8, 3)).astype(np.float32)
+    for trained in (False, True):
+        with hw2.IndexFile.open_existing(path) as out:
+            out.set_quantizer({"__module__": "fast_forward.quantizer.nanopq", "__name__": "NanoOPQ", "_trained": trained},
+                              {"M": 2, "Ks": 8, "Ds": None if not trained else 3, "metric": "dot", "verbose": False,
+                               "note": "grüße"}, {"codewords": cw, "R": np.eye(6, dtype=np.float32)} if trained else {})
+        with h5.H5File(path) as fp:
+            assert sorted(fp.keys()) == ["doc_ids", "psg_ids", "quantizer", "vectors"]
+            meta, attrs = fp.attrs("quantizer/meta"), fp.attrs("quantizer/attributes")
+            assert meta == {"__module__": "fast_forward.quantizer.nanopq", "__name__": "NanoOPQ", "_trained": trained}
+            assert meta["_trained"].dtype == np.bool_ and attrs["M"] == 2 and attrs["note"] == "grüße"
+            assert ("Ds" in attrs) == trained and attrs["metric"] == "dot" and not attrs["verbose"]
+            assert sorted(fp.keys("quantizer/data")) == (["R", "codewords"] if trained else [])
+            if trained:
+                assert (fp.read("quantizer/data/codewords") == cw).all()
+            assert (fp.read("vectors", 0, have) == vec[:have]).all()  # untouched by the new subtree
+    foreign = tmp_path / "foreign.h5"
+    root, _, _, _ = index_tree(rng, 10, 4, 4, 4)
+    hw.write_hdf5(root, foreign)
+    with pytest.raises(ValueError, match="needs h5py"):
+        hw2.IndexFile.open_existing(foreign)
