@@ -168,3 +168,42 @@ def test_coalescing_equals_the_reference_function(api):
             got, _ = target._get_vectors([f"doc{d}"])
             want, _ = plain_target._get_vectors([f"doc{d}"])
             assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_pyterrier_transformers_on_a_stand_in_module(api, monkeypatch):
+    """`pyterrier` is not installed here: a stand-in with the two things the glue touches
+    (`Transformer`, `model.add_ranks`) checks columns and values of FFScore -> FFInterpolate
+    (reference: util/pyterrier.py:14-87)."""
+    import sys
+    import types
+
+    import pandas as pd
+
+    pt = types.ModuleType("pyterrier")
+    pt.Transformer = type("Transformer", (), {})
+
+    def add_ranks(df, single_query=False):
+        out = df.copy()
+        out["rank"] = out.groupby("qid")["score"].rank(ascending=False, method="first").astype(int) - 1
+        return out
+
+    pt.model = types.SimpleNamespace(add_ranks=add_ranks)
+    monkeypatch.setitem(sys.modules, "pyterrier", pt)
+    sys.modules.pop("fast_forward.util.pyterrier", None)
+    from fast_forward.util.pyterrier import FFInterpolate, FFScore
+
+    index = api.InMemoryIndex(api.LambdaEncoder(lambda _: np.ones(5, np.float32)), mode=api.Mode.MAXP)
+    index.add(V, doc_ids=DOC)
+    inp = pd.DataFrame({"qid": ["q1"] * 4 + ["q2"] * 4, "docno": ["d0", "d1", "d2", "d3"] * 2,
+                        "score": [100.0, 2, 3, 200, 400, 5, 6, 800], "query": ["one"] * 4 + ["two"] * 4})
+    scorer = FFScore(index)
+    scored = scorer.transform(inp)
+    assert list(scored.columns) == ["qid", "docno", "score", "query", "score_0", "rank"]
+    by_pair = scored.set_index(["qid", "docno"])
+    assert by_pair.loc[("q1", "d0"), "score"] == 2.0 and by_pair.loc[("q2", "d3"), "score"] == 5.0  # MAXP of ones
+    assert by_pair.loc[("q1", "d3"), "score_0"] == 200.0 and len(scored) == 8
+    mixed = FFInterpolate(0.5).transform(scored).set_index(["qid", "docno"])
+    assert mixed.loc[("q1", "d0"), "score"] == 51.0 and mixed.loc[("q2", "d3"), "score"] == 402.5
+    assert mixed.loc[("q2", "d3"), "rank"] == 0 and "score_0" not in mixed.columns
+    assert repr(scorer) == f"FFScore({id(index)}, {id(index._query_encoder)})"
