@@ -63,15 +63,27 @@ def _coded_frame(df: pd.DataFrame, is_sorted: bool) -> pd.DataFrame | None:
     instead of pandas' `duplicated` + `sort_values` over two string columns: ids are coded by
     the C++ dictionary, pairs are checked as int64 keys, the order is one radix sort.  Returns
     None (the caller then takes the pandas route, with identical results) unless both id
-    columns already are strings without nulls and the scores are floats."""
+    columns are strings (or integers / Python strings, converted first) without nulls and the
+    scores are floats."""
     from fast_forward import _ffx, _ids
 
-    q_col, id_col, s_col = df["q_id"], df["id"], df["score"]
-    if not (pd.api.types.is_string_dtype(q_col.dtype) and pd.api.types.is_string_dtype(id_col.dtype)
-            and q_col.dtype != object and id_col.dtype != object and s_col.dtype.kind == "f"):
+    s_col = df["score"]
+    if len(df) == 0 or s_col.dtype.kind != "f":
         return None
-    if len(df) == 0 or q_col.isna().any() or id_col.isna().any():
-        return None
+    id_columns = {}
+    for col in ("q_id", "id"):
+        values = df[col]
+        if values.dtype.kind in "iu" or (values.dtype == object and pd.api.types.infer_dtype(values, skipna=False) == "string"):
+            # run files with numeric ids (MS MARCO), frames built from Python strings: the ids
+            # become strings anyway (ranking.py:107-113); doing it first changes nothing for such
+            # columns (no nulls, no mixed types) and opens the coded route
+            values = values.astype(str)
+        if not pd.api.types.is_string_dtype(values.dtype) or values.dtype == object or values.isna().any():
+            return None
+        id_columns[col] = values
+    if id_columns["q_id"] is not df["q_id"] or id_columns["id"] is not df["id"]:
+        df = df.assign(**id_columns)
+    q_col, id_col = df["q_id"], df["id"]
     import ctypes as C
 
     n = len(df)
