@@ -165,6 +165,68 @@ void parallel_ranges(int64_t n, int threads, F &&body) {
     for (auto &th : pool) th.join();
 }
 
+// order[j] = the element that comes j-th when n elements are sorted by key(i) ascending, equal
+// keys in index order: LSD radix sort, 8-bit digits, digits that never vary are skipped, every
+// pass (histogram, prefix, scatter) spread over the host cores.
+template <class KeyOf>
+int radix_order(int64_t n, int n_threads, int64_t *order, KeyOf &&key_of) {
+    if (n == 0) return FFX_OK;
+    struct Item {
+        uint64_t key;
+        uint32_t row;
+    };
+    std::vector<Item> a(static_cast<size_t>(n)), b(static_cast<size_t>(n));
+    const int threads = worker_count(n_threads, n / 16);
+    std::vector<uint64_t> seen_or(static_cast<size_t>(threads), 0), seen_and(static_cast<size_t>(threads), ~uint64_t(0));
+    const int64_t step = (n + threads - 1) / threads;
+    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+        const size_t t = static_cast<size_t>(lo / step);
+        uint64_t o = 0, an = ~uint64_t(0);
+        for (int64_t i = lo; i < hi; i++) {
+            const uint64_t k = key_of(i);
+            a[static_cast<size_t>(i)] = Item{k, static_cast<uint32_t>(i)};
+            o |= k;
+            an &= k;
+        }
+        seen_or[t] = o;
+        seen_and[t] = an;
+    });
+    uint64_t any = 0, all = ~uint64_t(0);
+    for (int t = 0; t < threads; t++) {
+        any |= seen_or[static_cast<size_t>(t)];
+        all &= seen_and[static_cast<size_t>(t)];
+    }
+    const uint64_t varying = any & ~all;  // bits that differ between at least two keys
+    std::vector<uint64_t> counts(static_cast<size_t>(threads) * 256);
+    Item *src = a.data(), *dst = b.data();
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 8 * pass;
+        if (((varying >> shift) & 0xff) == 0) continue;  // every key has the same digit here
+        parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+            uint64_t *c = counts.data() + static_cast<size_t>(lo / step) * 256;
+            std::fill(c, c + 256, 0);
+            for (int64_t i = lo; i < hi; i++) c[(src[i].key >> shift) & 0xff]++;
+        });
+        uint64_t at = 0;
+        for (int d = 0; d < 256; d++)
+            for (int t = 0; t < threads; t++) {
+                uint64_t &c = counts[static_cast<size_t>(t) * 256 + d];
+                const uint64_t mine = (static_cast<int64_t>(t) * step < n) ? c : 0;
+                c = at;
+                at += mine;
+            }
+        parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+            uint64_t *c = counts.data() + static_cast<size_t>(lo / step) * 256;
+            for (int64_t i = lo; i < hi; i++) dst[c[(src[i].key >> shift) & 0xff]++] = src[i];
+        });
+        std::swap(src, dst);
+    }
+    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; i++) order[i] = src[i].row;
+    });
+    return FFX_OK;
+}
+
 bool bad_strings(const int64_t *offsets, const char *data, int64_t n) {
     return n < 0 || (n > 0 && (!offsets || (!data && offsets[n] > offsets[0])));
 }
@@ -355,72 +417,51 @@ int ffx_ranking_order(const int32_t *q_rank, const float *score, int64_t n, int6
     if (n < 0 || (n > 0 && (!q_rank || !score || !order)))
         return fail(FFX_ERR_INVALID, "ffx_ranking_order: bad arguments");
     if (n >= (int64_t(1) << 32)) return fail(FFX_ERR_UNSUPPORTED, "ffx_ranking_order: more than 2^32 rows");
-    if (n == 0) return FFX_OK;
-    struct Item {
-        uint64_t key;
-        uint32_t row;
-    };
-    std::vector<Item> a(static_cast<size_t>(n)), b(static_cast<size_t>(n));
-    const int threads = worker_count(n_threads, n / 16);
-    std::vector<uint64_t> seen_or(static_cast<size_t>(threads), 0), seen_and(static_cast<size_t>(threads), ~uint64_t(0));
-    std::vector<int> negative(static_cast<size_t>(threads), 0);
-    const int64_t step = (n + threads - 1) / threads;
     // key: query rank ascending, then score DEscending (-0.0 == +0.0, NaN after every number),
     // the incoming row order breaking ties (LSD radix passes are stable)
-    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
-        const size_t t = static_cast<size_t>(lo / step);
-        uint64_t o = 0, an = ~uint64_t(0);
-        for (int64_t i = lo; i < hi; i++) {
-            float f = score[i];
-            uint32_t u;
-            if (f == 0.0f) f = 0.0f;  // drops the sign of -0.0
-            memcpy(&u, &f, 4);
-            uint32_t asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending in f
-            uint32_t desc = ~asc;
-            if (f != f) desc = 0xffffffffu;
-            if (q_rank[i] < 0) negative[t] = 1;
-            const uint64_t k = (static_cast<uint64_t>(static_cast<uint32_t>(q_rank[i])) << 32) | desc;
-            a[static_cast<size_t>(i)] = Item{k, static_cast<uint32_t>(i)};
-            o |= k;
-            an &= k;
-        }
-        seen_or[t] = o;
-        seen_and[t] = an;
+    std::atomic<int> negative{0};
+    const int rc = radix_order(n, n_threads, order, [&](int64_t i) {
+        float f = score[i];
+        uint32_t u;
+        if (f == 0.0f) f = 0.0f;  // drops the sign of -0.0
+        memcpy(&u, &f, 4);
+        const uint32_t asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending in f
+        uint32_t desc = ~asc;
+        if (f != f) desc = 0xffffffffu;
+        if (q_rank[i] < 0) negative.store(1, std::memory_order_relaxed);
+        return (static_cast<uint64_t>(static_cast<uint32_t>(q_rank[i])) << 32) | desc;
     });
-    uint64_t any = 0, all = ~uint64_t(0);
-    for (int t = 0; t < threads; t++) {
-        if (negative[static_cast<size_t>(t)]) return fail(FFX_ERR_INVALID, "ffx_ranking_order: negative query rank");
-        any |= seen_or[static_cast<size_t>(t)];
-        all &= seen_and[static_cast<size_t>(t)];
+    if (negative.load()) return fail(FFX_ERR_INVALID, "ffx_ranking_order: negative query rank");
+    return rc;
+}
+
+int ffx_order_u64(const uint64_t *keys, int64_t n, int64_t *order, int n_threads) {
+    if (n < 0 || (n > 0 && (!keys || !order))) return fail(FFX_ERR_INVALID, "ffx_order_u64: bad arguments");
+    if (n >= (int64_t(1) << 32)) return fail(FFX_ERR_UNSUPPORTED, "ffx_order_u64: more than 2^32 rows");
+    return radix_order(n, n_threads, order, [&](int64_t i) { return keys[i]; });
+}
+
+int ffx_match_keys(const int64_t *have, int64_t n_have, const int64_t *want, int64_t n_want, int64_t *pos) {
+    if (n_have < 0 || n_want < 0 || (n_have > 0 && !have) || (n_want > 0 && (!want || !pos)))
+        return fail(FFX_ERR_INVALID, "ffx_match_keys: bad arguments");
+    uint64_t cap = 1024;
+    while (cap < static_cast<uint64_t>(n_have) * 2) cap <<= 1;
+    const uint64_t mask = cap - 1;
+    std::vector<int64_t> slots(cap, -1);
+    const int kAhead = 16;
+    auto home = [&](int64_t key) { return mix(static_cast<uint64_t>(key) * 0x9E3779B97F4A7C15ull) & mask; };
+    for (int64_t i = 0; i < n_have; i++) {
+        if (i + kAhead < n_have) __builtin_prefetch(&slots[home(have[i + kAhead])], 1);
+        uint64_t s = home(have[i]);
+        while (slots[s] >= 0 && have[slots[s]] != have[i]) s = (s + 1) & mask;
+        if (slots[s] < 0) slots[s] = i;  // the first of equal keys stays
     }
-    const uint64_t varying = any & ~all;  // bits that differ between at least two keys
-    std::vector<uint64_t> counts(static_cast<size_t>(threads) * 256);
-    Item *src = a.data(), *dst = b.data();
-    for (int pass = 0; pass < 8; pass++) {
-        const int shift = 8 * pass;
-        if (((varying >> shift) & 0xff) == 0) continue;  // every key has the same digit here
-        parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
-            uint64_t *c = counts.data() + static_cast<size_t>(lo / step) * 256;
-            std::fill(c, c + 256, 0);
-            for (int64_t i = lo; i < hi; i++) c[(src[i].key >> shift) & 0xff]++;
-        });
-        uint64_t at = 0;
-        for (int d = 0; d < 256; d++)
-            for (int t = 0; t < threads; t++) {
-                uint64_t &c = counts[static_cast<size_t>(t) * 256 + d];
-                const uint64_t mine = (static_cast<int64_t>(t) * step < n) ? c : 0;
-                c = at;
-                at += mine;
-            }
-        parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
-            uint64_t *c = counts.data() + static_cast<size_t>(lo / step) * 256;
-            for (int64_t i = lo; i < hi; i++) dst[c[(src[i].key >> shift) & 0xff]++] = src[i];
-        });
-        std::swap(src, dst);
+    for (int64_t i = 0; i < n_want; i++) {
+        if (i + kAhead < n_want) __builtin_prefetch(&slots[home(want[i + kAhead])], 0);
+        uint64_t s = home(want[i]);
+        while (slots[s] >= 0 && have[slots[s]] != want[i]) s = (s + 1) & mask;
+        pos[i] = slots[s];
     }
-    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; i++) order[i] = src[i].row;
-    });
     return FFX_OK;
 }
 

@@ -51,6 +51,8 @@ SYMBOLS = {
     "ffx_launch_count": (_L, []),
     "ffx_first_repeat": (_I, [_P, _L, C.POINTER(_L)]),
     "ffx_ranking_order": (_I, [_P, _P, _L, _P, _I]),
+    "ffx_order_u64": (_I, [_P, _L, _P, _I]),
+    "ffx_match_keys": (_I, [_P, _L, _P, _L, _P]),
     "ffx_h5_open": (_I, [C.c_char_p, C.POINTER(_P)]),
     "ffx_h5_close": (None, [_P]),
     "ffx_h5_kind": (_I, [_P, C.c_char_p, C.POINTER(_I)]),

@@ -123,6 +123,61 @@ def _coded_frame(df: pd.DataFrame, is_sorted: bool) -> pd.DataFrame | None:
     return frame
 
 
+def _outer_coded(left: pd.DataFrame, right: pd.DataFrame) -> pd.DataFrame | None:
+    """`left.merge(right, on=[q_id, id], how="outer", suffixes=(None, "_other")).fillna(0)` for the
+    usual case of two rankings over the SAME set of pairs (a first-stage ranking and its
+    re-scored copy), on integer codes: ids of both frames go through one C++ dictionary, the
+    join is a hash match of int64 pair keys (`ffx_match_keys`), and the merge's key order —
+    q_id then id, ascending as strings — comes from ranking the distinct strings once and one
+    radix sort (`ffx_order_u64`).  None (pandas takes over, same result) when the pair sets
+    differ, the frames are small, or the key columns are not plain strings."""
+    if len(left) != len(right) or len(left) < _CODED_FROM:
+        return None
+    for frame in (left, right):
+        for col in _KEYS:
+            dtype = frame[col].dtype
+            if not pd.api.types.is_string_dtype(dtype) or dtype == object or frame[col].isna().any():
+                return None
+    try:
+        import pyarrow.compute as pc
+    except ImportError:  # pragma: no cover - depends on the environment
+        return None
+    import ctypes as C
+
+    from fast_forward import _ffx, _ids
+
+    def ptr(a):
+        return C.c_void_p(a.ctypes.data)
+
+    n = len(left)
+    q_dict, id_dict = _ids.IdDict(), _ids.IdDict()
+    lq, rq = q_dict.insert_ordinal(left["q_id"]), q_dict.insert_ordinal(right["q_id"])
+    li, ri = id_dict.insert_ordinal(left["id"]), id_dict.insert_ordinal(right["id"])
+    n_id = len(id_dict)
+    l_key, r_key = lq * n_id + li, rq * n_id + ri
+    pos = np.empty(n, np.int64)
+    _ffx.check(_ffx.lib().ffx_match_keys(ptr(r_key), n, ptr(l_key), n, ptr(pos)))
+    if (pos < 0).any():
+        return None  # a pair of `left` is missing on the right: a true outer join, left to pandas
+
+    def string_rank(dictionary) -> np.ndarray:
+        keys, _ = dictionary.export()
+        rank = np.empty(len(keys), np.uint64)
+        rank[pc.sort_indices(keys).to_numpy()] = np.arange(len(keys), dtype=np.uint64)
+        return rank
+
+    sort_key = (string_rank(q_dict)[lq] << np.uint64(32)) | string_rank(id_dict)[li]
+    order = np.empty(n, np.int64)
+    _ffx.check(_ffx.lib().ffx_order_u64(ptr(sort_key), n, ptr(order), 0))
+    out = left.take(order).reset_index(drop=True)
+    theirs = pos[order]
+    for col in right.columns:
+        if col not in _KEYS:
+            name = col + "_other" if col in left.columns else col
+            out[name] = right[col].take(theirs).reset_index(drop=True)
+    return out.fillna(0) if out.isna().any().any() else out
+
+
 class Ranking:
     """Rankings of documents/passages w.r.t. queries."""
 
@@ -231,7 +286,10 @@ class Ranking:
     def _outer(self, other: pd.DataFrame, mine: pd.DataFrame | None = None) -> pd.DataFrame:
         """Outer join on (q_id, id); a score missing on either side counts as 0."""
         left = self._df if mine is None else mine
-        return left.merge(other, on=_KEYS, suffixes=(None, "_other"), how="outer").fillna(0)
+        joined = _outer_coded(left, other)
+        if joined is None:
+            joined = left.merge(other, on=_KEYS, suffixes=(None, "_other"), how="outer").fillna(0)
+        return joined
 
     def __add__(self, o: "Ranking | float") -> "Ranking":
         """Add a constant or another ranking's scores (ranking.py:188-217)."""

@@ -182,6 +182,12 @@ int ffx_first_repeat(const int64_t *keys, int64_t n, int64_t *first);
  * order (pandas' lexsort is stable; -0.0 ties with +0.0; NaN sorts after every number):
  * order[j] = the row that comes j-th.  A radix sort on all host cores (n_threads 0). */
 int ffx_ranking_order(const int32_t *q_rank, const float *score, int64_t n, int64_t *order, int n_threads);
+/* The (q_id, id) key order of a pandas outer merge (`Ranking.interpolate` / `__add__`,
+ * ranking.py:188-217,310-318) on integer ranks: order[j] = the element that comes j-th by
+ * ascending key, equal keys in index order. */
+int ffx_order_u64(const uint64_t *keys, int64_t n, int64_t *order, int n_threads);
+/* The join itself: pos[i] = index of want[i] in have[] (its first occurrence), -1 if absent. */
+int ffx_match_keys(const int64_t *have, int64_t n_have, const int64_t *want, int64_t n_want, int64_t *pos);
 
 /* ---- the hot path ----------------------------------------------------------------- */
 /* Replaces, in one pass, `Index._compute_scores` (index/base.py:279-314) including
