@@ -123,14 +123,12 @@ def _coded_frame(df: pd.DataFrame, is_sorted: bool) -> pd.DataFrame | None:
     return frame
 
 
-def _outer_coded(left: pd.DataFrame, right: pd.DataFrame) -> pd.DataFrame | None:
-    """`left.merge(right, on=[q_id, id], how="outer", suffixes=(None, "_other")).fillna(0)` for the
-    usual case of two rankings over the SAME set of pairs (a first-stage ranking and its
-    re-scored copy), on integer codes: ids of both frames go through one C++ dictionary, the
-    join is a hash match of int64 pair keys (`ffx_match_keys`), and the merge's key order —
-    q_id then id, ascending as strings — comes from ranking the distinct strings once and one
-    radix sort (`ffx_order_u64`).  None (pandas takes over, same result) when the pair sets
-    differ, the frames are small, or the key columns are not plain strings."""
+def _match_pairs(left: pd.DataFrame, right: pd.DataFrame):
+    """Row of `right` holding the (q_id, id) pair of every row of `left`, on integer codes (one
+    C++ dictionary per key column, a hash match of int64 pair keys).  Returns (q codes of left,
+    id codes of left, q dictionary, id dictionary, positions), or None when the frames are
+    small, differ in length, hold different pairs, or have key columns that are not plain
+    strings — the callers then use pandas."""
     if len(left) != len(right) or len(left) < _CODED_FROM:
         return None
     for frame in (left, right):
@@ -138,16 +136,9 @@ def _outer_coded(left: pd.DataFrame, right: pd.DataFrame) -> pd.DataFrame | None
             dtype = frame[col].dtype
             if not pd.api.types.is_string_dtype(dtype) or dtype == object or frame[col].isna().any():
                 return None
-    try:
-        import pyarrow.compute as pc
-    except ImportError:  # pragma: no cover - depends on the environment
-        return None
     import ctypes as C
 
     from fast_forward import _ffx, _ids
-
-    def ptr(a):
-        return C.c_void_p(a.ctypes.data)
 
     n = len(left)
     q_dict, id_dict = _ids.IdDict(), _ids.IdDict()
@@ -156,9 +147,37 @@ def _outer_coded(left: pd.DataFrame, right: pd.DataFrame) -> pd.DataFrame | None
     n_id = len(id_dict)
     l_key, r_key = lq * n_id + li, rq * n_id + ri
     pos = np.empty(n, np.int64)
-    _ffx.check(_ffx.lib().ffx_match_keys(ptr(r_key), n, ptr(l_key), n, ptr(pos)))
+    _ffx.check(_ffx.lib().ffx_match_keys(C.c_void_p(r_key.ctypes.data), n, C.c_void_p(l_key.ctypes.data), n,
+                                         C.c_void_p(pos.ctypes.data)))
     if (pos < 0).any():
-        return None  # a pair of `left` is missing on the right: a true outer join, left to pandas
+        return None  # a pair of `left` is missing on the right
+    return lq, li, q_dict, id_dict, pos
+
+
+def _outer_coded(left: pd.DataFrame, right: pd.DataFrame) -> pd.DataFrame | None:
+    """`left.merge(right, on=[q_id, id], how="outer", suffixes=(None, "_other")).fillna(0)` for the
+    usual case of two rankings over the SAME set of pairs (a first-stage ranking and its
+    re-scored copy), on integer codes: ids of both frames go through one C++ dictionary, the
+    join is a hash match of int64 pair keys (`ffx_match_keys`), and the merge's key order —
+    q_id then id, ascending as strings — comes from ranking the distinct strings once and one
+    radix sort (`ffx_order_u64`).  None (pandas takes over, same result) when the pair sets
+    differ, the frames are small, or the key columns are not plain strings."""
+    matched = _match_pairs(left, right)
+    if matched is None:
+        return None
+    lq, li, q_dict, id_dict, pos = matched
+    try:
+        import pyarrow.compute as pc
+    except ImportError:  # pragma: no cover - depends on the environment
+        return None
+    import ctypes as C
+
+    from fast_forward import _ffx
+
+    def ptr(a):
+        return C.c_void_p(a.ctypes.data)
+
+    n = len(left)
 
     def string_rank(dictionary) -> np.ndarray:
         keys, _ = dictionary.export()
@@ -268,6 +287,10 @@ class Ranking:
         """Same (q_id, id, score) triples, exact float equality (ranking.py:171-186)."""
         if not isinstance(o, Ranking):
             return False
+        matched = _match_pairs(self._df, o._df)
+        if matched is not None:  # same pairs (both frames hold each pair once): compare aligned scores
+            mine, theirs = self._df["score"].to_numpy(), o._df["score"].to_numpy()
+            return bool(mine.dtype == theirs.dtype and (mine == theirs[matched[4]]).all())
         cols = ["q_id", "id", "score"]
         mine = self._df.sort_values(_KEYS).reset_index(drop=True)[cols]
         theirs = o._df.sort_values(_KEYS).reset_index(drop=True)[cols]
