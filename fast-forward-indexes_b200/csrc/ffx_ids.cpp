@@ -385,6 +385,30 @@ int ffx_csr_build(const int64_t *row_doc, int64_t n_rows, int64_t n_docs, int64_
     return FFX_OK;
 }
 
+// ---- fixed-width byte ids (the HDF5 id columns, index/disk.py:152-165,408-417) -> Arrow layout ----
+int ffx_fixed_width_to_arrow(const char *data, int64_t n, int width, int64_t *offsets, char *out,
+                             uint8_t *validity, int64_t *n_valid) {
+    if (n < 0 || width < 1 || (n > 0 && (!data || !offsets || !out || !validity)) || !n_valid)
+        return fail(FFX_ERR_INVALID, "ffx_fixed_width_to_arrow: bad arguments");
+    int64_t at = 0, valid = 0;
+    if (n > 0) std::fill(validity, validity + (n + 7) / 8, 0);
+    for (int64_t i = 0; i < n; i++) {
+        const char *p = data + i * static_cast<int64_t>(width);
+        int len = width;
+        while (len > 0 && p[len - 1] == 0) len--;  // NUL padding on the right (numpy 'S' semantics)
+        offsets[i] = at;
+        if (len > 0) {
+            memcpy(out + at, p, static_cast<size_t>(len));
+            at += len;
+            validity[i >> 3] |= static_cast<uint8_t>(1u << (i & 7));
+            valid++;
+        }
+    }
+    if (offsets) offsets[n] = at;
+    *n_valid = valid;
+    return FFX_OK;
+}
+
 // ---- Ranking.__init__ on integer codes (ranking.py:95-98,115-117) ------------------------------
 int ffx_first_repeat(const int64_t *keys, int64_t n, int64_t *first) {
     if (n < 0 || !first || (n > 0 && !keys)) return fail(FFX_ERR_INVALID, "ffx_first_repeat: bad arguments");

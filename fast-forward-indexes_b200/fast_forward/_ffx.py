@@ -49,6 +49,7 @@ SYMBOLS = {
     "ffx_interpolate_topk_host": (_I, [_P, _P, _P, _L, _P, _D, _I, _P, _P, _P]),
     "ffx_merge_topk": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _P]),
     "ffx_launch_count": (_L, []),
+    "ffx_fixed_width_to_arrow": (_I, [_P, _L, _I, _P, _P, _P, C.POINTER(_L)]),
     "ffx_first_repeat": (_I, [_P, _L, C.POINTER(_L)]),
     "ffx_ranking_order": (_I, [_P, _P, _L, _P, _I]),
     "ffx_order_u64": (_I, [_P, _L, _P, _I]),

@@ -54,15 +54,18 @@ def _text_ids(raw: np.ndarray):
         out = np.char.decode(raw, "utf-8").astype(object)
         out[out == ""] = None
         return out
+    import ctypes as C
+
     n, width = len(raw), raw.dtype.itemsize
-    lengths = np.char.str_len(raw).astype(np.int64)
-    offsets = np.zeros(n + 1, np.int64)
-    np.cumsum(lengths, out=offsets[1:])
-    data = raw.view(np.uint8).reshape(n, width)[np.arange(width) < lengths[:, None]]
-    present = lengths > 0
-    buffers = [pa.py_buffer(np.packbits(present, bitorder="little")), pa.py_buffer(offsets),
-               pa.py_buffer(np.ascontiguousarray(data) if len(data) else np.zeros(1, np.uint8))]
-    return pa.Array.from_buffers(pa.large_string(), n, buffers, null_count=int(n - present.sum()))
+    offsets = np.empty(n + 1, np.int64)
+    data = np.empty(max(n * width, 1), np.uint8)
+    validity = np.empty(max((n + 7) // 8, 1), np.uint8)
+    present = C.c_int64()
+    _ffx.check(_ffx.lib().ffx_fixed_width_to_arrow(
+        C.c_void_p(raw.ctypes.data), n, width, C.c_void_p(offsets.ctypes.data), C.c_void_p(data.ctypes.data),
+        C.c_void_p(validity.ctypes.data), C.byref(present)))
+    buffers = [pa.py_buffer(validity), pa.py_buffer(offsets), pa.py_buffer(data)]
+    return pa.Array.from_buffers(pa.large_string(), n, buffers, null_count=n - present.value)
 
 
 class OnDiskIndex(Index):

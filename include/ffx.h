@@ -173,6 +173,13 @@ int ffx_dict_export(const ffx_dict *d, int64_t *offsets, char *data, int64_t *va
  * be NULL to get the offsets only. */
 int ffx_csr_build(const int64_t *row_doc, int64_t n_rows, int64_t n_docs, int64_t *doc_off, int64_t *doc_rows);
 
+/* A column of fixed-width, NUL-padded byte ids (HDF5 `S{max_id_length}` datasets, "" = no id:
+ * index/disk.py:152-165,414-417) as Arrow string buffers for the dictionaries above:
+ * offsets[n+1], the concatenated bytes in `out` (room for n * width), a validity bitmap of
+ * (n + 7) / 8 bytes (bit i clear = empty id), *n_valid = ids present. */
+int ffx_fixed_width_to_arrow(const char *data, int64_t n, int width, int64_t *offsets, char *out,
+                             uint8_t *validity, int64_t *n_valid);
+
 /* ---- Ranking.__init__ on integer codes (host; ranking.py:67-121) ---------------------- */
 /* The duplicate-pair check (ranking.py:95-98) over keys = q_code * n_ids + id_code:
  * *first = index of the first key that equals an earlier one, -1 if all are distinct. */

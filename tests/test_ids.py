@@ -107,3 +107,22 @@ def test_errors_report_through_ffx_last_error(ids):
 
     with pytest.raises(_ffx.FFXError):
         ids.csr_from_ordinals(np.array([0, 5]), 3)  # ordinal out of range
+
+
+def test_fixed_width_id_columns_become_arrow_strings():
+    """The HDF5 id columns (`S{max_id_length}`, b"" = no id; index/disk.py:152-165,414-417) are
+    turned into Arrow string buffers by ffx_fixed_width_to_arrow, without one Python object per id."""
+    import __graft_entry__ as g
+
+    g.build()
+    from fast_forward.index.disk import _text_ids
+
+    rng = np.random.default_rng(0)
+    for width in (1, 3, 8, 21):
+        words = ["".join(chr(97 + c) for c in rng.integers(0, 26, rng.integers(0, width + 1))) for _ in range(3000)]
+        raw = np.array([w.encode() for w in words], dtype=f"S{width}")
+        got = _text_ids(raw)
+        assert got.to_pylist() == [w or None for w in words] and got.null_count == words.count("")
+    assert _text_ids(np.array([b"abcdefgh", b"", b"a\0b", b"\0x"], dtype="S8")).to_pylist() == ["abcdefgh", None, "a\0b", "\0x"]
+    assert len(_text_ids(np.zeros(0, "S8"))) == 0
+    assert _text_ids(np.array(["grüße".encode()], dtype="S8")).to_pylist() == ["grüße"]
