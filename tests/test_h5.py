@@ -298,3 +298,36 @@ def test_native_writer_grows_reopens_and_reads_back(h5, tmp_path):
     hw.write_hdf5(root, foreign)
     with pytest.raises(ValueError, match="needs h5py"):
         hw2.IndexFile.open_existing(foreign)
+
+
+def test_byte_format_does_not_drift(tmp_path):
+    """The writers are deterministic; their output is pinned by checksum so that a change of the
+    byte format is a deliberate act (update the digests together with DESIGN.md section 3a)."""
+    import hashlib
+
+    from fast_forward import _h5_write as hw2
+
+    rng = np.random.default_rng(123)
+    root = hw.Group()
+    root.attrs = {"num_vectors": np.int64(10), "ff_version": "0.8.0"}
+    root.children["vectors"] = hw.Dataset(rng.standard_normal((12, 4)).astype(np.float32), (4, 4), (None, 4))
+    root.children["doc_ids"] = hw.Dataset(np.array([f"d{i}".encode() for i in range(12)], "S8"), (8,), (None,))
+    extra = hw.Group()
+    extra.attrs = {"flag": True, "name": "x"}
+    root.children["quantizer"] = extra
+    digests = []
+    for modern in (False, True):
+        hw.write_hdf5(root, tmp_path / f"t{modern}.h5", modern=modern, split_headers=True)
+        digests.append(hashlib.sha256((tmp_path / f"t{modern}.h5").read_bytes()).hexdigest())
+    with hw2.IndexFile.create(tmp_path / "n.h5", "0.8.0") as out:
+        out.create_datasets(4, np.float32, 4, 4, 8)
+        out.resize(12)
+        out.write_at("doc_ids", [0, 1, 5], ["a", "b", "c"])
+        out.write_rows("vectors", 0, rng.standard_normal((10, 4)).astype(np.float32))
+        out.set_num_vectors(10)
+        out.set_quantizer({"__name__": "NanoPQ", "_trained": True}, {"M": 2, "metric": "dot"},
+                          {"codewords": np.arange(8, dtype=np.float32)})
+    digests.append(hashlib.sha256((tmp_path / "n.h5").read_bytes()).hexdigest())
+    assert digests == ["5a0e3b75ddca12f515358bbd44d631b95d982164b3061976ecf257f797287a52",
+                       "f3951d9f2d9e634b2810bc950dc606033dbe94a65fe2af974e3daace8dbfd47b",
+                       "be113f9c0e76a6df47d251baee462973926a46671acf4780a64cf4860c5e1ee3"]
