@@ -126,3 +126,58 @@ def test_fixed_width_id_columns_become_arrow_strings():
     assert _text_ids(np.array([b"abcdefgh", b"", b"a\0b", b"\0x"], dtype="S8")).to_pylist() == ["abcdefgh", None, "a\0b", "\0x"]
     assert len(_text_ids(np.zeros(0, "S8"))) == 0
     assert _text_ids(np.array(["grüße".encode()], dtype="S8")).to_pylist() == ["grüße"]
+
+
+def test_host_sort_and_match_routines_at_multithreaded_sizes():
+    """ffx_ranking_order / ffx_order_u64 split their radix passes over the host cores from ~130 k
+    rows up, ffx_first_repeat / ffx_match_keys prefetch ahead: checked against numpy at sizes
+    where those paths are active, with heavy ties (stability) and special floats."""
+    import ctypes as C
+
+    import __graft_entry__ as g
+
+    g.build()
+    from fast_forward import _ffx
+
+    lib = _ffx.lib()
+    rng = np.random.default_rng(4)
+
+    def ptr(a):
+        return C.c_void_p(a.ctypes.data)
+
+    for n in (1, 7, 70_000, 600_001):
+        q_rank = rng.integers(0, 300, n).astype(np.int32)
+        score = rng.choice(np.array([0.0, -0.0, 1.5, -2.25, 3e-7, 1e30, -1e30, np.inf, -np.inf], np.float32), n) \
+            if n % 2 else rng.standard_normal(n).astype(np.float32)
+        order = np.empty(n, np.int64)
+        _ffx.check(lib.ffx_ranking_order(ptr(q_rank), ptr(score), n, ptr(order), 0))
+        want = np.lexsort((np.arange(n), -(score + np.float32(0.0)).astype(np.float64), q_rank))
+        assert (order == want).all()
+        one = np.empty(n, np.int64)
+        _ffx.check(lib.ffx_ranking_order(ptr(q_rank), ptr(score), n, ptr(one), 1))  # single-threaded: same order
+        assert (one == order).all()
+
+        keys = rng.integers(0, 2**63, n, dtype=np.uint64) if n % 2 else rng.integers(0, 50, n).astype(np.uint64) << np.uint64(40)
+        _ffx.check(lib.ffx_order_u64(ptr(keys), n, ptr(order), 0))
+        assert (order == np.argsort(keys, kind="stable")).all()
+
+        have = rng.permutation(3 * n)[:n].astype(np.int64) - n  # distinct, some negative
+        want_keys = np.concatenate([have[rng.integers(0, n, n // 2 + 1)], rng.integers(5 * n, 6 * n, n // 3)]).astype(np.int64)
+        pos = np.empty(len(want_keys), np.int64)
+        _ffx.check(lib.ffx_match_keys(ptr(have), n, ptr(want_keys), len(want_keys), ptr(pos)))
+        lookup = {int(k): i for i, k in enumerate(have)}
+        assert pos.tolist() == [lookup.get(int(k), -1) for k in want_keys]
+
+        first = C.c_int64(0)
+        _ffx.check(lib.ffx_first_repeat(ptr(have), n, C.byref(first)))
+        assert first.value == -1
+        if n > 2:
+            again = have.copy()
+            a, b = sorted(rng.choice(n, 2, replace=False).tolist())
+            again[b] = again[a]
+            _ffx.check(lib.ffx_first_repeat(ptr(again), n, C.byref(first)))
+            assert first.value == b
+    nan_scores = np.array([1.0, np.nan, 2.0, np.nan, -1.0], np.float32)
+    order = np.empty(5, np.int64)
+    _ffx.check(lib.ffx_ranking_order(ptr(np.zeros(5, np.int32)), ptr(nan_scores), 5, ptr(order), 0))
+    assert order.tolist() == [2, 0, 4, 1, 3]  # NaN after every number, in incoming order
