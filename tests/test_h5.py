@@ -331,3 +331,21 @@ def test_byte_format_does_not_drift(tmp_path):
     assert digests == ["5a0e3b75ddca12f515358bbd44d631b95d982164b3061976ecf257f797287a52",
                        "f3951d9f2d9e634b2810bc950dc606033dbe94a65fe2af974e3daace8dbfd47b",
                        "be113f9c0e76a6df47d251baee462973926a46671acf4780a64cf4860c5e1ee3"]
+
+
+def test_large_reads_are_split_over_threads(h5, tmp_path):
+    """ffx_h5_read_rows copies reads of 32 MB and more with several threads (page faults of a
+    mapped file are per 4 KB): a 48 MB dataset with a partial last chunk and an unwritten one."""
+    rng = np.random.default_rng(10)
+    rows, dim, chunk = 12_345, 1024, 1000
+    vec = rng.integers(0, 2**31, (rows, dim), dtype=np.int64).astype(np.float32)
+    vec[3000:4000] = 0
+    root = hw.Group()
+    root.children["vectors"] = hw.Dataset(vec, (chunk, dim), (None, dim), missing_chunks={3})
+    root.children["flat"] = hw.Dataset(vec[:9000])  # contiguous layout, 36 MB
+    path = tmp_path / "big.h5"
+    hw.write_hdf5(root, path)
+    with h5.H5File(path) as fp:
+        assert (fp.read("vectors") == vec).all()
+        assert (fp.read("vectors", 17, 12_001) == vec[17:12_001]).all()
+        assert (fp.read("flat") == vec[:9000]).all()
