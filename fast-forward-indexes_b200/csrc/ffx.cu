@@ -6,10 +6,13 @@
 // device and fails with FFX_ERR_CUDA without one.
 #include <cuda_runtime.h>
 
+#include <cxxabi.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -29,6 +32,13 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<int64_t> g_launches{0};
+// the scoring kernel (fp32 or ADC) launched last, as a device-function pointer; ffx_last_kernel
+// asks the runtime for its symbol and demangles it (bench.py's roofline.kernel)
+std::atomic<const void *> g_last_kernel{nullptr};
+thread_local std::string g_kernel_name;
+
+template <typename K>
+void note_kernel(K kern) { g_last_kernel.store(reinterpret_cast<const void *>(kern)); }
 
 int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -253,8 +263,10 @@ int launch_score(const ffx::ScoreArgs &a, bool fuse, int grid, size_t smem, cuda
         FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
         kern<<<grid, ffx::kThreads, smem, st>>>(a);
+        note_kernel(kern);
     } else {
         ffx::ffx_score_kernel<CPL, S, false><<<grid, ffx::kThreads, 0, st>>>(a);
+        note_kernel(ffx::ffx_score_kernel<CPL, S, false>);
     }
     g_launches++;
     FFX_CUDA(cudaGetLastError());
@@ -269,10 +281,12 @@ int launch_score_tma(const ffx::ScoreArgs &a, bool fuse, int grid, int warps, in
         auto kern = ffx::ffx_score_tma_kernel<CPL, S, true, LPR>;
         FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         kern<<<grid, warps * 32, smem, st>>>(a, ns, batch);
+        note_kernel(kern);
     } else {
         auto kern = ffx::ffx_score_tma_kernel<CPL, S, false, LPR>;
         FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         kern<<<grid, warps * 32, smem, st>>>(a, ns, batch);
+        note_kernel(kern);
     }
     g_launches++;
     FFX_CUDA(cudaGetLastError());
@@ -284,6 +298,7 @@ int launch_adc_v(const ffx::AdcArgs &a, unsigned grid, size_t smem, cudaStream_t
     auto kern = ffx::ffx_adc_kernel<V16>;
     FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<grid, ffx::kThreads, smem, st>>>(a);
+    note_kernel(kern);
     g_launches++;
     FFX_CUDA(cudaGetLastError());
     return FFX_OK;
@@ -450,10 +465,12 @@ int launch_adc_xor(const ffx::AdcWarpArgs &w, bool fuse, unsigned grid, size_t s
         auto kern = ffx::ffx_adc_xor_kernel<NC, true>;
         FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         kern<<<grid, ffx::kAdcXorThreads, smem, st>>>(w);
+        note_kernel(kern);
     } else {
         auto kern = ffx::ffx_adc_xor_kernel<NC, false>;
         FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         kern<<<grid, ffx::kAdcXorThreads, smem, st>>>(w);
+        note_kernel(kern);
     }
     g_launches++;
     FFX_CUDA(cudaGetLastError());
@@ -465,6 +482,7 @@ int launch_adc_warp(const ffx::AdcWarpArgs &w, unsigned grid, size_t smem, cudaS
     auto kern = ffx::ffx_adc_warp_kernel<FUSE, INDIRECT>;
     FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<grid, ffx::kAdcWarpThreads, smem, st>>>(w);
+    note_kernel(kern);
     g_launches++;
     FFX_CUDA(cudaGetLastError());
     return FFX_OK;
@@ -576,6 +594,21 @@ int ffx_device_count(void) {
 }
 
 int64_t ffx_launch_count(void) { return g_launches.load(); }
+
+const char *ffx_last_kernel(void) {
+    g_kernel_name.clear();
+    const void *fn = g_last_kernel.load();
+    const char *mangled = nullptr;
+    if (fn && cudaFuncGetName(&mangled, fn) == cudaSuccess && mangled) {
+        int status = 0;
+        char *plain = abi::__cxa_demangle(mangled, nullptr, nullptr, &status);
+        g_kernel_name = (status == 0 && plain) ? plain : mangled;
+        free(plain);
+    } else {
+        cudaGetLastError();
+    }
+    return g_kernel_name.c_str();
+}
 
 int ffx_host_alloc(void **out, int64_t bytes) {
     if (!out || bytes < 0) return fail(FFX_ERR_INVALID, "ffx_host_alloc: bad arguments");
@@ -1173,6 +1206,7 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
                 const int64_t bound = nq * max_cand;
                 ffx::ffx_score_generic_kernel<<<static_cast<unsigned>((bound + 127) / 128), 128, 0, st>>>(
                     a, nq, bound);
+                note_kernel(ffx::ffx_score_generic_kernel);
                 g_launches++;
                 FFX_CUDA(cudaGetLastError());
             }

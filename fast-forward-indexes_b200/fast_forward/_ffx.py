@@ -49,6 +49,7 @@ SYMBOLS = {
     "ffx_interpolate_topk_host": (_I, [_P, _P, _P, _L, _P, _D, _I, _P, _P, _P]),
     "ffx_merge_topk": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _P]),
     "ffx_launch_count": (_L, []),
+    "ffx_last_kernel": (C.c_char_p, []),
     "ffx_fixed_width_to_arrow": (_I, [_P, _L, _I, _P, _P, _P, C.POINTER(_L)]),
     "ffx_first_repeat": (_I, [_P, _L, C.POINTER(_L)]),
     "ffx_ranking_order": (_I, [_P, _P, _L, _P, _I]),
@@ -123,6 +124,11 @@ def set_option(name: str, value: int) -> None:
 
 def launch_count() -> int:
     return lib().ffx_launch_count()
+
+
+def last_kernel() -> str:
+    """Demangled symbol of the scoring kernel launched last ("" before the first launch)."""
+    return lib().ffx_last_kernel().decode("utf-8", "replace")
 
 
 def _ptr(a):

@@ -61,6 +61,9 @@ class ShardedReranker:
         self.p2p = p2p
         self._p2p_sets = None  # (nq, k) -> two alternating sets of symmetric receive buffers
         self._p2p_step = 0
+        # bench.py sets this to a list: every rerank() then appends the CUDA events
+        # (start, local kernel done, exchange / barrier done, merge done) of its three phases
+        self.trace = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if index is not None:
@@ -87,6 +90,14 @@ class ShardedReranker:
         _ffx.merge_topk(all_score.device.index or 0, all_score.data_ptr(), all_pos.data_ptr(), world, nq, k,
                         score.data_ptr(), pos.data_ptr(), stream)
         return score, pos
+
+    def _mark(self, marks):
+        if self.trace is not None:
+            import torch
+
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
 
     # -- the exchange ---------------------------------------------------------------------------
     def owner_bounds(self, nq: int) -> list[int]:
@@ -145,14 +156,21 @@ class ShardedReranker:
         self._p2p_step += 1
         self.index.set_topk_scatter(self.world, self.rank, buf["cap"], buf["bounds"], buf["hs"].buffer_ptrs,
                                     buf["hp"].buffer_ptrs)
+        marks = []
+        self._mark(marks)
         try:
             self.index.rerank_device(mode, qvecs.data_ptr(), nq, q_off.data_ptr(), cand.data_ptr(),
                                      lex.data_ptr() if lex is not None else 0, alpha, k, max_cand, 0, 0, 0, 0, stream)
         finally:
             self.index.set_topk_scatter(0)
+        self._mark(marks)
         buf["hs"].barrier()  # every rank's stores have landed (stream-ordered, on the device)
+        self._mark(marks)
         mine = buf["bounds"][self.rank + 1] - buf["bounds"][self.rank]
         score, pos = self._merge(buf["score"], buf["pos"], k, stream)  # [cap, k]
+        self._mark(marks)
+        if self.trace is not None:
+            self.trace.append(marks)
         return score[:mine], pos[:mine]
 
     # -- public ---------------------------------------------------------------------------------
@@ -179,10 +197,18 @@ class ShardedReranker:
         if self.world > 1 and self.p2p:
             mine_s, mine_p = self._rerank_p2p(mode, qvecs, q_off, cand, lex, alpha, k, max_cand, stream)
         else:
+            marks = []
+            self._mark(marks)
             score, pos = self._local_topk(mode, qvecs, q_off, cand, lex, alpha, k, max_cand, stream)
+            self._mark(marks)
             if self.world == 1:
                 return score, pos
-            mine_s, mine_p = self._merge(self._to_owners(score, bounds), self._to_owners(pos, bounds), k, stream)
+            recv_s, recv_p = self._to_owners(score, bounds), self._to_owners(pos, bounds)
+            self._mark(marks)
+            mine_s, mine_p = self._merge(recv_s, recv_p, k, stream)
+            self._mark(marks)
+            if self.trace is not None:
+                self.trace.append(marks)
         if not gather_result:
             return mine_s, mine_p
         # owners hold unequal slices when world does not divide nq: gather padded slices

@@ -302,6 +302,10 @@ int ffx_merge_topk(int device, const float *shard_scores, const int32_t *shard_p
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t ffx_launch_count(void);
+/* Demangled symbol of the scoring kernel (fp32 gather-dot or ADC) launched last by this process,
+ * "" before the first launch — what bench.py reports as roofline.kernel and what the ncu launch
+ * list must show. */
+const char *ffx_last_kernel(void);
 
 /* ---- index files: the HDF5 layout OnDiskIndex writes, read without libhdf5 / h5py --------
  * Replaces the h5py reads of OnDiskIndex.load (index/disk.py:355-418), to_memory

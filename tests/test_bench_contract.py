@@ -19,7 +19,7 @@ REQUIRED = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_
 def test_reference_arm_line(kind):
     if kind == "reference" and not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "fast_forward")):
         pytest.skip("baseline/_ref is not installed here")
-    env = dict(os.environ, FFX_CPU_Q_PER_CORE="1", FFX_CPU_BASELINE="port" if kind == "port" else "")
+    env = dict(os.environ, FFX_CPU_Q_PER_CORE="1", FFX_CPU_DOCS="10000", FFX_CPU_BASELINE="port" if kind == "port" else "")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
