@@ -489,4 +489,83 @@ int ffx_match_keys(const int64_t *have, int64_t n_have, const int64_t *want, int
     return FFX_OK;
 }
 
+// ---- rankings on integer codes: the result side of Index.__call__ / rerank -------------------
+int ffx_lut_gather(const int32_t *lut, int64_t n_lut, const int32_t *codes, int64_t n, int32_t *out,
+                   int64_t *first_negative, int n_threads) {
+    if (n < 0 || n_lut < 0 || !first_negative || (n > 0 && (!lut || !codes || !out)))
+        return fail(FFX_ERR_INVALID, "ffx_lut_gather: bad arguments");
+    const int threads = worker_count(n_threads, n / 16);
+    std::vector<int64_t> first(static_cast<size_t>(std::max(threads, 1)), -1);
+    std::atomic<int> bad{0};
+    const int64_t step = threads > 0 ? (n + threads - 1) / threads : n;
+    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+        int64_t miss = -1;
+        for (int64_t i = lo; i < hi; i++) {
+            const int32_t c = codes[i];
+            if (c < 0 || c >= n_lut) {
+                bad.store(1, std::memory_order_relaxed);
+                out[i] = -1;
+                continue;
+            }
+            const int32_t v = lut[c];
+            out[i] = v;
+            if (v < 0 && miss < 0) miss = i;
+        }
+        first[static_cast<size_t>(step > 0 ? lo / step : 0)] = miss;
+    });
+    if (bad.load()) return fail(FFX_ERR_INVALID, "ffx_lut_gather: code outside the table");
+    *first_negative = -1;
+    for (int64_t m : first)
+        if (m >= 0 && (*first_negative < 0 || m < *first_negative)) *first_negative = m;
+    return FFX_OK;
+}
+
+int ffx_topk_gather(const int32_t *pos, const float *score, int64_t nq, int64_t k, int64_t keep,
+                    const int64_t *src_off, const int32_t *src_code, int64_t *out_off, int32_t *out_code,
+                    float *out_score, int64_t *n_ties, uint8_t *straddle, int n_threads) {
+    if (nq < 0 || k < 0 || keep < 0 || keep > k || !out_off || (nq > 0 && k > 0 && (!pos || !score || !src_off)) ||
+        (out_code && !src_code))
+        return fail(FFX_ERR_INVALID, "ffx_topk_gather: bad arguments");
+    const int threads = worker_count(n_threads, nq * std::max<int64_t>(k, 1) / 16);
+    // pass 1: entries kept per query (lists are padded with pos = -1 at the end)
+    out_off[0] = 0;
+    parallel_ranges(nq, threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t q = lo; q < hi; q++) {
+            const int32_t *p = pos + q * k;
+            int64_t c = 0;
+            while (c < keep && p[c] >= 0) c++;
+            out_off[q + 1] = c;
+            if (straddle)
+                straddle[q] = keep > 0 && keep < k && c == keep && p[keep] >= 0 &&
+                              score[q * k + keep - 1] == score[q * k + keep];
+        }
+    });
+    for (int64_t q = 0; q < nq; q++) out_off[q + 1] += out_off[q];
+    // pass 2: compact rows
+    std::atomic<int64_t> ties{0};
+    std::atomic<int> bad{0};
+    parallel_ranges(nq, threads, [&](int64_t lo, int64_t hi) {
+        int64_t my_ties = 0;
+        for (int64_t q = lo; q < hi; q++) {
+            const int32_t *p = pos + q * k;
+            const float *s = score + q * k;
+            const int64_t base = src_off[q], width = src_off[q + 1] - base, at = out_off[q];
+            const int64_t c = out_off[q + 1] - at;
+            for (int64_t j = 0; j < c; j++) {
+                if (p[j] >= width) {
+                    bad.store(1, std::memory_order_relaxed);
+                    continue;
+                }
+                if (out_code) out_code[at + j] = src_code[base + p[j]];
+                if (out_score) out_score[at + j] = s[j];
+                if (j > 0 && s[j] == s[j - 1]) my_ties++;
+            }
+        }
+        ties.fetch_add(my_ties, std::memory_order_relaxed);
+    });
+    if (bad.load()) return fail(FFX_ERR_INVALID, "ffx_topk_gather: a position lies outside its query's block");
+    if (n_ties) *n_ties = ties.load();
+    return FFX_OK;
+}
+
 }  // extern "C"

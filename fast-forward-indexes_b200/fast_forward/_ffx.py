@@ -55,6 +55,8 @@ SYMBOLS = {
     "ffx_ranking_order": (_I, [_P, _P, _L, _P, _I]),
     "ffx_order_u64": (_I, [_P, _L, _P, _I]),
     "ffx_match_keys": (_I, [_P, _L, _P, _L, _P]),
+    "ffx_lut_gather": (_I, [_P, _L, _P, _L, _P, C.POINTER(_L), _I]),
+    "ffx_topk_gather": (_I, [_P, _P, _L, _L, _L, _P, _P, _P, _P, _P, C.POINTER(_L), _P, _I]),
     "ffx_h5_open": (_I, [C.c_char_p, C.POINTER(_P)]),
     "ffx_h5_close": (None, [_P]),
     "ffx_h5_kind": (_I, [_P, C.c_char_p, C.POINTER(_I)]),
@@ -167,6 +169,77 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+class _PinnedPool:
+    """Free list of page-locked buffers by size class.  Allocating pinned memory costs far more
+    than using it (cudaHostAlloc of 200 MB: tens of milliseconds), so the large per-call arrays
+    of the Python shell — candidate codes, scores, ranked lists — are recycled: an array from
+    `pinned_empty` returns its buffer here when the last view of it is garbage-collected."""
+
+    MIN_BYTES = 1 << 20
+    KEEP_BYTES = 4 << 30  # idle buffers kept for reuse; beyond that they are freed
+
+    def __init__(self):
+        self.free: dict[int, list] = {}
+        self.idle = 0
+
+    @staticmethod
+    def size_class(nbytes: int) -> int:
+        c = 1 << 20
+        while c < nbytes:
+            c += max(c >> 2, 1 << 20)  # geometric steps of 25 %
+        return c
+
+    def take(self, nbytes: int):
+        c = self.size_class(nbytes)
+        stack = self.free.get(c)
+        if stack:
+            self.idle -= c
+            return c, stack.pop()
+        p = C.c_void_p()
+        check(lib().ffx_host_alloc(C.byref(p), c))
+        return c, p
+
+    def give(self, c: int, p) -> None:
+        if _lib is None:
+            return
+        if self.idle + c > self.KEEP_BYTES:
+            _lib.ffx_host_free(p)
+            return
+        self.free.setdefault(c, []).append(p)
+        self.idle += c
+
+
+_POOL = _PinnedPool()
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """np.empty in page-locked memory (recycled through a pool) for arrays that cross PCIe; small
+    arrays, and any array when no CUDA device is present, are ordinary numpy arrays."""
+    import weakref
+
+    shape = tuple(int(x) for x in np.atleast_1d(shape))
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    nbytes = count * dtype.itemsize
+    if nbytes < _PinnedPool.MIN_BYTES or not _has_device():
+        return np.empty(shape, dtype)
+    c, p = _POOL.take(nbytes)
+    raw = (C.c_char * nbytes).from_address(p.value)
+    root = np.frombuffer(raw, dtype=dtype, count=count)
+    weakref.finalize(root, _POOL.give, c, p)
+    return root.reshape(shape)
+
+
+_DEVICE = None
+
+
+def _has_device() -> bool:
+    global _DEVICE
+    if _DEVICE is None:
+        _DEVICE = device_count() > 0
+    return _DEVICE
 
 
 class DeviceIndex:

@@ -11,6 +11,7 @@ cross to the device — what goes there is the integer form, a CSR document-ordi
 
 from __future__ import annotations
 
+import itertools
 from collections.abc import Iterable, Sequence
 
 import numpy as np
@@ -26,11 +27,16 @@ def _take(keys, index: np.ndarray) -> list:
     return keys.take(picks).to_pylist()
 
 
+_TOKENS = itertools.count(1)
+
+
 class RowStore:
     """Rows in HBM (fp32 vectors or uint8 PQ codes) + the two id maps."""
 
     def __init__(self, device: int = 0) -> None:
         self.device = device
+        self.token = next(_TOKENS)  # identity of this store in the candidate caches of rankings
+        self.version = 0            # bumped whenever ids are added (cached candidates go stale)
         self.dev: _ffx.DeviceIndex | None = None
         self.count = 0
         self.docs = _ids.IdDict()   # document id -> ordinal (order of first appearance)
@@ -97,6 +103,7 @@ class RowStore:
             if dup >= 0:
                 raise RuntimeError(f"Passage ID {psg_ids[dup]} already exists.")
         self._maps_stale = True
+        self.version += 1
 
     def adopt_id_columns(self, doc_col, psg_col) -> None:
         """Name all `count` rows at once from two id columns (None = no id): the vectorised
@@ -127,6 +134,13 @@ class RowStore:
         codes, missing = (self.psgs if passage_mode else self.docs).lookup(ids)
         if missing >= 0:
             raise IndexError(f"ID {_ids.first_text(ids, missing)} not found in the index.")
+        return codes
+
+    def lookup_keys(self, keys, passage_mode: bool) -> np.ndarray:
+        """int32 candidate of every DISTINCT id of a ranking (`fast_forward._cols.IdTable`), -1 where
+        the index does not hold it — index/util.py:29-41 once per id instead of once per pair."""
+        self._refresh()
+        codes, _ = (self.psgs if passage_mode else self.docs).lookup(keys)
         return codes
 
     def rows_for(self, ids: Iterable[str], mode_name: str) -> tuple[np.ndarray, list[str]]:

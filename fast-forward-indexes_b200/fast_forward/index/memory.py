@@ -32,6 +32,19 @@ class InMemoryIndex(Index):
         super().__init__(query_encoder=query_encoder, quantizer=quantizer, mode=mode,
                          encoder_batch_size=encoder_batch_size)
 
+    @classmethod
+    def _adopt(cls, device_index: _ffx.DeviceIndex, doc_ids=None, psg_ids=None, **kwargs) -> "InMemoryIndex":
+        """An index over rows that already ARE in HBM (a `_ffx.DeviceIndex` staged from a device
+        source: bench.py generates its 61 GB corpus on the GPU).  `doc_ids` / `psg_ids`: one id per
+        row (sequence or pyarrow string array; None entries = no id), registered exactly as `add`
+        registers them.  Not part of the reference API."""
+        index = cls(device=device_index.device, **kwargs)
+        store = index._store
+        store.dev = device_index
+        store.count = len(device_index)
+        store.record_ids(doc_ids, psg_ids, 0, store.count)
+        return index
+
     # ---- Index contract -------------------------------------------------------------------
     def _get_num_vectors(self) -> int:
         return self._store.count

@@ -196,6 +196,24 @@ int ffx_order_u64(const uint64_t *keys, int64_t n, int64_t *order, int n_threads
 /* The join itself: pos[i] = index of want[i] in have[] (its first occurrence), -1 if absent. */
 int ffx_match_keys(const int64_t *have, int64_t n_have, const int64_t *want, int64_t n_want, int64_t *pos);
 
+/* Rankings on integer codes (host; the result side of index/base.py:461-469 and ranking.py:279-326,
+ * which the reference builds with pandas merges on two string columns).
+ * ffx_lut_gather: out[i] = lut[codes[i]] on all host cores — the candidate of every pair from the
+ *   candidate of every DISTINCT id of a ranking (index/util.py:29-41 resolved once per id, not once
+ *   per pair); *first_negative = lowest i with lut[codes[i]] < 0 (the id IndexError names), -1 if none.
+ * ffx_topk_gather: the [nq, k] (position, score) lists of ffx_rerank -> the rows of the result
+ *   ranking.  Query q keeps its first min(keep, valid) entries (lists are padded with pos = -1):
+ *   out_off[nq + 1] = prefix sums of the kept counts, out_code[j] = src_code[src_off[q] + pos]
+ *   (the id code of the source row), out_score[j] = score; either output may be NULL, both need
+ *   room for nq * keep entries.  *n_ties = adjacent equal scores inside kept lists (the rows the
+ *   host then orders by id, ranking.py:312-326); straddle[q] (optional, needs keep < k) = the
+ *   keep-th and (keep+1)-th scores of q are equal, i.e. the cut falls inside a tie. */
+int ffx_lut_gather(const int32_t *lut, int64_t n_lut, const int32_t *codes, int64_t n, int32_t *out,
+                   int64_t *first_negative, int n_threads);
+int ffx_topk_gather(const int32_t *pos, const float *score, int64_t nq, int64_t k, int64_t keep,
+                    const int64_t *src_off, const int32_t *src_code, int64_t *out_off, int32_t *out_code,
+                    float *out_score, int64_t *n_ties, uint8_t *straddle, int n_threads);
+
 /* ---- the hot path ----------------------------------------------------------------- */
 /* Replaces, in one pass, `Index._compute_scores` (index/base.py:279-314) including
  * `_get_vectors` (index/memory.py:139-140), `Ranking.interpolate`'s arithmetic
