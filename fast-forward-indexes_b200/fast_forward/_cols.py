@@ -217,10 +217,13 @@ class Cols:
             out_score = np.empty(m_cap, np.float32)
             _ffx.check(_ffx.lib().ffx_topk_gather(_ptr(pos), _ptr(score), nq, k, keep, _ptr(self.q_off), None,
                                                   _ptr(off), None, _ptr(out_score), None, None, 0))
-        cols = Cols(self.q_keys, off, self.ids, code[:m], out_score[:m], self.queries)
-        if m and (np.diff(off) == 0).any():  # a block without ranked rows (all-NaN scores) disappears
-            cols = cols.take_heads(np.diff(off))
-        return cols, int(ties.value), straddle
+        # blocks without ranked rows (all-NaN scores) stay as empty blocks: `drop_empty` removes them
+        return Cols(self.q_keys, off, self.ids, code[:m], out_score[:m], self.queries), int(ties.value), straddle
+
+    def drop_empty(self) -> "Cols":
+        """Blocks without rows disappear (q_ids = the queries with at least one scored row)."""
+        counts = self.counts()
+        return self if (counts > 0).all() else self.take_heads(counts)
 
     def order_ties_by_id(self) -> None:
         """The reference leaves equal scores of a query in ascending id order after an outer merge
@@ -371,6 +374,10 @@ def combine(a: Cols, b: Cols, fn):
     _ffx.check(_ffx.lib().ffx_ranking_order(_ptr(block), _ptr(score), len(score), _ptr(order), 0))
     # ffx_ranking_order breaks ties by incoming position; make the incoming order id-ascending
     # inside blocks only if there are ties at all (checked after the sort, on the sorted scores)
-    out = Cols(a.q_keys, a.q_off, a.ids, a.id_code[order], score[order], a.queries)
+    queries = a.queries
+    if queries is None and b.queries is not None:  # the merge carries the right frame's `query` column over
+        where = {k: i for i, k in enumerate(b.q_keys.to_pylist())}
+        queries = b.queries.take(pa.array([where[k] for k in a.q_keys.to_pylist()], type=pa.int64()))
+    out = Cols(a.q_keys, a.q_off, a.ids, a.id_code[order], score[order], queries)
     out.order_ties_by_id()
     return out

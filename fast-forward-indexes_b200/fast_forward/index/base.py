@@ -47,64 +47,27 @@ def _fl32_interpolate(alpha: float, lex, ff):
 
 
 class _Origin:
-    """Provenance of a ranking computed by `Index.__call__`: the source frame (identity),
-    its per-query block offsets and the semantic scores aligned with the source rows.
-    Lets `source.interpolate(result, alpha)` skip the string outer-merge and run on the GPU."""
+    """Provenance of a ranking computed by `Index.__call__`: the integer-coded columns of the
+    source ranking (identity) and the semantic scores aligned with its rows.  Lets
+    `source.interpolate(result, alpha)` skip the string outer-merge and run on the GPU."""
 
-    __slots__ = ("index", "source_df", "q_off", "ff")
+    __slots__ = ("index", "source", "ff")
 
-    def __init__(self, index: "Index", source_df: pd.DataFrame, q_off: np.ndarray, ff: np.ndarray):
-        self.index, self.source_df, self.q_off, self.ff = index, source_df, q_off, ff
+    def __init__(self, index: "Index", source, ff: np.ndarray):
+        self.index, self.source, self.ff = index, source, ff
 
     def matches(self, ranking: Ranking) -> bool:
-        df = ranking._df
-        return df is self.source_df and len(df) == len(self.ff) and df["score"].dtype == np.float32
+        return ranking._cols is self.source and len(self.source) == len(self.ff)
 
     def interpolate(self, first: Ranking, _other: Ranking, alpha: float) -> Ranking:
-        df = self.source_df
-        lex = df["score"].to_numpy()
-        max_c = int(np.diff(self.q_off).max()) if len(self.q_off) > 1 else 0
-        out = self.index._device().interpolate_topk_host(lex, self.ff, self.q_off, alpha, max_c,
+        src = self.source
+        max_c = int(src.counts().max()) if src.nq else 0
+        out = self.index._device().interpolate_topk_host(src.score, self.ff, src.q_off, alpha, max_c,
                                                          want_int=False)
-        rows, scores = _rows_from_topk(out["topk_pos"], out["topk_score"], self.q_off)
-        rows = _order_ties_by_id(rows, scores, df["id"], self.q_off)
-        return Ranking._reordered(first, rows, scores, name=first.name)
-
-
-def _rows_from_topk(pos: np.ndarray, score: np.ndarray, q_off: np.ndarray):
-    """[nq, k] per-query positions (-1 padded) -> flat source-row numbers + scores, query
-    blocks in order."""
-    valid = pos >= 0
-    rows = (pos + q_off[:-1, None])[valid]
-    return rows.astype(np.int64), score[valid]
-
-
-def _order_ties_by_id(rows, scores, ids, q_off):
-    """The reference leaves equal interpolated scores of a query in ascending id order (its
-    outer merge sorts the keys before the stable sort, ranking.py:312-326); the kernel orders
-    ties by position.  Re-order only the (rare) runs of equal scores.  `ids`: the id column
-    (Series or array) of the source frame; only the ids inside tie runs are materialised."""
-    if len(rows) < 2:
-        return rows
-    same = scores[1:] == scores[:-1]
-    if not same.any():
-        return rows
-    q_of_row = np.searchsorted(q_off, rows, side="right") - 1
-    same &= q_of_row[1:] == q_of_row[:-1]
-    if not same.any():
-        return rows
-    rows = rows.copy()
-    starts = np.flatnonzero(same & ~np.concatenate([[False], same[:-1]]))
-    ends = np.flatnonzero(same & ~np.concatenate([same[1:], [False]])) + 2
-    in_runs = np.concatenate([np.arange(s, e) for s, e in zip(starts, ends)])
-    picked = ids.iloc[rows[in_runs]] if hasattr(ids, "iloc") else np.asarray(ids)[rows[in_runs]]
-    names = np.asarray(picked, dtype=object).astype(str)
-    at = 0
-    for s, e in zip(starts, ends):
-        run = rows[s:e]
-        rows[s:e] = run[np.argsort(names[at:at + (e - s)], kind="stable")]
-        at += e - s
-    return rows
+        cols, ties, _ = src.from_lists(out["topk_pos"], out["topk_score"], max_c)
+        if ties:
+            cols.order_ties_by_id()
+        return Ranking._from_cols(cols, first.name)
 
 
 def _number_queries(q_ids: pd.Series):
@@ -227,6 +190,11 @@ class Index(abc.ABC):
         """The libffx index holding this index's rows in HBM, maps synchronised."""
 
     @abc.abstractmethod
+    def _candidates(self, cols, mode: Mode) -> np.ndarray:
+        """int32 candidate per row of an integer-coded ranking (`fast_forward._cols.Cols`), cached
+        on the columns; IndexError names the first unknown id (index/util.py:38-39)."""
+
+    @abc.abstractmethod
     def _resolve(self, ids, mode: Mode) -> np.ndarray:
         """An id column (Series / array, one entry per pair) -> int32 candidates for ffx_rerank
         (document ordinals, or row numbers in PASSAGE mode) with the semantics of
@@ -267,6 +235,27 @@ class Index(abc.ABC):
         out = self._device().rerank_host(mode.value, qv, q_off, cand, lex, alpha, k,
                                          want_ff=want_ff, want_int=False)
         return out, q_off
+
+    def _launch_cols(self, cols, mode: Mode, query_vectors: np.ndarray, lo: int, hi: int, alpha: float = 0.0,
+                     k: int = 0, interpolate: bool = False, want_ff: bool = True):
+        """ffx_rerank_host over the query blocks [lo, hi) of an integer-coded ranking: candidates
+        come from the cache on the columns (every distinct id is resolved once per index, not once
+        per pair and call), inputs and outputs live in recycled page-locked memory."""
+        qv = np.ascontiguousarray(query_vectors[lo:hi], dtype=np.float32)
+        if qv.ndim != 2 or (self.dim is not None and qv.shape[1] != self.dim):
+            raise ValueError(f"Query vectors of shape {qv.shape} do not match index dimensionality {self.dim}.")
+        cand = self._candidates(cols, mode)
+        r0, r1 = int(cols.q_off[lo]), int(cols.q_off[hi])
+        q_off = cols.q_off[lo:hi + 1] - r0 if lo else cols.q_off[:hi + 1]
+        out = {}
+        if want_ff:
+            out["ff"] = _ffx.pinned_empty(r1 - r0, np.float32)
+        if k > 0:
+            out["topk_score"] = _ffx.pinned_empty((hi - lo, k), np.float32)
+            out["topk_pos"] = _ffx.pinned_empty((hi - lo, k), np.int32)
+        self._device().rerank_host(mode.value, qv, q_off, cand[r0:r1], cols.score[r0:r1] if interpolate else None,
+                                   alpha, k, want_ff=want_ff, want_int=False, out=out)
+        return out
 
     def _compute_scores(self, data: pd.DataFrame, query_vectors: np.ndarray) -> pd.DataFrame:
         """Semantic scores for the (id, q_no) rows of `data` (index/base.py:279-314).
@@ -398,38 +387,40 @@ class Index(abc.ABC):
             raise ValueError("Early stopping requires alpha and depths.")
         started = perf_counter()
 
+        cols = ranking._columns() if early_stopping is None else None
+        if cols is not None and cols.queries is not None:
+            # integer-coded route: one launch per query batch gives the semantic scores AND the
+            # per-query order (ties keep the incoming order, like the reference's stable sort)
+            query_vectors = self.encode_queries(cols.queries.to_pylist())
+            nq, counts = cols.nq, cols.counts()
+            step = nq if batch_size is None or batch_size >= nq else max(int(batch_size), 1)
+            widest = int(counts.max())
+            if step >= nq:
+                out = self._launch_cols(cols, self.mode, query_vectors, 0, nq, k=widest)
+                ff, pos, top = out["ff"], out["topk_pos"], out["topk_score"]
+            else:
+                ff = np.empty(len(cols), np.float32)
+                pos = np.full((nq, widest), -1, np.int32)
+                top = np.full((nq, widest), -np.inf, np.float32)
+                for lo in range(0, nq, step):
+                    hi = min(nq, lo + step)
+                    w = int(counts[lo:hi].max())
+                    out = self._launch_cols(cols, self.mode, query_vectors, lo, hi, k=w)
+                    ff[cols.q_off[lo]:cols.q_off[hi]] = out["ff"]
+                    pos[lo:hi, :w], top[lo:hi, :w] = out["topk_pos"], out["topk_score"]
+            LOGGER.info("computed scores in %s seconds", perf_counter() - started)
+            if not np.isnan(ff).any():  # NaN rows are dropped by Ranking: those take the generic route
+                result, _, _ = cols.from_lists(pos, top, widest)
+                out_ranking = Ranking._from_cols(result.drop_empty(), "fast-forward")
+                out_ranking._origin = _Origin(self, cols, ff)
+                return out_ranking
+            frame = ranking._df[["q_id", "id", "query"]].assign(score=ff)
+            return Ranking(frame, name="fast-forward", dtype=np.float32, copy=False, is_sorted=False)
+
         src = ranking._df
         q_codes, nq, query_vectors = self._query_vectors_for(src)
-        grouped = not (np.diff(q_codes) < 0).any()
         step = nq if batch_size is None or batch_size >= nq else int(batch_size)
         dtype = src.dtypes["score"]
-
-        if early_stopping is None and grouped:
-            # one launch per query batch: semantic scores AND the per-query order (ties keep
-            # the incoming order, like the reference's stable sort), no pandas sort needed
-            ids = src["id"]
-            row_off = np.zeros(nq + 1, np.int64)
-            np.cumsum(np.bincount(q_codes, minlength=nq), out=row_off[1:])
-            ff = np.empty(len(src), np.float32)
-            order = []
-            for lo in range(0, nq, max(step, 1)):
-                hi = min(nq, lo + step)
-                r0, r1 = row_off[lo], row_off[hi]
-                widest = int(np.diff(row_off[lo:hi + 1]).max())
-                out, q_off = self._launch(self.mode, q_codes[r0:r1] - lo, ids.iloc[r0:r1],
-                                          query_vectors[lo:hi], k=widest)
-                ff[r0:r1] = out["ff"]
-                order.append(_rows_from_topk(out["topk_pos"], out["topk_score"], q_off)[0] + r0)
-            LOGGER.info("computed scores in %s seconds", perf_counter() - started)
-            if np.isnan(ff).any():  # NaN rows are dropped by Ranking: take the generic route
-                frame = src[["q_id", "id", "query"]].assign(score=ff)
-                return Ranking(frame, name="fast-forward", dtype=dtype, copy=False, is_sorted=False)
-            rows = np.concatenate(order) if order else np.zeros(0, np.int64)
-            out_ranking = Ranking._reordered(ranking, rows, ff[rows].astype(dtype, copy=False), name="fast-forward")
-            if dtype == np.float32:
-                out_ranking._origin = _Origin(self, src, row_off, ff)
-            return out_ranking
-
         work = src.assign(q_no=q_codes, orig_index=np.arange(len(src)))
 
         def run(part: pd.DataFrame) -> pd.DataFrame:
@@ -450,65 +441,54 @@ class Index(abc.ABC):
         """Fused re-ranking: the result of
         `ranking.interpolate(self(ranking), alpha).cut(cutoff)` from ONE kernel launch
         (look-up, dots, per-document reduce, interpolation and per-query top-k all on the GPU).
+        The ranking's ids are resolved against the index once; the integer candidates stay
+        cached on the ranking, so further calls hash no string.
         """
         if not ranking.has_queries:
             raise ValueError("Input ranking has no queries attached.")
-        src = ranking._df
-        if src["score"].dtype != np.float32:
+        cols = ranking._columns()
+        if cols is None or cols.queries is None:  # float64 scores, NaN queries, ...: the three-call route
             out = ranking.interpolate(self(ranking), alpha)
             return out if cutoff is None else out.cut(cutoff)
-        q_codes, nq, query_vectors = self._query_vectors_for(src)
-        if (np.diff(q_codes) < 0).any():
-            raise ValueError("Ranking frame is not grouped by query.")
-        if nq == 0:
-            return Ranking(src, name=ranking.name, dtype=np.float32, copy=True, is_sorted=True)
-        counts = np.bincount(q_codes, minlength=nq)
-        widest = int(counts.max())
-        k = widest if cutoff is None else int(min(cutoff, widest))
+        query_vectors = self.encode_queries(cols.queries.to_pylist())
+        nq = cols.nq
+        widest = int(cols.counts().max())
+        k = widest if cutoff is None else int(min(max(cutoff, 0), widest))
+        if k == 0:
+            return ranking.cut(0)
         # one slot more than the cut: it tells whether equal scores straddle the cut boundary
         kk = min(k + 1, widest)
-        ids, lex = src["id"], src["score"].to_numpy()
-        out, q_off = self._launch(self.mode, q_codes, ids, query_vectors, lex=lex, alpha=alpha, k=kk, want_ff=False)
-        pos, score = out["topk_pos"], out["topk_score"]
-        straddle = np.zeros(0, np.int64)
-        if kk > k:
-            straddle = np.flatnonzero((pos[:, k] >= 0) & (score[:, k - 1] == score[:, k]))
-            pos, score = pos[:, :k], score[:, :k]
-        rows, scores = _rows_from_topk(pos, score, q_off)
-        # ties inside the kept lists come out in ascending id order like the reference
-        rows = _order_ties_by_id(rows, scores, ids, q_off)
-        if len(straddle):
+        out = self._launch_cols(cols, self.mode, query_vectors, 0, nq, alpha=alpha, k=kk, interpolate=True,
+                                want_ff=False)
+        result, ties, straddle = cols.from_lists(out["topk_pos"], out["topk_score"], k, want_straddle=kk > k)
+        if straddle is not None and straddle.any():
             # equal scores on both sides of the cut (float32 collisions; a handful of queries in
             # millions of pairs): the reference keeps the smaller ids.  Rank those queries in
             # full, order their ties by id and cut again.
-            rows, scores = self._recut_straddling(straddle, rows, scores, pos, q_off, q_codes, ids, lex,
-                                                  query_vectors, alpha, k)
-        return Ranking._reordered(ranking, rows, scores, name=ranking.name)
+            self._recut_straddling(np.flatnonzero(straddle), cols, result, query_vectors, alpha, k)
+        if ties:
+            result.order_ties_by_id()  # ties inside the kept lists: ascending id, like the reference
+        return Ranking._from_cols(result.drop_empty(), ranking.name)
 
-    def _recut_straddling(self, queries, rows, scores, pos, q_off, q_codes, ids, lex, query_vectors, alpha, k):
-        """Exact cut for the queries whose k-th and (k+1)-th interpolated scores are equal."""
-        kept = (pos >= 0).sum(axis=1)
-        starts = np.concatenate([[0], np.cumsum(kept)])
-        take = np.concatenate([np.arange(q_off[q], q_off[q + 1]) for q in queries])
-        sub_q = np.repeat(np.arange(len(queries)), [q_off[q + 1] - q_off[q] for q in queries])
-        full, sub_off = self._launch(self.mode, sub_q, ids.iloc[take], query_vectors[queries], lex=lex[take],
-                                     alpha=alpha, k=int(np.diff(q_off)[queries].max()), want_ff=False)
-        sub_rows, sub_scores = _rows_from_topk(full["topk_pos"], full["topk_score"], sub_off)
-        sub_rows = _order_ties_by_id(sub_rows, sub_scores, ids.iloc[take].reset_index(drop=True), sub_off)
-        row_parts, score_parts, at = [], [], 0
-        done = 0
-        for j, q in enumerate(queries):
-            row_parts.append(rows[done:starts[q]])
-            score_parts.append(scores[done:starts[q]])
-            n_q = int(sub_off[j + 1] - sub_off[j])
-            sel = sub_rows[at:at + n_q][:k]
-            row_parts.append(take[sel])
-            score_parts.append(sub_scores[at:at + n_q][:k])
-            at += n_q
-            done = starts[q + 1]
-        row_parts.append(rows[done:])
-        score_parts.append(scores[done:])
-        return np.concatenate(row_parts), np.concatenate(score_parts)
+    def _recut_straddling(self, blocks, cols, result, query_vectors, alpha, k) -> None:
+        """Exact cut for the queries whose k-th and (k+1)-th interpolated scores are equal;
+        overwrites their (full, k-row) blocks of `result`."""
+        from fast_forward._cols import Cols
+
+        for b in blocks.tolist():
+            n_b = int(cols.q_off[b + 1] - cols.q_off[b])
+            full = self._launch_cols(cols, self.mode, query_vectors, b, b + 1, alpha=alpha, k=n_b, interpolate=True,
+                                     want_ff=False)
+            pos, score = full["topk_pos"][0], full["topk_score"][0]
+            valid = pos >= 0
+            codes = cols.id_code[cols.q_off[b] + pos[valid]]
+            one = Cols(cols.q_keys.slice(b, 1), np.array([0, len(codes)], np.int64), cols.ids, codes,
+                       np.array(score[valid], np.float32), None)
+            one.order_ties_by_id()
+            at = int(result.q_off[b])
+            assert int(result.q_off[b + 1]) - at == k
+            result.id_code[at:at + k] = one.id_code[:k]
+            result.score[at:at + k] = one.score[:k]
 
     # ------------------------------------------------------------------ iteration
     def batch_iter(self, batch_size: int) -> Iterator[tuple[np.ndarray, IDSequence, IDSequence]]:

@@ -87,5 +87,8 @@ class InMemoryIndex(Index):
     def _device(self) -> _ffx.DeviceIndex:
         return self._store.device_index(self.quantizer)
 
+    def _candidates(self, cols, mode: Mode) -> np.ndarray:
+        return cols.candidates(self._store, mode == Mode.PASSAGE)
+
     def _resolve(self, ids, mode: Mode) -> np.ndarray:
         return self._store.resolve(ids, mode == Mode.PASSAGE)

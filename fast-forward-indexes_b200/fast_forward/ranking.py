@@ -57,144 +57,10 @@ def _minmax(df: pd.DataFrame) -> pd.DataFrame:
 _CODED_FROM = 50_000  # rows from which the integer-coded constructor path pays off
 
 
-def _coded_frame(df: pd.DataFrame, is_sorted: bool) -> pd.DataFrame | None:
-    """The frame `Ranking.__init__` builds (ranking.py:95-117: duplicate check, NaN rows dropped,
-    q_id DESC / score DESC stable order), computed on integer codes by libffx's host routines
-    instead of pandas' `duplicated` + `sort_values` over two string columns: ids are coded by
-    the C++ dictionary, pairs are checked as int64 keys, the order is one radix sort.  Returns
-    None (the caller then takes the pandas route, with identical results) unless both id
-    columns are strings (or integers / Python strings, converted first) without nulls and the
-    scores are floats."""
-    from fast_forward import _ffx, _ids
+def _cols_module():
+    from fast_forward import _cols
 
-    s_col = df["score"]
-    if len(df) == 0 or s_col.dtype.kind != "f":
-        return None
-    id_columns = {}
-    for col in ("q_id", "id"):
-        values = df[col]
-        if values.dtype.kind in "iu" or (values.dtype == object and pd.api.types.infer_dtype(values, skipna=False) == "string"):
-            # run files with numeric ids (MS MARCO), frames built from Python strings: the ids
-            # become strings anyway (ranking.py:107-113); doing it first changes nothing for such
-            # columns (no nulls, no mixed types) and opens the coded route
-            values = values.astype(str)
-        if not pd.api.types.is_string_dtype(values.dtype) or values.dtype == object or values.isna().any():
-            return None
-        id_columns[col] = values
-    if id_columns["q_id"] is not df["q_id"] or id_columns["id"] is not df["id"]:
-        df = df.assign(**id_columns)
-    q_col, id_col = df["q_id"], df["id"]
-    import ctypes as C
-
-    n = len(df)
-    q_code, q_keys = pd.factorize(q_col)
-    id_code = _ids.IdDict().insert_ordinal(id_col)
-    pair = q_code.astype(np.int64) * (int(id_code.max()) + 1) + id_code
-    first = C.c_int64(-1)
-    _ffx.check(_ffx.lib().ffx_first_repeat(C.c_void_p(pair.ctypes.data), n, C.byref(first)))
-    if first.value >= 0:
-        raise ValueError("Only one score per query-document/passage pair is allowed.")
-
-    keep = ["q_id", "id", "score"] + (["query"] if "query" in df.columns else [])
-    score = np.ascontiguousarray(s_col.to_numpy(), dtype=np.float32)  # cast first, then order (ranking.py:107-117)
-    alive = ~np.isnan(score)
-    if "query" in df.columns:
-        alive &= ~df["query"].isna().to_numpy()
-    rows = None if alive.all() else np.flatnonzero(alive)  # rows that survive dropna, in frame order
-    if not is_sorted:
-        # rank of every distinct q_id in DEscending string order, then one stable radix sort
-        q_rank_of = np.empty(len(q_keys), np.int32)
-        q_rank_of[np.argsort(np.asarray(q_keys, dtype=object), kind="stable")[::-1]] = np.arange(len(q_keys), dtype=np.int32)
-        q_rank = q_rank_of[q_code]
-        kept_score = score
-        if rows is not None:
-            q_rank, kept_score = q_rank[rows], score[rows]
-        order = np.empty(len(q_rank), np.int64)
-        _ffx.check(_ffx.lib().ffx_ranking_order(C.c_void_p(q_rank.ctypes.data), C.c_void_p(kept_score.ctypes.data),
-                                                len(q_rank), C.c_void_p(order.ctypes.data), 0))
-        rows = order if rows is None else rows[order]
-    if rows is None:
-        frame = df.loc[:, keep].copy()
-    else:
-        frame = df.loc[:, keep].take(rows)
-        score = score[rows]
-    frame["score"] = score
-    frame.reset_index(drop=True, inplace=True)
-    return frame
-
-
-def _match_pairs(left: pd.DataFrame, right: pd.DataFrame):
-    """Row of `right` holding the (q_id, id) pair of every row of `left`, on integer codes (one
-    C++ dictionary per key column, a hash match of int64 pair keys).  Returns (q codes of left,
-    id codes of left, q dictionary, id dictionary, positions), or None when the frames are
-    small, differ in length, hold different pairs, or have key columns that are not plain
-    strings — the callers then use pandas."""
-    if len(left) != len(right) or len(left) < _CODED_FROM:
-        return None
-    for frame in (left, right):
-        for col in _KEYS:
-            dtype = frame[col].dtype
-            if not pd.api.types.is_string_dtype(dtype) or dtype == object or frame[col].isna().any():
-                return None
-    import ctypes as C
-
-    from fast_forward import _ffx, _ids
-
-    n = len(left)
-    q_dict, id_dict = _ids.IdDict(), _ids.IdDict()
-    lq, rq = q_dict.insert_ordinal(left["q_id"]), q_dict.insert_ordinal(right["q_id"])
-    li, ri = id_dict.insert_ordinal(left["id"]), id_dict.insert_ordinal(right["id"])
-    n_id = len(id_dict)
-    l_key, r_key = lq * n_id + li, rq * n_id + ri
-    pos = np.empty(n, np.int64)
-    _ffx.check(_ffx.lib().ffx_match_keys(C.c_void_p(r_key.ctypes.data), n, C.c_void_p(l_key.ctypes.data), n,
-                                         C.c_void_p(pos.ctypes.data)))
-    if (pos < 0).any():
-        return None  # a pair of `left` is missing on the right
-    return lq, li, q_dict, id_dict, pos
-
-
-def _outer_coded(left: pd.DataFrame, right: pd.DataFrame) -> pd.DataFrame | None:
-    """`left.merge(right, on=[q_id, id], how="outer", suffixes=(None, "_other")).fillna(0)` for the
-    usual case of two rankings over the SAME set of pairs (a first-stage ranking and its
-    re-scored copy), on integer codes: ids of both frames go through one C++ dictionary, the
-    join is a hash match of int64 pair keys (`ffx_match_keys`), and the merge's key order —
-    q_id then id, ascending as strings — comes from ranking the distinct strings once and one
-    radix sort (`ffx_order_u64`).  None (pandas takes over, same result) when the pair sets
-    differ, the frames are small, or the key columns are not plain strings."""
-    matched = _match_pairs(left, right)
-    if matched is None:
-        return None
-    lq, li, q_dict, id_dict, pos = matched
-    try:
-        import pyarrow.compute as pc
-    except ImportError:  # pragma: no cover - depends on the environment
-        return None
-    import ctypes as C
-
-    from fast_forward import _ffx
-
-    def ptr(a):
-        return C.c_void_p(a.ctypes.data)
-
-    n = len(left)
-
-    def string_rank(dictionary) -> np.ndarray:
-        keys, _ = dictionary.export()
-        rank = np.empty(len(keys), np.uint64)
-        rank[pc.sort_indices(keys).to_numpy()] = np.arange(len(keys), dtype=np.uint64)
-        return rank
-
-    sort_key = (string_rank(q_dict)[lq] << np.uint64(32)) | string_rank(id_dict)[li]
-    order = np.empty(n, np.int64)
-    _ffx.check(_ffx.lib().ffx_order_u64(ptr(sort_key), n, ptr(order), 0))
-    out = left.take(order).reset_index(drop=True)
-    theirs = pos[order]
-    for col in right.columns:
-        if col not in _KEYS:
-            name = col + "_other" if col in left.columns else col
-            out[name] = right[col].take(theirs).reset_index(drop=True)
-    return out.fillna(0) if out.isna().any().any() else out
+    return _cols
 
 
 class Ranking:
@@ -216,12 +82,14 @@ class Ranking:
         """
         self.name = name
         self._origin = None  # set by Index.__call__ (device-side provenance)
+        self._frame = None   # the pandas frame of the reference (`_df`), built on first access ...
+        self._cols = None    # ... from the integer-coded columns, where those came first
+        self._q_id_set = None
 
         if len(df) >= _CODED_FROM and np.dtype(dtype) == np.float32:
-            frame = _coded_frame(df, is_sorted)
-            if frame is not None:
-                self._q_ids = set(pd.unique(frame["q_id"]))
-                self._df = frame if queries is None else _with_queries(frame, queries)
+            cols = _cols_module().from_frame(df, is_sorted, queries)
+            if cols is not None:
+                self._cols = cols
                 return
 
         if df.duplicated(subset=_KEYS).any():
@@ -239,25 +107,67 @@ class Ranking:
             frame.sort_values(by=["q_id", "score"], ascending=False, inplace=True)
         frame.reset_index(drop=True, inplace=True)
 
-        self._q_ids = set(pd.unique(frame["q_id"]))
-        self._df = frame if queries is None else _with_queries(frame, queries)
+        self._q_id_set = set(pd.unique(frame["q_id"]))
+        self._frame = frame if queries is None else _with_queries(frame, queries)
 
     @classmethod
-    def _reordered(cls, source: "Ranking", rows: np.ndarray, scores: np.ndarray, name: str | None) -> "Ranking":
-        """Rows `rows` of `source` (a selection without repeats, already in ranking order: query
-        blocks in frame order, scores descending inside a block) with new scores.  The checks of
-        `__init__` would only re-derive what holds by construction — keys of a valid ranking
-        stay unique under row selection, dtypes are kept, the order is the kernel's — so the
-        frame is adopted as is (at 26 M rows `duplicated()` alone costs more than the GPU pass).
-        NaN scores never get here: the kernel does not rank them."""
+    def _from_cols(cls, cols, name: str | None) -> "Ranking":
+        """Adopt integer-coded columns that already satisfy the invariants of `__init__` (unique
+        pairs, no NaN, float32, blocks by q_id, scores descending inside a block)."""
         out = cls.__new__(cls)
         out.name = name
         out._origin = None
-        frame = source._df.iloc[rows].reset_index(drop=True)
-        frame["score"] = scores
-        out._df = frame
-        out._q_ids = set(pd.unique(frame["q_id"])) if len(rows) != len(source._df) else set(source._q_ids)
+        out._frame = None
+        out._cols = cols
+        out._q_id_set = None
         return out
+
+    # ------------------------------------------------------------------ the two representations
+    @property
+    def _df(self) -> pd.DataFrame:
+        """The frame the reference keeps (q_id, id, score[, query]; RangeIndex)."""
+        if self._frame is None:
+            self._frame = self._cols.to_frame()
+        return self._frame
+
+    @_df.setter
+    def _df(self, frame: pd.DataFrame) -> None:
+        self._frame = frame
+        self._cols = None
+        self._q_id_set = None
+
+    @property
+    def _q_ids(self) -> set[str]:
+        if self._q_id_set is None:
+            self._q_id_set = set(self._cols.q_keys.to_pylist()) if self._frame is None else \
+                set(pd.unique(self._frame["q_id"]))
+        return self._q_id_set
+
+    def _columns(self):
+        """Integer-coded columns of this ranking (`fast_forward._cols.Cols`), or None when the frame
+        is not of the plain kind (float32 scores, string ids, blocks by query, no NaN queries)."""
+        if self._cols is None and self._frame is not None and len(self._frame):
+            frame = self._frame
+            if frame["score"].dtype != np.float32:
+                return None
+            cm = _cols_module()
+            if "query" in frame.columns:
+                if frame["query"].isna().any() or not pd.api.types.is_string_dtype(frame["query"].dtype):
+                    return None
+                cols = cm.from_frame(frame[["q_id", "id", "score"]], True, None)
+                if cols is None:
+                    return None
+                texts = frame["query"].iloc[cols.q_off[:-1]]
+                cols.queries = cm.pa.array(texts.to_numpy(dtype=object), type=cm.pa.large_string())
+            else:
+                cols = cm.from_frame(frame, True, None)
+            self._cols = cols
+        return self._cols
+
+    @property
+    def num_rows(self) -> int:
+        """Number of (query, id) pairs."""
+        return len(self._cols) if self._frame is None else len(self._frame)
 
     # ------------------------------------------------------------------ container protocol
     @property
@@ -271,6 +181,14 @@ class Ranking:
         return self._q_ids
 
     def __getitem__(self, q_id: str) -> dict[str, float]:
+        if self._frame is None:
+            cols = self._cols
+            b = cols.block_of(q_id)
+            if b < 0:
+                return {}
+            lo, hi = int(cols.q_off[b]), int(cols.q_off[b + 1])
+            names = cols.ids.keys.take(_cols_module().pa.array(cols.id_code[lo:hi])).to_pylist()
+            return dict(zip(names, cols.score[lo:hi]))
         rows = self._df.loc[self._df["q_id"] == q_id, ["id", "score"]]
         return dict(rows.values)
 
@@ -287,10 +205,11 @@ class Ranking:
         """Same (q_id, id, score) triples, exact float equality (ranking.py:171-186)."""
         if not isinstance(o, Ranking):
             return False
-        matched = _match_pairs(self._df, o._df)
-        if matched is not None:  # same pairs (both frames hold each pair once): compare aligned scores
-            mine, theirs = self._df["score"].to_numpy(), o._df["score"].to_numpy()
-            return bool(mine.dtype == theirs.dtype and (mine == theirs[matched[4]]).all())
+        if self.num_rows >= _CODED_FROM and self.num_rows == o.num_rows:
+            a, b = self._columns(), o._columns()
+            if a is not None and b is not None:  # both float32: same pairs with the same scores
+                pos = _cols_module().match_pairs(a, b)
+                return bool(pos is not None and (a.score == b.score[pos]).all())
         cols = ["q_id", "id", "score"]
         mine = self._df.sort_values(_KEYS).reset_index(drop=True)[cols]
         theirs = o._df.sort_values(_KEYS).reset_index(drop=True)[cols]
@@ -306,21 +225,49 @@ class Ranking:
         return Ranking(frame, name=self.name, dtype=self._df.dtypes["score"], copy=copy,
                        is_sorted=is_sorted)
 
+    def _coded(self):
+        """Columns to compute on: present already, or worth building (large plain frames)."""
+        if self._cols is not None:
+            return self._cols
+        return self._columns() if self.num_rows >= _CODED_FROM else None
+
+    def _rescored(self, score: np.ndarray) -> "Ranking | None":
+        """Same rows, same order (`is_sorted=True`), new float32 scores; None if a NaN appeared
+        (`__init__` would drop that row: the pandas route handles it)."""
+        if score.dtype != np.float32 or np.isnan(score).any():
+            return None
+        return Ranking._from_cols(self._cols.with_scores(score), self.name)
+
     def _outer(self, other: pd.DataFrame, mine: pd.DataFrame | None = None) -> pd.DataFrame:
         """Outer join on (q_id, id); a score missing on either side counts as 0."""
         left = self._df if mine is None else mine
-        joined = _outer_coded(left, other)
-        if joined is None:
-            joined = left.merge(other, on=_KEYS, suffixes=(None, "_other"), how="outer").fillna(0)
-        return joined
+        return left.merge(other, on=_KEYS, suffixes=(None, "_other"), how="outer").fillna(0)
+
+    def _combined(self, other: "Ranking", fn) -> "Ranking | None":
+        """`fn(self.score, other.score)` over the outer merge of two rankings that hold the SAME
+        pairs, on integer codes (fast_forward._cols.combine); None = take the pandas route."""
+        if max(self.num_rows, other.num_rows) < _CODED_FROM and (self._cols is None or other._cols is None):
+            return None
+        a, b = self._columns(), other._columns()
+        if a is None or b is None:
+            return None
+        cols = _cols_module().combine(a, b, fn)
+        return None if cols is None else Ranking._from_cols(cols, self.name)
 
     def __add__(self, o: "Ranking | float") -> "Ranking":
         """Add a constant or another ranking's scores (ranking.py:188-217)."""
         if isinstance(o, Ranking):
+            out = self._combined(o, lambda mine, theirs: mine + theirs)
+            if out is not None:
+                return out
             joined = self._outer(o._df)
             joined["score"] = joined["score"] + joined["score_other"]
             return self._derive(joined, is_sorted=False)
         if isinstance(o, (int, float)):
+            if self._coded() is not None:
+                out = self._rescored(self._cols.score + o)
+                if out is not None:
+                    return out
             frame = self._df.copy()
             frame["score"] += o
             return self._derive(frame, is_sorted=True)
@@ -332,6 +279,10 @@ class Ranking:
         """Multiply the scores by a constant (ranking.py:221-239)."""
         if not isinstance(o, (int, float)):
             return NotImplemented
+        if self._coded() is not None:
+            out = self._rescored(self._cols.score * o)
+            if out is not None:
+                return out
         frame = self._df.copy()
         frame["score"] *= o
         return self._derive(frame, is_sorted=True)
@@ -341,15 +292,36 @@ class Ranking:
     # ------------------------------------------------------------------ transformations
     def attach_queries(self, queries: Mapping[str, str]) -> "Ranking":
         """Return a copy with query texts attached (ValueError if incomplete)."""
+        cols = self._coded()
+        if cols is not None and cols.queries is None:
+            cm = _cols_module()
+            try:
+                texts = cm.pa.array([queries[k] for k in cols.q_keys.to_pylist()], type=cm.pa.large_string())
+            except KeyError:
+                raise ValueError("Queries are incomplete.") from None
+            return Ranking._from_cols(cm.Cols(cols.q_keys, cols.q_off, cols.ids, cols.id_code.copy(),
+                                              cols.score.copy(), texts), self.name)
         return Ranking(self._df, self.name, queries=queries, dtype=self._df.dtypes["score"],
                        copy=True, is_sorted=True)
 
     def normalize(self) -> "Ranking":
         """Min-max normalise scores into [0, 1] (all-equal scores become 0)."""
+        if self._coded() is not None and len(self._cols):
+            s = self._cols.score
+            lo, hi = s.min(), s.max()
+            if lo == hi:
+                LOGGER.warning("all scores are equal, setting scores to 0")
+                out = self._rescored(np.zeros(len(s), np.float32))
+            else:
+                out = self._rescored((s - lo) / (hi - lo))
+            if out is not None:
+                return out
         return self._derive(_minmax(self._df), is_sorted=True)
 
     def cut(self, cutoff: int) -> "Ranking":
         """Keep the `cutoff` best rows of every query (ranking.py:279-291)."""
+        if self._coded() is not None:
+            return Ranking._from_cols(self._cols.head(cutoff), self.name)
         top = self._df.groupby("q_id").head(cutoff).reset_index(drop=True)
         return self._derive(top, is_sorted=True, copy=True)
 
@@ -363,6 +335,10 @@ class Ranking:
         if origin is not None and not normalize and origin.matches(self):
             return origin.interpolate(self, other, float(alpha))
 
+        a_r, b_r = (self.normalize(), other.normalize()) if normalize else (self, other)
+        out = a_r._combined(b_r, lambda mine, theirs: alpha * mine + (1 - alpha) * theirs)
+        if out is not None:
+            return Ranking._from_cols(out._cols, self.name)
         a = _minmax(self._df) if normalize else self._df
         b = _minmax(other._df) if normalize else other._df
         joined = self._outer(b, mine=a)
@@ -371,6 +347,12 @@ class Ranking:
 
     def rr_scores(self, k: int = 60) -> "Ranking":
         """Reciprocal-rank scores `1 / (rank + k)` (ranking.py:328-346)."""
+        if self._coded() is not None:
+            cols = self._cols
+            rank = np.arange(1, len(cols) + 1, dtype=np.int64) - np.repeat(cols.q_off[:-1], cols.counts())
+            out = self._rescored((1 / (rank + k)).astype(np.float32))
+            if out is not None:
+                return out
         frame = self._df.copy()
         frame["score"] = 1 / (_rank_column(self._df) + k)
         return self._derive(frame, is_sorted=True)

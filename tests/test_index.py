@@ -356,3 +356,47 @@ def test_mid_size_random_vs_oracle(api):
         ts, tp = fo.topk_per_query(np.arange(nq + 1) * C, s, 50)
         assert (inter._df["score"].to_numpy().view(np.uint32) == ts.ravel().view(np.uint32)).all()
         assert index.rerank(first, 0.1, cutoff=50) == inter
+
+
+def test_candidates_are_cached_on_the_ranking_and_follow_the_index(api):
+    """A ranking's ids are resolved against an index once (per distinct id), the integer candidates
+    stay on the ranking's columns, and a later `add` (new documents, a document extended by more
+    rows) is seen: the cache is keyed by the index's contents version.  Results stay those of the
+    reference semantics (index/util.py:29-41): IndexError for an id the index does not hold yet."""
+    rng = np.random.default_rng(3)
+    dim = 384
+    vec = rng.standard_normal((60, dim)).astype(np.float32)
+    qv = {f"query {i}": rng.standard_normal(dim).astype(np.float32) for i in range(4)}
+    index = api.InMemoryIndex(api.LambdaEncoder(lambda t: qv[t]), mode=api.Mode.MAXP)
+    index.add(vec[:40], doc_ids=[f"d{i // 2}" for i in range(40)])
+    frame = pd.DataFrame({"q_id": np.repeat([f"q{i}" for i in range(4)], 10),
+                          "id": [f"d{(7 * i) % 20}" for i in range(40)], "score": rng.uniform(0, 5, 40).astype(np.float32)})
+    queries = {f"q{i}": f"query {i}" for i in range(4)}
+    r = api.Ranking(frame, queries=queries)
+    first = index.rerank(r, 0.3, 5)
+    cols = r._cols
+    assert cols is not None and len(cols._cand) == 1
+    cached = next(iter(cols._cand.values()))
+    second = index.rerank(r, 0.3, 5)
+    assert next(iter(cols._cand.values())) is cached  # no second resolve
+    pd.testing.assert_frame_equal(first._df, second._df)
+    pd.testing.assert_frame_equal(first._df, r.interpolate(index(r), 0.3).cut(5)._df)
+    # other mode, other cache entry; back again
+    index.mode = api.Mode.FIRSTP
+    fp = index.rerank(r, 0.3, 5)
+    index.mode = api.Mode.MAXP
+    assert not fp._df.equals(first._df)
+    # a ranking naming a document the index does not hold yet
+    frame2 = pd.concat([frame, pd.DataFrame({"q_id": ["q0"], "id": ["d25"], "score": np.float32([9.0])})])
+    r2 = api.Ranking(frame2, queries=queries)
+    with pytest.raises(IndexError, match="ID d25 not found in the index."):
+        index.rerank(r2, 0.3, 5)
+    index.add(vec[40:], doc_ids=[f"d{20 + i // 2}" for i in range(18)] + ["d0", "d0"])  # d25 arrives, d0 grows
+    third = index.rerank(r2, 0.3, 5)
+    assert "d25" in third._df["id"].tolist()
+    grown = index.rerank(r, 0.3, 5)  # d0 has four rows now: its MAXP score may only go up
+    old, new = index(r)["q0"], None
+    ref_index = api.InMemoryIndex(api.LambdaEncoder(lambda t: qv[t]), mode=api.Mode.MAXP)
+    ref_index.add(vec, doc_ids=[f"d{i // 2}" for i in range(40)] + [f"d{20 + i // 2}" for i in range(18)] + ["d0", "d0"])
+    pd.testing.assert_frame_equal(grown._df, ref_index.rerank(api.Ranking(frame, queries=queries), 0.3, 5)._df)
+    assert old == ref_index(api.Ranking(frame, queries=queries))["q0"] and new is None
