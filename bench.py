@@ -743,17 +743,16 @@ def run_sharded(ctx, _ffx, args, wl, m, emulate, warmup):
     # full candidate list), results = this rank's merged lists read back
     host = {kk: q[kk].cpu().pin_memory() for kk in ("qv", "q_off", "cand", "lex")}
     h2d = sum(t.numel() * t.element_size() for t in host.values())
-    res_s = res_p = None
+    res = None
 
     def e2e_step():
-        nonlocal res_s, res_p
-        d = {kk: t.to(ctx.dev, non_blocking=True) for kk, t in host.items()}
-        s, p = rr.rerank(mode, d["qv"], d["q_off"], d["cand"], d["lex"], args.alpha, k, cands, gather_result=False)
-        res_s, res_p = s.cpu(), p.cpu()
+        nonlocal res
+        res = rr.rerank_host(mode, host["qv"], host["q_off"], host["cand"], host["lex"], args.alpha, k, cands)
 
     del q["cand"], q["lex"]
     torch.cuda.empty_cache()
     e2e_step()
+    assert res[1].shape[0] > 0 and res[1].shape[1] == k
     ctx.barrier()
     e_steps = max(2, min(args.steps, 5))
     t0 = time.perf_counter()
@@ -761,6 +760,7 @@ def run_sharded(ctx, _ffx, args, wl, m, emulate, warmup):
         e2e_step()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+    res_s, res_p = res[1], res[2]
     d2h = res_s.numel() * 4 + res_p.numel() * 4
     total_ms, e2e_ms = ctx.max_over_ranks([total_ms, e2e_ms])
     kern_ms = float(np.mean(per_step))
@@ -780,7 +780,8 @@ def run_sharded(ctx, _ffx, args, wl, m, emulate, warmup):
         "algorithmic_bytes_per_gpu": algo, "own_pairs_per_gpu": my_pairs,
         "e2e": {"value": nq * cands / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": "per rank: the full candidate lists H2D from pinned memory, sharded re-rank, D2H of the "
+                "note": "ShardedReranker.rerank_host, per rank: the full candidate lists H2D from pinned memory in 8 "
+                        "query chunks pipelined against the sharded re-rank of the previous chunk, D2H of the "
                         "merged lists of the queries this rank owns"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
@@ -806,14 +807,14 @@ def run_api(ctx, args, wl, m, q_host, alpha, k):
     t0 = time.perf_counter()
     text_to_row = {f"text {i}": i for i in range(nq)}
     enc = LambdaEncoder(lambda text: qv[text_to_row[text]])
-    doc_ids = pc.binary_join_element_wise(pa.scalar("D"), pa.array(np.repeat(np.arange(m["n_docs"]), m["cnt"])).cast(
-        pa.large_string()), pa.scalar(""))
+    doc_ids = pc.binary_join_element_wise(pa.scalar("D", pa.large_string()), pa.array(np.repeat(np.arange(m["n_docs"]), m["cnt"])).cast(
+        pa.large_string()), pa.scalar("", pa.large_string()))
     index = InMemoryIndex._adopt(m["idx"], doc_ids=doc_ids, query_encoder=enc, mode=Mode[wl["mode"]])
     t_index = time.perf_counter() - t0
     t0 = time.perf_counter()
-    ids = pc.binary_join_element_wise(pa.scalar("D"), pa.array(q_host["cand"].array).cast(pa.large_string()), pa.scalar(""))
-    q_ids = pc.binary_join_element_wise(pa.scalar("q"), pa.array(np.repeat(np.arange(nq), cands)).cast(
-        pa.large_string()), pa.scalar(""))
+    ids = pc.binary_join_element_wise(pa.scalar("D", pa.large_string()), pa.array(q_host["cand"].array).cast(pa.large_string()), pa.scalar("", pa.large_string()))
+    q_ids = pc.binary_join_element_wise(pa.scalar("q", pa.large_string()), pa.array(np.repeat(np.arange(nq), cands)).cast(
+        pa.large_string()), pa.scalar("", pa.large_string()))
     frame = pd.DataFrame({"q_id": pd.Series(pd.arrays.ArrowStringArray(pa.chunked_array([q_ids]))),
                           "id": pd.Series(pd.arrays.ArrowStringArray(pa.chunked_array([ids]))),
                           "score": q_host["lex"].array})

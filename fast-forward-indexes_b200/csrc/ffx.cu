@@ -1728,4 +1728,31 @@ int ffx_merge_topk(int device, const float *shard_scores, const int32_t *shard_p
     return FFX_OK;
 }
 
+
+int ffx_merge_topk_host(ffx_index *idx, const float *shard_scores, const int32_t *shard_pos, int n_shards,
+                        int64_t nq, int k, float *out_score, int32_t *out_pos) {
+    if (!idx) return fail(FFX_ERR_INVALID, "ffx_merge_topk_host: NULL index");
+    if (n_shards <= 0 || nq < 0 || k <= 0 || !shard_scores || !shard_pos || !out_score || !out_pos)
+        return fail(FFX_ERR_INVALID, "ffx_merge_topk_host: bad arguments");
+    if (nq == 0) return FFX_OK;
+    FFX_TRY(bind(idx));
+    auto pad = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+    const size_t b_in = pad(static_cast<size_t>(n_shards) * nq * k * 4), b_out = pad(static_cast<size_t>(nq) * k * 4);
+    FFX_TRY(scratch_reserve(idx->hostio, 2 * b_in + 2 * b_out));
+    char *p = static_cast<char *>(idx->hostio.p);
+    float *d_s = reinterpret_cast<float *>(p);
+    int32_t *d_p = reinterpret_cast<int32_t *>(p + b_in);
+    float *d_os = reinterpret_cast<float *>(p + 2 * b_in);
+    int32_t *d_op = reinterpret_cast<int32_t *>(p + 2 * b_in + b_out);
+    cudaStream_t st = idx->stream;
+    const size_t in_bytes = static_cast<size_t>(n_shards) * nq * k * 4, out_bytes = static_cast<size_t>(nq) * k * 4;
+    FFX_CUDA(cudaMemcpyAsync(d_s, shard_scores, in_bytes, cudaMemcpyHostToDevice, st));
+    FFX_CUDA(cudaMemcpyAsync(d_p, shard_pos, in_bytes, cudaMemcpyHostToDevice, st));
+    FFX_TRY(ffx_merge_topk(idx->device, d_s, d_p, n_shards, nq, k, d_os, d_op, st));
+    FFX_CUDA(cudaMemcpyAsync(out_score, d_os, out_bytes, cudaMemcpyDeviceToHost, st));
+    FFX_CUDA(cudaMemcpyAsync(out_pos, d_op, out_bytes, cudaMemcpyDeviceToHost, st));
+    FFX_CUDA(cudaStreamSynchronize(st));
+    return FFX_OK;
+}
+
 }  // extern "C"

@@ -48,6 +48,7 @@ SYMBOLS = {
     "ffx_interpolate_topk": (_I, [_P, _P, _P, _L, _P, _D, _I, _L, _P, _P, _P, _P]),
     "ffx_interpolate_topk_host": (_I, [_P, _P, _P, _L, _P, _D, _I, _P, _P, _P]),
     "ffx_merge_topk": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _P]),
+    "ffx_merge_topk_host": (_I, [_P, _P, _P, _I, _L, _I, _P, _P]),
     "ffx_launch_count": (_L, []),
     "ffx_last_kernel": (C.c_char_p, []),
     "ffx_fixed_width_to_arrow": (_I, [_P, _L, _I, _P, _P, _P, C.POINTER(_L)]),
@@ -404,6 +405,17 @@ class DeviceIndex:
         check(lib().ffx_interpolate_topk_host(self.handle, _ptr(lex), _ptr(ff), nq, _ptr(q_off),
                                               float(alpha), int(k), _ptr(it), _ptr(ts), _ptr(tp)))
         return out
+
+    def merge_topk_host(self, shard_scores, shard_pos):
+        """ffx_merge_topk_host: [S, nq, k] per-shard lists (positions in the full candidate blocks)
+        -> the merged [nq, k] lists."""
+        shard_scores = _arr(shard_scores, np.float32)
+        shard_pos = _arr(shard_pos, np.int32)
+        S, nq, k = shard_scores.shape
+        out_s, out_p = np.empty((nq, k), np.float32), np.empty((nq, k), np.int32)
+        check(lib().ffx_merge_topk_host(self.handle, _ptr(shard_scores), _ptr(shard_pos), S, nq, k, _ptr(out_s),
+                                        _ptr(out_p)))
+        return out_s, out_p
 
     def rerank_device(self, mode, qvecs_ptr, nq, q_off_ptr, cand_ptr, lex_ptr, alpha, k, max_cand,
                       out_ff_ptr=0, out_int_ptr=0, topk_score_ptr=0, topk_pos_ptr=0, stream=0):

@@ -190,6 +190,15 @@ class Index(abc.ABC):
         """The libffx index holding this index's rows in HBM, maps synchronised."""
 
     @abc.abstractmethod
+    def _score(self, mode: Mode, qv, q_off, cand, lex=None, alpha: float = 0.0, k: int = 0, want_ff: bool = True,
+               out: dict | None = None) -> dict:
+        """ffx_rerank_host over the index's device(s): ff [n] and / or topk_score, topk_pos [nq, k]."""
+
+    @abc.abstractmethod
+    def _early_stop(self, mode: Mode, qv, q_off, cand, lex, alpha, cutoff, depths) -> dict:
+        """ffx_rerank_early_stop_host over the index's device(s)."""
+
+    @abc.abstractmethod
     def _candidates(self, cols, mode: Mode) -> np.ndarray:
         """int32 candidate per row of an integer-coded ranking (`fast_forward._cols.Cols`), cached
         on the columns; IndexError names the first unknown id (index/util.py:38-39)."""
@@ -232,8 +241,7 @@ class Index(abc.ABC):
         cand = self._resolve(id_values, mode)  # every pair's id, coded in C++ on all host cores
         q_off = np.zeros(qv.shape[0] + 1, np.int64)
         np.cumsum(np.bincount(q_no, minlength=qv.shape[0]), out=q_off[1:])
-        out = self._device().rerank_host(mode.value, qv, q_off, cand, lex, alpha, k,
-                                         want_ff=want_ff, want_int=False)
+        out = self._score(mode, qv, q_off, cand, lex, alpha, k, want_ff=want_ff)
         return out, q_off
 
     def _launch_cols(self, cols, mode: Mode, query_vectors: np.ndarray, lo: int, hi: int, alpha: float = 0.0,
@@ -253,9 +261,8 @@ class Index(abc.ABC):
         if k > 0:
             out["topk_score"] = _ffx.pinned_empty((hi - lo, k), np.float32)
             out["topk_pos"] = _ffx.pinned_empty((hi - lo, k), np.int32)
-        self._device().rerank_host(mode.value, qv, q_off, cand[r0:r1], cols.score[r0:r1] if interpolate else None,
-                                   alpha, k, want_ff=want_ff, want_int=False, out=out)
-        return out
+        return self._score(mode, qv, q_off, cand[r0:r1], cols.score[r0:r1] if interpolate else None, alpha, k,
+                           want_ff=want_ff, out=out)
 
     def _compute_scores(self, data: pd.DataFrame, query_vectors: np.ndarray) -> pd.DataFrame:
         """Semantic scores for the (id, q_no) rows of `data` (index/base.py:279-314).
@@ -304,14 +311,13 @@ class Index(abc.ABC):
         depth_of_row = np.arange(n) - np.repeat(start, count)
         slot_of_row = np.repeat(np.arange(len(present)), count)
 
-        dev = self._device()
         on_device = int(count.max()) <= 16384 and len({d for d in depths if d >= cutoff}) <= 32
         qv = np.ascontiguousarray(query_vectors, dtype=np.float32)[present]
         cand = self._resolve(df["id"], self.mode)  # every id coded once, whatever the number of depths
         if on_device:
             q_off = np.concatenate([[0], np.cumsum(count)]).astype(np.int64)
             try:
-                out = dev.rerank_early_stop_host(self.mode.value, qv, q_off, cand, lex, alpha, cutoff, depths)
+                out = self._early_stop(self.mode, qv, q_off, cand, lex, alpha, cutoff, depths)
             except _ffx.FFXError as e:
                 if e.code != -5:  # FFX_ERR_UNSUPPORTED: beyond the device walk's limits
                     raise
@@ -358,8 +364,7 @@ class Index(abc.ABC):
                 break
             taken = np.flatnonzero(take)
             part_off = np.concatenate([[0], np.cumsum(np.bincount(slot_of_row[taken], minlength=len(start)))])
-            ff[taken] = self._device().rerank_host(self.mode.value, qv, part_off.astype(np.int64), cand[taken],
-                                                   want_ff=True)["ff"]
+            ff[taken] = self._score(self.mode, qv, part_off.astype(np.int64), cand[taken])["ff"]
             done_depth[active] = np.minimum(count[active], hi)
             lo = hi
         return ff, done_depth

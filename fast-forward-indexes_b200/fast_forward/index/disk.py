@@ -26,7 +26,7 @@ import numpy as np
 import fast_forward
 from fast_forward import _ffx, _h5, _h5_write
 from fast_forward.encoder.base import Encoder
-from fast_forward.index._store import RowStore
+from fast_forward.index._store import RowStore, make_store
 from fast_forward.index.base import IDSequence, Index, Mode
 from fast_forward.index.memory import InMemoryIndex
 from fast_forward.quantizer import Quantizer
@@ -79,12 +79,13 @@ class OnDiskIndex(Index):
                  quantizer: Quantizer | None = None, mode: Mode = Mode.MAXP,
                  encoder_batch_size: int = 32, init_size: int = 2**16, chunk_size: int = 2**16,
                  max_id_length: int = 8, overwrite: bool = False, memory_mapped: bool = False,
-                 max_indexing_size: int = 2**10, device: int = 0) -> None:
-        """Create (or overwrite) an index file.  ValueError if it exists and `overwrite=False`."""
+                 max_indexing_size: int = 2**10, device: int = 0, devices=None, shard: str = "query") -> None:
+        """Create (or overwrite) an index file.  ValueError if it exists and `overwrite=False`.
+        `devices` / `shard`: as `InMemoryIndex` (several GPUs driven by this process)."""
         if index_file.exists() and not overwrite:
             raise ValueError(f"File {index_file} exists.")
         self._index_file = index_file.absolute()
-        self._store = RowStore(device)
+        self._store = make_store(device, devices, shard)
         self._init_size = init_size
         self._chunk_size = chunk_size
         self._max_id_length = max_id_length
@@ -215,6 +216,12 @@ class OnDiskIndex(Index):
     def _device(self) -> _ffx.DeviceIndex:
         return self._store.device_index(self.quantizer)
 
+    def _score(self, mode: Mode, qv, q_off, cand, lex=None, alpha=0.0, k=0, want_ff=True, out=None) -> dict:
+        return self._store.score(self.quantizer, mode.value, qv, q_off, cand, lex, alpha, k, want_ff, out)
+
+    def _early_stop(self, mode: Mode, qv, q_off, cand, lex, alpha, cutoff, depths) -> dict:
+        return self._store.early_stop(self.quantizer, mode.value, qv, q_off, cand, lex, alpha, cutoff, depths)
+
     def _candidates(self, cols, mode: Mode) -> np.ndarray:
         return cols.candidates(self._store, mode == Mode.PASSAGE)
 
@@ -226,7 +233,9 @@ class OnDiskIndex(Index):
         """An `InMemoryIndex` with the same contents (disk.py:177-205)."""
         index = InMemoryIndex(query_encoder=self._query_encoder, quantizer=self._quantizer,
                               mode=self.mode, encoder_batch_size=self._encoder_batch_size,
-                              init_size=max(len(self), 1), device=self._store.device)
+                              init_size=max(len(self), 1), device=self._store.device,
+                              devices=getattr(self._store, "devices", None),
+                              shard="doc" if hasattr(self._store, "shards") else "query")
         for rows, doc_ids, psg_ids in self._batch_iter(batch_size or max(self._store.count, 1)):
             index._add(rows, doc_ids=doc_ids, psg_ids=psg_ids)
         return index
@@ -234,14 +243,16 @@ class OnDiskIndex(Index):
     @classmethod
     def load(cls, index_file: Path, query_encoder: Encoder | None = None, mode: Mode = Mode.MAXP,
              encoder_batch_size: int = 32, memory_mapped: bool = False,
-             max_indexing_size: int = 2**10, device: int = 0) -> "OnDiskIndex":
-        """Open an existing index file and stage it into GPU memory (disk.py:355-418)."""
+             max_indexing_size: int = 2**10, device: int = 0, devices=None, shard: str = "query") -> "OnDiskIndex":
+        """Open an existing index file and stage it into GPU memory (disk.py:355-418).
+        `devices` / `shard`: as `InMemoryIndex` — `shard="query"` stages a replica on every device,
+        `shard="doc"` spreads the documents over the devices (files larger than one GPU)."""
         LOGGER.debug("reading file %s", index_file)
         index = cls.__new__(cls)
         Index.__init__(index, query_encoder=query_encoder, quantizer=None, mode=mode,
                        encoder_batch_size=encoder_batch_size)
         index._index_file = index_file.absolute()
-        index._store = RowStore(device)
+        index._store = make_store(device, devices, shard)
         index._memory_mapped = memory_mapped
         index._max_indexing_size = max_indexing_size
 
@@ -263,9 +274,14 @@ class OnDiskIndex(Index):
 
             # one HDF5 chunk (a contiguous byte range of the file) per staging step, read in place
             codes = index._quantizer is not None and meta["dtype"] == np.uint8
-            for _, block in fp.spans("vectors", 0, total):
+            by_ids = hasattr(index._store, "shards")  # doc shards place every row by its ids
+            if by_ids:
+                doc_col, psg_col = _text_ids(fp.read("doc_ids", 0, total)), _text_ids(fp.read("psg_ids", 0, total))
+            for row0, block in fp.spans("vectors", 0, total):
                 rows = block if codes or block.dtype == np.float32 else block.astype(np.float32)
-                index._store.append(rows, None, None, first_capacity=total, grow_by=index._chunk_size)
+                ids = (doc_col.slice(row0, len(rows)), psg_col.slice(row0, len(rows))) if by_ids else (None, None)
+                index._store.append(rows, ids[0], ids[1], first_capacity=total, grow_by=index._chunk_size)
             # the O(N) Python loop of disk.py:408-417, as two calls into the C++ id dictionaries
-            index._store.adopt_id_columns(_text_ids(fp.read("doc_ids", 0, total)), _text_ids(fp.read("psg_ids", 0, total)))
+            if not by_ids:
+                index._store.adopt_id_columns(_text_ids(fp.read("doc_ids", 0, total)), _text_ids(fp.read("psg_ids", 0, total)))
         return index

@@ -5,13 +5,13 @@ row store and never copied back for scoring."""
 from __future__ import annotations
 
 import logging
-from collections.abc import Iterable, Iterator
+from collections.abc import Iterable, Iterator, Sequence
 
 import numpy as np
 
 from fast_forward import _ffx
 from fast_forward.encoder.base import Encoder
-from fast_forward.index._store import RowStore
+from fast_forward.index._store import RowStore, make_store
 from fast_forward.index.base import IDSequence, Index, Mode
 from fast_forward.quantizer import Quantizer
 
@@ -23,10 +23,16 @@ class InMemoryIndex(Index):
 
     def __init__(self, query_encoder: Encoder | None = None, quantizer: Quantizer | None = None,
                  mode: Mode = Mode.MAXP, encoder_batch_size: int = 32, init_size: int = 2**16,
-                 alloc_size: int = 2**16, device: int = 0) -> None:
+                 alloc_size: int = 2**16, device: int = 0, devices: Sequence[int] | None = None,
+                 shard: str = "query") -> None:
         """:param init_size: rows allocated up front. :param alloc_size: granularity of later
-        growth (rows). :param device: CUDA device ordinal.  Other parameters as `Index`."""
-        self._store = RowStore(device)
+        growth (rows). :param device: CUDA device ordinal.
+        :param devices: several CUDA devices driven by this process (not in the reference, which is
+            single-process CPU code): with `shard="query"` every device holds a replica of the rows
+            and each call splits its queries over them; with `shard="doc"` the documents are spread
+            over the devices (a corpus larger than one GPU) and every device scores its part of
+            every query.  Results are identical to one device's.  Other parameters as `Index`."""
+        self._store = make_store(device, devices, shard)
         self._init_size = init_size
         self._alloc_size = alloc_size
         super().__init__(query_encoder=query_encoder, quantizer=quantizer, mode=mode,
@@ -42,6 +48,16 @@ class InMemoryIndex(Index):
         store = index._store
         store.dev = device_index
         store.count = len(device_index)
+        store.record_ids(doc_ids, psg_ids, 0, store.count)
+        return index
+
+    @classmethod
+    def _adopt_replicas(cls, device_indexes, doc_ids=None, psg_ids=None, **kwargs) -> "InMemoryIndex":
+        """`_adopt` for identical row stores on several devices (`devices=[...]`, `shard="query"`)."""
+        index = cls(devices=[d.device for d in device_indexes], shard="query", **kwargs)
+        store = index._store
+        store.dev, store.replicas = device_indexes[0], list(device_indexes[1:])
+        store.count = len(device_indexes[0])
         store.record_ids(doc_ids, psg_ids, 0, store.count)
         return index
 
@@ -86,6 +102,12 @@ class InMemoryIndex(Index):
 
     def _device(self) -> _ffx.DeviceIndex:
         return self._store.device_index(self.quantizer)
+
+    def _score(self, mode: Mode, qv, q_off, cand, lex=None, alpha=0.0, k=0, want_ff=True, out=None) -> dict:
+        return self._store.score(self.quantizer, mode.value, qv, q_off, cand, lex, alpha, k, want_ff, out)
+
+    def _early_stop(self, mode: Mode, qv, q_off, cand, lex, alpha, cutoff, depths) -> dict:
+        return self._store.early_stop(self.quantizer, mode.value, qv, q_off, cand, lex, alpha, cutoff, depths)
 
     def _candidates(self, cols, mode: Mode) -> np.ndarray:
         return cols.candidates(self._store, mode == Mode.PASSAGE)

@@ -64,6 +64,7 @@ class ShardedReranker:
         # bench.py sets this to a list: every rerank() then appends the CUDA events
         # (start, local kernel done, exchange / barrier done, merge done) of its three phases
         self.trace = None
+        self._io = None  # copy streams of rerank_host
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if index is not None:
@@ -134,8 +135,10 @@ class ShardedReranker:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
 
-        if self._p2p_sets is not None and self._p2p_sets[0] == (nq, k):
-            return self._p2p_sets[1]
+        if self._p2p_sets is None:
+            self._p2p_sets = {}
+        if (nq, k) in self._p2p_sets:
+            return self._p2p_sets[(nq, k)]
         bounds = self.owner_bounds(nq)
         cap = max(bounds[r + 1] - bounds[r] for r in range(self.world))
         group = self.group if self.group is not None else dist.group.WORLD
@@ -145,7 +148,7 @@ class ShardedReranker:
             pos = symm.empty((self.world, cap, k), dtype=torch.int32, device=device)
             hs, hp = symm.rendezvous(score, group), symm.rendezvous(pos, group)
             sets.append({"score": score, "pos": pos, "hs": hs, "hp": hp, "cap": cap, "bounds": bounds})
-        self._p2p_sets = ((nq, k), sets)
+        self._p2p_sets[(nq, k)] = sets
         return sets
 
     def _rerank_p2p(self, mode, qvecs, q_off, cand, lex, alpha, k, max_cand, stream):
@@ -186,7 +189,7 @@ class ShardedReranker:
         stream = torch.cuda.current_stream().cuda_stream if qvecs.is_cuda else 0
         nq = qvecs.shape[0]
         bounds = self.owner_bounds(nq)
-        if self.world > 1 and self.p2p and self._p2p_sets is None:
+        if self.world > 1 and self.p2p and (self._p2p_sets is None or (nq, k) not in self._p2p_sets):
             try:  # collective set-up: it fails on every rank or on none
                 self._p2p_buffers(nq, k, qvecs.device)
             except Exception as e:  # no peer access between the GPUs: say so, use NCCL
@@ -221,6 +224,72 @@ class ShardedReranker:
             dist.all_gather(list(everyone.unbind(0)), padded, group=self.group)
             out.append(torch.cat([everyone[r, :bounds[r + 1] - bounds[r]] for r in range(self.world)]))
         return out[0], out[1]
+
+    def rerank_host(self, mode: int, qvecs, q_off, cand, lex, alpha: float, k: int, max_cand: int,
+                    chunk_queries: int = 0):
+        """`rerank(..., gather_result=False)` from HOST inputs (torch CPU tensors, ideally pinned;
+        identical on all ranks), pipelined: the job is cut into chunks of `chunk_queries` queries
+        (default: 8 chunks); while chunk i is scored and exchanged, chunk i+1 crosses PCIe on a copy
+        stream and the merged lists of chunk i-1 go back on another.  Returns host tensors
+        `(query index [m], score [m, k], position [m, k])`: the queries this rank owns (every
+        chunk is split over the ranks by `owner_bounds`) and their merged lists."""
+        import torch
+
+        dev = torch.device("cuda", self.index.device)
+        nq = qvecs.shape[0]
+        step = int(chunk_queries) if chunk_queries else -(-nq // 8)
+        step = max(1, min(step, nq))
+        chunks = [(lo, min(nq, lo + step)) for lo in range(0, nq, step)]
+        if len(chunks) > 1 and chunks[-1][1] - chunks[-1][0] < step // 2:  # a short tail rides with the last chunk
+            chunks[-2:] = [(chunks[-2][0], nq)]
+        main = torch.cuda.current_stream(dev)
+        if self._io is None:
+            self._io = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        h2d, d2h = self._io
+        q_off_cpu = q_off if not q_off.is_cuda else q_off.cpu()
+        starts = q_off_cpu[[lo for lo, _ in chunks] + [nq]].tolist()
+        widest_rows = max(starts[i + 1] - starts[i] for i in range(len(chunks)))
+        widest_q = max(hi - lo for lo, hi in chunks)
+        # two sets of device buffers alternate between chunks
+        bufs = [{"qv": torch.empty((widest_q, qvecs.shape[1]), dtype=torch.float32, device=dev),
+                 "off": torch.empty(widest_q + 1, dtype=torch.int64, device=dev),
+                 "cand": torch.empty(widest_rows, dtype=torch.int32, device=dev),
+                 "lex": torch.empty(widest_rows, dtype=torch.float32, device=dev) if lex is not None else None,
+                 "free": torch.cuda.Event(), "ready": torch.cuda.Event()} for _ in range(2)]
+        results = []
+        for i, (lo, hi) in enumerate(chunks):
+            b = bufs[i & 1]
+            r0, r1 = starts[i], starts[i + 1]
+            with torch.cuda.stream(h2d):
+                if i >= 2:
+                    h2d.wait_event(b["free"])  # the chunk that used this buffer set has been scored
+                b["qv"][:hi - lo].copy_(qvecs[lo:hi], non_blocking=True)
+                b["off"][:hi - lo + 1].copy_(q_off_cpu[lo:hi + 1] - r0, non_blocking=True)
+                b["cand"][:r1 - r0].copy_(cand[r0:r1], non_blocking=True)
+                if lex is not None:
+                    b["lex"][:r1 - r0].copy_(lex[r0:r1], non_blocking=True)
+                b["ready"].record(h2d)
+            main.wait_event(b["ready"])
+            s, p = self.rerank(mode, b["qv"][:hi - lo], b["off"][:hi - lo + 1], b["cand"][:r1 - r0],
+                               b["lex"][:r1 - r0] if lex is not None else None, alpha, k, max_cand, gather_result=False)
+            b["free"].record(main)
+            done = torch.cuda.Event()
+            done.record(main)
+            bounds = self.owner_bounds(hi - lo)
+            mine = torch.arange(lo + bounds[self.rank], lo + bounds[self.rank + 1])
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                hs = torch.empty(s.shape, dtype=s.dtype, pin_memory=True)
+                hp = torch.empty(p.shape, dtype=p.dtype, pin_memory=True)
+                hs.copy_(s, non_blocking=True)
+                hp.copy_(p, non_blocking=True)
+                s.record_stream(d2h)
+                p.record_stream(d2h)
+            results.append((mine, hs, hp))
+        d2h.synchronize()
+        main.synchronize()
+        return (torch.cat([r[0] for r in results]), torch.cat([r[1] for r in results]),
+                torch.cat([r[2] for r in results]))
 
     def scores(self, mode: int, qvecs, q_off, cand, max_cand: int):
         """Semantic score of EVERY pair on every rank (plain `Index.__call__` over a sharded

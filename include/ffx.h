@@ -318,6 +318,11 @@ int ffx_interpolate_topk_host(ffx_index *idx, const float *lex, const float *ff,
 int ffx_merge_topk(int device, const float *shard_scores, const int32_t *shard_pos, int n_shards,
                    int64_t nq, int k, float *out_score, int32_t *out_pos, void *stream);
 
+/* The same merge from HOST buffers (one process driving several GPUs: the per-device lists come
+ * back through ffx_rerank_host); `idx` provides the device, stream and scratch.  Synchronises. */
+int ffx_merge_topk_host(ffx_index *idx, const float *shard_scores, const int32_t *shard_pos, int n_shards,
+                        int64_t nq, int k, float *out_score, int32_t *out_pos);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t ffx_launch_count(void);
 /* Demangled symbol of the scoring kernel (fp32 gather-dot or ADC) launched last by this process,
