@@ -48,10 +48,9 @@ def corpus(rng, n_docs, dim, max_psg=6):
     # some rows carry only one kind of id (reference tests/test_index.py:58-69)
     for i in range(0, len(vec), 17):
         psg_ids[i] = None
-    seen = set()
     for i in range(5, len(vec), 23):
-        if doc_ids[i] in seen or sum(1 for d in doc_ids if d == doc_ids[i]) > 1:
-            doc_ids[i] = None if psg_ids[i] is not None else doc_ids[i]
+        if psg_ids[i] is not None:
+            doc_ids[i] = None
     return vec, doc_ids, psg_ids
 
 
