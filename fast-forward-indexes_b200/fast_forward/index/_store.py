@@ -344,7 +344,7 @@ class DocShardedStore(RowStore):
 
         self.devices = list(devices)
         n = len(devices)
-        self.stride = (1 << 31) // n
+        self.stride = ((1 << 31) - 1) // n  # device * stride + local stays a non-negative int32
         self.shards: list[_ffx.DeviceIndex | None] = [None] * n
         self.loads = np.zeros(n, np.int64)       # rows per shard
         self.local_docs = np.zeros(n, np.int64)  # documents per shard

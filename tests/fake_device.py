@@ -44,6 +44,9 @@ class FakeDeviceIndex:
         self.doc_rows = np.arange(self.off[-1]) if doc_rows is None else np.asarray(doc_rows, np.int64)
 
     def set_shard(self, doc_base=0, global_docs=0, row_base=0, global_rows=0):
+        # the limits ffx_index_set_shard enforces
+        assert global_docs <= 0x7fffffff and global_rows <= 0xffffffff
+        assert doc_base + (len(self.off) - 1 if self.off is not None else 0) <= global_docs and row_base + self.n <= global_rows
         self.shard = (doc_base, global_docs, row_base, global_rows)
 
     def set_pq(self, codewords, R=None):
