@@ -799,30 +799,32 @@ def run_api(ctx, args, wl, m, q_host, alpha, k):
 
     sys.path.insert(0, PKG)
     import fast_forward
-    from fast_forward.encoder import LambdaEncoder
+    from fast_forward.encoder import TableEncoder
     from fast_forward.index import InMemoryIndex, Mode
 
     nq, cands = len(q_host["qv"].array), wl["cands"]
     qv = q_host["qv"].array
     t0 = time.perf_counter()
-    text_to_row = {f"text {i}": i for i in range(nq)}
-    enc = LambdaEncoder(lambda text: qv[text_to_row[text]])
+    enc = TableEncoder({f"text {i}": qv[i] for i in range(nq)})
     doc_ids = pc.binary_join_element_wise(pa.scalar("D", pa.large_string()), pa.array(np.repeat(np.arange(m["n_docs"]), m["cnt"])).cast(
         pa.large_string()), pa.scalar("", pa.large_string()))
-    index = InMemoryIndex._adopt(m["idx"], doc_ids=doc_ids, query_encoder=enc, mode=Mode[wl["mode"]])
+    index = InMemoryIndex._adopt(m["idx"], doc_ids=doc_ids, query_encoder=enc, mode=Mode[wl["mode"]],
+                                 encoder_batch_size=1024)
+    index._device()  # document id -> rows table pushed to the device (once per index)
     t_index = time.perf_counter() - t0
     t0 = time.perf_counter()
     ids = pc.binary_join_element_wise(pa.scalar("D", pa.large_string()), pa.array(q_host["cand"].array).cast(pa.large_string()), pa.scalar("", pa.large_string()))
     q_ids = pc.binary_join_element_wise(pa.scalar("q", pa.large_string()), pa.array(np.repeat(np.arange(nq), cands)).cast(
         pa.large_string()), pa.scalar("", pa.large_string()))
-    frame = pd.DataFrame({"q_id": pd.Series(pd.arrays.ArrowStringArray(pa.chunked_array([q_ids]))),
-                          "id": pd.Series(pd.arrays.ArrowStringArray(pa.chunked_array([ids]))),
+    str_dtype = pd.StringDtype("pyarrow", na_value=np.nan)  # pandas' `str`
+    frame = pd.DataFrame({"q_id": pd.Series(pd.arrays.ArrowStringArray(pa.chunked_array([q_ids]), dtype=str_dtype)),
+                          "id": pd.Series(pd.arrays.ArrowStringArray(pa.chunked_array([ids]), dtype=str_dtype)),
                           "score": q_host["lex"].array})
     first = fast_forward.Ranking(frame, queries={f"q{i}": f"text {i}" for i in range(nq)})
     t_ranking = time.perf_counter() - t0
     times = []
     out = None
-    for _ in range(3):
+    for _ in range(6):
         t0 = time.perf_counter()
         out = index.rerank(first, alpha, k)
         n_out = out.num_rows
@@ -833,8 +835,8 @@ def run_api(ctx, args, wl, m, q_host, alpha, k):
     t_frame = time.perf_counter() - t0
     assert len(df) == n_out
     pairs = nq * cands
-    return {"value": pairs / min(times[1:]), "unit": "pairs/s", "first_call_s": times[0], "second_call_s": times[1],
-            "third_call_s": times[2], "result_frame_s": t_frame, "build_index_ids_s": t_index,
+    return {"value": pairs / times[1], "unit": "pairs/s", "first_call_s": times[0], "second_call_s": times[1],
+            "later_calls_s": times[2:], "result_frame_s": t_frame, "build_index_ids_s": t_index,
             "build_first_stage_ranking_s": t_ranking,
             "call": "Ranking(q_id / id strings, float32 scores, queries attached) -> index.rerank(ranking, alpha, "
                     f"{k}) -> Ranking; query encoder = table look-up of the precomputed vectors",

@@ -26,6 +26,7 @@
 #include "ffx_pq_build.cuh"
 #include "ffx_kernels.cuh"
 #include "ffx_score_tma.cuh"
+#include "ffx_score_any.cuh"
 #include "ffx_layout.h"
 
 namespace {
@@ -117,7 +118,9 @@ struct ffx_index {
     int64_t capacity = 0;
     int64_t num_rows = 0;
     ffx_plan plan{0, 0, 32};
-    size_t row_bytes = 0;
+    ffx_any_plan any{};   // fp32 rows of a dimension without a lane-major plan: the numpy tree as data
+    size_t row_bytes = 0; // bytes per STORED row (fp32 rows of the any-plan are padded to 16 bytes)
+    size_t src_row_bytes = 0;  // bytes per row as callers pass / receive them
     void *store = nullptr;
     int sm_count = 148;
 
@@ -191,11 +194,17 @@ int settle(ffx_index *idx) {
     return FFX_OK;
 }
 
+// rows change shape between the caller's buffers and the store: lane-major permutation, or
+// padding of the row stride to 16 bytes (any-plan dimensions that are not a multiple of 4)
+bool transforms_rows(const ffx_index *idx) {
+    return idx->row_kind == FFX_ROWS_F32 && (idx->plan.cpl || idx->row_bytes != idx->src_row_bytes);
+}
+
 int ensure_staging(ffx_index *idx) {
     if (idx->pinned[0]) return FFX_OK;
     for (int i = 0; i < 2; i++) {
         FFX_CUDA(cudaMallocHost(&idx->pinned[i], kStageBytes));
-        if (idx->row_kind == FFX_ROWS_F32 && idx->plan.cpl)
+        if (transforms_rows(idx))
             FFX_CUDA(cudaMalloc(&idx->landing[i], kStageBytes));
         FFX_CUDA(cudaEventCreateWithFlags(&idx->done[i], cudaEventDisableTiming));
     }
@@ -246,6 +255,12 @@ int launch_to_store(ffx_index *idx, int64_t row0, int64_t nrows, const void *src
                                        idx->stream>>>(
             reinterpret_cast<float *>(dst), static_cast<const float *>(src_dev), nrows,
             static_cast<int>(idx->dim), idx->plan.cpl, idx->plan.steps, idx->plan.lanes, 1, nullptr);
+        g_launches++;
+        FFX_CUDA(cudaGetLastError());
+    } else if (transforms_rows(idx)) {
+        ffx::ffx_pad_rows_kernel<<<permute_grid(nrows * idx->any.stride, idx->sm_count), 256, 0, idx->stream>>>(
+            reinterpret_cast<float *>(dst), static_cast<const float *>(src_dev), nrows, static_cast<int>(idx->dim),
+            idx->any.stride, 1, nullptr);
         g_launches++;
         FFX_CUDA(cudaGetLastError());
     } else {
@@ -401,6 +416,82 @@ ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, 
     return p;
 }
 
+// ---- dimensions without a lane-major plan: ffx_score_any_kernel ------------------------------
+template <int CPL, int LPR>
+int launch_score_any(const ffx::ScoreArgs &a, const ffx_any_plan &plan, bool fuse, int grid, int warps, int ns,
+                     int batch, cudaStream_t st) {
+    const size_t smem = ffx::any_smem_bytes(fuse ? a.cpad : 0, warps, ns, plan.stride * 4);
+    if (fuse) {
+        auto kern = ffx::ffx_score_any_kernel<CPL, LPR, true>;
+        FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kern<<<grid, warps * 32, smem, st>>>(a, plan, ns, batch);
+        note_kernel(kern);
+    } else {
+        auto kern = ffx::ffx_score_any_kernel<CPL, LPR, false>;
+        FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kern<<<grid, warps * 32, smem, st>>>(a, plan, ns, batch);
+        note_kernel(kern);
+    }
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
+int dispatch_score_any(const ffx_any_plan &p, const ScorePlan &sp, const ffx::ScoreArgs &a, bool fuse, int grid,
+                       cudaStream_t st) {
+#define FFX_CASE(C, L) \
+    if (p.cpl == C && p.lpr == L) return launch_score_any<C, L>(a, p, fuse, grid, sp.warps, sp.ns, sp.batch, st)
+    FFX_CASE(1, 8);
+    FFX_CASE(1, 16);
+    FFX_CASE(1, 32);
+    FFX_CASE(2, 32);
+    FFX_CASE(4, 32);
+    FFX_CASE(8, 32);
+#undef FFX_CASE
+    return fail(FFX_ERR_UNSUPPORTED, "no kernel for tree plan (%d chains per lane, %d lanes per row)", p.cpl, p.lpr);
+}
+
+// ring slots per warp for `ctas_per_sm` resident CTAs; 0 if the shape does not fit (the fused
+// top-k sorts its 64-bit keys inside the drained ring)
+int any_ring_slots(int keys, int warps, int row_bytes, int ctas_per_sm) {
+    const size_t budget = kSmemBudget / ctas_per_sm - 1024;  // static shared memory of the fused epilogue: 2.3 KB
+    const size_t fixed = ffx::any_smem_bytes(keys, warps, 0, row_bytes);
+    if (fixed >= budget) return 0;
+    int ns = static_cast<int>((budget - fixed) / (static_cast<size_t>(warps) * (row_bytes + 8)));
+    ns = std::min(ns, 32);
+    if (static_cast<size_t>(ns) * warps * row_bytes < static_cast<size_t>(keys) * 8) return 0;
+    return ns;
+}
+
+ScorePlan plan_score_any(const ffx_any_plan &p, int mode, bool fuse, int cpad, bool sparse, bool few_pairs) {
+    ScorePlan sp;
+    const int row_bytes = p.stride * 4, rps = 32 / p.lpr, keys = fuse ? cpad : 0;
+    const bool one_row = mode == FFX_MODE_PASSAGE || mode == FFX_MODE_FIRSTP;
+    sp.batch = g_tune.batch > 0 ? std::min(32, g_tune.batch) : (one_row || sparse ? 32 : 16);
+    const int need = 2 * rps;  // a warp step consumes `rps` slots while the next ones load
+    const int want = row_bytes >= 2048 ? 6 : (row_bytes >= 1024 ? 8 : 16);
+    if (fuse) {
+        // two CTAs per SM where the keys leave room, else one large CTA
+        sp.warps = 8;
+        sp.ns = std::min(want, any_ring_slots(keys, 8, row_bytes, 2));
+        if (sp.ns < need) {
+            for (sp.warps = 16; sp.warps >= 4; sp.warps -= 4) {
+                sp.ns = std::min(want, any_ring_slots(keys, sp.warps, row_bytes, 1));
+                if (sp.ns >= need) break;
+            }
+        }
+    } else {
+        sp.warps = few_pairs ? 2 : 4;
+        if (few_pairs && g_tune.batch <= 0) sp.batch = 8;
+        sp.ns = std::min(want, any_ring_slots(0, sp.warps, row_bytes, 4));
+        if (sp.ns < need) sp.ns = std::min(want, any_ring_slots(0, sp.warps, row_bytes, 1));
+    }
+    if (g_tune.tma_stages > 0) sp.ns = std::max(need, std::min(sp.ns, g_tune.tma_stages));
+    if (g_tune.tma_warps > 0 && any_ring_slots(keys, g_tune.tma_warps, row_bytes, 1) >= sp.ns) sp.warps = g_tune.tma_warps;
+    sp.tma = sp.ns >= need && sp.warps >= 1;
+    return sp;
+}
+
 int dispatch_score(const ffx_plan &p, const ScorePlan &sp, const ffx::ScoreArgs &a, bool fuse, int grid,
                    cudaStream_t st) {
     if (sp.tma) {
@@ -456,7 +547,7 @@ bool will_fuse(const ffx_index *idx, int64_t nq, int k, int cpad) {
                    static_cast<size_t>(cpad) * 8 <= ffx::adc_xor_smem_bytes(idx->M, idx->Ks, 0) - 128;
         return ffx::adc_warp_smem_bytes(idx->Ks, cpad) <= kSmemBudget;
     }
-    return idx->plan.cpl != 0 && nq >= static_cast<int64_t>(idx->sm_count) * 2;
+    return (idx->plan.cpl != 0 || idx->any.valid) && nq >= static_cast<int64_t>(idx->sm_count) * 2;
 }
 
 template <int NC>
@@ -646,9 +737,14 @@ int ffx_index_create(int device, int row_kind, int64_t dim, int64_t capacity_row
     if (row_kind == FFX_ROWS_F32) {
         idx->plan = ffx_plan_for_dim(dim);
         idx->row_bytes = static_cast<size_t>(dim) * 4;
+        if (!idx->plan.cpl) {
+            idx->any = ffx_any_plan_for_dim(dim);
+            if (idx->any.valid) idx->row_bytes = static_cast<size_t>(idx->any.stride) * 4;
+        }
     } else {
         idx->row_bytes = static_cast<size_t>(dim);
     }
+    idx->src_row_bytes = static_cast<size_t>(dim) * (row_kind == FFX_ROWS_F32 ? 4 : 1);
     cudaDeviceGetAttribute(&idx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -749,13 +845,13 @@ int ffx_index_stage_rows(ffx_index *idx, int64_t row0, int64_t nrows, const void
         const int64_t rows_per_buf = std::max<int64_t>(1, kStageBytes / static_cast<int64_t>(idx->row_bytes));
         if (static_cast<int64_t>(idx->row_bytes) > kStageBytes)
             return fail(FFX_ERR_UNSUPPORTED, "row of %zu bytes exceeds the staging buffer", idx->row_bytes);
-        const bool permute = idx->row_kind == FFX_ROWS_F32 && idx->plan.cpl;
+        const bool permute = transforms_rows(idx);
         int b = 0;
         for (int64_t r = 0; r < nrows; r += rows_per_buf, b ^= 1) {
             const int64_t nr = std::min(rows_per_buf, nrows - r);
-            const size_t bytes = static_cast<size_t>(nr) * idx->row_bytes;
+            const size_t bytes = static_cast<size_t>(nr) * idx->src_row_bytes;
             FFX_CUDA(cudaEventSynchronize(idx->done[b]));  // buffer b free again
-            parallel_memcpy(idx->pinned[b], static_cast<const char *>(rows) + static_cast<size_t>(r) * idx->row_bytes, bytes);
+            parallel_memcpy(idx->pinned[b], static_cast<const char *>(rows) + static_cast<size_t>(r) * idx->src_row_bytes, bytes);
             if (permute) {
                 FFX_CUDA(cudaMemcpyAsync(idx->landing[b], idx->pinned[b], bytes,
                                          cudaMemcpyHostToDevice, idx->stream));
@@ -789,13 +885,18 @@ int ffx_index_read_rows(ffx_index *idx, const int64_t *rows, int64_t n, void *ou
     const size_t chunk_rows = static_cast<size_t>(std::min(per, n));
     const size_t ids_bytes = (chunk_rows * 8 + 255) & ~static_cast<size_t>(255);
     FFX_TRY(scratch_reserve(idx->work, ids_bytes + chunk_rows * idx->row_bytes));
+    const bool padded = idx->row_kind == FFX_ROWS_F32 && !idx->plan.cpl && idx->row_bytes != idx->src_row_bytes;
     int64_t *d_rows = static_cast<int64_t *>(idx->work.p);
     char *d_out = static_cast<char *>(idx->work.p) + ids_bytes;
     for (int64_t r = 0; r < n; r += per) {
         const int64_t nr = std::min(per, n - r);
         FFX_CUDA(cudaMemcpyAsync(d_rows, rows + r, static_cast<size_t>(nr) * 8,
                                  cudaMemcpyHostToDevice, idx->stream));
-        if (idx->row_kind == FFX_ROWS_F32) {
+        if (padded) {
+            ffx::ffx_pad_rows_kernel<<<permute_grid(nr * idx->any.stride, idx->sm_count), 256, 0, idx->stream>>>(
+                reinterpret_cast<float *>(d_out), static_cast<const float *>(idx->store), nr, static_cast<int>(idx->dim),
+                idx->any.stride, 0, d_rows);
+        } else if (idx->row_kind == FFX_ROWS_F32) {
             ffx::ffx_permute_rows_kernel<<<permute_grid(nr * idx->dim, idx->sm_count), 256, 0,
                                            idx->stream>>>(
                 reinterpret_cast<float *>(d_out), static_cast<const float *>(idx->store), nr,
@@ -808,8 +909,8 @@ int ffx_index_read_rows(ffx_index *idx, const int64_t *rows, int64_t n, void *ou
         }
         g_launches++;
         FFX_CUDA(cudaGetLastError());
-        FFX_CUDA(cudaMemcpyAsync(static_cast<char *>(out) + static_cast<size_t>(r) * idx->row_bytes,
-                                 d_out, static_cast<size_t>(nr) * idx->row_bytes,
+        FFX_CUDA(cudaMemcpyAsync(static_cast<char *>(out) + static_cast<size_t>(r) * idx->src_row_bytes,
+                                 d_out, static_cast<size_t>(nr) * idx->src_row_bytes,
                                  cudaMemcpyDeviceToHost, idx->stream));
         FFX_CUDA(cudaStreamSynchronize(idx->stream));
     }
@@ -820,7 +921,7 @@ int64_t ffx_index_num_rows(const ffx_index *idx) { return idx ? idx->num_rows : 
 int64_t ffx_index_capacity(const ffx_index *idx) { return idx ? idx->capacity : -1; }
 int64_t ffx_index_dim(const ffx_index *idx) { return idx ? idx->dim : -1; }
 int ffx_index_has_fast_path(const ffx_index *idx) {
-    return idx && idx->row_kind == FFX_ROWS_F32 && idx->plan.cpl != 0;
+    return idx && idx->row_kind == FFX_ROWS_F32 && (idx->plan.cpl != 0 || idx->any.valid);
 }
 
 int ffx_index_set_docs(ffx_index *idx, int64_t n_docs, const int64_t *doc_off,
@@ -1010,6 +1111,7 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     const int cpad = next_pow2(std::max<int64_t>(max_cand, 1));
     const bool pq = idx->row_kind == FFX_ROWS_PQ_U8;
     const bool fast = !pq && idx->plan.cpl != 0;
+    const bool any = !pq && !fast && idx->any.valid;  // the numpy tree as data (ffx_score_any_kernel)
     const int64_t D = pq ? static_cast<int64_t>(idx->M) * idx->Ds : idx->dim;
     const float alpha32 = static_cast<float>(alpha);
     const float beta32 = static_cast<float>(1.0 - alpha);
@@ -1023,7 +1125,16 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     // one CTA per query with the top-k fused needs enough queries to fill the machine
     const int64_t slots = static_cast<int64_t>(idx->sm_count) * 2;
     // nothing to score (every list empty): the separate top-k pass still writes the (-inf, -1) padding
-    const bool fuse = max_cand > 0 && will_fuse(idx, nq, k, cpad);
+    bool fuse = max_cand > 0 && will_fuse(idx, nq, k, cpad);
+    const bool few_pairs = nq * max_cand < static_cast<int64_t>(idx->sm_count) * 8 * 64;
+    ScorePlan sp_any{};
+    if (any) {
+        sp_any = plan_score_any(idx->any, mode, fuse, cpad, idx->sharded, few_pairs);
+        if (fuse && !sp_any.tma) {  // the keys do not fit beside the ring: separate top-k pass
+            fuse = false;
+            sp_any = plan_score_any(idx->any, mode, false, cpad, idx->sharded, few_pairs);
+        }
+    }
 
     // scratch plan: [scores n_total?][keys nq*cpad?][qeff nq*D?]
     // a separate top-k pass reads out_int when the caller asked for it; a shard must not (pairs
@@ -1052,15 +1163,14 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     const float *topk_src = rank_scores ? rank_scores : out_int;  // input of a separate top-k pass
 
     // tiles: split a query over several CTAs when there are few queries
-    const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4, idx->sharded,
-                                                     nq * max_cand < static_cast<int64_t>(idx->sm_count) * 8 * 64,
-                                                     idx->plan.lanes != 32) : ScorePlan{};
+    const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4, idx->sharded, few_pairs,
+                                           idx->plan.lanes != 32) : sp_any;
     int tiles = 1, tile = static_cast<int>(std::max<int64_t>(max_cand, 1));
     if (!fuse) {
         // enough CTAs for ~2 waves at the plan's occupancy, but a tile keeps every warp of its
         // CTA busy with at least one candidate batch
         const int64_t want = slots * 4;
-        const int64_t grain = (fast && sp.tma) ? static_cast<int64_t>(sp.warps) * sp.batch : 32;
+        const int64_t grain = ((fast || any) && sp.tma) ? static_cast<int64_t>(sp.warps) * sp.batch : 32;
         tiles = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((want + nq - 1) / nq,
                                                                         (max_cand + grain - 1) / grain)));
         tile = static_cast<int>((std::max<int64_t>(max_cand, 1) + tiles - 1) / tiles);
@@ -1177,7 +1287,7 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
             a.err = idx->err_flag;
             if (idx->sc_world) {
                 // the fused exchange lives in the epilogue of the fused TMA-staged kernel only
-                if (!(fast && fuse && sp.tma))
+                if (!((fast || any) && fuse && sp.tma))
                     return fail(FFX_ERR_UNSUPPORTED, "ffx_rerank: a scatter plan needs the fused fp32 kernel "
                                 "(lane-major dimension, k > 0, >= 2 queries per SM, <= %d candidates per query)",
                                 ffx::kMaxFusedCand);
@@ -1200,6 +1310,10 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
             }
             if (fast) {
                 FFX_TRY(dispatch_score(idx->plan, sp, a, fuse, static_cast<int>(nq * tiles), st));
+            } else if (any) {
+                if (!sp.tma) return fail(FFX_ERR_UNSUPPORTED, "ffx_rerank: rows of %lld floats do not fit the row rings",
+                                         static_cast<long long>(idx->dim));
+                FFX_TRY(dispatch_score_any(idx->any, sp, a, fuse, static_cast<int>(nq * tiles), st));
             } else {
                 // generic exact kernel: one thread per pair over the [0, nq*max_cand) bound;
                 // the kernel reads the true pair count from q_off[nq]

@@ -53,3 +53,73 @@ FFX_HD static inline int ffx_orig_index(int cpl, int steps, int k, int lanes = 3
     const int g = l * cpl + ch;
     return (g >> 3) * (8 * steps) + 8 * s + (g & 7);
 }
+
+
+// ---- any other dimension: the numpy tree as data ------------------------------------------------
+// For a D without a uniform tree the recursion of numpy's pairwise sum (split n > 128 at
+// n2 = n/2 - (n/2) % 8; a leaf of 8 <= n <= 128 elements keeps 8 accumulators over its whole groups
+// of 8 and then adds its n % 8 last elements one by one; n < 8 is summed one by one from 0) gives
+// leaves of different lengths at different depths.  The plan places every leaf in a slot of a
+// BALANCED tree of 2^t slots (a leaf at depth d < t takes the first of its 2^(t-d) slots, the
+// others stay empty: x + 0 == x), so that the combine is the same xor-butterfly as in the uniform
+// case: 8 chains per slot, CPL = 8 * slots / lanes chains per lane.  Rows stay in ORIGINAL element
+// order in the store (row stride = D rounded up to 4 floats, for the 16-byte bulk copies); a lane
+// reads its chains' elements from the staged row with computed addresses.  Only the last leaf
+// can have a tail (every left part of a split is a multiple of 8).
+struct ffx_any_plan {
+    int valid;       // 0: more than 32 leaf slots (D beyond ~4096): thread-per-pair kernel
+    int dim, stride; // elements, stored floats per row
+    int lpr;         // lanes sharing one row: 8, 16, 32
+    int cpl;         // chains per lane: 1, 2, 4, 8
+    int n_slots;     // leaf slots, a power of two <= 32
+    int max_steps;   // longest chain (groups of 8 in the longest leaf)
+    int tail_slot, tail_start, tail_len;
+    int16_t start[32];  // first element of the slot's leaf
+    int16_t steps[32];  // whole groups of 8 in the slot's leaf; 0 = empty slot (or a leaf of < 8 elements)
+};
+
+struct ffx_any_leaf_ { int start, len, depth, index; };
+
+static inline int ffx_any_collect_(int start, int n, int depth, int index, ffx_any_leaf_ *out, int cap, int at) {
+    if (n <= 128) {
+        if (at < cap) out[at] = ffx_any_leaf_{start, n, depth, index};
+        return at + 1;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    at = ffx_any_collect_(start, n2, depth + 1, 2 * index, out, cap, at);
+    return ffx_any_collect_(start + n2, n - n2, depth + 1, 2 * index + 1, out, cap, at);
+}
+
+static inline ffx_any_plan ffx_any_plan_for_dim(int64_t dim) {
+    ffx_any_plan p{};
+    if (dim <= 0 || dim > 32 * 128) return p;
+    ffx_any_leaf_ leaves[64];
+    const int n = ffx_any_collect_(0, static_cast<int>(dim), 0, 0, leaves, 64, 0);
+    if (n > 64) return p;
+    int depth = 0;
+    for (int i = 0; i < n; i++) depth = leaves[i].depth > depth ? leaves[i].depth : depth;
+    if (depth > 5) return p;
+    p.n_slots = 1 << depth;
+    p.dim = static_cast<int>(dim);
+    p.stride = (p.dim + 3) & ~3;
+    p.tail_slot = -1;
+    for (int i = 0; i < n; i++) {
+        const int slot = leaves[i].index << (depth - leaves[i].depth);
+        const int len = leaves[i].len;
+        p.start[slot] = static_cast<int16_t>(leaves[i].start);
+        p.steps[slot] = static_cast<int16_t>(len < 8 ? 0 : len / 8);
+        if (p.steps[slot] > p.max_steps) p.max_steps = p.steps[slot];
+        const int tail = len < 8 ? len : len % 8;
+        if (tail) {
+            p.tail_slot = slot;
+            p.tail_start = leaves[i].start + len - tail;
+            p.tail_len = tail;
+        }
+    }
+    const int chains = 8 * p.n_slots;
+    p.lpr = chains >= 32 ? 32 : chains;
+    p.cpl = chains / p.lpr;
+    p.valid = 1;
+    return p;
+}

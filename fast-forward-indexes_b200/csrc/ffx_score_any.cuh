@@ -1,0 +1,373 @@
+// ffx_score_any.cuh — the scoring kernel for every dimension WITHOUT a uniform numpy tree
+// (D = 100, 130, 300, 1000, ... up to 4096; the uniform ones have the lane-major kernels of
+// ffx_score_tma.cuh).  Same contract, same pipeline as ffx_score_tma_kernel — per-warp rings of
+// row slots filled by `cp.async.bulk`, candidate batches resolved three deep, dynamic balance
+// over ragged documents, fused interpolation and per-query top-k — but the summation tree is
+// DATA (ffx_any_plan, ffx_layout.h): rows stay in original element order, every lane owns CPL
+// chains (leaf slot, accumulator j) of the numpy tree and reads their elements from the staged
+// row with computed addresses; the query vector sits beside the ring in shared memory.  Short
+// rows (one or two leaves) are shared by 8 / 16 lanes, 4 / 2 rows per warp step.
+//
+// Replaces the thread-per-pair ffx_score_generic_kernel (index/base.py:279-314 for any D,
+// bit-exact: N1 of DESIGN.md).  HBM-bound; no tensor cores.
+#pragma once
+#include "ffx_score_tma.cuh"
+
+namespace ffx {
+
+__host__ __device__ inline size_t any_smem_bytes(int cpad_scores, int warps, int ns, int row_bytes) {
+    const size_t keys = (static_cast<size_t>(cpad_scores) * 4 + 127) & ~static_cast<size_t>(127);
+    const size_t qv = (static_cast<size_t>(row_bytes) + 127) & ~static_cast<size_t>(127);
+    return keys + qv + static_cast<size_t>(warps) * ns * row_bytes + static_cast<size_t>(warps) * ns * 8 +
+           static_cast<size_t>(warps) * 2 * 32 * sizeof(CandDesc) + 128;
+}
+
+template <int N>
+struct AnyVec {
+    float v[N];
+};
+template <int N>
+__device__ __forceinline__ AnyVec<N> lds_vec(uint32_t addr) {
+    AnyVec<N> r;
+    if constexpr (N == 1) {
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r.v[0]) : "r"(addr));
+    } else if constexpr (N == 2) {
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "r"(addr));
+    } else if constexpr (N == 4) {
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+                     : "r"(addr));
+    } else {
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+                     : "r"(addr));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                     : "r"(addr + 16));
+    }
+    return r;
+}
+
+// One staged row (shared memory, original element order) against the query vector (same
+// order): numpy's np.sum(q * d) for this D.  Lane `sub` of the LPR lanes sharing the row owns
+// chains sub*CPL .. sub*CPL+CPL-1 = accumulators j0 .. j0+CPL-1 of leaf slot (sub*CPL)/8:
+//   chain sums (products rounded, sequential adds), balanced combine inside the lane, xor
+//   butterfly over the lanes of the leaf, the last leaf's tail elements one by one, xor
+//   butterfly over the leaf slots, 0 + total.
+template <int CPL, int LPR>
+__device__ __forceinline__ float any_row_dot(uint32_t row, uint32_t qv, uint32_t my_byte, int my_steps, int max_steps,
+                                             bool tail_mine, uint32_t tail_byte, int tail_len) {
+    float acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; c++) acc[c] = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < max_steps; s++) {
+        if (s < my_steps) {
+            const AnyVec<CPL> d = lds_vec<CPL>(row + my_byte + s * 32);
+            const AnyVec<CPL> q = lds_vec<CPL>(qv + my_byte + s * 32);
+#pragma unroll
+            for (int c = 0; c < CPL; c++) {
+                const float prod = __fmul_rn(q.v[c], d.v[c]);
+                acc[c] = s == 0 ? prod : __fadd_rn(acc[c], prod);
+            }
+        }
+    }
+#pragma unroll
+    for (int w = 1; w < CPL; w <<= 1) {
+#pragma unroll
+        for (int c = 0; c < CPL; c += 2 * w) acc[c] = __fadd_rn(acc[c], acc[c + w]);
+    }
+    float v = acc[0];
+    constexpr int kLeafLanes = 8 / CPL;  // lanes that share one leaf slot
+#pragma unroll
+    for (int o = 1; o < kLeafLanes; o <<= 1) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, o));
+    if (tail_len) {  // warp-uniform
+        if (tail_mine) {
+            for (int t = 0; t < tail_len; t++) {
+                const AnyVec<1> d = lds_vec<1>(row + tail_byte + 4 * t);
+                const AnyVec<1> q = lds_vec<1>(qv + tail_byte + 4 * t);
+                v = __fadd_rn(v, __fmul_rn(q.v[0], d.v[0]));
+            }
+        }
+    }
+#pragma unroll
+    for (int o = kLeafLanes; o < LPR; o <<= 1) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, o));
+    return __fadd_rn(0.f, v);
+}
+
+template <int CPL, int LPR, bool FUSE>
+__global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_any_kernel(const ScoreArgs a, const ffx_any_plan plan,
+                                                                        const int ns, const int batch) {
+    constexpr int RPS = 32 / LPR;  // rows per warp step
+    static_assert(LPR == 32 || CPL == 1, "short rows: one chain per lane");
+    const uint32_t ROWB = static_cast<uint32_t>(plan.stride) * 4u;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_next;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_warps = blockDim.x >> 5;
+    const int64_t q_idx = blockIdx.x / a.tiles_per_query;
+    const int t_idx = blockIdx.x % a.tiles_per_query;
+    const int64_t q_begin = a.q_off[q_idx];
+    const int n_query = static_cast<int>(a.q_off[q_idx + 1] - q_begin);
+    const int c0 = t_idx * a.tile;
+    const int n_tile = min(a.tile, n_query - c0);
+    if (!FUSE && n_tile <= 0) return;
+
+    // ---- carve shared memory: [scores][query vector][ring][mbarriers][descriptors]
+    float *s_scores = reinterpret_cast<float *>(smem_raw);
+    size_t off = FUSE ? ((static_cast<size_t>(a.cpad) * 4 + 127) & ~static_cast<size_t>(127)) : 0;
+    float *s_q = reinterpret_cast<float *>(smem_raw + off);
+    off += (static_cast<size_t>(ROWB) + 127) & ~static_cast<size_t>(127);
+    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem_raw + off);  // = ring, after the drain
+    const uint32_t ring = smem_u32(smem_raw + off) + static_cast<uint32_t>(warp) * ns * ROWB;
+    off += static_cast<size_t>(n_warps) * ns * ROWB;
+    const uint32_t bars = smem_u32(smem_raw + off) + static_cast<uint32_t>(warp) * ns * 8;
+    off += static_cast<size_t>(n_warps) * ns * 8;
+    off = (off + 15) & ~static_cast<size_t>(15);
+    CandDesc *desc = reinterpret_cast<CandDesc *>(smem_raw + off) + warp * 64;  // [2][32]
+
+    float *rank = a.rank_scores ? a.rank_scores - a.q_off[0] : nullptr;
+    if (threadIdx.x == 0) s_next = 0;
+    if (FUSE) {
+        for (int i = threadIdx.x; i < n_query; i += blockDim.x) s_scores[i] = __int_as_float(0x7fc00000);
+    }
+    if (lane == 0) {
+        for (int s = 0; s < ns; s++) mbar_init(bars + s * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    const float *qsrc = a.qvecs + q_idx * plan.dim;
+    for (int k = threadIdx.x; k < plan.stride; k += blockDim.x) s_q[k] = k < plan.dim ? __ldg(qsrc + k) : 0.f;
+
+    // this lane's place in the tree
+    const int sub = lane % LPR;
+    const int slot = (sub * CPL) >> 3;
+    const uint32_t my_byte = static_cast<uint32_t>(plan.start[slot] + ((sub * CPL) & 7)) * 4u;
+    const int my_steps = plan.steps[slot];
+    const bool tail_mine = slot == plan.tail_slot;
+    const uint32_t tail_byte = static_cast<uint32_t>(plan.tail_start) * 4u;
+    const uint32_t q_addr = smem_u32(s_q);
+    __syncthreads();
+
+    const char *rows_base = reinterpret_cast<const char *>(a.vectors);
+    const bool indirect = a.indirect && a.mode != FFX_MODE_PASSAGE;
+    const int64_t pair0 = q_begin + c0;
+
+    // ---- candidate-batch pipeline (as in ffx_score_tma_kernel)
+    int g_base = 0, g_nb = 0, g_cand = 0;
+    float g_lex = 0.f;
+    int h_base = 0, h_nb = 0;
+    uint32_t h_start = 0, h_cnt = 0, h_mine = 0;
+    float h_lex = 0.f;
+
+    auto grab = [&]() {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_next, batch);
+        base = __shfl_sync(kFull, base, 0);
+        g_base = base;
+        g_nb = max(0, min(batch, n_tile - base));
+        g_cand = 0;
+        g_lex = 0.f;
+        if (lane < g_nb) {
+            g_cand = __ldg(a.cand + pair0 + base + lane);
+            if (a.lex) g_lex = __ldg(a.lex + pair0 + base + lane);
+        }
+    };
+    auto resolve = [&]() {
+        h_base = g_base;
+        h_nb = g_nb;
+        h_lex = g_lex;
+        h_start = 0;
+        h_cnt = 0;
+        h_mine = 0;
+        if (lane < g_nb) {
+            uint32_t loc = 0;
+            if (!candidate_ok(g_cand, a.limit, a.err, pair0 + g_base + lane)) {
+                h_mine = 1;
+            } else if (candidate_mine(g_cand, a.base, a.count, &loc)) {
+                h_mine = 1;
+                if (a.mode == FFX_MODE_PASSAGE) {
+                    h_start = loc;
+                    h_cnt = 1;
+                } else {
+                    const uint2 sp = __ldg(a.doc_span + loc);
+                    h_start = sp.x;
+                    h_cnt = a.mode == FFX_MODE_FIRSTP ? 1u : sp.y;
+                }
+            }
+        }
+    };
+    auto publish = [&](int slot_) {
+        CandDesc d;
+        d.start = h_start;
+        d.cnt = h_cnt;
+        d.lex = h_lex;
+        d.mine = h_mine;
+        desc[slot_ * 32 + lane] = d;
+        __syncwarp();
+    };
+
+    int cur = 0;
+    int nbA, nbB, baseA, baseB;
+    grab();
+    resolve();
+    publish(0);
+    nbA = h_nb;
+    baseA = h_base;
+    grab();
+    resolve();
+    publish(1);
+    nbB = h_nb;
+    baseB = h_base;
+    grab();
+    resolve();
+    grab();
+
+    bool p_inB = false;
+    int pj = -1;
+    uint32_t pk = 0, pcnt = 0, pstart = 0, p_rows = 0;
+    int p_stage = 0, c_stage = 0, inflight = 0;
+    uint32_t c_phase = 0;
+
+    auto top_up = [&]() {
+        while (inflight < ns) {
+            bool have = false;
+            for (;;) {
+                if (pk < pcnt) {
+                    have = true;
+                    break;
+                }
+                const int nb = p_inB ? nbB : nbA;
+                if (pj + 1 < nb) {
+                    pj++;
+                    const CandDesc d = desc[((p_inB ? cur ^ 1 : cur) << 5) + pj];
+                    pstart = d.start;
+                    pcnt = d.cnt;
+                    pk = 0;
+                    continue;
+                }
+                if (!p_inB && nbB > 0) {
+                    p_inB = true;
+                    pj = -1;
+                    pk = 0;
+                    pcnt = 0;
+                    continue;
+                }
+                break;
+            }
+            if (!have) break;
+            uint32_t row = pstart + pk;
+            if (indirect) {
+                if ((pk & 31u) == 0)
+                    p_rows = (pk + lane < pcnt) ? static_cast<uint32_t>(__ldg(a.doc_rows + pstart + pk + lane)) : 0u;
+                row = __shfl_sync(kFull, p_rows, pk & 31u);
+            }
+            pk++;
+            if (lane == 0) {
+                const uint32_t bar = bars + p_stage * 8;
+                mbar_expect_tx(bar, ROWB);
+                bulk_g2s(ring + p_stage * ROWB, rows_base + static_cast<size_t>(row) * ROWB, ROWB, bar);
+            }
+            p_stage = p_stage + 1 == ns ? 0 : p_stage + 1;
+            inflight++;
+        }
+    };
+
+    while (nbA > 0) {
+        float my_ff = 0.f;
+        for (int cj = 0; cj < nbA; cj++) {
+            const uint32_t cnt = desc[(cur << 5) + cj].cnt;
+            DocReduce red;
+            red.init();
+            for (uint32_t ck = 0; ck < cnt;) {
+                // lane group g takes row ck + g of the document from ring slot c_stage + g
+                top_up();
+                const int nr = static_cast<int>(min(static_cast<uint32_t>(RPS), cnt - ck));  // warp-uniform
+                const int grp = lane / LPR;
+                int sg = c_stage + grp;
+                if (sg >= ns) sg -= ns;
+                const bool busy = grp < nr;
+                if (busy) mbar_wait(bars + sg * 8, (c_phase >> sg) & 1u);
+                // idle groups run the arithmetic on their (stale) slot: the shuffles stay convergent
+                const float part = any_row_dot<CPL, LPR>(ring + sg * ROWB, q_addr, my_byte, my_steps, plan.max_steps,
+                                                         tail_mine, tail_byte, plan.tail_len);
+                __syncwarp();  // every lane has consumed its row: the slots may be refilled
+                for (int g = 0; g < nr; g++) {
+                    int slot_ = c_stage + g;
+                    if (slot_ >= ns) slot_ -= ns;
+                    c_phase ^= 1u << slot_;
+                    red.add(__shfl_sync(kFull, part, g * LPR), ck + g == 0, a.mode);
+                }
+                c_stage += nr;
+                if (c_stage >= ns) c_stage -= ns;
+                inflight -= nr;
+                ck += nr;
+            }
+            const float ff = red.finish(cnt, a.mode);
+            if (lane == cj) my_ff = ff;
+        }
+
+        if (lane < nbA) {
+            const CandDesc d = desc[(cur << 5) + lane];
+            const int64_t my_pair = pair0 + baseA + lane;
+            if (d.mine) {
+                float inter = my_ff;
+                if (a.lex) inter = __fadd_rn(__fmul_rn(a.alpha, d.lex), __fmul_rn(a.beta, my_ff));
+                if (a.out_ff) a.out_ff[my_pair] = my_ff;
+                if (a.out_int) a.out_int[my_pair] = inter;
+                if (rank) rank[my_pair] = inter;
+                if (FUSE) s_scores[c0 + baseA + lane] = inter;
+            } else if (rank) {
+                rank[my_pair] = __int_as_float(0x7fc00000);
+            }
+        }
+        __syncwarp();
+
+        publish(cur);
+        cur ^= 1;
+        nbA = nbB;
+        baseA = baseB;
+        nbB = h_nb;
+        baseB = h_base;
+        if (p_inB) {
+            p_inB = false;
+        } else {
+            pj = -1;
+            pk = 0;
+            pcnt = 0;
+        }
+        resolve();
+        grab();
+    }
+
+    if (FUSE) {
+        __syncthreads();
+        float *out_s;
+        int32_t *out_p;
+        topk_destination(a, q_idx, &out_s, &out_p);
+        rank_scores_topk<16>(s_scores, n_query, s_keys, a.k, out_s, out_p, static_cast<size_t>(n_warps) * ns * ROWB);
+        if (a.sc_world) __threadfence_system();
+    }
+}
+
+// staging for dimensions that are not a multiple of 4: rows <-> the 16-byte padded store
+__global__ void ffx_pad_rows_kernel(float *dst, const float *src, int64_t nrows, int dim, int stride, int to_store,
+                                    const int64_t *rows) {
+    const int64_t total = nrows * stride;
+    for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = t / stride;
+        const int k = static_cast<int>(t % stride);
+        if (to_store) {
+            dst[r * stride + k] = k < dim ? src[r * dim + k] : 0.f;
+        } else if (k < dim) {
+            const int64_t sr = rows ? rows[r] : r;
+            dst[r * dim + k] = src[sr * stride + k];
+        }
+    }
+}
+
+}  // namespace ffx

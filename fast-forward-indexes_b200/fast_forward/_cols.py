@@ -200,7 +200,7 @@ class Cols:
         off = np.empty(nq + 1, np.int64)
         dense = keep == k or nq == 0
         m_cap = nq * keep
-        code = np.empty(m_cap, np.int32)
+        code = _ffx.pinned_empty(m_cap, np.int32)  # recycled block: no page faults on 100 MB per call
         # when every list is full (no -1 padding) the [nq, keep] score matrix IS the column
         out_score = None if dense else np.empty(m_cap, np.float32)
         ties = C.c_int64(0)

@@ -173,17 +173,19 @@ class PinnedBuffer:
 
 
 class _PinnedPool:
-    """Free list of page-locked buffers by size class.  Allocating pinned memory costs far more
-    than using it (cudaHostAlloc of 200 MB: tens of milliseconds), so the large per-call arrays
-    of the Python shell — candidate codes, scores, ranked lists — are recycled: an array from
-    `pinned_empty` returns its buffer here when the last view of it is garbage-collected."""
+    """Caching allocator for page-locked host memory.  Pinning pages costs far more than using
+    them (cudaHostAlloc of 200 MB: tens of milliseconds), so the large per-call arrays of the
+    Python shell — candidate codes, scores, ranked lists — come out of SLABS pinned four blocks
+    at a time and are recycled through per-size free lists: an array from `pinned_empty` returns
+    its block here when the last view of it is garbage-collected.  Slabs are kept until exit."""
 
     MIN_BYTES = 1 << 20
-    KEEP_BYTES = 4 << 30  # idle buffers kept for reuse; beyond that they are freed
+    MAX_SLAB = 1 << 30
 
     def __init__(self):
-        self.free: dict[int, list] = {}
-        self.idle = 0
+        self.free: dict[int, list[int]] = {}   # size class -> addresses of free blocks
+        self.slabs: list[tuple[int, int, int]] = []  # (base address, bytes, bump offset) of live slabs
+        self.pinned_bytes = 0
 
     @staticmethod
     def size_class(nbytes: int) -> int:
@@ -192,24 +194,24 @@ class _PinnedPool:
             c += max(c >> 2, 1 << 20)  # geometric steps of 25 %
         return c
 
-    def take(self, nbytes: int):
+    def take(self, nbytes: int) -> tuple[int, int]:
         c = self.size_class(nbytes)
         stack = self.free.get(c)
         if stack:
-            self.idle -= c
             return c, stack.pop()
+        for i, (base, size, used) in enumerate(self.slabs):
+            if size - used >= c:
+                self.slabs[i] = (base, size, used + c)
+                return c, base + used
+        slab = c if c >= self.MAX_SLAB else min(self.MAX_SLAB, 4 * c)
         p = C.c_void_p()
-        check(lib().ffx_host_alloc(C.byref(p), c))
-        return c, p
+        check(lib().ffx_host_alloc(C.byref(p), slab))
+        self.pinned_bytes += slab
+        self.slabs.append((p.value, slab, c))
+        return c, p.value
 
-    def give(self, c: int, p) -> None:
-        if _lib is None:
-            return
-        if self.idle + c > self.KEEP_BYTES:
-            _lib.ffx_host_free(p)
-            return
-        self.free.setdefault(c, []).append(p)
-        self.idle += c
+    def give(self, c: int, address: int) -> None:
+        self.free.setdefault(c, []).append(address)
 
 
 _POOL = _PinnedPool()
@@ -227,7 +229,7 @@ def pinned_empty(shape, dtype) -> np.ndarray:
     if nbytes < _PinnedPool.MIN_BYTES or not _has_device():
         return np.empty(shape, dtype)
     c, p = _POOL.take(nbytes)
-    raw = (C.c_char * nbytes).from_address(p.value)
+    raw = (C.c_char * nbytes).from_address(p)
     root = np.frombuffer(raw, dtype=dtype, count=count)
     weakref.finalize(root, _POOL.give, c, p)
     return root.reshape(shape)

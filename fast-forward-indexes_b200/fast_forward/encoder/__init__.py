@@ -37,11 +37,13 @@ class LambdaEncoder(Encoder):
 
 
 class TableEncoder(Encoder):
-    """Looks precomputed vectors up by query text (benchmarks, cached encoders)."""
+    """Looks precomputed vectors up by query text (benchmarks, cached encoders): one dictionary
+    probe per text and ONE gather from the stacked table per call."""
 
     def __init__(self, table: Mapping[str, np.ndarray]) -> None:
         super().__init__()
-        self._table = table
+        self._row = {text: i for i, text in enumerate(table)}
+        self._matrix = np.stack([np.asarray(v) for v in table.values()]) if len(self._row) else np.zeros((0, 0), np.float32)
 
     def _encode(self, texts: Sequence[str]) -> np.ndarray:
-        return np.stack([self._table[t] for t in texts])
+        return self._matrix[[self._row[t] for t in texts]]

@@ -175,7 +175,7 @@ def test_reference_known_answers(ffx, golden_kat):
 # seeded random problems against the oracle
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dim", [768, 384, 512, 640, 896, 1024, 1536, 2048, 2560, 3072, 3584, 4096, 64, 96, 128, 192,
-                                 256, 100, 5, 130])
+                                 256, 100, 5, 130, 1, 7, 8, 9, 50, 200, 260, 300, 312, 1000, 1280, 2000, 4000, 4100])
 @pytest.mark.parametrize("contiguous", [True, False])
 def test_scores_bit_exact_all_modes(ffx, oracle_c, dim, contiguous):
     rng = np.random.default_rng(dim * 2 + contiguous)
@@ -274,6 +274,51 @@ def test_long_and_short_rows_fused_path(ffx, oracle_c, dim):
         assert (bits(out["ff"]) == bits(ff)).all()
         assert (out["topk_pos"] == tp).all() and (bits(out["topk_score"]) == bits(ts)).all()
     idx.close()
+
+
+@pytest.mark.parametrize("dim", [5, 50, 100, 130, 200, 260, 300, 1000, 1280, 2000, 4000])
+def test_any_dimension_kernel_fused_and_tiled(ffx, oracle_c, dim):
+    """Dimensions without a uniform numpy tree (ffx_score_any_kernel, the tree as data: leaves of
+    different lengths and depths, a tail after the last leaf, row stride padded to 16 bytes):
+    fused one-CTA-per-query launches, tiled launches, scattered documents, ring depths and
+    batch sizes — bit for bit against the plain-C oracle; rows read back unchanged."""
+    rng = np.random.default_rng(dim)
+    for contiguous in (True, False):
+        off, rows, vec = make_corpus(rng, 500, 7, dim, contiguous)
+        idx = ffx.DeviceIndex(dim, capacity=len(vec))
+        idx.stage(0, vec[:100])
+        idx.stage(100, vec[100:])
+        assert idx.has_fast_path
+        some = rng.choice(len(vec), 50, replace=False)
+        assert (idx.read_rows(some) == vec[some]).all()
+        idx.set_docs(off, rows)
+        nq = 310
+        qv = rng.standard_normal((nq, dim)).astype(np.float32)
+        for mode in (fo.MODE_MAXP, fo.MODE_AVEP, fo.MODE_FIRSTP, fo.MODE_PASSAGE):
+            pool = len(vec) if mode == fo.MODE_PASSAGE else 500
+            q_off, cand, pair_q = make_pairs(rng, nq, pool, 0, 120)
+            lex = (rng.integers(0, 8, len(cand)) * 4).astype(np.float32)
+            u_off, u_rows = units_for_mode(off, rows, len(vec), mode)
+            ff = c_scores(oracle_c, vec, u_off, u_rows, pair_q, cand, qv, mode)
+            it = fo.interpolate_f32(lex, ff, 0.2)
+            ts, tp = fo.topk_per_query(q_off, it, 20)
+            for stages, batch in ((0, 0), (2, 5), (7, 32)):
+                ffx.set_option("tma_stages", stages)
+                ffx.set_option("batch", batch)
+                try:
+                    for sub in (nq, 9):  # fused and tiled launches
+                        n_sub = int(q_off[sub])
+                        out = idx.rerank_host(mode, qv[:sub], q_off[:sub + 1], cand[:n_sub], lex[:n_sub], 0.2, 20,
+                                              want_ff=True, want_int=True)
+                        assert "ffx_score_any_kernel" in ffx.last_kernel()
+                        assert ("true>" in ffx.last_kernel()) == (sub == nq)
+                        assert (bits(out["ff"]) == bits(ff[:n_sub])).all(), (mode, stages, batch, sub)
+                        assert (bits(out["int"]) == bits(it[:n_sub])).all()
+                        assert (out["topk_pos"] == tp[:sub]).all() and (bits(out["topk_score"]) == bits(ts[:sub])).all()
+                finally:
+                    ffx.set_option("tma_stages", 0)
+                    ffx.set_option("batch", 0)
+        idx.close()
 
 
 @pytest.mark.parametrize("stages,batch", [(2, 5), (3, 32), (16, 1)])

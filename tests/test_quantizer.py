@@ -74,3 +74,30 @@ def test_guards(pair):
     q.set_attached()
     with pytest.raises(RuntimeError):
         q.fit(x)
+
+
+def test_encode_is_scipy_vq_and_decode_is_the_codeword_gather(pair):
+    """The one pin available without nanopq (absent from the image and the wheelhouse, like h5py
+    and libhdf5): nanopq 0.2.1's `PQ.encode` IS `scipy.cluster.vq.vq` per subspace and its
+    `PQ.decode` IS the gather `codewords[m][codes[:, m], :]` (the calls the reference makes at
+    quantizer/nanopq.py:41-44,109-112).  scipy is installed: same data through both must give
+    identical codes, and decode must be the pure gather (then `@ R.T` for OPQ)."""
+    from scipy.cluster.vq import vq
+
+    _, q = pair
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(300, 768)).astype(np.float32)
+    cw, R = q.adc_tables()
+    M, Ks, Ds = cw.shape
+    xr = x if R is None else x @ R
+    want = np.empty((len(x), M), np.uint8)
+    for m in range(M):
+        want[:, m], _ = vq(xr[:, m * Ds:(m + 1) * Ds], cw[m])
+    codes = q.encode(x)
+    assert codes.dtype == np.uint8 and np.array_equal(codes, want)
+    gathered = np.concatenate([cw[m][codes[:, m], :] for m in range(M)], axis=1)
+    assert np.array_equal(q.decode(codes), gathered if R is None else gathered @ R.T)
+    # random codes, not only the ones encode produces
+    rnd = rng.integers(0, Ks, (200, M)).astype(np.uint8)
+    gathered = np.concatenate([cw[m][rnd[:, m], :] for m in range(M)], axis=1)
+    assert np.array_equal(q.decode(rnd), gathered if R is None else gathered @ R.T)
