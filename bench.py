@@ -830,6 +830,15 @@ def run_api(ctx, args, wl, m, q_host, alpha, k):
         n_out = out.num_rows
         times.append(time.perf_counter() - t0)
     assert n_out == nq * min(k, cands)
+    if os.environ.get("FFX_API_PROFILE"):  # where a steady-state call spends its time (stderr)
+        import cProfile
+        import pstats
+
+        prof = cProfile.Profile()
+        prof.enable()
+        index.rerank(first, alpha, k)
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(18)
     t0 = time.perf_counter()
     df = out._df
     t_frame = time.perf_counter() - t0

@@ -471,13 +471,19 @@ ScorePlan plan_score_any(const ffx_any_plan &p, int mode, bool fuse, int cpad, b
     const int need = 2 * rps;  // a warp step consumes `rps` slots while the next ones load
     const int want = row_bytes >= 2048 ? 6 : (row_bytes >= 1024 ? 8 : 16);
     if (fuse) {
-        // two CTAs per SM where the keys leave room, else one large CTA
-        sp.warps = 8;
-        sp.ns = std::min(want, any_ring_slots(keys, 8, row_bytes, 2));
-        if (sp.ns < need) {
-            for (sp.warps = 16; sp.warps >= 4; sp.warps -= 4) {
-                sp.ns = std::min(want, any_ring_slots(keys, sp.warps, row_bytes, 1));
-                if (sp.ns >= need) break;
+        // the shape that keeps the most row slots (bytes) in flight per SM: two 8-warp CTAs, or one
+        // CTA of up to 16 warps when the keys and the query vector leave too little for two
+        const int shapes[][2] = {{8, 2}, {16, 1}, {14, 1}, {12, 1}, {8, 1}, {4, 1}};
+        int best = 0;
+        sp.ns = 0;
+        for (const auto &shape : shapes) {
+            const int ns = std::min(want, any_ring_slots(keys, shape[0], row_bytes, shape[1]));
+            if (ns < need) continue;
+            const int slots = ns * shape[0] * shape[1];
+            if (slots > best) {
+                best = slots;
+                sp.warps = shape[0];
+                sp.ns = ns;
             }
         }
     } else {

@@ -79,6 +79,58 @@ __device__ __forceinline__ void add_f32x2(float2 &acc, float a, float b) {
         : "f"(a), "f"(b));
 }
 
+// ld.shared.f32 [addr + OFF] with the offset as an immediate of the instruction
+template <uint32_t OFF>
+__device__ __forceinline__ float lds_f32_imm(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(r) : "r"(addr), "n"(OFF));
+    return r;
+}
+
+// The 32 look-ups of word position `wi` in all NC chunks when chunk j uses table j and the tables
+// are TB bytes apart (TB known at compile time: Ks = 256): the swizzled line offset
+// (table 0 | 4t) ^ 4p is formed once per static position p and shared by the NC tables.
+template <int NC, uint32_t TB, int J = 0>
+__device__ __forceinline__ void adc_xor_word(const uint32_t (&wd)[NC][8], int wi, const uint32_t (&sel)[4], uint32_t x0,
+                                             uint32_t x1, uint32_t x2, uint32_t x3, float2 &acc01, float2 &acc23) {
+    if constexpr (J < NC) {
+        const float v0 = lds_f32_imm<J * TB>(__dp4a(wd[J][wi], sel[0], x0));
+        const float v1 = lds_f32_imm<J * TB>(__dp4a(wd[J][wi], sel[1], x1));
+        const float v2 = lds_f32_imm<J * TB>(__dp4a(wd[J][wi], sel[2], x2));
+        const float v3 = lds_f32_imm<J * TB>(__dp4a(wd[J][wi], sel[3], x3));
+        add_f32x2(acc01, v0, v1);
+        add_f32x2(acc23, v2, v3);
+        adc_xor_word<NC, TB, J + 1>(wd, wi, sel, x0, x1, x2, x3, acc01, acc23);
+    }
+}
+
+// L2 residency (ncu of the first version: 19.5 GB of DRAM reads for 16.2 GB of codes — the
+// 786 KB codebook every query's table is built from was being evicted by the streaming code rows
+// and re-fetched from HBM): code rows pass through L2 as evict-first, the codebook is evict-last.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float4 *p, uint64_t policy) {
+    float4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t r;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
@@ -92,7 +144,8 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
     constexpr int M = NC * 32;
     extern __shared__ __align__(128) unsigned char adc_smem[];
     float *s_lut = reinterpret_cast<float *>(adc_smem);  // 128-byte aligned (the XOR addressing relies on it)
-    __shared__ int s_next;
+    __shared__ int s_next, s_next_small;
+    const uint64_t keep_l2 = l2_policy_evict_last(), stream_l2 = l2_policy_evict_first();
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -110,7 +163,10 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
     if (!FUSE && n_tile <= 0) return;
     // the scratch scores of a separate top-k pass are indexed relative to the launch's first pair
     float *rank = a.rank_scores ? a.rank_scores - a.q_off[0] : nullptr;
-    if (threadIdx.x == 0) s_next = 0;
+    if (threadIdx.x == 0) {
+        s_next = 0;
+        s_next_small = 0;
+    }
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -135,7 +191,7 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
             float acc = 0.f;
             if (vec4) {
                 for (int d = 0; d < a.Ds; d += 4) {
-                    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(cw + d));
+                    const float4 c4 = ldg_f4_hint(reinterpret_cast<const float4 *>(cw + d), keep_l2);
                     const float4 q4 = __ldg(reinterpret_cast<const float4 *>(qm + d));
                     acc = fmaf(q4.x, c4.x, acc);
                     acc = fmaf(q4.y, c4.y, acc);
@@ -175,12 +231,24 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
     const bool segmented = a.mode == FFX_MODE_MAXP || a.mode == FFX_MODE_AVEP;
     const bool is_max = a.mode == FFX_MODE_MAXP;
 
+    // Guided self-scheduling: batches of 32 candidates up to `t_small`, batches of 8 for the last
+    // half round, so that the warps of the CTA finish within a quarter batch of one another (with
+    // 5000 candidates and 32 warps a warp takes ~5 batches: a whole-batch tail idled ~10 % of the SM).
+    const int t_small = max(0, (n_tile - 16 * static_cast<int>(blockDim.x >> 5)) & ~31);
+    bool small = false;
     for (;;) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(&s_next, 32);
-        base = __shfl_sync(kFull, base, 0);
+        if (!small) {
+            if (lane == 0) base = atomicAdd(&s_next, 32);
+            base = __shfl_sync(kFull, base, 0);
+            small = base >= t_small;
+        }
+        if (small) {
+            if (lane == 0) base = t_small + atomicAdd(&s_next_small, 8);
+            base = __shfl_sync(kFull, base, 0);
+        }
         if (base >= n_tile) break;
-        const int nb = min(32, n_tile - base);
+        const int nb = min(small ? 8 : 32, n_tile - base);
         const int64_t p = q_begin + c0 + base + lane;
 
         // lane j resolves candidate j of the batch
@@ -224,10 +292,11 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
                 const uint32_t dst = slots + (lo - r0) * M;
                 const uint32_t first = start + (lo - pre);
                 if (!indirect) {
-                    bulk_g2s(dst, a.codes + static_cast<uint64_t>(first) * M, (hi - lo) * M, bar);
+                    bulk_g2s_hint(dst, a.codes + static_cast<uint64_t>(first) * M, (hi - lo) * M, bar, stream_l2);
                 } else {
                     for (uint32_t i = 0; i < hi - lo; i++)
-                        bulk_g2s(dst + i * M, a.codes + static_cast<uint64_t>(__ldg(a.doc_rows + first + i)) * M, M, bar);
+                        bulk_g2s_hint(dst + i * M, a.codes + static_cast<uint64_t>(__ldg(a.doc_rows + first + i)) * M, M, bar,
+                                      stream_l2);
                 }
             }
         };
@@ -268,18 +337,43 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
             float s = 0.f;
             if (g < total) {
                 float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
+                if constexpr (NC == 2 || NC == 4) {
 #pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const uint32_t tj = (NC == 2 || NC == 4) ? tab_l[j] : tab[0] + static_cast<uint32_t>(j) * tab_bytes;
+                    for (int j = 0; j < NC; j++) {
+                        const uint32_t tj = tab_l[j];
+#pragma unroll
+                        for (int wi = 0; wi < 8; wi++) {
+                            const uint32_t pos = static_cast<uint32_t>(4 * wi);
+                            const float v0 = lds_f32(__dp4a(wd[j][wi], sel[0], tj ^ ((pos + 0u) << 2)));
+                            const float v1 = lds_f32(__dp4a(wd[j][wi], sel[1], tj ^ ((pos + 1u) << 2)));
+                            const float v2 = lds_f32(__dp4a(wd[j][wi], sel[2], tj ^ ((pos + 2u) << 2)));
+                            const float v3 = lds_f32(__dp4a(wd[j][wi], sel[3], tj ^ ((pos + 3u) << 2)));
+                            add_f32x2(acc01, v0, v1);
+                            add_f32x2(acc23, v2, v3);
+                        }
+                    }
+                } else if (a.Ks == 256) {
+                    // chunk j uses table j, 32 KB apart: one XOR per static position instead of one per look-up
 #pragma unroll
                     for (int wi = 0; wi < 8; wi++) {
                         const uint32_t pos = static_cast<uint32_t>(4 * wi);
-                        const float v0 = lds_f32(__dp4a(wd[j][wi], sel[0], tj ^ ((pos + 0u) << 2)));
-                        const float v1 = lds_f32(__dp4a(wd[j][wi], sel[1], tj ^ ((pos + 1u) << 2)));
-                        const float v2 = lds_f32(__dp4a(wd[j][wi], sel[2], tj ^ ((pos + 2u) << 2)));
-                        const float v3 = lds_f32(__dp4a(wd[j][wi], sel[3], tj ^ ((pos + 3u) << 2)));
-                        add_f32x2(acc01, v0, v1);
-                        add_f32x2(acc23, v2, v3);
+                        adc_xor_word<NC, 256u * 128u>(wd, wi, sel, tab[0] ^ ((pos + 0u) << 2), tab[0] ^ ((pos + 1u) << 2),
+                                                      tab[0] ^ ((pos + 2u) << 2), tab[0] ^ ((pos + 3u) << 2), acc01, acc23);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NC; j++) {
+                        const uint32_t tj = tab[0] + static_cast<uint32_t>(j) * tab_bytes;
+#pragma unroll
+                        for (int wi = 0; wi < 8; wi++) {
+                            const uint32_t pos = static_cast<uint32_t>(4 * wi);
+                            const float v0 = lds_f32(__dp4a(wd[j][wi], sel[0], tj ^ ((pos + 0u) << 2)));
+                            const float v1 = lds_f32(__dp4a(wd[j][wi], sel[1], tj ^ ((pos + 1u) << 2)));
+                            const float v2 = lds_f32(__dp4a(wd[j][wi], sel[2], tj ^ ((pos + 2u) << 2)));
+                            const float v3 = lds_f32(__dp4a(wd[j][wi], sel[3], tj ^ ((pos + 3u) << 2)));
+                            add_f32x2(acc01, v0, v1);
+                            add_f32x2(acc23, v2, v3);
+                        }
                     }
                 }
                 s = (acc01.x + acc01.y) + (acc23.x + acc23.y);

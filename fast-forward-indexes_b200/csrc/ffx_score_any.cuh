@@ -48,27 +48,68 @@ __device__ __forceinline__ AnyVec<N> lds_vec(uint32_t addr) {
     return r;
 }
 
-// One staged row (shared memory, original element order) against the query vector (same
-// order): numpy's np.sum(q * d) for this D.  Lane `sub` of the LPR lanes sharing the row owns
-// chains sub*CPL .. sub*CPL+CPL-1 = accumulators j0 .. j0+CPL-1 of leaf slot (sub*CPL)/8:
+// One staged row (shared memory, original element order) against the query vector: numpy's
+// np.sum(q * d) for this D.  Lane `sub` of the LPR lanes sharing the row owns chains
+// sub*CPL .. sub*CPL+CPL-1 = accumulators j0 .. j0+CPL-1 of leaf slot (sub*CPL)/8:
 //   chain sums (products rounded, sequential adds), balanced combine inside the lane, xor
 //   butterfly over the lanes of the leaf, the last leaf's tail elements one by one, xor
 //   butterfly over the leaf slots, 0 + total.
+// A chain has at most 16 terms (a leaf is at most 128 elements).  The lane's slice of the query
+// vector lives in registers when it fits (QREG: CPL <= 4, up to 64 floats), else beside the ring
+// in shared memory; the row's elements are all loaded before the arithmetic starts.
+constexpr int kAnyMaxSteps = 16;
+
+template <int CPL>
+struct AnyQuery {
+    float v[CPL <= 4 ? CPL * kAnyMaxSteps : 1];
+};
+
+template <int CPL>
+__device__ __forceinline__ void any_load_query(AnyQuery<CPL> &q, uint32_t qv, uint32_t my_byte, int my_steps) {
+    if constexpr (CPL <= 4) {
+#pragma unroll
+        for (int s = 0; s < kAnyMaxSteps; s++) {
+            AnyVec<CPL> x;
+#pragma unroll
+            for (int c = 0; c < CPL; c++) x.v[c] = 0.f;
+            if (s < my_steps) x = lds_vec<CPL>(qv + my_byte + s * 32);
+#pragma unroll
+            for (int c = 0; c < CPL; c++) q.v[s * CPL + c] = x.v[c];
+        }
+    }
+}
+
 template <int CPL, int LPR>
-__device__ __forceinline__ float any_row_dot(uint32_t row, uint32_t qv, uint32_t my_byte, int my_steps, int max_steps,
-                                             bool tail_mine, uint32_t tail_byte, int tail_len) {
+__device__ __forceinline__ float any_row_dot(uint32_t row, uint32_t qv, const AnyQuery<CPL> &qr, uint32_t my_byte,
+                                             int my_steps, bool tail_mine, uint32_t tail_byte, int tail_len) {
     float acc[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; c++) acc[c] = 0.f;
-#pragma unroll 4
-    for (int s = 0; s < max_steps; s++) {
-        if (s < my_steps) {
-            const AnyVec<CPL> d = lds_vec<CPL>(row + my_byte + s * 32);
-            const AnyVec<CPL> q = lds_vec<CPL>(qv + my_byte + s * 32);
+    constexpr int HALF = CPL <= 2 ? kAnyMaxSteps : kAnyMaxSteps / 2;  // steps whose elements are in registers at once
 #pragma unroll
-            for (int c = 0; c < CPL; c++) {
-                const float prod = __fmul_rn(q.v[c], d.v[c]);
-                acc[c] = s == 0 ? prod : __fadd_rn(acc[c], prod);
+    for (int h = 0; h < kAnyMaxSteps; h += HALF) {
+        AnyVec<CPL> d[HALF];
+#pragma unroll
+        for (int s = 0; s < HALF; s++) {
+#pragma unroll
+            for (int c = 0; c < CPL; c++) d[s].v[c] = 0.f;
+            if (h + s < my_steps) d[s] = lds_vec<CPL>(row + my_byte + (h + s) * 32);
+        }
+#pragma unroll
+        for (int s = 0; s < HALF; s++) {
+            if (h + s < my_steps) {
+                AnyVec<CPL> q;
+                if constexpr (CPL <= 4) {
+#pragma unroll
+                    for (int c = 0; c < CPL; c++) q.v[c] = qr.v[(h + s) * CPL + c];
+                } else {
+                    q = lds_vec<CPL>(qv + my_byte + (h + s) * 32);
+                }
+#pragma unroll
+                for (int c = 0; c < CPL; c++) {
+                    const float prod = __fmul_rn(q.v[c], d[s].v[c]);
+                    acc[c] = (h + s) == 0 ? prod : __fadd_rn(acc[c], prod);
+                }
             }
         }
     }
@@ -151,6 +192,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_any_kernel(const 
     const uint32_t tail_byte = static_cast<uint32_t>(plan.tail_start) * 4u;
     const uint32_t q_addr = smem_u32(s_q);
     __syncthreads();
+    AnyQuery<CPL> q_regs;
+    any_load_query<CPL>(q_regs, q_addr, my_byte, my_steps);
 
     const char *rows_base = reinterpret_cast<const char *>(a.vectors);
     const bool indirect = a.indirect && a.mode != FFX_MODE_PASSAGE;
@@ -292,8 +335,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_any_kernel(const 
                 const bool busy = grp < nr;
                 if (busy) mbar_wait(bars + sg * 8, (c_phase >> sg) & 1u);
                 // idle groups run the arithmetic on their (stale) slot: the shuffles stay convergent
-                const float part = any_row_dot<CPL, LPR>(ring + sg * ROWB, q_addr, my_byte, my_steps, plan.max_steps,
-                                                         tail_mine, tail_byte, plan.tail_len);
+                const float part = any_row_dot<CPL, LPR>(ring + sg * ROWB, q_addr, q_regs, my_byte, my_steps, tail_mine,
+                                                         tail_byte, plan.tail_len);
                 __syncwarp();  // every lane has consumed its row: the slots may be refilled
                 for (int g = 0; g < nr; g++) {
                     int slot_ = c_stage + g;

@@ -69,16 +69,12 @@ class RowStore:
             raise RuntimeError(f"Passage ID {psg_ids[dup]} already exists.")
 
     # ---- growth -------------------------------------------------------------------------
-    def append(self, rows: np.ndarray, doc_ids, psg_ids, first_capacity: int, grow_by: int) -> None:
-        """Stage `rows` at the end of the store and record their ids (`None` for both id
-        arguments: a bulk loader names the rows afterwards with `adopt_id_columns`)."""
-        n_new = rows.shape[0]
-        if psg_ids is not None:
-            self.check_new_passages(psg_ids)
+    def reserve_for(self, n_new: int, width: int, dtype, first_capacity: int, grow_by: int) -> None:
+        """Device memory for `n_new` more rows (creates the store on first use).  The only step of
+        an append that can fail for lack of HBM — callers that also persist the rows do it first."""
         if self.dev is None:
-            kind = _ffx.ROWS_PQ_U8 if rows.dtype == np.uint8 else _ffx.ROWS_F32
-            self.dev = _ffx.DeviceIndex(rows.shape[1], capacity=max(first_capacity, n_new),
-                                        row_kind=kind, device=self.device)
+            kind = _ffx.ROWS_PQ_U8 if np.dtype(dtype) == np.uint8 else _ffx.ROWS_F32
+            self.dev = _ffx.DeviceIndex(width, capacity=max(first_capacity, n_new), row_kind=kind, device=self.device)
         need = self.count + n_new
         if need > self.dev.capacity:
             # whole `grow_by` chunks like the reference, but at least 1.5x so that repeated
@@ -86,6 +82,15 @@ class RowStore:
             chunks = -(-(need - self.dev.capacity) // max(grow_by, 1))
             self.dev.reserve(max(self.dev.capacity + chunks * max(grow_by, 1),
                                  int(self.dev.capacity * 1.5)))
+
+    def append(self, rows: np.ndarray, doc_ids, psg_ids, first_capacity: int, grow_by: int) -> None:
+        """Stage `rows` at the end of the store and record their ids (`None` for both id
+        arguments: a bulk loader names the rows afterwards with `adopt_id_columns`)."""
+        n_new = rows.shape[0]
+        if psg_ids is not None:
+            self.check_new_passages(psg_ids)
+        self.reserve_for(n_new, rows.shape[1], rows.dtype, first_capacity, grow_by)
+        need = self.count + n_new
         self.dev.stage(self.count, rows)
         if doc_ids is not None or psg_ids is not None:
             self.record_ids(doc_ids, psg_ids, self.count, n_new)
@@ -256,19 +261,19 @@ class ReplicatedStore(RowStore):
     def all_devices(self) -> list[_ffx.DeviceIndex]:
         return [self.dev, *self.replicas]
 
-    def append(self, rows: np.ndarray, doc_ids, psg_ids, first_capacity: int, grow_by: int) -> None:
-        start = self.count
-        super().append(rows, doc_ids, psg_ids, first_capacity, grow_by)
+    def reserve_for(self, n_new: int, width: int, dtype, first_capacity: int, grow_by: int) -> None:
+        super().reserve_for(n_new, width, dtype, first_capacity, grow_by)
         if not self.replicas:
             self.replicas = [_ffx.DeviceIndex(self.dev.dim, capacity=self.dev.capacity, row_kind=self.dev.row_kind, device=d)
                              for d in self.devices[1:]]
-
-        def stage(replica):
+        for replica in self.replicas:
             if replica.capacity < self.dev.capacity:
                 replica.reserve(self.dev.capacity)
-            replica.stage(start, rows)
 
-        list(self._pool.map(stage, self.replicas))
+    def append(self, rows: np.ndarray, doc_ids, psg_ids, first_capacity: int, grow_by: int) -> None:
+        start = self.count
+        super().append(rows, doc_ids, psg_ids, first_capacity, grow_by)
+        list(self._pool.map(lambda replica: replica.stage(start, rows), self.replicas))
 
     def _push_maps(self) -> None:
         super()._push_maps()
@@ -424,6 +429,9 @@ class DocShardedStore(RowStore):
         self._row_enc_parts.append(row_enc)
         self.count += n_new
         self._maps_stale = True
+
+    def reserve_for(self, n_new: int, width: int, dtype, first_capacity: int, grow_by: int) -> None:
+        """Nothing to reserve ahead: which shard grows depends on the ids of the rows."""
 
     def adopt_id_columns(self, doc_col, psg_col) -> None:
         raise RuntimeError("a doc-sharded store places rows by their ids: pass them with the rows")

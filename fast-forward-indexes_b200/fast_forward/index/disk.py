@@ -148,6 +148,7 @@ class OnDiskIndex(Index):
             self._validate_ids(doc_ids, psg_ids, out.datasets["doc_ids"].dtype.itemsize,
                                out.datasets["psg_ids"].dtype.itemsize)
             have, extra = out.num_vectors, vectors.shape[0]
+            assert have == self._store.count, "index file and device store are out of step"
             if extra > out.capacity - have:
                 LOGGER.debug("resizing index from %s to %s", out.capacity, self._grown(have, extra))
                 out.resize(self._grown(have, extra))
@@ -158,6 +159,14 @@ class OnDiskIndex(Index):
             out.set_num_vectors(have + extra)  # bumped last: the file stays consistent
 
     def _add(self, vectors: np.ndarray, doc_ids: IDSequence, psg_ids: IDSequence) -> None:
+        if self.quantizer is not None and vectors.dtype != np.uint8:
+            raise NotImplementedError(
+                f"Quantizer codes of type {vectors.dtype.name} (Ks > 256) cannot be scored on the device: only uint8 "
+                "codes (Ks <= 256) are supported.")
+        # device memory first: if the store cannot grow (out of HBM) nothing has been written, and the
+        # file and the row store cannot drift apart
+        rows_kind = np.uint8 if vectors.dtype == np.uint8 and self.quantizer is not None else np.float32
+        self._store.reserve_for(vectors.shape[0], vectors.shape[-1], rows_kind, self._init_size, self._chunk_size)
         h5py = _h5py()
         if h5py is None:
             self._add_native(vectors, doc_ids, psg_ids)
@@ -169,6 +178,7 @@ class OnDiskIndex(Index):
             self._validate_ids(doc_ids, psg_ids, fp["doc_ids"].dtype.itemsize, fp["psg_ids"].dtype.itemsize)
 
             have = int(fp.attrs["num_vectors"])
+            assert have == self._store.count, "index file and device store are out of step"
             extra = vectors.shape[0]
             if extra > fp["vectors"].shape[0] - have:
                 grown = self._grown(have, extra)
@@ -256,6 +266,31 @@ class OnDiskIndex(Index):
         index._memory_mapped = memory_mapped
         index._max_indexing_size = max_indexing_size
 
+        try:
+            cls._stage_native(index, index_file)
+        except _ffx.FFXError as error:
+            h5py = _h5py()
+            if h5py is None:
+                raise
+            # a file the native reader does not cover (libver="latest" chunk indexes, filters, dense
+            # link / attribute storage, ...): h5py can read whatever libhdf5 wrote
+            LOGGER.warning("native HDF5 reader: %s; reading %s through h5py", error, index_file)
+            index._quantizer = None
+            index._store = make_store(device, devices, shard)
+            cls._stage_h5py(index, h5py, index_file)
+        return index
+
+    @staticmethod
+    def _check_code_dtype(index: "OnDiskIndex", stored_dtype) -> None:
+        if index._quantizer is not None and index._quantizer.dtype != np.uint8:
+            raise NotImplementedError(
+                f"Quantizer codes of type {np.dtype(index._quantizer.dtype).name} (Ks > 256) cannot be scored on the "
+                "device: only uint8 codes (Ks <= 256) are supported.")
+
+    @classmethod
+    def _stage_native(cls, index: "OnDiskIndex", index_file: Path) -> None:
+        """File -> HBM through the library's own reader: every HDF5 chunk is a pointer into the
+        mapped file, handed to the staging buffers as is."""
         with _h5.H5File(index_file) as fp:
             if "quantizer" in fp:
                 index._quantizer = Quantizer.deserialize(
@@ -265,12 +300,13 @@ class OnDiskIndex(Index):
             index._chunk_size = index._init_size = 2**16
             index._max_id_length = 8
             if "vectors" not in fp:
-                return index
+                return
             meta = fp.info("vectors")
             index._chunk_size = index._init_size = meta["chunk_rows"] or 2**16
             index._max_id_length = fp.info("doc_ids")["dtype"].itemsize
             if total == 0:
-                return index
+                return
+            cls._check_code_dtype(index, meta["dtype"])
 
             # one HDF5 chunk (a contiguous byte range of the file) per staging step, read in place
             codes = index._quantizer is not None and meta["dtype"] == np.uint8
@@ -284,4 +320,31 @@ class OnDiskIndex(Index):
             # the O(N) Python loop of disk.py:408-417, as two calls into the C++ id dictionaries
             if not by_ids:
                 index._store.adopt_id_columns(_text_ids(fp.read("doc_ids", 0, total)), _text_ids(fp.read("psg_ids", 0, total)))
-        return index
+
+    @classmethod
+    def _stage_h5py(cls, index: "OnDiskIndex", h5py, index_file: Path) -> None:
+        """File -> HBM through h5py, chunk by chunk (disk.py:380-417 of the reference with the
+        per-row Python loop replaced by the C++ id dictionaries)."""
+        with h5py.File(index_file, "r") as fp:
+            if "quantizer" in fp:
+                index._quantizer = Quantizer.deserialize(
+                    dict(fp["quantizer/meta"].attrs), dict(fp["quantizer/attributes"].attrs),
+                    {k: v[:] for k, v in fp["quantizer/data"].items()})
+            total = int(fp.attrs["num_vectors"])
+            index._chunk_size = index._init_size = 2**16
+            index._max_id_length = 8
+            if "vectors" not in fp:
+                return
+            vectors = fp["vectors"]
+            index._chunk_size = index._init_size = (vectors.chunks[0] if vectors.chunks else 0) or 2**16
+            index._max_id_length = fp["doc_ids"].dtype.itemsize
+            if total == 0:
+                return
+            cls._check_code_dtype(index, vectors.dtype)
+            codes = index._quantizer is not None and vectors.dtype == np.uint8
+            for lo in range(0, total, index._chunk_size):
+                hi = min(total, lo + index._chunk_size)
+                block = vectors[lo:hi]
+                rows = block if codes or block.dtype == np.float32 else block.astype(np.float32)
+                index._store.append(np.ascontiguousarray(rows), _text_ids(fp["doc_ids"][lo:hi]),
+                                    _text_ids(fp["psg_ids"][lo:hi]), first_capacity=total, grow_by=index._chunk_size)

@@ -117,3 +117,54 @@ def test_quantizer_is_persisted(api, tmp_path):
     loaded.mode = api.Mode.MAXP
     codes, _ = loaded._get_vectors(["d0", "d1", "d2", "d3"])
     assert np.array_equal(codes, pq.encode(x))
+
+
+def test_load_falls_back_to_h5py_for_files_the_native_reader_refuses(api, tmp_path, monkeypatch):
+    """The native HDF5 reader covers what h5py's defaults write; a file with anything else
+    (libver="latest" chunk indexes, filters, dense link storage) makes it return
+    FFX_ERR_UNSUPPORTED — `load` then reads the file through h5py when that is installed, and
+    fails with the reader's message when it is not."""
+    import fast_forward.index.disk as disk
+    from fast_forward import _ffx, _h5
+
+    path = tmp_path / "index.h5"
+    rng = np.random.default_rng(0)
+    vec = rng.standard_normal((300, 32)).astype(np.float32)
+    doc_ids = [f"d{i // 3}" for i in range(300)]
+    psg_ids = [None if i % 7 == 0 else f"p{i}" for i in range(300)]
+    index = api.OnDiskIndex(path, api.ones, chunk_size=64, init_size=64)
+    index.add(vec, doc_ids=doc_ids, psg_ids=psg_ids)
+    want = api.OnDiskIndex.load(path)
+
+    class Refusing:
+        def __init__(self, *a, **kw):
+            raise _ffx.FFXError(-5, "chunk index version 4 is not supported")
+
+    class Wrapped:
+        H5File = Refusing
+
+    monkeypatch.setattr(disk, "_h5", Wrapped)
+    if disk._h5py() is None:  # native-writer variant: no h5py, the reader's error surfaces
+        with pytest.raises(_ffx.FFXError, match="not supported"):
+            api.OnDiskIndex.load(path)
+        return
+    got = api.OnDiskIndex.load(path)
+    monkeypatch.setattr(disk, "_h5", _h5)
+    assert len(got) == len(want) == 300 and got.doc_ids == want.doc_ids and got.psg_ids == want.psg_ids
+    ids = sorted(want.doc_ids)[::5]
+    v1, i1 = got._get_vectors(ids)
+    v2, i2 = want._get_vectors(ids)
+    assert i1 == i2 and (v1 == v2).all()
+    assert [(v.tobytes(), d, p) for v, d, p in got] == [(v.tobytes(), d, p) for v, d, p in want]
+
+
+def test_wide_codes_are_refused_up_front(api, tmp_path):
+    """Ks > 256 gives uint16 codes, which the device kernels do not score: `add` says so at once
+    instead of storing float copies that fail later (the in-memory index does the same)."""
+    quant = api.NanoPQ(2, 300)
+    quant.fit(np.random.default_rng(1).standard_normal((400, 8)).astype(np.float32), iter=2)
+    assert quant.dtype == np.uint16
+    for index in (api.OnDiskIndex(tmp_path / "wide.h5", api.ones, quantizer=quant), api.InMemoryIndex(api.ones, quantizer=quant)):
+        with pytest.raises((NotImplementedError, RuntimeError), match="Ks"):
+            index.add(np.ones((3, 8), np.float32), doc_ids=["a", "b", "c"])
+        assert len(index) == 0

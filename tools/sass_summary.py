@@ -26,7 +26,7 @@ def main():
         ops = collections.Counter()
         keep = []
         for line in body.splitlines():
-            m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
+            m = re.search(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
             if not m:
                 continue
             op = m.group(1)
