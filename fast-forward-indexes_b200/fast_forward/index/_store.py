@@ -141,16 +141,16 @@ class RowStore:
         identity on one device, `device * stride + local` on a doc-sharded store."""
         return codes
 
-    def resolve(self, ids, passage_mode: bool) -> np.ndarray:
+    def resolve(self, ids, passage_mode: bool, missing_ok: bool = False) -> np.ndarray:
         """An id column (one entry per pair, repeats welcome) -> int32 candidates for ffx_rerank:
         document ordinals, or row numbers in PASSAGE mode.  IndexError names the first id that
         is not in the index (index/util.py:38-39)."""
-        return self._encode(self._ordinals(ids, passage_mode), passage_mode)
+        return self._encode(self._ordinals(ids, passage_mode, missing_ok), passage_mode)
 
-    def _ordinals(self, ids, passage_mode: bool) -> np.ndarray:
+    def _ordinals(self, ids, passage_mode: bool, missing_ok: bool = False) -> np.ndarray:
         self._refresh()
         codes, missing = (self.psgs if passage_mode else self.docs).lookup(ids)
-        if missing >= 0:
+        if missing >= 0 and not missing_ok:
             raise IndexError(f"ID {_ids.first_text(ids, missing)} not found in the index.")
         return codes
 

@@ -204,10 +204,11 @@ class Index(abc.ABC):
         on the columns; IndexError names the first unknown id (index/util.py:38-39)."""
 
     @abc.abstractmethod
-    def _resolve(self, ids, mode: Mode) -> np.ndarray:
+    def _resolve(self, ids, mode: Mode, missing_ok: bool = False) -> np.ndarray:
         """An id column (Series / array, one entry per pair) -> int32 candidates for ffx_rerank
         (document ordinals, or row numbers in PASSAGE mode) with the semantics of
-        index/util.py:29-41; IndexError names the first unknown id."""
+        index/util.py:29-41; IndexError names the first unknown id — or, with `missing_ok`, unknown
+        ids come back as -1 (early stopping only fails for the ids it actually scores)."""
 
     # ------------------------------------------------------------------ adding
     def add(self, vectors: np.ndarray, doc_ids: IDSequence | None = None,
@@ -313,7 +314,16 @@ class Index(abc.ABC):
 
         on_device = int(count.max()) <= 16384 and len({d for d in depths if d >= cutoff}) <= 32
         qv = np.ascontiguousarray(query_vectors, dtype=np.float32)[present]
-        cand = self._resolve(df["id"], self.mode)  # every id coded once, whatever the number of depths
+        # every id coded once, whatever the number of depths.  The reference looks ids up depth by depth
+        # (index/base.py:373 -> index/util.py:38-39), so an id the index does not hold only raises if
+        # its row is actually scored: unknown ids are scored as a stand-in candidate and checked
+        # against the scored prefixes afterwards.
+        cand = self._resolve(df["id"], self.mode, missing_ok=True)
+        unknown = cand < 0
+        if unknown.any():
+            if unknown.all():
+                raise IndexError(f"ID {df['id'].iloc[0]} not found in the index.")
+            cand = np.where(unknown, cand[~unknown][0], cand).astype(np.int32)
         if on_device:
             q_off = np.concatenate([[0], np.cumsum(count)]).astype(np.int64)
             try:
@@ -329,6 +339,13 @@ class Index(abc.ABC):
             ff, done_depth = self._early_stopping_walk(qv, cand, cutoff, alpha, depths, lex, start, count,
                                                        depth_of_row, slot_of_row)
         scored = depth_of_row < done_depth[slot_of_row]
+        if unknown.any() and (unknown & scored).any():
+            # the first one the reference would have met: earliest depth interval, then frame order
+            bad = np.flatnonzero(unknown & scored)
+            walked = sorted(d for d in set(depths) if d >= cutoff)
+            interval = np.searchsorted(walked, depth_of_row[bad], side="right")
+            first = bad[np.lexsort((bad, interval))[0]]
+            raise IndexError(f"ID {df['id'].iloc[first]} not found in the index.")
         result = df.loc[scored].copy()
         result["ff_score"] = ff[scored]
         return result
@@ -400,6 +417,13 @@ class Index(abc.ABC):
             nq, counts = cols.nq, cols.counts()
             step = nq if batch_size is None or batch_size >= nq else max(int(batch_size), 1)
             widest = int(counts.max())
+            if self._lists_are_skewed(nq, widest, len(cols)):
+                result = self._ordered_on_host(cols, query_vectors, None)
+                if result is not None:
+                    LOGGER.info("computed scores in %s seconds", perf_counter() - started)
+                    out_ranking = Ranking._from_cols(result[0], "fast-forward")
+                    out_ranking._origin = _Origin(self, cols, result[1])
+                    return out_ranking
             if step >= nq:
                 out = self._launch_cols(cols, self.mode, query_vectors, 0, nq, k=widest)
                 ff, pos, top = out["ff"], out["topk_pos"], out["topk_score"]
@@ -461,6 +485,10 @@ class Index(abc.ABC):
         k = widest if cutoff is None else int(min(max(cutoff, 0), widest))
         if k == 0:
             return ranking.cut(0)
+        if self._lists_are_skewed(nq, widest, len(cols)):
+            result = self._ordered_on_host(cols, query_vectors, alpha)
+            if result is not None:
+                return Ranking._from_cols(result[0].head(k) if k < widest else result[0], ranking.name)
         # one slot more than the cut: it tells whether equal scores straddle the cut boundary
         kk = min(k + 1, widest)
         out = self._launch_cols(cols, self.mode, query_vectors, 0, nq, alpha=alpha, k=kk, interpolate=True,
@@ -474,6 +502,36 @@ class Index(abc.ABC):
         if ties:
             result.order_ties_by_id()  # ties inside the kept lists: ascending id, like the reference
         return Ranking._from_cols(result.drop_empty(), ranking.name)
+
+    @staticmethod
+    def _lists_are_skewed(nq: int, widest: int, n: int) -> bool:
+        """The per-query lists of ffx_rerank are dense [nq, widest] matrices: fine when the lists
+        are about equally long, quadratic when one query has a million candidates and ten thousand
+        others have ten (the reference is O(n) there)."""
+        return nq * widest > 4 * n + (1 << 20)
+
+    def _ordered_on_host(self, cols, query_vectors, alpha):
+        """Skewed list lengths: semantic scores only from the device (O(n) memory), the
+        interpolation (ranking.py:319, same two roundings in float32) and the per-query order
+        (stable radix sort, ffx_ranking_order) on the host.  Returns (ordered columns, ff in source
+        order), or None when a NaN score needs the generic route."""
+        import ctypes as C
+
+        from fast_forward._cols import Cols
+
+        ff = self._launch_cols(cols, self.mode, query_vectors, 0, cols.nq, k=0, want_ff=True)["ff"]
+        score = ff if alpha is None else _fl32_interpolate(alpha, cols.score, ff)
+        if np.isnan(score).any():
+            return None
+        score = np.ascontiguousarray(score, np.float32)
+        block = np.repeat(np.arange(cols.nq, dtype=np.int32), cols.counts())
+        order = np.empty(len(score), np.int64)
+        _ffx.check(_ffx.lib().ffx_ranking_order(C.c_void_p(block.ctypes.data), C.c_void_p(score.ctypes.data), len(score),
+                                                C.c_void_p(order.ctypes.data), 0))
+        ordered = Cols(cols.q_keys, cols.q_off, cols.ids, cols.id_code[order], score[order], cols.queries)
+        if alpha is not None:
+            ordered.order_ties_by_id()
+        return ordered, ff
 
     def _recut_straddling(self, blocks, cols, result, query_vectors, alpha, k) -> None:
         """Exact cut for the queries whose k-th and (k+1)-th interpolated scores are equal;

@@ -112,5 +112,5 @@ class InMemoryIndex(Index):
     def _candidates(self, cols, mode: Mode) -> np.ndarray:
         return cols.candidates(self._store, mode == Mode.PASSAGE)
 
-    def _resolve(self, ids, mode: Mode) -> np.ndarray:
-        return self._store.resolve(ids, mode == Mode.PASSAGE)
+    def _resolve(self, ids, mode: Mode, missing_ok: bool = False) -> np.ndarray:
+        return self._store.resolve(ids, mode == Mode.PASSAGE, missing_ok)

@@ -400,3 +400,57 @@ def test_candidates_are_cached_on_the_ranking_and_follow_the_index(api):
     ref_index.add(vec, doc_ids=[f"d{i // 2}" for i in range(40)] + [f"d{20 + i // 2}" for i in range(18)] + ["d0", "d0"])
     pd.testing.assert_frame_equal(grown._df, ref_index.rerank(api.Ranking(frame, queries=queries), 0.3, 5)._df)
     assert old == ref_index(api.Ranking(frame, queries=queries))["q0"] and new is None
+
+
+def test_early_stopping_only_fails_for_ids_it_scores(api):
+    """The reference resolves ids depth by depth (index/base.py:373 -> index/util.py:38-39): an id
+    the index does not hold raises IndexError only when its row is reached.  Here all ids are coded
+    up front, so unknown ones are checked against the scored prefixes afterwards."""
+    rng = np.random.default_rng(11)
+    dim = 384
+    vec = rng.standard_normal((200, dim)).astype(np.float32)
+    index = api.InMemoryIndex(api.LambdaEncoder(lambda t: np.ones(dim, np.float32)), mode=api.Mode.MAXP)
+    index.add(vec, doc_ids=[f"d{i}" for i in range(200)])
+    # first-stage scores fall fast: with alpha = 1 a query stops after the first interval
+    ids = [f"d{i}" for i in range(60)]
+    frame = pd.DataFrame({"q_id": ["q1"] * 60, "id": ids, "score": np.linspace(100, 1, 60).astype(np.float32)})
+    late = frame.copy()
+    late.loc[45, "id"] = "unknown-late"
+    early = frame.copy()
+    early.loc[3, "id"] = "unknown-early"
+    kw = dict(early_stopping=5, early_stopping_alpha=1.0, early_stopping_depths=[10, 30, 60])
+    want = index(api.Ranking(frame, queries=QUERIES), **kw)
+    got = index(api.Ranking(late, queries=QUERIES), **kw)  # the walk stops at depth 10: row 45 is never looked up
+    assert len(want._df) == 10
+    pd.testing.assert_frame_equal(got._df, want._df)
+    with pytest.raises(IndexError, match="ID unknown-early not found in the index."):
+        index(api.Ranking(early, queries=QUERIES), **kw)
+    with pytest.raises(IndexError, match="ID unknown-late not found in the index."):  # alpha 0: every depth is walked
+        index(api.Ranking(late, queries=QUERIES), early_stopping=5, early_stopping_alpha=0.0,
+              early_stopping_depths=[10, 30, 60])
+    with pytest.raises(IndexError, match="ID unknown-late not found in the index."):  # no early stopping: all rows
+        index(api.Ranking(late, queries=QUERIES))
+
+
+def test_one_very_long_list_among_many_short_ones(api, monkeypatch):
+    """Memory follows the number of pairs, not queries x longest list: with skewed list lengths
+    the order comes from a host radix sort over the device's semantic scores instead of dense
+    [nq, widest] list matrices.  Same frames as the dense route."""
+    from fast_forward.index.base import Index
+
+    rng = np.random.default_rng(12)
+    dim, n_docs, nq = 64, 30_000, 1500
+    vec = rng.standard_normal((n_docs, dim)).astype(np.float32)
+    qv = rng.standard_normal((nq, dim)).astype(np.float32)
+    index = api.InMemoryIndex(api.TableEncoder({f"text {i}": qv[i] for i in range(nq)}), mode=api.Mode.MAXP)
+    index.add(vec, doc_ids=[f"d{i}" for i in range(n_docs)])
+    q_ids = np.concatenate([np.repeat("q0", n_docs), np.repeat([f"q{i}" for i in range(1, nq)], 3)])
+    ids = np.concatenate([np.arange(n_docs), rng.integers(0, n_docs - 2, nq - 1).repeat(3) + np.tile([0, 1, 2], nq - 1)])
+    frame = pd.DataFrame({"q_id": q_ids, "id": [f"d{i}" for i in ids], "score": (rng.integers(0, 50, len(ids)) * 0.25).astype(np.float32)})
+    r = api.Ranking(frame, queries={f"q{i}": f"text {i}" for i in range(nq)})
+    assert Index._lists_are_skewed(nq, n_docs, len(frame))
+    skewed = (index(r), index.rerank(r, 0.3, 10), index.rerank(r, 0.3), r.interpolate(index(r), 0.3).cut(7))
+    monkeypatch.setattr(Index, "_lists_are_skewed", staticmethod(lambda *a: False))
+    dense = (index(r), index.rerank(r, 0.3, 10), index.rerank(r, 0.3), r.interpolate(index(r), 0.3).cut(7))
+    for a, b in zip(skewed, dense):
+        pd.testing.assert_frame_equal(a._df, b._df)

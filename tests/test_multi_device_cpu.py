@@ -105,3 +105,36 @@ def test_store_factory_arguments():
         make_store(0, [0, 1], "rows")
     with pytest.raises(ValueError):
         make_store(0, [1, 1], "query")
+
+
+def test_skewed_lists_and_lazy_early_stopping_ids_on_the_fake_device(api, monkeypatch):
+    """Host logic that does not depend on the GPU: the O(n) route for skewed list lengths gives the
+    dense route's frames, and early stopping raises only for unknown ids it reaches."""
+    from fast_forward.index.base import Index
+
+    rng = np.random.default_rng(31)
+    dim, n_docs, nq = 16, 400, 30
+    vec = rng.standard_normal((n_docs, dim)).astype(np.float32)
+    qv = {f"query {i}": rng.standard_normal(dim).astype(np.float32) for i in range(nq)}
+    queries = {f"q{i}": f"query {i}" for i in range(nq)}
+    index = api.InMemoryIndex(api.LambdaEncoder(lambda t: qv[t]))
+    index.add(vec, doc_ids=[f"d{i}" for i in range(n_docs)])
+    rows = [("q0", f"d{i}", np.float32(rng.integers(0, 9) * 0.5)) for i in range(n_docs)]
+    for q in range(1, nq):
+        rows += [(f"q{q}", f"d{i}", np.float32(rng.integers(0, 9) * 0.5)) for i in rng.choice(n_docs, 3, replace=False)]
+    r = api.Ranking(pd.DataFrame(rows, columns=["q_id", "id", "score"]), queries=queries)
+    monkeypatch.setattr(Index, "_lists_are_skewed", staticmethod(lambda *a: True))
+    skewed = (index(r), index.rerank(r, 0.3, 5), index.rerank(r, 0.3))
+    monkeypatch.setattr(Index, "_lists_are_skewed", staticmethod(lambda *a: False))
+    dense = (index(r), index.rerank(r, 0.3, 5), index.rerank(r, 0.3))
+    for a, b in zip(skewed, dense):
+        pd.testing.assert_frame_equal(a._df, b._df)
+
+    frame = pd.DataFrame({"q_id": ["q1"] * 40, "id": [f"d{i}" for i in range(40)], "score": np.linspace(90, 1, 40).astype(np.float32)})
+    late = frame.copy()
+    late.loc[33, "id"] = "unknown-late"
+    kw = dict(early_stopping=4, early_stopping_alpha=1.0, early_stopping_depths=[8, 20, 40])
+    pd.testing.assert_frame_equal(index(api.Ranking(late, queries=queries), **kw)._df,
+                                  index(api.Ranking(frame, queries=queries), **kw)._df)
+    with pytest.raises(IndexError, match="ID unknown-late not found in the index."):
+        index(api.Ranking(late, queries=queries), early_stopping=4, early_stopping_alpha=0.0, early_stopping_depths=[8, 20, 40])
