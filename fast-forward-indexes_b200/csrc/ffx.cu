@@ -68,6 +68,7 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 constexpr int64_t kStageBytes = 32ll << 20;  // per pinned / device staging buffer
+constexpr size_t kAdcLutScratch = 768ull << 20;  // tables of one launch built ahead (C4: 5193 x 96 KB = 510 MB)
 constexpr size_t kSmemBudget = 227 * 1024 - 2048;  // opt-in shared memory per CTA on sm_100, minus static (<= 1.5 KB)
 
 // Tuning / diagnostic knobs (ffx_set_option).  0 = automatic.
@@ -1095,7 +1096,7 @@ int ffx_index_set_pq(ffx_index *idx, int M, int Ks, int Ds, const float *codewor
 static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const int64_t *q_off,
                        const int32_t *cand, const float *lex, double alpha, int k, int64_t max_cand,
                        float *out_ff, float *out_int, float *out_topk_score, int32_t *out_topk_pos,
-                       void *stream, float *qeff_buf) {
+                       void *stream, float *qeff_buf, float *lut_buf = nullptr) {
     if (!idx) return fail(FFX_ERR_INVALID, "ffx_rerank: NULL index");
     if (mode < FFX_MODE_PASSAGE || mode > FFX_MODE_AVEP)
         return fail(FFX_ERR_INVALID, "ffx_rerank: unknown mode %d", mode);
@@ -1162,6 +1163,17 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     if (pq && idx->R && !qeff_buf) {
         off_qeff = total;
         total += static_cast<size_t>(nq) * D * 4;
+    }
+    // XOR-swizzled ADC kernel: the tables of all queries are built by one launch beforehand
+    // (ffx_adc_xor_lut_kernel) when they fit the scratch budget, else inside the scoring kernel
+    size_t off_lut = 0;
+    const size_t lut_floats = pq ? static_cast<size_t>(idx->M) * idx->Ks : 0;
+    const bool lut_ahead = pq && max_cand > 0 && adc_kind(idx) == 3 && (lut_floats * 4) % 16 == 0 &&
+                           (lut_buf || static_cast<size_t>(nq) * lut_floats * 4 <= kAdcLutScratch);
+    if (lut_ahead && !lut_buf) {
+        total = (total + 255) & ~static_cast<size_t>(255);
+        off_lut = total;
+        total += static_cast<size_t>(nq) * lut_floats * 4;
     }
     if (total) FFX_TRY(scratch_reserve(idx->work, total));
     char *work = static_cast<char *>(idx->work.p);
@@ -1237,6 +1249,20 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
                 w.cpad = cpad;
                 w.topk_score = out_topk_score;
                 w.topk_pos = out_topk_pos;
+                if (lut_ahead) {
+                    float *lut = lut_buf ? lut_buf : reinterpret_cast<float *>(work + off_lut);
+                    const dim3 grid_l(static_cast<unsigned>((lut_floats + ffx::kAdcLutThreads - 1) / ffx::kAdcLutThreads),
+                                      static_cast<unsigned>((nq + ffx::kAdcLutQueries - 1) / ffx::kAdcLutQueries));
+                    switch (idx->Ds) {
+                        case 4: ffx::ffx_adc_xor_lut_kernel<4><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
+                        case 8: ffx::ffx_adc_xor_lut_kernel<8><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
+                        case 16: ffx::ffx_adc_xor_lut_kernel<16><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
+                        default: ffx::ffx_adc_xor_lut_kernel<0><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
+                    }
+                    g_launches++;
+                    FFX_CUDA(cudaGetLastError());
+                    w.lut = lut;
+                }
                 const size_t smem = ffx::adc_xor_smem_bytes(idx->M, idx->Ks, fuse ? cpad : 0);
                 const unsigned grid = static_cast<unsigned>(fuse ? nq : nq * tiles);
                 switch (idx->M / 32) {
@@ -1374,8 +1400,12 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     const size_t b_q = pad(static_cast<size_t>(nq) * D * 4), b_off = pad(static_cast<size_t>(nq + 1) * 8);
     const size_t b_n = pad(static_cast<size_t>(n) * 4), b_k = pad(static_cast<size_t>(nq) * k * 4);
     const bool rotated = pq && idx->R;
+    // tables of the XOR-swizzled ADC kernel, built ahead per chunk: every chunk needs its own slice
+    const size_t lut_floats = pq && adc_kind(idx) == 3 ? static_cast<size_t>(idx->M) * idx->Ks : 0;
+    const size_t b_lut = lut_floats && static_cast<size_t>(nq) * lut_floats * 4 <= kAdcLutScratch
+                             ? pad(static_cast<size_t>(nq) * lut_floats * 4) : 0;
     size_t total = b_q + (rotated ? b_q : 0) + b_off + b_n /*cand*/ + (lex ? b_n : 0) + (out_ff ? b_n : 0) +
-                   (out_int ? b_n : 0) + (k > 0 ? 2 * b_k : 0);
+                   (out_int ? b_n : 0) + (k > 0 ? 2 * b_k : 0) + b_lut;
     FFX_TRY(scratch_reserve(idx->hostio, total));
     char *p = static_cast<char *>(idx->hostio.p);
     auto take = [&](size_t b) { char *r = p; p += b; return r; };
@@ -1388,6 +1418,7 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     float *d_int = out_int ? reinterpret_cast<float *>(take(b_n)) : nullptr;
     float *d_ts = k > 0 ? reinterpret_cast<float *>(take(b_k)) : nullptr;
     int32_t *d_tp = k > 0 ? reinterpret_cast<int32_t *>(take(b_k)) : nullptr;
+    float *d_lut = b_lut ? reinterpret_cast<float *>(take(b_lut)) : nullptr;
 
     // Query chunks flow through H2D -> kernel -> D2H on separate streams, so the PCIe copies
     // of chunk i+1 / i-1 hide behind the kernel of chunk i.  Every chunk has its own slice of
@@ -1428,7 +1459,7 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
         // unshifted per-pair arrays; per-query outputs are shifted to the chunk
         FFX_TRY(rerank_impl(idx, mode, d_q + q0 * D, cq, d_off + q0, d_cand, d_lex, alpha, k, max_cand,
                             d_ff, d_int, d_ts ? d_ts + q0 * k : nullptr, d_tp ? d_tp + q0 * k : nullptr,
-                            comp, d_qe ? d_qe + q0 * D : nullptr));
+                            comp, d_qe ? d_qe + q0 * D : nullptr, d_lut ? d_lut + q0 * lut_floats : nullptr));
         cudaEvent_t out_ready = event_at(idx, ev++);
         FFX_CUDA(cudaEventRecord(out_ready, comp));
         FFX_CUDA(cudaStreamWaitEvent(idx->s_d2h, out_ready, 0));

@@ -74,6 +74,7 @@ struct AdcWarpArgs {
     int k, cpad;         // FUSE
     float *topk_score;
     int32_t *topk_pos;
+    const float *lut;    // XOR kernel: [nq][M * Ks] tables built by ffx_adc_xor_lut_kernel (nullptr: built in the kernel)
 };
 
 __host__ __device__ inline size_t adc_warp_smem_bytes(int Ks, int cpad_scores) {

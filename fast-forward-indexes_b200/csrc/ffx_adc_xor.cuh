@@ -58,6 +58,46 @@ __global__ void ffx_adc_xor_codewords_kernel(const float *cw, int M, int Ks, int
     }
 }
 
+// The per-query tables, all queries of a launch at once: lut[q][(j3*Ks + c)*32 + b] =
+// qeff[q][m*Ds ..] . codewords[m][c], m = 32*j3 + b — the layout ffx_adc_xor_kernel keeps in shared
+// memory, so that a CTA fetches its query's table with ONE bulk copy instead of building it
+// (building in place cost every query ~20 us of latency-bound codebook reads with the
+// look-up pipe idle: 12 % of the kernel, ncu profiles/r2_adc_xor_full_raw.csv).  A thread owns
+// one table entry, keeps its codeword in registers and walks QT queries: the codebook is read
+// once per QT queries.  Same arithmetic as the in-kernel build (fmaf over d, ascending).
+constexpr int kAdcLutThreads = 256;
+constexpr int kAdcLutQueries = 16;
+
+template <int DS>
+__global__ void __launch_bounds__(kAdcLutThreads) ffx_adc_xor_lut_kernel(const float *cw_x, const float *qeff, int M, int Ks,
+                                                                        int Ds, int64_t nq, float *lut) {
+    const int total = M * Ks;
+    const int e = blockIdx.x * kAdcLutThreads + threadIdx.x;
+    if (e >= total) return;
+    const int per_table = Ks * 32;
+    const int m = 32 * (e / per_table) + (e & 31);
+    const int ds = DS ? DS : Ds;
+    float c[DS ? DS : 1];
+    const float *cw = cw_x + static_cast<size_t>(e) * ds;
+    if constexpr (DS != 0) {
+#pragma unroll
+        for (int d = 0; d < DS; d++) c[d] = __ldg(cw + d);
+    }
+    const int64_t q0 = static_cast<int64_t>(blockIdx.y) * kAdcLutQueries;
+    const int64_t q1 = q0 + kAdcLutQueries < nq ? q0 + kAdcLutQueries : nq;
+    for (int64_t q = q0; q < q1; q++) {
+        const float *qm = qeff + q * (static_cast<int64_t>(M) * ds) + m * ds;
+        float acc = 0.f;
+        if constexpr (DS != 0) {
+#pragma unroll
+            for (int d = 0; d < DS; d++) acc = fmaf(__ldg(qm + d), c[d], acc);
+        } else {
+            for (int d = 0; d < ds; d++) acc = fmaf(__ldg(qm + d), __ldg(cw + d), acc);
+        }
+        lut[q * total + e] = acc;
+    }
+}
+
 // [table][slots: warps x 32 x M][mbarriers][FUSE: cpad interpolated scores]; the sort keys of the
 // fused top-k overlay table + slots once they are dead
 __host__ __device__ inline size_t adc_xor_smem_bytes(int M, int Ks, int cpad_scores) {
@@ -177,7 +217,20 @@ __global__ void __launch_bounds__(kAdcXorThreads, 1) ffx_adc_xor_kernel(const Ad
     }
 
     // ---- per-query table: s_lut[(j3*Ks + c)*32 + b] = qeff[m*Ds..] . codewords[m][c],  m = 32*j3 + b
-    {
+    if (w.lut) {
+        // built for the whole launch by ffx_adc_xor_lut_kernel: one bulk copy
+        __shared__ __align__(8) unsigned long long s_lut_bar;
+        const uint32_t lbar = smem_u32(&s_lut_bar);
+        if (threadIdx.x == 0) {
+            mbar_init(lbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(lbar, lut_bytes);
+            bulk_g2s_hint(smem_u32(s_lut), w.lut + q_idx * (static_cast<int64_t>(M) * a.Ks), lut_bytes, lbar, stream_l2);
+        }
+        __syncthreads();
+        mbar_wait(lbar, 0);
+    } else {
         const float *qe = a.qeff + q_idx * (static_cast<int64_t>(M) * a.Ds);
         const int total = M * a.Ks;
         const int per_table = a.Ks * 32;

@@ -568,4 +568,43 @@ int ffx_topk_gather(const int32_t *pos, const float *score, int64_t nq, int64_t 
     return FFX_OK;
 }
 
+int ffx_tie_runs(const float *score, const int64_t *off, int64_t nq, int64_t cap, int64_t *run_start,
+                 int64_t *run_len, int64_t *n_runs, int n_threads) {
+    if (nq < 0 || cap < 0 || !n_runs || (nq > 0 && (!score || !off)) || (cap > 0 && (!run_start || !run_len)))
+        return fail(FFX_ERR_INVALID, "ffx_tie_runs: bad arguments");
+    const int64_t n = nq > 0 ? off[nq] : 0;
+    const int threads = worker_count(n_threads, n / 16);
+    std::vector<std::vector<int64_t>> found(static_cast<size_t>(std::max(threads, 1)));
+    const int64_t step = threads > 0 ? (nq + threads - 1) / threads : nq;
+    parallel_ranges(nq, threads, [&](int64_t lo, int64_t hi) {
+        std::vector<int64_t> &mine = found[static_cast<size_t>(step > 0 ? lo / step : 0)];
+        for (int64_t q = lo; q < hi; q++) {
+            int64_t i = off[q];
+            const int64_t end = off[q + 1];
+            while (i + 1 < end) {
+                if (score[i + 1] != score[i]) {
+                    i++;
+                    continue;
+                }
+                int64_t j = i + 1;
+                while (j + 1 < end && score[j + 1] == score[i]) j++;
+                mine.push_back(i);
+                mine.push_back(j - i + 1);
+                i = j + 1;
+            }
+        }
+    });
+    int64_t total = 0;
+    for (const auto &v : found) total += static_cast<int64_t>(v.size() / 2);
+    *n_runs = total;
+    if (total > cap) return FFX_OK;  // the caller retries with room for *n_runs
+    int64_t at = 0;
+    for (const auto &v : found)
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            run_start[at] = v[i];
+            run_len[at++] = v[i + 1];
+        }
+    return FFX_OK;
+}
+
 }  // extern "C"

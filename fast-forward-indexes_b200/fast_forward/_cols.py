@@ -225,33 +225,36 @@ class Cols:
         counts = self.counts()
         return self if (counts > 0).all() else self.take_heads(counts)
 
-    def order_ties_by_id(self) -> None:
+    def order_ties_by_id(self, ties_hint: int | None = None) -> None:
         """The reference leaves equal scores of a query in ascending id order after an outer merge
         (ranking.py:312-326: the merge sorts its keys, the sort that follows is stable); the
-        kernels order ties by position.  Re-orders, in place, the runs of equal scores."""
+        kernels order ties by position.  Re-orders, in place, the runs of equal scores (found by
+        ffx_tie_runs on all host cores; `ties_hint` = an upper bound of their number, if known)."""
         n = len(self.score)
-        if n < 2:
+        if n < 2 or ties_hint == 0:
             return
-        s = self.score
-        same = s[1:] == s[:-1]
-        if not same.any():
+        score = np.ascontiguousarray(self.score, np.float32)
+        cap = int(ties_hint) if ties_hint else 1024
+        while True:
+            starts, lens = np.empty(cap, np.int64), np.empty(cap, np.int64)
+            found = C.c_int64(0)
+            _ffx.check(_ffx.lib().ffx_tie_runs(_ptr(score), _ptr(self.q_off), self.nq, cap, _ptr(starts), _ptr(lens),
+                                               C.byref(found), 0))
+            if found.value <= cap:
+                break
+            cap = int(found.value)
+        runs = int(found.value)
+        if runs == 0:
             return
-        block_start = np.zeros(n, bool)
-        block_start[self.q_off[:-1][self.q_off[:-1] < n]] = True
-        same &= ~block_start[1:]
-        if not same.any():
-            return
-        starts = np.flatnonzero(same & ~np.concatenate([[False], same[:-1]]))
-        ends = np.flatnonzero(same & ~np.concatenate([same[1:], [False]])) + 2
-        rank = self.ids.string_rank() if len(starts) > 64 else None
-        for s0, e0 in zip(starts.tolist(), ends.tolist()):
-            run = self.id_code[s0:e0]
+        rank = self.ids.string_rank() if runs > 64 else None
+        for s0, length in zip(starts[:runs].tolist(), lens[:runs].tolist()):
+            run = self.id_code[s0:s0 + length]
             if rank is not None:
                 order = np.argsort(rank[run], kind="stable")
             else:
                 names = np.asarray(self.ids.keys.take(pa.array(run)).to_pylist(), dtype=object)
                 order = np.argsort(names, kind="stable")
-            self.id_code[s0:e0] = run[order]
+            self.id_code[s0:s0 + length] = run[order]
         self._cand.clear()
 
 

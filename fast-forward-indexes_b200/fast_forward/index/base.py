@@ -65,8 +65,7 @@ class _Origin:
         out = self.index._device().interpolate_topk_host(src.score, self.ff, src.q_off, alpha, max_c,
                                                          want_int=False)
         cols, ties, _ = src.from_lists(out["topk_pos"], out["topk_score"], max_c)
-        if ties:
-            cols.order_ties_by_id()
+        cols.order_ties_by_id(ties)
         return Ranking._from_cols(cols, first.name)
 
 
@@ -499,8 +498,7 @@ class Index(abc.ABC):
             # millions of pairs): the reference keeps the smaller ids.  Rank those queries in
             # full, order their ties by id and cut again.
             self._recut_straddling(np.flatnonzero(straddle), cols, result, query_vectors, alpha, k)
-        if ties:
-            result.order_ties_by_id()  # ties inside the kept lists: ascending id, like the reference
+        result.order_ties_by_id(ties)  # ties inside the kept lists: ascending id, like the reference
         return Ranking._from_cols(result.drop_empty(), ranking.name)
 
     @staticmethod

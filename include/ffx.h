@@ -208,6 +208,11 @@ int ffx_match_keys(const int64_t *have, int64_t n_have, const int64_t *want, int
  *   room for nq * keep entries.  *n_ties = adjacent equal scores inside kept lists (the rows the
  *   host then orders by id, ranking.py:312-326); straddle[q] (optional, needs keep < k) = the
  *   keep-th and (keep+1)-th scores of q are equal, i.e. the cut falls inside a tie. */
+/* ffx_tie_runs: the runs of equal scores inside the blocks [off[q], off[q+1]) of a ranked score
+ *   column (blocks sorted descending): run_start[i] / run_len[i] (>= 2) in row order, *n_runs =
+ *   their number; when that exceeds `cap` nothing is written (call again with room). */
+int ffx_tie_runs(const float *score, const int64_t *off, int64_t nq, int64_t cap, int64_t *run_start,
+                 int64_t *run_len, int64_t *n_runs, int n_threads);
 int ffx_lut_gather(const int32_t *lut, int64_t n_lut, const int32_t *codes, int64_t n, int32_t *out,
                    int64_t *first_negative, int n_threads);
 int ffx_topk_gather(const int32_t *pos, const float *score, int64_t nq, int64_t k, int64_t keep,
