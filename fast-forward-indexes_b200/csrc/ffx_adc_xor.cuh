@@ -66,7 +66,7 @@ __global__ void ffx_adc_xor_codewords_kernel(const float *cw, int M, int Ks, int
 // one table entry, keeps its codeword in registers and walks QT queries: the codebook is read
 // once per QT queries.  Same arithmetic as the in-kernel build (fmaf over d, ascending).
 constexpr int kAdcLutThreads = 256;
-constexpr int kAdcLutQueries = 16;
+constexpr int kAdcLutQueries = 32;
 
 template <int DS>
 __global__ void __launch_bounds__(kAdcLutThreads) ffx_adc_xor_lut_kernel(const float *cw_x, const float *qeff, int M, int Ks,
@@ -81,20 +81,40 @@ __global__ void __launch_bounds__(kAdcLutThreads) ffx_adc_xor_lut_kernel(const f
     const float *cw = cw_x + static_cast<size_t>(e) * ds;
     if constexpr (DS != 0) {
 #pragma unroll
-        for (int d = 0; d < DS; d++) c[d] = __ldg(cw + d);
+        for (int d = 0; d < DS; d += 4) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4 *>(cw + d));
+            c[d] = c4.x, c[d + 1] = c4.y, c[d + 2] = c4.z, c[d + 3] = c4.w;
+        }
     }
     const int64_t q0 = static_cast<int64_t>(blockIdx.y) * kAdcLutQueries;
     const int64_t q1 = q0 + kAdcLutQueries < nq ? q0 + kAdcLutQueries : nq;
+    const int64_t D = static_cast<int64_t>(M) * ds;
+    // 32 consecutive threads = 32 consecutive sub-quantizers m: their query slices are one
+    // contiguous 32 * Ds floats, read as float4s (DS is a multiple of 4: rows of D floats stay 16-byte
+    // aligned when D is)
+    const bool vec = DS != 0 && (D & 3) == 0 && (reinterpret_cast<uintptr_t>(qeff) & 15) == 0;
+#pragma unroll 4
     for (int64_t q = q0; q < q1; q++) {
-        const float *qm = qeff + q * (static_cast<int64_t>(M) * ds) + m * ds;
+        const float *qm = qeff + q * D + m * ds;
         float acc = 0.f;
         if constexpr (DS != 0) {
+            if (vec) {
 #pragma unroll
-            for (int d = 0; d < DS; d++) acc = fmaf(__ldg(qm + d), c[d], acc);
+                for (int d = 0; d < DS; d += 4) {
+                    const float4 q4 = __ldg(reinterpret_cast<const float4 *>(qm + d));
+                    acc = fmaf(q4.x, c[d], acc);
+                    acc = fmaf(q4.y, c[d + 1], acc);
+                    acc = fmaf(q4.z, c[d + 2], acc);
+                    acc = fmaf(q4.w, c[d + 3], acc);
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < DS; d++) acc = fmaf(__ldg(qm + d), c[d], acc);
+            }
         } else {
             for (int d = 0; d < ds; d++) acc = fmaf(__ldg(qm + d), __ldg(cw + d), acc);
         }
-        lut[q * total + e] = acc;
+        __stcs(lut + q * total + e, acc);  // read once, by another SM: streaming store
     }
 }
 

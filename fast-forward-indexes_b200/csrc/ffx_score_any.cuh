@@ -83,7 +83,8 @@ __device__ __forceinline__ void any_load_query(AnyQuery<CPL> &q, uint32_t qv, ui
 
 template <int CPL, int LPR>
 __device__ __forceinline__ float any_row_dot(uint32_t row, uint32_t qv, const AnyQuery<CPL> &qr, uint32_t my_byte,
-                                             int my_steps, bool tail_mine, uint32_t tail_byte, int tail_len) {
+                                             int my_steps, int max_steps, bool tail_mine, uint32_t tail_byte,
+                                             int tail_len) {
     float acc[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; c++) acc[c] = 0.f;
@@ -107,7 +108,7 @@ __device__ __forceinline__ float any_row_dot(uint32_t row, uint32_t qv, const An
         }
     } else {
 #pragma unroll 4
-        for (int s = 0; s < kAnyMaxSteps; s++) {
+        for (int s = 0; s < max_steps; s++) {  // warp-uniform bound: the longest chain of this dimension
             if (s < my_steps) {
                 const AnyVec<CPL> d = lds_vec<CPL>(row + my_byte + s * 32);
                 const AnyVec<CPL> q = lds_vec<CPL>(qv + my_byte + s * 32);
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_any_kernel(const 
                 const bool busy = grp < nr;
                 if (busy) mbar_wait(bars + sg * 8, (c_phase >> sg) & 1u);
                 // idle groups run the arithmetic on their (stale) slot: the shuffles stay convergent
-                const float part = any_row_dot<CPL, LPR>(ring + sg * ROWB, q_addr, q_regs, my_byte, my_steps, tail_mine,
-                                                         tail_byte, plan.tail_len);
+                const float part = any_row_dot<CPL, LPR>(ring + sg * ROWB, q_addr, q_regs, my_byte, my_steps,
+                                                         plan.max_steps, tail_mine, tail_byte, plan.tail_len);
                 __syncwarp();  // every lane has consumed its row: the slots may be refilled
                 for (int g = 0; g < nr; g++) {
                     int slot_ = c_stage + g;

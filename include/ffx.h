@@ -96,7 +96,8 @@ int ffx_index_read_rows(ffx_index *idx, const int64_t *rows, int64_t n, void *ou
 int64_t ffx_index_num_rows(const ffx_index *idx);     /* highest staged row + 1 */
 int64_t ffx_index_capacity(const ffx_index *idx);
 int64_t ffx_index_dim(const ffx_index *idx);
-/* 1 when `dim` has a lane-major fast kernel, 0 when the generic exact kernel is used */
+/* 1 when `dim` has a warp-per-row kernel (lane-major plan, or the tree-as-data kernel for every
+ * other dimension up to 4096), 0 when the thread-per-pair exact kernel is used */
 int ffx_index_has_fast_path(const ffx_index *idx);
 
 /* Replaces `doc_id_to_idx` (index/memory.py:86-88, index/disk.py:408-417): document
