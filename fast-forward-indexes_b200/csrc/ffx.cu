@@ -1203,7 +1203,11 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
             if (idx->R) {
                 float *qe = qeff_buf ? qeff_buf : reinterpret_cast<float *>(work + off_qeff);
                 const size_t rot_smem = static_cast<size_t>(D) * 8 * 4;
-                if (rot_smem <= 48 * 1024) {
+                if (D % 16 == 0 && nq >= 64 && (reinterpret_cast<uintptr_t>(qvecs) & 15) == 0) {
+                    const dim3 grid_r(static_cast<unsigned>((D + ffx::kRotTile - 1) / ffx::kRotTile),
+                                      static_cast<unsigned>((nq + ffx::kRotTile - 1) / ffx::kRotTile));
+                    ffx::ffx_rotate_queries_tiled_kernel<<<grid_r, 256, 0, st>>>(qvecs, idx->R, static_cast<int>(D), nq, qe);
+                } else if (rot_smem <= 48 * 1024) {
                     ffx::ffx_rotate_queries8_kernel<<<static_cast<unsigned>((nq + 7) / 8), 256, rot_smem, st>>>(
                         qvecs, idx->R, static_cast<int>(D), nq, qe);
                 } else {
