@@ -1875,7 +1875,10 @@ int ffx_merge_topk(int device, const float *shard_scores, const int32_t *shard_p
     if (smem > 48 * 1024)
         FFX_CUDA(cudaFuncSetAttribute(ffx::ffx_merge_topk_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    ffx::ffx_merge_topk_kernel<<<static_cast<unsigned>(nq), ffx::kThreads, smem,
+    // 8 keys per thread where the list is long enough for the register sort (cpad >= 2048), never
+    // fewer than 256 threads
+    const int merge_threads = std::max(256, std::min(1024, cpad / 8));
+    ffx::ffx_merge_topk_kernel<<<static_cast<unsigned>(nq), merge_threads, smem,
                                  static_cast<cudaStream_t>(stream)>>>(
         shard_scores, shard_pos, n_shards, nq, k, cpad, out_score, out_pos);
     g_launches++;

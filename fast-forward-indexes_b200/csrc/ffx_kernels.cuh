@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(1024) ffx_topk_kernel(const float *scores, int
 
 // Merge per-shard top-k lists [n_shards, nq, k] -> [nq, k]; positions are global positions
 // inside the query's candidate block, so the ordering rule is the same key.
-__global__ void __launch_bounds__(kThreads) ffx_merge_topk_kernel(const float *sh_s,
+__global__ void __launch_bounds__(1024) ffx_merge_topk_kernel(const float *sh_s,
                                                                   const int32_t *sh_p,
                                                                   int n_shards, int64_t nq, int k,
                                                                   int cpad, float *out_s,
@@ -769,7 +769,9 @@ __global__ void __launch_bounds__(kThreads) ffx_merge_topk_kernel(const float *s
         s_keys[i] = key;
     }
     __syncthreads();
-    bitonic_sort_desc(s_keys, cpad);
+    // cpad == 4, 8 or 16 keys per thread: the register / shuffle / shared-memory hybrid network
+    // (15 shared-memory stages instead of 91 at 8192 keys), else the plain one
+    block_sort_desc(s_keys, cpad);
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
         const bool ok = s_keys[i] != 0ull;
         out_s[q * k + i] = ok ? key_score(s_keys[i]) : -INFINITY;

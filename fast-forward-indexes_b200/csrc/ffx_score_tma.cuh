@@ -227,18 +227,22 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
         d.mine = h_mine;
         desc[slot * 32 + lane] = d;
         __syncwarp();
+        // candidates of the batch that have rows to read (a doc-id-range shard owns a fraction of
+        // them: producer and consumer walk the set bits instead of all 32 entries)
+        return __ballot_sync(kFull, lane < h_nb && h_cnt > 0);
     };
 
     int cur = 0;  // slot of batch A (being consumed); batch B lives in slot cur ^ 1
     int nbA, nbB, baseA, baseB;
+    uint32_t liveA, liveB;
     grab();
     resolve();
-    publish(0);
+    liveA = publish(0);
     nbA = h_nb;
     baseA = h_base;
     grab();
     resolve();
-    publish(1);
+    liveB = publish(1);
     nbB = h_nb;
     baseB = h_base;
     grab();
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
     // ---- producer cursor (warp-uniform): walks the same row sequence as the consumer, up to
     // `ns` rows ahead
     bool p_inB = false;
-    int pj = -1;
+    uint32_t p_left = liveA;  // candidates of the producer's batch it has not entered yet
     uint32_t pk = 0, pcnt = 0, pstart = 0, p_rows = 0;
     int p_stage = 0, c_stage = 0, inflight = 0;
     uint32_t c_phase = 0;
@@ -262,9 +266,9 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
                     have = true;
                     break;
                 }
-                const int nb = p_inB ? nbB : nbA;
-                if (pj + 1 < nb) {
-                    pj++;
+                if (p_left) {
+                    const int pj = __ffs(p_left) - 1;
+                    p_left &= p_left - 1;
                     const CandDesc d = desc[((p_inB ? cur ^ 1 : cur) << 5) + pj];
                     pstart = d.start;
                     pcnt = d.cnt;
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
                 }
                 if (!p_inB && nbB > 0) {
                     p_inB = true;
-                    pj = -1;
+                    p_left = liveB;
                     pk = 0;
                     pcnt = 0;
                     continue;
@@ -300,7 +304,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
 
     while (nbA > 0) {
         float my_ff = 0.f;
-        for (int cj = 0; cj < nbA; cj++) {
+        for (uint32_t todo = liveA; todo; todo &= todo - 1) {
+            const int cj = __ffs(todo) - 1;
             const uint32_t cnt = desc[(cur << 5) + cj].cnt;
             DocReduce red;
             red.init();
@@ -396,16 +401,18 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
 
         // shift: B becomes A, the resolved batch is published into the freed slot, the
         // look-ahead loads advance by one batch
-        publish(cur);
+        const uint32_t live_new = publish(cur);
         cur ^= 1;
         nbA = nbB;
         baseA = baseB;
+        liveA = liveB;
         nbB = h_nb;
         baseB = h_base;
+        liveB = live_new;
         if (p_inB) {
             p_inB = false;  // the producer's position in old B is a position in new A
         } else {
-            pj = -1;  // it had exhausted old A without entering B
+            p_left = liveA;  // it had exhausted old A without entering B
             pk = 0;
             pcnt = 0;
         }
