@@ -384,3 +384,69 @@ def combine(a: Cols, b: Cols, fn):
     out = Cols(a.q_keys, a.q_off, a.ids, a.id_code[order], score[order], queries)
     out.order_ties_by_id()
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# run files
+# ------------------------------------------------------------------------------------------
+def read_run(path) -> tuple[pd.DataFrame, str] | None:
+    """`pd.read_csv(f, sep=r"\\s+", header=None, names=[q_id, q0, id, rank, score, name])` of
+    ranking.py:401-402 for the columns a ranking keeps, tokenised on all host cores by libffx
+    (`ffx_run_open`): a frame with q_id / id (pandas `str`) and score (float64, the very doubles
+    pandas' default float parser yields) plus the first row's name.  None when pandas would have
+    produced something else from this file — all-numeric id columns whose tokens are not
+    canonical integers (pandas renumbers them), NA or boolean tokens, quotes, lines without six
+    fields, scores that are not plain decimals — the caller then lets pandas read it."""
+    info = np.zeros(16, np.int64)
+    handle = C.c_void_p()
+    _ffx.check(_ffx.lib().ffx_run_open(str(path).encode(), 0, C.byref(handle), _ptr(info)))
+    try:
+        rows = int(info[0])
+        if rows == 0 or info[3] or info[4] or info[5] or info[14]:
+            return None
+        for col in (0, 1):
+            numeric, canonical, na, boolean = (int(x) for x in info[6 + 4 * col:10 + 4 * col])
+            if na or boolean == rows or (numeric == rows and canonical != rows):
+                return None
+        q_off, id_off = np.empty(rows + 1, np.int64), np.empty(rows + 1, np.int64)
+        q_data, id_data = np.empty(max(int(info[1]), 1), np.uint8), np.empty(max(int(info[2]), 1), np.uint8)
+        score = np.empty(rows, np.float64)
+        name = C.create_string_buffer(int(info[15]) + 1)
+        _ffx.check(_ffx.lib().ffx_run_read(handle, _ptr(q_off), _ptr(q_data), _ptr(id_off), _ptr(id_data), _ptr(score), name))
+    finally:
+        _ffx.lib().ffx_run_close(handle)
+    q_arr = pa.Array.from_buffers(pa.large_string(), rows, [None, pa.py_buffer(q_off), pa.py_buffer(q_data)])
+    id_arr = pa.Array.from_buffers(pa.large_string(), rows, [None, pa.py_buffer(id_off), pa.py_buffer(id_data)])
+    frame = pd.DataFrame({"q_id": _series(q_arr), "id": _series(id_arr), "score": score}, copy=False)
+    return frame, name.raw[:int(info[15])].decode("utf-8")
+
+
+def write_run(cols: "Cols", path, name: str) -> bool:
+    """`Ranking.save` (ranking.py:348-366) from the columns, formatted on all host cores
+    (`ffx_run_write`); False when an id needs the csv writer's quoting (tab, quote, newline in an
+    id or in the name): pandas writes those files."""
+    import pyarrow.compute as pc
+
+    for strings in (cols.q_keys, cols.ids.keys):
+        if len(strings) and pc.any(pc.match_substring_regex(strings, '[\\t\\n\\r"]')).as_py():
+            return False
+    if any(ch in name for ch in "\t\n\r\""):
+        return False
+
+    def buffers(arr):
+        if arr.type != pa.large_string():
+            arr = arr.cast(pa.large_string())
+        _, offsets, data = arr.buffers()
+        return arr, offsets.address + 8 * arr.offset, (data.address if data is not None else 0)
+
+    qk, qk_off, qk_data = buffers(cols.q_keys)
+    ik, ik_off, ik_data = buffers(cols.ids.keys)
+    score = np.ascontiguousarray(cols.score, np.float32)
+    code = np.ascontiguousarray(cols.id_code, np.int32)
+    dummy = np.zeros(1, np.uint8)
+    _ffx.check(_ffx.lib().ffx_run_write(str(path).encode(), cols.nq, _ptr(cols.q_off), C.c_void_p(qk_off),
+                                        C.c_void_p(qk_data or dummy.ctypes.data), C.c_void_p(ik_off),
+                                        C.c_void_p(ik_data or dummy.ctypes.data), _ptr(code), _ptr(score),
+                                        name.encode("utf-8"), 0))
+    del qk, ik
+    return True

@@ -56,6 +56,10 @@ SYMBOLS = {
     "ffx_ranking_order": (_I, [_P, _P, _L, _P, _I]),
     "ffx_order_u64": (_I, [_P, _L, _P, _I]),
     "ffx_match_keys": (_I, [_P, _L, _P, _L, _P]),
+    "ffx_run_open": (_I, [C.c_char_p, _I, C.POINTER(_P), _P]),
+    "ffx_run_read": (_I, [_P, _P, _P, _P, _P, _P, _P]),
+    "ffx_run_close": (None, [_P]),
+    "ffx_run_write": (_I, [C.c_char_p, _L, _P, _P, _P, _P, _P, _P, _P, C.c_char_p, _I]),
     "ffx_tie_runs": (_I, [_P, _P, _L, _L, _P, _P, C.POINTER(_L), _I]),
     "ffx_lut_gather": (_I, [_P, _L, _P, _L, _P, C.POINTER(_L), _I]),
     "ffx_topk_gather": (_I, [_P, _P, _L, _L, _L, _P, _P, _P, _P, _P, C.POINTER(_L), _P, _I]),

@@ -55,6 +55,7 @@ def _minmax(df: pd.DataFrame) -> pd.DataFrame:
 
 
 _CODED_FROM = 50_000  # rows from which the integer-coded constructor path pays off
+_NATIVE_RUN_FROM = 1 << 20  # bytes from which a run file is tokenised by libffx instead of pandas
 
 
 def _cols_module():
@@ -360,6 +361,11 @@ class Ranking:
     # ------------------------------------------------------------------ I/O
     def save(self, target: Path) -> None:
         """Write a TREC run file: q_id Q0 id rank score name (ranking.py:348-366)."""
+        cols = self._coded()
+        if cols is not None and len(cols):
+            target.parent.mkdir(parents=True, exist_ok=True)
+            if _cols_module().write_run(cols, target, str(self.name)):
+                return
         out = self._df.join(_rank_column(self._df))
         out["name"] = str(self.name)
         out["q0"] = "Q0"
@@ -380,6 +386,12 @@ class Ranking:
     def from_file(cls, f: Path, queries: Mapping[str, str] | None = None,
                   dtype: np.dtype = np.dtype(np.float32)) -> "Ranking":
         """Read a whitespace-separated TREC run file (ranking.py:388-409)."""
+        import os
+
+        if os.path.getsize(f) >= _NATIVE_RUN_FROM:  # large files: tokenised on all host cores by libffx
+            parsed = _cols_module().read_run(f)
+            if parsed is not None:
+                return cls(parsed[0], name=parsed[1], queries=queries, dtype=dtype, copy=False)
         table = pd.read_csv(f, sep=r"\s+", skipinitialspace=True, header=None,
                             names=["q_id", "q0", "id", "rank", "score", "name"])
         return cls(table, name=table["name"][0], queries=queries, dtype=dtype, copy=False)

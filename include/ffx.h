@@ -220,6 +220,32 @@ int ffx_topk_gather(const int32_t *pos, const float *score, int64_t nq, int64_t 
                     const int64_t *src_off, const int32_t *src_code, int64_t *out_off, int32_t *out_code,
                     float *out_score, int64_t *n_ties, uint8_t *straddle, int n_threads);
 
+/* ---- TREC run files (host; ranking.py:348-366,388-409) --------------------------------------
+ * ffx_run_open maps a whitespace-separated run file (q_id Q0 id rank score name), tokenises it
+ * on n_threads cores (0 = all) and reports in info[16]:
+ *   [0] rows, [1] bytes of all q_id tokens, [2] bytes of all id tokens, [3] lines without exactly six
+ *   fields, [4] scores that are not plain decimals (or out of double range), [5] quote characters,
+ *   [6..9] q_id column: tokens that look numeric / are canonical integers / are pandas NA strings /
+ *   are boolean words, [10..13] the same for the id column, [14] bit 0/1/2: the first row's name looks
+ *   numeric / NA / boolean, [15] length of the first row's name.
+ * The caller decides from those whether pandas would have produced the same strings (it renumbers
+ * all-numeric columns, drops NA tokens, ...) and then fetches the columns with ffx_run_read: Arrow
+ * layout offsets[rows + 1] + data for the two id columns, scores as the doubles pandas' default
+ * float parser produces (not correctly rounded — the reference's float32 scores are reproduced
+ * bit for bit), the first row's name.  ffx_run_close unmaps.
+ * ffx_run_write writes a ranking held as integer-coded columns (q_keys per block, block offsets,
+ * the distinct ids + one code per row, float32 scores) as `q_id \t Q0 \t id \t rank \t score \t name`
+ * lines, scores formatted as numpy / pandas print float32 (shortest round trip; positional for
+ * 1e-4 <= |x| < 1e6, else scientific). */
+typedef struct ffx_run ffx_run;
+int ffx_run_open(const char *file_name, int n_threads, ffx_run **out, int64_t *info);
+int ffx_run_read(ffx_run *run, int64_t *q_offsets, char *q_data, int64_t *id_offsets, char *id_data, double *score,
+                 char *first_name);
+void ffx_run_close(ffx_run *run);
+int ffx_run_write(const char *file_name, int64_t nq, const int64_t *q_off, const int64_t *qk_offsets, const char *qk_data,
+                  const int64_t *idk_offsets, const char *idk_data, const int32_t *id_code, const float *score,
+                  const char *name, int n_threads);
+
 /* ---- the hot path ----------------------------------------------------------------- */
 /* Replaces, in one pass, `Index._compute_scores` (index/base.py:279-314) including
  * `_get_vectors` (index/memory.py:139-140), `Ranking.interpolate`'s arithmetic
