@@ -1791,6 +1791,46 @@ int ffx_pq_kmeans(int device, const float *vecs, int64_t n, int M, int Ks, int D
     return FFX_OK;
 }
 
+int ffx_sgemm(int device, int trans_a, int64_t m, int64_t n, int64_t k, const float *A, const float *B, float *C) {
+    if (m <= 0 || n <= 0 || k <= 0 || !A || !B || !C) return fail(FFX_ERR_INVALID, "ffx_sgemm: bad arguments");
+    const int n_dev = ffx_device_count();
+    if (n_dev <= 0) return fail(FFX_ERR_CUDA, "no CUDA device (ffx has no CPU path)");
+    if (device < 0 || device >= n_dev) return fail(FFX_ERR_INVALID, "ffx_sgemm: device %d of %d", device, n_dev);
+    FFX_CUDA(cudaSetDevice(device));
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+    const int64_t tiles = ((m + ffx::kGemmTile - 1) / ffx::kGemmTile) * ((n + ffx::kGemmTile - 1) / ffx::kGemmTile);
+    // slices of k: enough CTAs for ~4 waves, pieces of at least 1024 values of k, at most 64 partial results
+    int64_t slices = std::max<int64_t>(1, std::min<int64_t>({64, (4 * sm_count + tiles - 1) / tiles, (k + 1023) / 1024}));
+    const int64_t per_slice = ((k + slices - 1) / slices + ffx::kGemmK - 1) / ffx::kGemmK * ffx::kGemmK;
+    slices = (k + per_slice - 1) / per_slice;
+    DevBuf d_a, d_b, d_c, d_part;
+    FFX_CUDA(cudaMalloc(&d_a.p, static_cast<size_t>(m) * k * 4));
+    FFX_CUDA(cudaMalloc(&d_b.p, static_cast<size_t>(k) * n * 4));
+    FFX_CUDA(cudaMalloc(&d_c.p, static_cast<size_t>(m) * n * 4));
+    if (slices > 1) FFX_CUDA(cudaMalloc(&d_part.p, static_cast<size_t>(slices) * m * n * 4));
+    FFX_CUDA(cudaMemcpy(d_a.p, A, static_cast<size_t>(m) * k * 4, cudaMemcpyHostToDevice));
+    FFX_CUDA(cudaMemcpy(d_b.p, B, static_cast<size_t>(k) * n * 4, cudaMemcpyHostToDevice));
+    const dim3 grid(static_cast<unsigned>((n + ffx::kGemmTile - 1) / ffx::kGemmTile),
+                    static_cast<unsigned>((m + ffx::kGemmTile - 1) / ffx::kGemmTile), static_cast<unsigned>(slices));
+    float *target = static_cast<float *>(slices > 1 ? d_part.p : d_c.p);
+    if (trans_a)
+        ffx::ffx_sgemm_kernel<true><<<grid, 256>>>(static_cast<const float *>(d_a.p), static_cast<const float *>(d_b.p), target, m, n, k, per_slice);
+    else
+        ffx::ffx_sgemm_kernel<false><<<grid, 256>>>(static_cast<const float *>(d_a.p), static_cast<const float *>(d_b.p), target, m, n, k, per_slice);
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    if (slices > 1) {
+        ffx::ffx_sgemm_reduce_kernel<<<permute_grid(m * n, sm_count), 256>>>(static_cast<const float *>(d_part.p),
+                                                                             static_cast<float *>(d_c.p), m * n,
+                                                                             static_cast<int>(slices));
+        g_launches++;
+        FFX_CUDA(cudaGetLastError());
+    }
+    FFX_CUDA(cudaMemcpy(C, d_c.p, static_cast<size_t>(m) * n * 4, cudaMemcpyDeviceToHost));
+    return FFX_OK;
+}
+
 int ffx_index_sync(ffx_index *idx, void *stream) {
     if (!idx) return fail(FFX_ERR_INVALID, "ffx_index_sync: NULL index");
     FFX_TRY(bind(idx));

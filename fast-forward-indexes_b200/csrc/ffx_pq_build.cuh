@@ -128,4 +128,81 @@ __global__ void ffx_pq_means_kernel(float *codewords, const double *sums, const 
     }
 }
 
+// ---- OPQ rotation update (quantizer/nanopq.py:94-98 -> nanopq OPQ.fit) ----------------------------
+// Each round of OPQ training is two matrix products around the k-means: X = vecs @ R  ([N, D] x
+// [D, D]) and the Procrustes matrix vecs^T @ X_hat ([D, N] x [N, D]); the D x D SVD stays on the host.
+// One register-tiled fp32 kernel serves both: C[m, n] (+)= op(A)[m, k] . B[k, n], 64 x 64 tile per
+// CTA, 4 x 4 per thread, 16 values of k staged through shared memory; gridDim.z slices of k write
+// their own partial C (reduced in fixed order by ffx_sgemm_reduce_kernel: deterministic, and the
+// long sums over N are accumulated in shorter pieces).  fp32 FMA throughout — TF32 / BF16 tensor
+// cores would drop the products to 10 / 7 mantissa bits, and the rotation must stay orthogonal to
+// ~1e-6 for the ADC identity q.(dec(c) R^T) = (q R).dec(c) that scoring relies on.
+constexpr int kGemmTile = 64, kGemmK = 16;
+
+template <bool TRANS_A>
+__global__ void __launch_bounds__(256) ffx_sgemm_kernel(const float *A, const float *B, float *C, int64_t M, int64_t N,
+                                                        int64_t K, int64_t k_per_slice) {
+    __shared__ float s_a[kGemmK][kGemmTile + 4];
+    __shared__ float s_b[kGemmK][kGemmTile + 4];
+    const int64_t m0 = static_cast<int64_t>(blockIdx.y) * kGemmTile, n0 = static_cast<int64_t>(blockIdx.x) * kGemmTile;
+    const int64_t k_lo = static_cast<int64_t>(blockIdx.z) * k_per_slice;
+    const int64_t k_hi = k_lo + k_per_slice < K ? k_lo + k_per_slice : K;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[r][c] = 0.f;
+    for (int64_t k0 = k_lo; k0 < k_hi; k0 += kGemmK) {
+#pragma unroll
+        for (int e = threadIdx.x; e < kGemmK * kGemmTile; e += 256) {
+            // op(A) tile: [16 k][64 m]
+            if constexpr (TRANS_A) {  // A is [K, M]: rows of A run along m
+                const int kk = e / kGemmTile, mm = e % kGemmTile;
+                const int64_t k = k0 + kk, m = m0 + mm;
+                s_a[kk][mm] = (k < k_hi && m < M) ? __ldg(A + k * M + m) : 0.f;
+            } else {  // A is [M, K]: rows of A run along k
+                const int mm = e / kGemmK, kk = e % kGemmK;
+                const int64_t k = k0 + kk, m = m0 + mm;
+                s_a[kk][mm] = (k < k_hi && m < M) ? __ldg(A + m * K + k) : 0.f;
+            }
+            const int kk = e / kGemmTile, nn = e % kGemmTile;
+            const int64_t k = k0 + kk, n = n0 + nn;
+            s_b[kk][nn] = (k < k_hi && n < N) ? __ldg(B + k * N + n) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kGemmK; kk++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) a[r] = s_a[kk][4 * ty + r];
+#pragma unroll
+            for (int c = 0; c < 4; c++) b[c] = s_b[kk][4 * tx + c];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+    float *out = C + static_cast<int64_t>(blockIdx.z) * M * N;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int64_t m = m0 + 4 * ty + r, n = n0 + 4 * tx + c;
+            if (m < M && n < N) out[m * N + n] = acc[r][c];
+        }
+}
+
+// C[i] = sum over slices, in slice order
+__global__ void ffx_sgemm_reduce_kernel(const float *partial, float *C, int64_t elems, int slices) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < elems;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float acc = partial[i];
+        for (int s = 1; s < slices; s++) acc += partial[static_cast<int64_t>(s) * elems + i];
+        C[i] = acc;
+    }
+}
+
 }  // namespace ffx

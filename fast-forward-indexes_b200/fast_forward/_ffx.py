@@ -74,6 +74,7 @@ SYMBOLS = {
     "ffx_h5_attr_read": (_I, [_P, C.c_char_p, C.c_char_p, _P, _P, _L, C.POINTER(_L)]),
     "ffx_pq_encode": (_I, [_I, _P, _L, _I, _I, _I, _P, _P]),
     "ffx_pq_kmeans": (_I, [_I, _P, _L, _I, _I, _I, _P, _I]),
+    "ffx_sgemm": (_I, [_I, _I, _L, _L, _L, _P, _P, _P]),
     "ffx_dict_create": (_I, [C.POINTER(_P)]),
     "ffx_dict_destroy": (_I, [_P]),
     "ffx_dict_size": (_L, [_P]),
@@ -455,6 +456,17 @@ def pq_kmeans(vecs, init_codewords, iters: int, device: int = 0) -> np.ndarray:
         raise ValueError(f"expected vectors of shape [n, {M * Ds}], got {vecs.shape}")
     check(lib().ffx_pq_kmeans(int(device), _ptr(vecs), vecs.shape[0], M, Ks, Ds, _ptr(codewords), int(iters)))
     return codewords
+
+
+def sgemm(a, b, trans_a: bool = False, device: int = 0) -> np.ndarray:
+    """ffx_sgemm: `a @ b` (or `a.T @ b`) in fp32 on the GPU; a is [m, k] (or [k, m]), b is [k, n]."""
+    a, b = _arr(a, np.float32), _arr(b, np.float32)
+    m, k = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    if b.shape[0] != k:
+        raise ValueError(f"shapes {a.shape} and {b.shape} do not multiply")
+    out = np.empty((m, b.shape[1]), np.float32)
+    check(lib().ffx_sgemm(int(device), int(trans_a), m, b.shape[1], k, _ptr(a), _ptr(b), _ptr(out)))
+    return out
 
 
 def merge_topk(device, shard_scores_ptr, shard_pos_ptr, n_shards, nq, k, out_score_ptr, out_pos_ptr,

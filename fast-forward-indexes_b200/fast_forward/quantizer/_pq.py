@@ -8,8 +8,9 @@ and serialised quantizers are interchangeable with the reference.  Training and 
 offline index-build steps; scoring never decodes (see ffx_adc_xor.cuh).
 
 By default they run on the host (scipy), like the reference.  With `device=<cuda ordinal>` the
-two expensive pieces — the Lloyd iterations of `fit` and the nearest-codeword search of
-`encode` — run on the GPU instead (libffx `ffx_pq_kmeans` / `ffx_pq_encode`,
+expensive pieces — the Lloyd iterations of `fit`, the nearest-codeword search of `encode` and
+the two matrix products of every OPQ rotation round (`vecs @ R`, `vecs.T @ X_hat`; the D x D SVD
+stays in numpy) — run on the GPU instead (libffx `ffx_pq_kmeans` / `ffx_pq_encode` / `ffx_sgemm`,
 csrc/ffx_pq_build.cuh): same algorithm and same initial centroids (the `minit="points"` draws
 of kmeans2 are repeated on the host), direct fp32 distances.  That is an explicit choice, not a
 fallback: with `device` set and no CUDA device the calls raise.
@@ -106,17 +107,26 @@ class Codebook:
             return
         D = vecs.shape[1]
         R = np.eye(D, dtype=np.float32)
+
+        def product(a, b, trans_a=False):
+            """The two O(N D^2) products of a round: on the GPU with `device` (ffx_sgemm), else numpy."""
+            if self.device is None:
+                return (a.T if trans_a else a) @ b
+            from fast_forward import _ffx
+
+            return _ffx.sgemm(a, b, trans_a, self.device)
+
         for it in range(rotation_iter):
             last = it == rotation_iter - 1
-            X = vecs @ R
+            X = product(vecs, R)
             words = self._fit_pq(X, pq_iter if last else 1, seed, minit)
             if last:
                 self.codewords, self.R = words, R
                 return
             X_hat = self._lookup(self._assign(X, words), words)
-            U, _, Vt = np.linalg.svd(vecs.T @ X_hat)  # orthogonal Procrustes
+            U, _, Vt = np.linalg.svd(product(vecs, X_hat, trans_a=True))  # orthogonal Procrustes (D x D, host)
             R = (U @ Vt).astype(np.float32)
-        self.codewords, self.R = self._fit_pq(vecs @ R, pq_iter, seed, minit), R
+        self.codewords, self.R = self._fit_pq(product(vecs, R), pq_iter, seed, minit), R
 
     def _check(self, vecs: np.ndarray, train: bool = False) -> np.ndarray:
         if vecs.ndim != 2 or vecs.dtype != np.float32:

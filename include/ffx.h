@@ -323,6 +323,11 @@ int ffx_rerank_early_stop_host(ffx_index *idx, int mode, const float *qvecs, int
 int ffx_pq_encode(int device, const float *vecs, int64_t n, int M, int Ks, int Ds, const float *codewords,
                   uint8_t *codes);
 int ffx_pq_kmeans(int device, const float *vecs, int64_t n, int M, int Ks, int Ds, float *codewords, int iters);
+/* The two matrix products of an OPQ rotation round (quantizer/nanopq.py:94-98 -> nanopq `OPQ.fit`:
+ * X = vecs @ R and the Procrustes matrix vecs^T @ X_hat; the D x D SVD stays with the caller):
+ * C[m, n] = op(A) . B in fp32 (FMA, no tensor cores), row-major host pointers, B is [k, n],
+ * A is [m, k] (trans_a = 0) or [k, m] (trans_a != 0: C = A^T . B).  Deterministic. */
+int ffx_sgemm(int device, int trans_a, int64_t m, int64_t n, int64_t k, const float *A, const float *B, float *C);
 
 /* Synchronises `stream` and reports what the asynchronous launches on this index saw: the
  * kernels never dereference a candidate outside [0, #documents) (or [0, #rows) in PASSAGE

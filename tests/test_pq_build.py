@@ -111,3 +111,40 @@ def test_limits(ffx):
         ffx.pq_encode(x, np.zeros((2, 4, 3), np.float32))  # 2*3 != 8
     with pytest.raises(ffx.FFXError):
         ffx.pq_encode(np.zeros((10, 600), np.float32), np.zeros((2, 300, 300), np.float32))  # Ks > 256
+
+
+@pytest.mark.parametrize("m,n,k", [(1000, 768, 768), (768, 768, 50_000), (70, 33, 17), (1, 5, 3), (130, 64, 4100)])
+@pytest.mark.parametrize("trans_a", [False, True])
+def test_sgemm_against_float64(ffx, m, n, k, trans_a):
+    """ffx_sgemm — the two products of an OPQ rotation round (`vecs @ R`, `vecs.T @ X_hat`,
+    quantizer/nanopq.py:94-98 -> nanopq OPQ.fit) — against float64 numpy: fp32 FMA accumulation in
+    k-slices, so the error stays within a few fp32 ulps of |a||b| even for k = 50 000; repeated calls
+    are bit-identical (fixed slice order)."""
+    rng = np.random.default_rng(m + n + k)
+    a = rng.standard_normal((k, m) if trans_a else (m, k)).astype(np.float32)
+    b = rng.standard_normal((k, n)).astype(np.float32)
+    got = ffx.sgemm(a, b, trans_a)
+    want = (a.T if trans_a else a).astype(np.float64) @ b.astype(np.float64)
+    scale = np.sqrt(k)  # |row of a| |column of b| ~ k for unit-variance entries; rounding errors add up like sqrt(k)
+    assert got.shape == want.shape and np.abs(got - want).max() <= 4e-6 * scale * max(1.0, np.sqrt(k) / 16)
+    assert np.array_equal(got, ffx.sgemm(a, b, trans_a))
+
+
+def test_device_opq_rotation_is_orthogonal_and_reduces_the_error(ffx):
+    """`NanoOPQ(device=0).fit`: rotation products on the GPU (ffx_sgemm), SVD on the host.  R stays
+    orthogonal, and the rotated quantizer reconstructs correlated data better than plain PQ —
+    what OPQ is for — as well as the host-trained one."""
+    from fast_forward.quantizer import NanoOPQ, NanoPQ
+
+    rng = np.random.default_rng(9)
+    mix = rng.standard_normal((64, 64)).astype(np.float32)
+    x = (rng.standard_normal((6000, 64)).astype(np.float32) * np.linspace(3, 0.2, 64, dtype=np.float32)) @ mix
+    y = (rng.standard_normal((1500, 64)).astype(np.float32) * np.linspace(3, 0.2, 64, dtype=np.float32)) @ mix
+    dev, host, plain = NanoOPQ(8, 32, device=0), NanoOPQ(8, 32), NanoPQ(8, 32)
+    dev.fit(x, pq_iter=5, rotation_iter=4)
+    host.fit(x, pq_iter=5, rotation_iter=4)
+    plain.fit(x, iter=5)
+    R = dev.adc_tables()[1]
+    assert np.allclose(R @ R.T, np.eye(64), atol=1e-4)
+    err = {name: float(((q.decode(q.encode(y)) - y) ** 2).mean()) for name, q in (("dev", dev), ("host", host), ("plain", plain))}
+    assert err["dev"] < err["plain"] and err["dev"] <= err["host"] * 1.05, err
