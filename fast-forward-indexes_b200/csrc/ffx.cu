@@ -27,6 +27,7 @@
 #include "ffx_kernels.cuh"
 #include "ffx_score_tma.cuh"
 #include "ffx_score_any.cuh"
+#include "ffx_coalesce.cuh"
 #include "ffx_layout.h"
 
 namespace {
@@ -1828,6 +1829,57 @@ int ffx_sgemm(int device, int trans_a, int64_t m, int64_t n, int64_t k, const fl
         FFX_CUDA(cudaGetLastError());
     }
     FFX_CUDA(cudaMemcpy(C, d_c.p, static_cast<size_t>(m) * n * 4, cudaMemcpyDeviceToHost));
+    return FFX_OK;
+}
+
+int ffx_index_coalesce(ffx_index *idx, int64_t doc0, int64_t n_docs, const int64_t *doc_off, double delta,
+                       float *out_vectors, int32_t *out_groups) {
+    if (!idx || doc0 < 0 || n_docs < 0 || !doc_off || !out_groups)
+        return fail(FFX_ERR_INVALID, "ffx_index_coalesce: bad arguments");
+    if (idx->row_kind != FFX_ROWS_F32) return fail(FFX_ERR_STATE, "ffx_index_coalesce: the index holds codes, not vectors");
+    if (doc0 + n_docs > idx->n_docs) return fail(FFX_ERR_INVALID, "ffx_index_coalesce: documents out of range");
+    if (n_docs == 0) return FFX_OK;
+    const int64_t total = doc_off[n_docs];
+    if (doc_off[0] != 0 || total <= 0 || !out_vectors) return fail(FFX_ERR_INVALID, "ffx_index_coalesce: bad offsets");
+    FFX_TRY(bind(idx));
+    FFX_TRY(settle(idx));
+    const int stride = static_cast<int>(idx->row_bytes / 4);
+    const size_t smem = static_cast<size_t>(ffx::kCoalesceWarps) * 2 * stride * 4;
+    if (smem > kSmemBudget) return fail(FFX_ERR_UNSUPPORTED, "ffx_index_coalesce: rows of %d floats exceed shared memory", stride);
+    auto pad = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+    const size_t b_off = pad(static_cast<size_t>(n_docs + 1) * 8), b_g = pad(static_cast<size_t>(n_docs) * 4);
+    const size_t b_out = static_cast<size_t>(total) * idx->dim * 4;
+    FFX_TRY(scratch_reserve(idx->work, b_off + b_g + b_out));
+    char *p = static_cast<char *>(idx->work.p);
+    int64_t *d_off = reinterpret_cast<int64_t *>(p);
+    int32_t *d_groups = reinterpret_cast<int32_t *>(p + b_off);
+    float *d_out = reinterpret_cast<float *>(p + b_off + b_g);
+    cudaStream_t st = idx->stream;
+    FFX_CUDA(cudaMemcpyAsync(d_off, doc_off, static_cast<size_t>(n_docs + 1) * 8, cudaMemcpyHostToDevice, st));
+    ffx::CoalesceArgs a{};
+    a.vectors = static_cast<const float *>(idx->store);
+    a.stride = stride;
+    a.dim = static_cast<int>(idx->dim);
+    a.cpl = idx->plan.cpl;
+    a.steps = idx->plan.steps;
+    a.lanes = idx->plan.lanes;
+    a.doc_span = idx->doc_span;
+    a.doc_rows = idx->doc_rows;
+    a.indirect = idx->indirect;
+    a.doc0 = doc0;
+    a.n_docs = n_docs;
+    a.out_off = d_off;
+    a.delta = delta;
+    a.out = d_out;
+    a.out_groups = d_groups;
+    FFX_CUDA(cudaFuncSetAttribute(ffx::ffx_coalesce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    ffx::ffx_coalesce_kernel<<<static_cast<unsigned>((n_docs + ffx::kCoalesceWarps - 1) / ffx::kCoalesceWarps),
+                               ffx::kCoalesceWarps * 32, smem, st>>>(a);
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    FFX_CUDA(cudaMemcpyAsync(out_groups, d_groups, static_cast<size_t>(n_docs) * 4, cudaMemcpyDeviceToHost, st));
+    FFX_CUDA(cudaMemcpyAsync(out_vectors, d_out, b_out, cudaMemcpyDeviceToHost, st));
+    FFX_CUDA(cudaStreamSynchronize(st));
     return FFX_OK;
 }
 

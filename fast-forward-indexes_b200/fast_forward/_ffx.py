@@ -45,6 +45,7 @@ SYMBOLS = {
     "ffx_rerank_early_stop": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _P, _I, _L, _P, _P, _P, _P]),
     "ffx_rerank_early_stop_host": (_I, [_P, _I, _P, _L, _P, _P, _P, _D, _I, _P, _I, _P, _P, _P]),
     "ffx_index_sync": (_I, [_P, _P]),
+    "ffx_index_coalesce": (_I, [_P, _L, _L, _P, _D, _P, _P]),
     "ffx_interpolate_topk": (_I, [_P, _P, _P, _L, _P, _D, _I, _L, _P, _P, _P, _P]),
     "ffx_interpolate_topk_host": (_I, [_P, _P, _P, _L, _P, _D, _I, _P, _P, _P]),
     "ffx_merge_topk": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _P]),
@@ -413,6 +414,16 @@ class DeviceIndex:
         check(lib().ffx_interpolate_topk_host(self.handle, _ptr(lex), _ptr(ff), nq, _ptr(q_off),
                                               float(alpha), int(k), _ptr(it), _ptr(ts), _ptr(tp)))
         return out
+
+    def coalesce(self, doc0: int, doc_off, delta: float):
+        """ffx_index_coalesce over documents [doc0, doc0 + len(doc_off) - 1): (vectors [rows, dim] with
+        every document's group means at the start of its row range, groups per document)."""
+        doc_off = _arr(doc_off, np.int64)
+        n_docs = len(doc_off) - 1
+        out = np.empty((int(doc_off[-1]), self.dim), np.float32)
+        groups = np.empty(n_docs, np.int32)
+        check(lib().ffx_index_coalesce(self.handle, int(doc0), n_docs, _ptr(doc_off), float(delta), _ptr(out), _ptr(groups)))
+        return out, groups
 
     def merge_topk_host(self, shard_scores, shard_pos):
         """ffx_merge_topk_host: [S, nq, k] per-shard lists (positions in the full candidate blocks)

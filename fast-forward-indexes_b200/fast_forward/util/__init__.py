@@ -45,6 +45,58 @@ def _coalesced(passages: np.ndarray, delta: float, distance: Callable[[np.ndarra
         yield mean
 
 
+def _coalesce_on_device(source_index: "Index", target_index: "Index", delta: float, batch_size: int | None) -> bool:
+    """The default distance on a single-device fp32 index: every document is coalesced by one warp
+    (libffx `ffx_index_coalesce`), a block of documents per launch; the host only keeps the id
+    bookkeeping and feeds `target_index.add`.  False when the source is of another kind (codes,
+    several devices, another back-end): the host loop below takes over."""
+    store = getattr(source_index, "_store", None)
+    if store is None or getattr(source_index, "quantizer", None) is not None or store.dev is None:
+        return False
+    if hasattr(store, "shards") or store.dev.row_kind != 0:
+        return False
+    dev = source_index._device()
+    doc_keys = store.docs.keys()
+    off = store._doc_off
+    n_docs = len(doc_keys)
+    if n_docs == 0:
+        return True
+    per_block = max(1, (256 << 20) // (4 * store.dev.dim))  # rows per launch: ~256 MB of output
+    held_vectors, held_ids, held = [], [], 0
+    batch_size = batch_size or None
+
+    def flush(everything: bool) -> None:
+        nonlocal held_vectors, held_ids, held
+        if not held:
+            return
+        vectors, ids = np.concatenate(held_vectors), [i for part in held_ids for i in part]
+        step = batch_size or len(vectors)
+        done = 0
+        while len(vectors) - done >= step or (everything and done < len(vectors)):
+            hi = min(len(vectors), done + step)
+            target_index.add(vectors[done:hi], doc_ids=ids[done:hi])
+            done = hi
+        held_vectors, held_ids, held = ([vectors[done:]], [ids[done:]], len(vectors) - done) if done < len(vectors) else ([], [], 0)
+
+    d0 = 0
+    while d0 < n_docs:
+        d1 = int(np.searchsorted(off, off[d0] + per_block, side="right")) - 1
+        d1 = min(n_docs, max(d1, d0 + 1))
+        rel = (off[d0:d1 + 1] - off[d0]).astype(np.int64)
+        vectors, groups = dev.coalesce(d0, rel, delta)
+        counts = np.diff(rel)
+        within = np.arange(int(rel[-1])) - np.repeat(rel[:-1], counts)
+        keep = within < np.repeat(groups, counts)
+        held_vectors.append(vectors[keep])
+        held_ids.append(np.repeat(np.asarray(doc_keys[d0:d1], dtype=object), groups).tolist())
+        held += int(keep.sum())
+        if batch_size and held >= batch_size:
+            flush(False)
+        d0 = d1
+    flush(True)
+    return True
+
+
 def create_coalesced_index(source_index: "Index", target_index: "Index", delta: float,
                            distance_function: Callable[[np.ndarray, np.ndarray], float] = cos_dist,
                            batch_size: int | None = None) -> None:
@@ -58,6 +110,9 @@ def create_coalesced_index(source_index: "Index", target_index: "Index", delta: 
     because `distance_function` is an arbitrary Python callable."""
     if len(target_index) > 0:
         raise ValueError("Target index is not empty.")
+    if distance_function is cos_dist and _coalesce_on_device(source_index, target_index, delta, batch_size):
+        assert source_index.doc_ids == target_index.doc_ids
+        return
     doc_ids = list(source_index.doc_ids)
     batch_size = batch_size or len(doc_ids)
     held_vectors: list[np.ndarray] = []

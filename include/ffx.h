@@ -329,6 +329,15 @@ int ffx_pq_kmeans(int device, const float *vecs, int64_t n, int M, int Ks, int D
  * A is [m, k] (trans_a = 0) or [k, m] (trans_a != 0: C = A^T . B).  Deterministic. */
 int ffx_sgemm(int device, int trans_a, int64_t m, int64_t n, int64_t k, const float *A, const float *B, float *C);
 
+/* Replaces the per-document loop of `create_coalesced_index` (util/__init__.py:51-101) for its
+ * default distance `cos_dist` (:40-48): sequential coalescing of the passage vectors of documents
+ * [doc0, doc0 + n_docs) with threshold `delta`, one warp per document.  doc_off[n_docs + 1] (host)
+ * = cumulative row counts of those documents; the means of document d's groups are written to rows
+ * doc_off[d] .. doc_off[d] + out_groups[d] - 1 of out_vectors (host, [doc_off[n_docs], dim], original
+ * element order; the remaining rows of a document's range are not written).  fp32 vector index only. */
+int ffx_index_coalesce(ffx_index *idx, int64_t doc0, int64_t n_docs, const int64_t *doc_off, double delta,
+                       float *out_vectors, int32_t *out_groups);
+
 /* Synchronises `stream` and reports what the asynchronous launches on this index saw: the
  * kernels never dereference a candidate outside [0, #documents) (or [0, #rows) in PASSAGE
  * mode) — such a pair scores as an empty document and this call (like ffx_rerank_host)

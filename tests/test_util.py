@@ -55,6 +55,7 @@ def api():
 
     a = Api()
     a.util, a.LambdaEncoder, a.InMemoryIndex, a.Mode, a.NanoPQ = util, LambdaEncoder, InMemoryIndex, Mode, NanoPQ
+    a.ffx = _ffx
     return a
 
 
@@ -168,6 +169,39 @@ def test_coalescing_equals_the_reference_function(api):
             got, _ = target._get_vectors([f"doc{d}"])
             want, _ = plain_target._get_vectors([f"doc{d}"])
             assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [768, 100, 64])
+def test_device_coalescing_equals_the_host_loop(api, dim):
+    """The default distance runs on the device (ffx_index_coalesce: one warp per document); any
+    other callable — here the same function behind a lambda — takes the host loop.  Documents
+    own scattered rows (extended by later adds); lane-major (768, 64) and tree-as-data (100)
+    store layouts.  Same groups, bit-identical means."""
+    rng = np.random.default_rng(dim)
+    centres = rng.standard_normal((8, dim)).astype(np.float32)
+    owner = np.repeat(np.arange(400), rng.integers(1, 15, 400))
+    rng.shuffle(owner)
+    vectors = (centres[(owner % 4) * 2 + rng.integers(0, 2, len(owner))] +
+               0.3 * rng.standard_normal((len(owner), dim))).astype(np.float32)
+    doc_ids = [f"doc{d}" for d in owner]
+    source = api.InMemoryIndex(mode=api.Mode.MAXP)
+    half = len(vectors) // 2
+    source.add(vectors[:half], doc_ids=doc_ids[:half])
+    source.add(vectors[half:], doc_ids=doc_ids[half:])
+    for delta in (0.2, 0.5, 5.0):
+        on_device, on_host = api.InMemoryIndex(mode=api.Mode.MAXP), api.InMemoryIndex(mode=api.Mode.MAXP)
+        before = api.ffx.launch_count()
+        api.util.create_coalesced_index(source, on_device, delta, batch_size=300)
+        assert api.ffx.launch_count() > before
+        api.util.create_coalesced_index(source, on_host, delta, distance_function=lambda a, b: api.util.cos_dist(a, b))
+        assert len(on_device) == len(on_host) <= len(vectors) and on_device.doc_ids == on_host.doc_ids
+        if delta == 5.0:  # nothing is farther than that: one mean per document
+            assert len(on_device) == 400
+        for d in range(0, 400, 9):
+            got, _ = on_device._get_vectors([f"doc{d}"])
+            want, _ = on_host._get_vectors([f"doc{d}"])
+            assert np.array_equal(got, want), (delta, d)
 
 
 @pytest.mark.gpu
