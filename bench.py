@@ -747,7 +747,8 @@ def run_sharded(ctx, _ffx, args, wl, m, emulate, warmup):
 
     def e2e_step():
         nonlocal res
-        res = rr.rerank_host(mode, host["qv"], host["q_off"], host["cand"], host["lex"], args.alpha, k, cands)
+        res = rr.rerank_host(mode, host["qv"], host["q_off"], host["cand"], host["lex"], args.alpha, k, cands,
+                             chunk_queries=-(-nq // int(os.environ.get("FFX_SHARD_CHUNKS", "8"))))
 
     del q["cand"], q["lex"]
     torch.cuda.empty_cache()

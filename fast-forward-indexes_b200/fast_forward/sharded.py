@@ -65,6 +65,7 @@ class ShardedReranker:
         # (start, local kernel done, exchange / barrier done, merge done) of its three phases
         self.trace = None
         self._io = None  # copy streams of rerank_host
+        self._host_out = None  # its pinned result tensors
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if index is not None:
@@ -233,7 +234,8 @@ class ShardedReranker:
         stream — with NCCL only this rank's 1/world piece of it, the pieces being all-gathered over
         NVLink — and the merged lists of chunk i-1 go back on another.  Returns host tensors
         `(query index [m], score [m, k], position [m, k])`: the queries this rank owns (every
-        chunk is split over the ranks by `owner_bounds`) and their merged lists."""
+        chunk is split over the ranks by `owner_bounds`) and their merged lists; the two pinned
+        list tensors are reused by the next call of the same shape."""
         import torch
 
         dev = torch.device("cuda", self.index.device)
@@ -289,7 +291,17 @@ class ShardedReranker:
             flat_out, flat_in = dst[:per * W], landing[:per]
             dist.all_gather_into_tensor(flat_out.view(-1), flat_in.reshape(-1), group=self.group, async_op=True).wait()
 
-        results = []
+        # the merged lists of the queries this rank owns land in ONE pair of pinned tensors
+        owned = [self.owner_bounds(hi - lo) for lo, hi in chunks]
+        counts = [ob[self.rank + 1] - ob[self.rank] for ob in owned]
+        total_mine = sum(counts)
+        cache = self._host_out
+        if cache is None or cache[0].shape != (total_mine, k):
+            cache = (torch.empty((total_mine, k), dtype=torch.float32, pin_memory=True),
+                     torch.empty((total_mine, k), dtype=torch.int32, pin_memory=True))
+            self._host_out = cache
+        out_s, out_p = cache
+        index_parts, at = [], 0
         for i, (lo, hi) in enumerate(chunks):
             b = bufs[i & 1]
             r0, r1 = starts[i], starts[i + 1]
@@ -308,21 +320,18 @@ class ShardedReranker:
             b["free"].record(main)
             done = torch.cuda.Event()
             done.record(main)
-            bounds = self.owner_bounds(hi - lo)
-            mine = torch.arange(lo + bounds[self.rank], lo + bounds[self.rank + 1])
+            bounds = owned[i]
+            index_parts.append(torch.arange(lo + bounds[self.rank], lo + bounds[self.rank + 1]))
             with torch.cuda.stream(d2h):
                 d2h.wait_event(done)
-                hs = torch.empty(s.shape, dtype=s.dtype, pin_memory=True)
-                hp = torch.empty(p.shape, dtype=p.dtype, pin_memory=True)
-                hs.copy_(s, non_blocking=True)
-                hp.copy_(p, non_blocking=True)
+                out_s[at:at + counts[i]].copy_(s, non_blocking=True)
+                out_p[at:at + counts[i]].copy_(p, non_blocking=True)
                 s.record_stream(d2h)
                 p.record_stream(d2h)
-            results.append((mine, hs, hp))
+            at += counts[i]
         d2h.synchronize()
         main.synchronize()
-        return (torch.cat([r[0] for r in results]), torch.cat([r[1] for r in results]),
-                torch.cat([r[2] for r in results]))
+        return torch.cat(index_parts), out_s, out_p  # (the two tensors are reused by the next call)
 
     def scores(self, mode: int, qvecs, q_off, cand, max_cand: int):
         """Semantic score of EVERY pair on every rank (plain `Index.__call__` over a sharded
