@@ -293,7 +293,8 @@ int launch_score(const ffx::ScoreArgs &a, bool fuse, int grid, size_t smem, cuda
 template <int CPL, int S, int LPR = 32>
 int launch_score_tma(const ffx::ScoreArgs &a, bool fuse, int grid, int warps, int ns, int batch,
                      cudaStream_t st) {
-    const size_t smem = ffx::tma_smem_bytes(fuse ? a.cpad : 0, warps, ns, LPR * CPL * S * 4);
+    // a ring slot = what one warp step consumes: 32 lanes' worth of elements (a row, or 2 / 4 short rows)
+    const size_t smem = ffx::tma_smem_bytes(fuse ? a.cpad : 0, warps, ns, 32 * CPL * S * 4);
     if (fuse) {
         auto kern = ffx::ffx_score_tma_kernel<CPL, S, true, LPR>;
         FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -379,13 +380,14 @@ ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, 
         return p;
     }
     if (short_rows) {
-        // 256-1024 byte rows (D <= 256), 2 or 4 per warp step: deep rings keep enough bytes in flight
+        // 256-1024 byte rows (D <= 256), 2 or 4 per warp step and ring slot (`row_bytes` is the slot
+        // here): deep rings keep enough bytes in flight
         p.warps = fuse ? 8 : (few_pairs ? 2 : 4);
         if (!fuse && few_pairs && g_tune.batch <= 0) p.batch = 8;
         p.ns = std::min(16, ring_slots(keys, p.warps, row_bytes, fuse ? 2 : 4));
-        if (p.ns < 4) p.ns = std::min(16, ring_slots(keys, p.warps, row_bytes, 1));
-        if (g_tune.tma_stages > 0) p.ns = std::min(p.ns, std::max(4, g_tune.tma_stages));
-        p.tma = p.ns >= 4;
+        if (p.ns < 3) p.ns = std::min(16, ring_slots(keys, p.warps, row_bytes, 1));
+        if (g_tune.tma_stages > 0) p.ns = std::min(p.ns, std::max(2, g_tune.tma_stages));
+        p.tma = p.ns >= 2;
         return p;
     }
     if (g_tune.kernel == 1) return p;
@@ -422,7 +424,7 @@ ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, 
 template <int CPL, int LPR>
 int launch_score_any(const ffx::ScoreArgs &a, const ffx_any_plan &plan, bool fuse, int grid, int warps, int ns,
                      int batch, cudaStream_t st) {
-    const size_t smem = ffx::any_smem_bytes(fuse ? a.cpad : 0, warps, ns, plan.stride * 4);
+    const size_t smem = ffx::any_smem_bytes(fuse ? a.cpad : 0, warps, ns, plan.stride * 4, plan.stride * 4 * (32 / plan.lpr));
     if (fuse) {
         auto kern = ffx::ffx_score_any_kernel<CPL, LPR, true>;
         FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -455,31 +457,31 @@ int dispatch_score_any(const ffx_any_plan &p, const ScorePlan &sp, const ffx::Sc
 
 // ring slots per warp for `ctas_per_sm` resident CTAs; 0 if the shape does not fit (the fused
 // top-k sorts its 64-bit keys inside the drained ring)
-int any_ring_slots(int keys, int warps, int row_bytes, int ctas_per_sm) {
+int any_ring_slots(int keys, int warps, int row_bytes, int slot_bytes, int ctas_per_sm) {
     const size_t budget = kSmemBudget / ctas_per_sm - 1024;  // static shared memory of the fused epilogue: 2.3 KB
-    const size_t fixed = ffx::any_smem_bytes(keys, warps, 0, row_bytes);
+    const size_t fixed = ffx::any_smem_bytes(keys, warps, 0, row_bytes, slot_bytes);
     if (fixed >= budget) return 0;
-    int ns = static_cast<int>((budget - fixed) / (static_cast<size_t>(warps) * (row_bytes + 8)));
+    int ns = static_cast<int>((budget - fixed) / (static_cast<size_t>(warps) * (slot_bytes + 8)));
     ns = std::min(ns, 32);
-    if (static_cast<size_t>(ns) * warps * row_bytes < static_cast<size_t>(keys) * 8) return 0;
+    if (static_cast<size_t>(ns) * warps * slot_bytes < static_cast<size_t>(keys) * 8) return 0;
     return ns;
 }
 
 ScorePlan plan_score_any(const ffx_any_plan &p, int mode, bool fuse, int cpad, bool sparse, bool few_pairs) {
     ScorePlan sp;
-    const int row_bytes = p.stride * 4, rps = 32 / p.lpr, keys = fuse ? cpad : 0;
+    const int row_bytes = p.stride * 4, rps = 32 / p.lpr, slot_bytes = row_bytes * rps, keys = fuse ? cpad : 0;
     const bool one_row = mode == FFX_MODE_PASSAGE || mode == FFX_MODE_FIRSTP;
     sp.batch = g_tune.batch > 0 ? std::min(32, g_tune.batch) : (one_row || sparse ? 32 : 16);
-    const int need = 2 * rps;  // a warp step consumes `rps` slots while the next ones load
-    const int want = row_bytes >= 2048 ? 6 : (row_bytes >= 1024 ? 8 : 16);
+    const int need = 2;  // a warp step consumes one slot while the next one loads
+    const int want = slot_bytes >= 2048 ? 6 : (slot_bytes >= 1024 ? 8 : 16);
     if (fuse) {
-        // the shape that keeps the most row slots (bytes) in flight per SM: two 8-warp CTAs, or one
+        // the shape that keeps the most ring slots (bytes) in flight per SM: two 8-warp CTAs, or one
         // CTA of up to 16 warps when the keys and the query vector leave too little for two
         const int shapes[][2] = {{8, 2}, {16, 1}, {14, 1}, {12, 1}, {8, 1}, {4, 1}};
         int best = 0;
         sp.ns = 0;
         for (const auto &shape : shapes) {
-            const int ns = std::min(want, any_ring_slots(keys, shape[0], row_bytes, shape[1]));
+            const int ns = std::min(want, any_ring_slots(keys, shape[0], row_bytes, slot_bytes, shape[1]));
             if (ns < need) continue;
             const int slots = ns * shape[0] * shape[1];
             if (slots > best) {
@@ -491,11 +493,11 @@ ScorePlan plan_score_any(const ffx_any_plan &p, int mode, bool fuse, int cpad, b
     } else {
         sp.warps = few_pairs ? 2 : 4;
         if (few_pairs && g_tune.batch <= 0) sp.batch = 8;
-        sp.ns = std::min(want, any_ring_slots(0, sp.warps, row_bytes, 4));
-        if (sp.ns < need) sp.ns = std::min(want, any_ring_slots(0, sp.warps, row_bytes, 1));
+        sp.ns = std::min(want, any_ring_slots(0, sp.warps, row_bytes, slot_bytes, 4));
+        if (sp.ns < need) sp.ns = std::min(want, any_ring_slots(0, sp.warps, row_bytes, slot_bytes, 1));
     }
     if (g_tune.tma_stages > 0) sp.ns = std::max(need, std::min(sp.ns, g_tune.tma_stages));
-    if (g_tune.tma_warps > 0 && any_ring_slots(keys, g_tune.tma_warps, row_bytes, 1) >= sp.ns) sp.warps = g_tune.tma_warps;
+    if (g_tune.tma_warps > 0 && any_ring_slots(keys, g_tune.tma_warps, row_bytes, slot_bytes, 1) >= sp.ns) sp.warps = g_tune.tma_warps;
     sp.tma = sp.ns >= need && sp.warps >= 1;
     return sp;
 }
@@ -1182,8 +1184,8 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     const float *topk_src = rank_scores ? rank_scores : out_int;  // input of a separate top-k pass
 
     // tiles: split a query over several CTAs when there are few queries
-    const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4, idx->sharded, few_pairs,
-                                           idx->plan.lanes != 32) : sp_any;
+    const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4 * (32 / idx->plan.lanes),
+                                           idx->sharded, few_pairs, idx->plan.lanes != 32) : sp_any;
     int tiles = 1, tile = static_cast<int>(std::max<int64_t>(max_cand, 1));
     if (!fuse) {
         // enough CTAs for ~2 waves at the plan's occupancy, but a tile keeps every warp of its

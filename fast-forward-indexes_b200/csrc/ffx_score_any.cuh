@@ -15,10 +15,11 @@
 
 namespace ffx {
 
-__host__ __device__ inline size_t any_smem_bytes(int cpad_scores, int warps, int ns, int row_bytes) {
+// `slot_bytes`: what one warp step consumes — a row, or the 2 / 4 rows of a short-row step
+__host__ __device__ inline size_t any_smem_bytes(int cpad_scores, int warps, int ns, int row_bytes, int slot_bytes) {
     const size_t keys = (static_cast<size_t>(cpad_scores) * 4 + 127) & ~static_cast<size_t>(127);
     const size_t qv = (static_cast<size_t>(row_bytes) + 127) & ~static_cast<size_t>(127);
-    return keys + qv + static_cast<size_t>(warps) * ns * row_bytes + static_cast<size_t>(warps) * ns * 8 +
+    return keys + qv + static_cast<size_t>(warps) * ns * slot_bytes + static_cast<size_t>(warps) * ns * 8 +
            static_cast<size_t>(warps) * 2 * 32 * sizeof(CandDesc) + 128;
 }
 
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_any_kernel(const 
     constexpr int RPS = 32 / LPR;  // rows per warp step
     static_assert(LPR == 32 || CPL == 1, "short rows: one chain per lane");
     const uint32_t ROWB = static_cast<uint32_t>(plan.stride) * 4u;
+    const uint32_t SLOTB = ROWB * RPS;  // a ring slot holds the up to RPS rows of one warp step
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_next;
@@ -170,8 +172,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_any_kernel(const 
     float *s_q = reinterpret_cast<float *>(smem_raw + off);
     off += (static_cast<size_t>(ROWB) + 127) & ~static_cast<size_t>(127);
     unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem_raw + off);  // = ring, after the drain
-    const uint32_t ring = smem_u32(smem_raw + off) + static_cast<uint32_t>(warp) * ns * ROWB;
-    off += static_cast<size_t>(n_warps) * ns * ROWB;
+    const uint32_t ring = smem_u32(smem_raw + off) + static_cast<uint32_t>(warp) * ns * SLOTB;
+    off += static_cast<size_t>(n_warps) * ns * SLOTB;
     const uint32_t bars = smem_u32(smem_raw + off) + static_cast<uint32_t>(warp) * ns * 8;
     off += static_cast<size_t>(n_warps) * ns * 8;
     off = (off + 15) & ~static_cast<size_t>(15);
@@ -313,17 +315,23 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_any_kernel(const 
                 break;
             }
             if (!have) break;
-            uint32_t row = pstart + pk;
-            if (indirect) {
-                if ((pk & 31u) == 0)
-                    p_rows = (pk + lane < pcnt) ? static_cast<uint32_t>(__ldg(a.doc_rows + pstart + pk + lane)) : 0u;
-                row = __shfl_sync(kFull, p_rows, pk & 31u);
-            }
-            pk++;
-            if (lane == 0) {
-                const uint32_t bar = bars + p_stage * 8;
-                mbar_expect_tx(bar, ROWB);
-                bulk_g2s(ring + p_stage * ROWB, rows_base + static_cast<size_t>(row) * ROWB, ROWB, bar);
+            // the next min(RPS, rows left) rows of the document into one slot: one bulk copy when the
+            // document's rows are consecutive, one per row otherwise; one barrier either way
+            const uint32_t nr = min(static_cast<uint32_t>(RPS), pcnt - pk);
+            const uint32_t bar = bars + p_stage * 8;
+            if (lane == 0) mbar_expect_tx(bar, nr * ROWB);
+            if (!indirect) {
+                if (lane == 0)
+                    bulk_g2s(ring + p_stage * SLOTB, rows_base + static_cast<size_t>(pstart + pk) * ROWB, nr * ROWB, bar);
+                pk += nr;
+            } else {
+                for (uint32_t g = 0; g < nr; g++, pk++) {
+                    if ((pk & 31u) == 0 || g == 0)
+                        p_rows = ((pk & ~31u) + lane < pcnt) ? static_cast<uint32_t>(__ldg(a.doc_rows + pstart + (pk & ~31u) + lane)) : 0u;
+                    const uint32_t row = __shfl_sync(kFull, p_rows, pk & 31u);
+                    if (lane == 0)
+                        bulk_g2s(ring + p_stage * SLOTB + g * ROWB, rows_base + static_cast<size_t>(row) * ROWB, ROWB, bar);
+                }
             }
             p_stage = p_stage + 1 == ns ? 0 : p_stage + 1;
             inflight++;
@@ -338,27 +346,19 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_any_kernel(const 
             DocReduce red;
             red.init();
             for (uint32_t ck = 0; ck < cnt;) {
-                // lane group g takes row ck + g of the document from ring slot c_stage + g
+                // lane group g takes row ck + g of the document, all from ring slot c_stage
                 top_up();
                 const int nr = static_cast<int>(min(static_cast<uint32_t>(RPS), cnt - ck));  // warp-uniform
                 const int grp = lane / LPR;
-                int sg = c_stage + grp;
-                if (sg >= ns) sg -= ns;
-                const bool busy = grp < nr;
-                if (busy) mbar_wait(bars + sg * 8, (c_phase >> sg) & 1u);
-                // idle groups run the arithmetic on their (stale) slot: the shuffles stay convergent
-                const float part = any_row_dot<CPL, LPR>(ring + sg * ROWB, q_addr, q_regs, my_byte, my_steps,
-                                                         plan.max_steps, tail_mine, tail_byte, plan.tail_len);
-                __syncwarp();  // every lane has consumed its row: the slots may be refilled
-                for (int g = 0; g < nr; g++) {
-                    int slot_ = c_stage + g;
-                    if (slot_ >= ns) slot_ -= ns;
-                    c_phase ^= 1u << slot_;
-                    red.add(__shfl_sync(kFull, part, g * LPR), ck + g == 0, a.mode);
-                }
-                c_stage += nr;
-                if (c_stage >= ns) c_stage -= ns;
-                inflight -= nr;
+                mbar_wait(bars + c_stage * 8, (c_phase >> c_stage) & 1u);
+                // idle groups run the arithmetic on their (stale) part of the slot: the shuffles stay convergent
+                const float part = any_row_dot<CPL, LPR>(ring + c_stage * SLOTB + grp * ROWB, q_addr, q_regs, my_byte,
+                                                         my_steps, plan.max_steps, tail_mine, tail_byte, plan.tail_len);
+                __syncwarp();  // every lane has consumed its row: the slot may be refilled
+                c_phase ^= 1u << c_stage;
+                for (int g = 0; g < nr; g++) red.add(__shfl_sync(kFull, part, g * LPR), ck + g == 0, a.mode);
+                c_stage = c_stage + 1 == ns ? 0 : c_stage + 1;
+                inflight--;
                 ck += nr;
             }
             const float ff = red.finish(cnt, a.mode);
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_any_kernel(const 
         float *out_s;
         int32_t *out_p;
         topk_destination(a, q_idx, &out_s, &out_p);
-        rank_scores_topk<16>(s_scores, n_query, s_keys, a.k, out_s, out_p, static_cast<size_t>(n_warps) * ns * ROWB);
+        rank_scores_topk<16>(s_scores, n_query, s_keys, a.k, out_s, out_p, static_cast<size_t>(n_warps) * ns * SLOTB);
         if (a.sc_world) __threadfence_system();
     }
 }

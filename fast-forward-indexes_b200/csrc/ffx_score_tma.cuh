@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
     constexpr int NV4 = EPL / 4;
     constexpr uint32_t ROWB = static_cast<uint32_t>(LPR) * EPL * 4u;
     constexpr int RPS = 32 / LPR;                        // rows per warp step (short rows)
+    // a ring slot holds what ONE warp step consumes: a row, or — short rows — the up to RPS consecutive
+    // rows of a document that the lane groups take together (one bulk copy, one barrier per step)
+    constexpr uint32_t SLOTB = ROWB * RPS;
     constexpr bool kPairRows = LPR == 32 && EPL <= 32;   // two rows of registers per lane only while they fit
     constexpr bool kStream = EPL > 64;                   // query vector in shared memory, rows streamed against it
     static_assert(EPL % 4 == 0, "lane slice must be whole float4s");
@@ -135,8 +138,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
     float *s_q = reinterpret_cast<float *>(smem_raw + off);  // kStream: the query vector, lane-major
     if (kStream) off += ROWB;
     unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem_raw + off);  // = ring, after the drain
-    const uint32_t ring = smem_u32(smem_raw + off) + static_cast<uint32_t>(warp) * ns * ROWB;
-    off += static_cast<size_t>(n_warps) * ns * ROWB;
+    const uint32_t ring = smem_u32(smem_raw + off) + static_cast<uint32_t>(warp) * ns * SLOTB;
+    off += static_cast<size_t>(n_warps) * ns * SLOTB;
     const uint32_t bars = smem_u32(smem_raw + off) + static_cast<uint32_t>(warp) * ns * 8;
     off += static_cast<size_t>(n_warps) * ns * 8;
     off = (off + 15) & ~static_cast<size_t>(15);
@@ -285,17 +288,38 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
                 break;
             }
             if (!have) break;
-            uint32_t row = pstart + pk;
-            if (indirect) {
-                if ((pk & 31u) == 0)
-                    p_rows = (pk + lane < pcnt) ? static_cast<uint32_t>(__ldg(a.doc_rows + pstart + pk + lane)) : 0u;
-                row = __shfl_sync(kFull, p_rows, pk & 31u);
-            }
-            pk++;
-            if (lane == 0) {
+            if constexpr (RPS > 1) {
+                // the next min(RPS, rows left) rows of the document into one slot
+                const uint32_t nr = min(static_cast<uint32_t>(RPS), pcnt - pk);
                 const uint32_t bar = bars + p_stage * 8;
-                mbar_expect_tx(bar, ROWB);
-                bulk_g2s(ring + p_stage * ROWB, rows_base + static_cast<size_t>(row) * ROWB, ROWB, bar);
+                if (lane == 0) mbar_expect_tx(bar, nr * ROWB);
+                if (!indirect) {
+                    if (lane == 0)
+                        bulk_g2s(ring + p_stage * SLOTB, rows_base + static_cast<size_t>(pstart + pk) * ROWB, nr * ROWB, bar);
+                } else {
+                    for (uint32_t g = 0; g < nr; g++, pk++) {
+                        if ((pk & 31u) == 0 || g == 0)
+                            p_rows = ((pk & ~31u) + lane < pcnt) ? static_cast<uint32_t>(__ldg(a.doc_rows + pstart + (pk & ~31u) + lane)) : 0u;
+                        const uint32_t row = __shfl_sync(kFull, p_rows, pk & 31u);
+                        if (lane == 0)
+                            bulk_g2s(ring + p_stage * SLOTB + g * ROWB, rows_base + static_cast<size_t>(row) * ROWB, ROWB, bar);
+                    }
+                    pk -= nr;
+                }
+                pk += nr;
+            } else {
+                uint32_t row = pstart + pk;
+                if (indirect) {
+                    if ((pk & 31u) == 0)
+                        p_rows = (pk + lane < pcnt) ? static_cast<uint32_t>(__ldg(a.doc_rows + pstart + pk + lane)) : 0u;
+                    row = __shfl_sync(kFull, p_rows, pk & 31u);
+                }
+                pk++;
+                if (lane == 0) {
+                    const uint32_t bar = bars + p_stage * 8;
+                    mbar_expect_tx(bar, ROWB);
+                    bulk_g2s(ring + p_stage * ROWB, rows_base + static_cast<size_t>(row) * ROWB, ROWB, bar);
+                }
             }
             p_stage = p_stage + 1 == ns ? 0 : p_stage + 1;
             inflight++;
@@ -311,18 +335,16 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
             red.init();
             for (uint32_t ck = 0; ck < cnt;) {
                 if constexpr (LPR < 32) {
-                    // short rows: lane group g takes row ck + g of the document from ring slot
-                    // c_stage + g; the butterfly stays inside the group
+                    // short rows: lane group g takes row ck + g of the document, all from ring slot
+                    // c_stage (one copy, one barrier per step); the butterfly stays inside the group
                     top_up();
                     const int nr = static_cast<int>(min(static_cast<uint32_t>(RPS), cnt - ck));  // warp-uniform
                     const int grp = lane / LPR, sub = lane % LPR;
-                    int sg = c_stage + grp;
-                    if (sg >= ns) sg -= ns;
                     float part = 0.f;
+                    mbar_wait(bars + c_stage * 8, (c_phase >> c_stage) & 1u);
                     if (grp < nr) {
                         float4 v[NV4];
-                        mbar_wait(bars + sg * 8, (c_phase >> sg) & 1u);
-                        const uint32_t src = ring + sg * ROWB + sub * 16;
+                        const uint32_t src = ring + c_stage * SLOTB + grp * ROWB + sub * 16;
 #pragma unroll
                         for (int i = 0; i < NV4; i++) v[i] = lds_f4(src + i * (LPR * 16));
                         part = lane_chain_sum<CPL, S>(q, v);
@@ -330,16 +352,11 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
 #pragma unroll
                     for (int o = 1; o < LPR; o <<= 1) part = __fadd_rn(part, __shfl_xor_sync(kFull, part, o));
                     part = __fadd_rn(0.f, part);
-                    __syncwarp();  // the rows are in registers: the slots may be refilled
-                    for (int g = 0; g < nr; g++) {
-                        int slot = c_stage + g;
-                        if (slot >= ns) slot -= ns;
-                        c_phase ^= 1u << slot;
-                        red.add(__shfl_sync(kFull, part, g * LPR), ck + g == 0, a.mode);
-                    }
-                    c_stage += nr;
-                    if (c_stage >= ns) c_stage -= ns;
-                    inflight -= nr;
+                    __syncwarp();  // the rows are in registers: the slot may be refilled
+                    c_phase ^= 1u << c_stage;
+                    for (int g = 0; g < nr; g++) red.add(__shfl_sync(kFull, part, g * LPR), ck + g == 0, a.mode);
+                    c_stage = c_stage + 1 == ns ? 0 : c_stage + 1;
+                    inflight--;
                     ck += nr;
                     continue;
                 }
@@ -428,7 +445,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
         int32_t *out_p;
         topk_destination(a, q_idx, &out_s, &out_p);
         rank_scores_topk<16>(s_scores, n_query, s_keys, a.k, out_s, out_p,
-                             static_cast<size_t>(n_warps) * ns * ROWB);  // the drained ring
+                             static_cast<size_t>(n_warps) * ns * SLOTB);  // the drained ring
         if (a.sc_world) __threadfence_system();  // peer stores: visible to the owner once the kernel ends
     }
 }
