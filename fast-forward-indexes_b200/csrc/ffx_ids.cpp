@@ -607,4 +607,146 @@ int ffx_tie_runs(const float *score, const int64_t *off, int64_t nq, int64_t cap
     return FFX_OK;
 }
 
+// ---- factorising a string column on all cores --------------------------------------------------
+// `Ranking.__init__` needs ONE integer per id string, equal strings <-> equal integers; which
+// integer is irrelevant (the distinct strings are kept beside the codes).  The dictionary above
+// assigns ordinals in order of first appearance and is therefore serial; here rows are
+// partitioned by the top bits of their hash (64 partitions), every partition is deduplicated in
+// its own small open-addressing table by one thread at a time, and a string's code is
+// (distinct strings of the lower partitions) + (its rank of first appearance inside its partition).
+}  // extern "C"
+
+struct ffx_factor {
+    const int64_t *offsets = nullptr;
+    const char *data = nullptr;
+    std::vector<std::vector<uint32_t>> first_row;  // per partition: the row a distinct string was first seen in
+    std::vector<int64_t> base;                     // per partition: code of its first distinct string
+    int64_t n_keys = 0, key_bytes = 0;
+};
+
+namespace {
+constexpr int kFactorBits = 6, kFactorParts = 1 << kFactorBits;
+}
+
+extern "C" {
+
+int ffx_factorize(const int64_t *offsets, const char *data, int64_t n, int32_t *codes, ffx_factor **out, int64_t *n_keys,
+                  int64_t *key_bytes, int n_threads) {
+    if (!out || !n_keys || !key_bytes || bad_strings(offsets, data, n) || (n > 0 && !codes))
+        return fail(FFX_ERR_INVALID, "ffx_factorize: bad arguments");
+    if (n >= (int64_t(1) << 31)) return fail(FFX_ERR_UNSUPPORTED, "ffx_factorize: more than 2^31 rows");
+    ffx_factor *f = new ffx_factor();
+    f->offsets = offsets;
+    f->data = data;
+    f->first_row.resize(kFactorParts);
+    f->base.assign(kFactorParts + 1, 0);
+    *out = f;
+    const int threads = worker_count(n_threads, n / 8);
+    const int64_t step = (n + threads - 1) / std::max(threads, 1);
+    // pass 1: hash every row, count rows per (thread, partition)
+    std::vector<uint32_t> hash_lo(static_cast<size_t>(n));
+    std::vector<uint8_t> part(static_cast<size_t>(n));
+    std::vector<int64_t> counts(static_cast<size_t>(threads) * kFactorParts, 0);
+    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+        int64_t *mine = counts.data() + static_cast<size_t>(step > 0 ? lo / step : 0) * kFactorParts;
+        for (int64_t i = lo; i < hi; i++) {
+            const uint64_t h = hash_bytes(data + offsets[i], offsets[i + 1] - offsets[i]);
+            hash_lo[static_cast<size_t>(i)] = static_cast<uint32_t>(h);
+            const uint8_t p = static_cast<uint8_t>(h >> (64 - kFactorBits));
+            part[static_cast<size_t>(i)] = p;
+            mine[p]++;
+        }
+    });
+    // pass 2: rows grouped by partition, in increasing row order inside a partition
+    std::vector<int64_t> part_begin(kFactorParts + 1, 0);
+    {
+        int64_t at = 0;
+        for (int p = 0; p < kFactorParts; p++) {
+            part_begin[static_cast<size_t>(p)] = at;
+            for (int t = 0; t < threads; t++) {
+                int64_t &c = counts[static_cast<size_t>(t) * kFactorParts + p];
+                const int64_t mine = c;
+                c = at;
+                at += mine;
+            }
+        }
+        part_begin[kFactorParts] = at;
+    }
+    std::vector<uint32_t> rows(static_cast<size_t>(n));
+    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+        int64_t *cursor = counts.data() + static_cast<size_t>(step > 0 ? lo / step : 0) * kFactorParts;
+        for (int64_t i = lo; i < hi; i++) rows[static_cast<size_t>(cursor[part[static_cast<size_t>(i)]]++)] = static_cast<uint32_t>(i);
+    });
+    // pass 3: one table per partition; partitions are handed out dynamically
+    std::atomic<int> next{0};
+    auto dedupe = [&]() {
+        std::vector<uint32_t> slots;
+        for (int p = next.fetch_add(1); p < kFactorParts; p = next.fetch_add(1)) {
+            const int64_t b = part_begin[static_cast<size_t>(p)], e = part_begin[static_cast<size_t>(p) + 1];
+            uint64_t cap = 64;
+            while (cap < static_cast<uint64_t>(e - b) * 2) cap <<= 1;
+            slots.assign(cap, 0);  // local code + 1
+            const uint64_t mask = cap - 1;
+            std::vector<uint32_t> &first = f->first_row[static_cast<size_t>(p)];
+            const int kAhead = 8;
+            for (int64_t j = b; j < e; j++) {
+                if (j + kAhead < e) __builtin_prefetch(&slots[mix(hash_lo[rows[static_cast<size_t>(j + kAhead)]]) & mask], 1);
+                const uint32_t r = rows[static_cast<size_t>(j)];
+                const char *s = data + offsets[r];
+                const int64_t len = offsets[r + 1] - offsets[r];
+                uint64_t at = mix(hash_lo[r]) & mask;
+                for (;; at = (at + 1) & mask) {
+                    const uint32_t v = slots[at];
+                    if (v == 0) {
+                        first.push_back(r);
+                        slots[at] = static_cast<uint32_t>(first.size());
+                        codes[r] = static_cast<int32_t>(first.size() - 1);
+                        break;
+                    }
+                    const uint32_t o = first[v - 1];
+                    if (offsets[o + 1] - offsets[o] == len && memcmp(data + offsets[o], s, static_cast<size_t>(len)) == 0) {
+                        codes[r] = static_cast<int32_t>(v - 1);
+                        break;
+                    }
+                }
+            }
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; t++) pool.emplace_back(dedupe);
+        dedupe();
+        for (auto &th : pool) th.join();
+    }
+    // pass 4: partition-local codes -> global codes
+    for (int p = 0; p < kFactorParts; p++) {
+        f->base[static_cast<size_t>(p) + 1] = f->base[static_cast<size_t>(p)] + static_cast<int64_t>(f->first_row[static_cast<size_t>(p)].size());
+        for (uint32_t r : f->first_row[static_cast<size_t>(p)]) f->key_bytes += offsets[r + 1] - offsets[r];
+    }
+    f->n_keys = f->base[kFactorParts];
+    if (f->n_keys >= (int64_t(1) << 31)) return fail(FFX_ERR_UNSUPPORTED, "ffx_factorize: more than 2^31 distinct strings");
+    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; i++) codes[i] += static_cast<int32_t>(f->base[part[static_cast<size_t>(i)]]);
+    });
+    *n_keys = f->n_keys;
+    *key_bytes = f->key_bytes;
+    return FFX_OK;
+}
+
+int ffx_factor_export(const ffx_factor *f, int64_t *key_offsets, char *key_data) {
+    if (!f || !key_offsets || (f->key_bytes > 0 && !key_data)) return fail(FFX_ERR_INVALID, "ffx_factor_export: bad arguments");
+    int64_t code = 0, at = 0;
+    for (int p = 0; p < kFactorParts; p++)
+        for (uint32_t r : f->first_row[static_cast<size_t>(p)]) {
+            const int64_t len = f->offsets[r + 1] - f->offsets[r];
+            key_offsets[code++] = at;
+            memcpy(key_data + at, f->data + f->offsets[r], static_cast<size_t>(len));
+            at += len;
+        }
+    key_offsets[code] = at;
+    return FFX_OK;
+}
+
+void ffx_factor_free(ffx_factor *f) { delete f; }
+
 }  // extern "C"

@@ -246,15 +246,20 @@ class Cols:
         runs = int(found.value)
         if runs == 0:
             return
-        rank = self.ids.string_rank() if runs > 64 else None
-        for s0, length in zip(starts[:runs].tolist(), lens[:runs].tolist()):
-            run = self.id_code[s0:s0 + length]
-            if rank is not None:
-                order = np.argsort(rank[run], kind="stable")
-            else:
-                names = np.asarray(self.ids.keys.take(pa.array(run)).to_pylist(), dtype=object)
-                order = np.argsort(names, kind="stable")
-            self.id_code[s0:s0 + length] = run[order]
+        starts, lens = starts[:runs], lens[:runs]
+        # only the ids inside runs need an order: rank their DISTINCT strings among themselves
+        # (a few thousand), never the whole id table (millions)
+        members = np.repeat(starts - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens) + np.arange(int(lens.sum()))
+        codes = self.id_code[members]
+        distinct, inverse = np.unique(codes, return_inverse=True)
+        names = np.asarray(self.ids.keys.take(pa.array(distinct)).to_pylist(), dtype=object)
+        rank_of_distinct = np.empty(len(distinct), np.int64)
+        rank_of_distinct[np.argsort(names, kind="stable")] = np.arange(len(distinct))
+        rank = rank_of_distinct[inverse]
+        # one stable sort by (run, id rank) re-orders every run at once
+        run_of = np.repeat(np.arange(runs), lens)
+        order = np.lexsort((rank, run_of))
+        self.id_code[members] = codes[order]
         self._cand.clear()
 
 
@@ -285,9 +290,8 @@ def from_frame(df: pd.DataFrame, is_sorted: bool, queries=None):
         return None
     n = len(df)
     q_code, q_uniques = pd.factorize(q_col)
-    id_dict = _ids.IdDict()
-    id_code = id_dict.insert_ordinal(id_col)
-    n_ids = len(id_dict)
+    id_code, id_keys = _ids.factorize(id_col)  # all host cores; the numbering is arbitrary
+    n_ids = len(id_keys)
     pair = q_code.astype(np.int64) * n_ids + id_code
     first = C.c_int64(-1)
     _ffx.check(_ffx.lib().ffx_first_repeat(_ptr(pair), n, C.byref(first)))
@@ -327,10 +331,9 @@ def from_frame(df: pd.DataFrame, is_sorted: bool, queries=None):
             texts = pa.array([queries[k] for k in q_names[block_q]], type=pa.large_string())
         except KeyError:
             raise ValueError("Queries are incomplete.") from None
-    keys, _ = id_dict.export()
     pinned = _ffx.pinned_empty(len(score), np.float32)
     pinned[:] = score
-    return Cols(q_keys, q_off, IdTable(keys), id_code.astype(np.int32), pinned, texts)
+    return Cols(q_keys, q_off, IdTable(id_keys), np.ascontiguousarray(id_code, np.int32), pinned, texts)
 
 
 def match_pairs(a: Cols, b: Cols):

@@ -85,6 +85,9 @@ SYMBOLS = {
     "ffx_dict_lookup": (_I, [_P, _P, _P, _P, _L, _L, _P, C.POINTER(_L), _I]),
     "ffx_dict_export": (_I, [_P, _P, _P, _P]),
     "ffx_csr_build": (_I, [_P, _L, _L, _P, _P]),
+    "ffx_factorize": (_I, [_P, _P, _L, _P, C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), _I]),
+    "ffx_factor_export": (_I, [_P, _P, _P]),
+    "ffx_factor_free": (None, [_P]),
 }
 
 _lib = None

@@ -162,6 +162,30 @@ class IdDict:
         return keys if isinstance(keys, list) else keys.to_pylist()
 
 
+def factorize(values) -> tuple[np.ndarray, object]:
+    """(int32 code per string, the distinct strings in code order) for a null-free string column,
+    on all host cores (libffx `ffx_factorize`); the numbering is arbitrary but consistent."""
+    views = string_views(values)
+    if len(views) != 1:
+        merged = pa.concat_arrays([v.keep for v in views]) if views else pa.array([], pa.large_string())
+        views = string_views(merged) or [_from_arrow(merged)]
+    v = views[0]
+    if v.validity:
+        raise ValueError("factorize: the column holds nulls")
+    codes = np.empty(v.n, np.int32)
+    handle, n_keys, key_bytes = C.c_void_p(), C.c_int64(), C.c_int64()
+    _ffx.check(_ffx.lib().ffx_factorize(_vp(v.offsets), _vp(v.data), v.n, C.c_void_p(codes.ctypes.data) if v.n else None,
+                                        C.byref(handle), C.byref(n_keys), C.byref(key_bytes), 0))
+    try:
+        offsets = np.empty(n_keys.value + 1, np.int64)
+        data = np.empty(max(key_bytes.value, 1), np.uint8)
+        _ffx.check(_ffx.lib().ffx_factor_export(handle, C.c_void_p(offsets.ctypes.data), C.c_void_p(data.ctypes.data)))
+    finally:
+        _ffx.lib().ffx_factor_free(handle)
+    keys = pa.Array.from_buffers(pa.large_string(), n_keys.value, [None, pa.py_buffer(offsets), pa.py_buffer(data)])
+    return codes, keys
+
+
 def csr_from_ordinals(row_doc: np.ndarray, n_docs: int) -> tuple[np.ndarray, np.ndarray]:
     """doc -> rows CSR (offsets [n_docs+1], rows) from per-row document ordinals (-1 = none)."""
     row_doc = np.ascontiguousarray(row_doc, np.int64)

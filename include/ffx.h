@@ -174,6 +174,18 @@ int ffx_dict_export(const ffx_dict *d, int64_t *offsets, char *data, int64_t *va
  * be NULL to get the offsets only. */
 int ffx_csr_build(const int64_t *row_doc, int64_t n_rows, int64_t n_docs, int64_t *doc_off, int64_t *doc_rows);
 
+/* Factorises a string column (Arrow layout, no nulls) on all host cores: codes[i] == codes[j] iff the
+ * strings are equal, codes in [0, *n_keys); unlike ffx_dict_insert_ordinal the numbering is NOT the
+ * order of first appearance (rows are partitioned by hash and deduplicated per partition) — what
+ * `Ranking.__init__` needs for its id column (ranking.py:95-117 on integer codes).  The distinct
+ * strings, in code order, come from ffx_factor_export (key_offsets[n_keys + 1], key_data[key_bytes]);
+ * the input buffers must stay alive until then.  ffx_factor_free releases the handle. */
+typedef struct ffx_factor ffx_factor;
+int ffx_factorize(const int64_t *offsets, const char *data, int64_t n, int32_t *codes, ffx_factor **out, int64_t *n_keys,
+                  int64_t *key_bytes, int n_threads);
+int ffx_factor_export(const ffx_factor *f, int64_t *key_offsets, char *key_data);
+void ffx_factor_free(ffx_factor *f);
+
 /* A column of fixed-width, NUL-padded byte ids (HDF5 `S{max_id_length}` datasets, "" = no id:
  * index/disk.py:152-165,414-417) as Arrow string buffers for the dictionaries above:
  * offsets[n+1], the concatenated bytes in `out` (room for n * width), a validity bitmap of

@@ -181,3 +181,23 @@ def test_host_sort_and_match_routines_at_multithreaded_sizes():
     order = np.empty(5, np.int64)
     _ffx.check(lib.ffx_ranking_order(ptr(np.zeros(5, np.int32)), ptr(nan_scores), 5, ptr(order), 0))
     assert order.tolist() == [2, 0, 4, 1, 3]  # NaN after every number, in incoming order
+
+
+@pytest.mark.parametrize("n, distinct", [(0, 1), (7, 3), (300_000, 41_000)])
+def test_factorize_gives_equal_codes_to_equal_strings(ids, n, distinct):
+    """`ffx_factorize` (all cores, hash-partitioned) against pandas.factorize: the numbering differs,
+    the partition of the rows into equal strings must not; the exported keys are the distinct strings."""
+    rng = np.random.default_rng(n)
+    pool = np.array([f"doc-{i * 7919 % 100_003}" + "x" * (i % 5) for i in range(distinct)] + [""], dtype=object)
+    col = pool[rng.integers(0, len(pool), n)]
+    for values in (col, pd.array(col, dtype="string[pyarrow]"), pa.chunked_array([pa.array(col[: n // 2], pa.string()), pa.array(col[n // 2 :], pa.string())])):
+        codes, keys = ids.factorize(values)
+        assert codes.dtype == np.int32 and len(codes) == n
+        want_codes, want_keys = pd.factorize(col)
+        assert len(keys) == len(want_keys)
+        assert sorted(keys.to_pylist()) == sorted(want_keys.tolist())
+        if n:
+            assert codes.min() >= 0 and codes.max() < len(keys)
+            assert np.array_equal(np.asarray(keys.to_pylist(), dtype=object)[codes], col)
+    with pytest.raises(ValueError):
+        ids.factorize(pa.array(["a", None]))
