@@ -14,6 +14,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <memory>
 #include <vector>
 
 #include "../../include/ffx.h"
@@ -165,6 +166,26 @@ void parallel_ranges(int64_t n, int threads, F &&body) {
     for (auto &th : pool) th.join();
 }
 
+// hash partitions for the parallel de-duplication passes: about 32k rows each (a table that stays in
+// a core's L2), 2^6 .. 2^most of them
+inline int partition_bits(int64_t n, int most) {
+    int bits = 6;
+    while (bits < most && (n >> bits) > 32768) bits++;
+    return bits;
+}
+
+// n elements WITHOUT value-initialisation: the pages are first touched by the worker threads that
+// fill them, not by one serial memset
+template <typename T>
+struct raw_array {
+    std::unique_ptr<T[]> p;
+    explicit raw_array(int64_t n) : p(new T[static_cast<size_t>(std::max<int64_t>(n, 1))]) {}
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    T *data() { return p.get(); }
+    T *begin() { return p.get(); }
+};
+
 // order[j] = the element that comes j-th when n elements are sorted by key(i) ascending, equal
 // keys in index order: LSD radix sort, 8-bit digits, digits that never vary are skipped, every
 // pass (histogram, prefix, scatter) spread over the host cores.
@@ -175,7 +196,7 @@ int radix_order(int64_t n, int n_threads, int64_t *order, KeyOf &&key_of) {
         uint64_t key;
         uint32_t row;
     };
-    std::vector<Item> a(static_cast<size_t>(n)), b(static_cast<size_t>(n));
+    raw_array<Item> a(n), b(n);
     const int threads = worker_count(n_threads, n / 16);
     std::vector<uint64_t> seen_or(static_cast<size_t>(threads), 0), seen_and(static_cast<size_t>(threads), ~uint64_t(0));
     const int64_t step = (n + threads - 1) / threads;
@@ -414,26 +435,84 @@ int ffx_first_repeat(const int64_t *keys, int64_t n, int64_t *first) {
     if (n < 0 || !first || (n > 0 && !keys)) return fail(FFX_ERR_INVALID, "ffx_first_repeat: bad arguments");
     *first = -1;
     if (n < 2) return FFX_OK;
-    uint64_t cap = 1024;
-    while (cap < static_cast<uint64_t>(n) * 2) cap <<= 1;
-    const uint64_t mask = cap - 1;
-    std::vector<int64_t> slots(cap, -1);  // index of the key stored in the slot
-    const int kAhead = 16;
-    auto home = [&](int64_t i) { return mix(static_cast<uint64_t>(keys[i]) * 0x9E3779B97F4A7C15ull) & mask; };
-    for (int64_t i = 0; i < std::min<int64_t>(kAhead, n); i++) __builtin_prefetch(&slots[home(i)], 1);
-    for (int64_t i = 0; i < n; i++) {
-        if (i + kAhead < n) __builtin_prefetch(&slots[home(i + kAhead)], 1);
-        for (uint64_t s = home(i);; s = (s + 1) & mask) {
-            if (slots[s] < 0) {
-                slots[s] = i;
-                break;
-            }
-            if (keys[slots[s]] == keys[i]) {
-                *first = i;
-                return FFX_OK;
-            }
+    if (n >= (int64_t(1) << 32)) return fail(FFX_ERR_UNSUPPORTED, "ffx_first_repeat: more than 2^32 keys");
+    // equal keys share a hash: rows are partitioned by its top bits, every partition is checked in its
+    // own cache-sized table.  Reports the lowest row that repeats an earlier one INSIDE its partition,
+    // minimised over partitions — the row pandas' duplicated() would flag first.
+    const int kBits = partition_bits(n, 10), kParts = 1 << kBits;
+    const int threads = worker_count(0, n / 4096);
+    const int64_t step = (n + threads - 1) / threads;
+    auto hash_of = [&](int64_t i) { return mix(static_cast<uint64_t>(keys[i]) * 0x9E3779B97F4A7C15ull); };
+    std::vector<int64_t> counts(static_cast<size_t>(threads) * kParts, 0);
+    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+        int64_t *mine = counts.data() + static_cast<size_t>(lo / step) * kParts;
+        for (int64_t i = lo; i < hi; i++) mine[hash_of(i) >> (64 - kBits)]++;
+    });
+    std::vector<int64_t> begin(kParts + 1, 0);
+    int64_t at = 0;
+    for (int p = 0; p < kParts; p++) {
+        begin[static_cast<size_t>(p)] = at;
+        for (int t = 0; t < threads; t++) {
+            int64_t &c = counts[static_cast<size_t>(t) * kParts + p];
+            const int64_t mine = c;
+            c = at;
+            at += mine;
         }
     }
+    begin[kParts] = at;
+    struct Item {
+        int64_t key;
+        uint32_t row;
+    };
+    raw_array<Item> items(n);
+    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+        int64_t *cursor = counts.data() + static_cast<size_t>(lo / step) * kParts;
+        for (int64_t i = lo; i < hi; i++) items[static_cast<size_t>(cursor[hash_of(i) >> (64 - kBits)]++)] = Item{keys[i], static_cast<uint32_t>(i)};
+    });
+    std::atomic<int> next{0};
+    std::atomic<int64_t> lowest{INT64_MAX};
+    auto hash_key = [](int64_t k) { return mix(static_cast<uint64_t>(k) * 0x9E3779B97F4A7C15ull); };
+    auto check = [&]() {
+        std::vector<uint32_t> slots;  // position inside the partition + 1, 0 = free
+        for (int p = next.fetch_add(1); p < kParts; p = next.fetch_add(1)) {
+            const int64_t b = begin[static_cast<size_t>(p)], e = begin[static_cast<size_t>(p) + 1];
+            uint64_t cap = 64;
+            while (cap < static_cast<uint64_t>(e - b) * 2) cap <<= 1;
+            slots.assign(cap, 0);
+            const uint64_t mask = cap - 1;
+            const Item *it = items.data() + b;
+            const int64_t m = e - b;
+            const int kAhead = 8;
+            for (int64_t j = 0; j < m; j++) {
+                if (j + kAhead < m) __builtin_prefetch(&slots[hash_key(it[j + kAhead].key) & mask], 1);
+                bool repeat = false;
+                for (uint64_t s = hash_key(it[j].key) & mask;; s = (s + 1) & mask) {
+                    if (slots[s] == 0) {
+                        slots[s] = static_cast<uint32_t>(j + 1);
+                        break;
+                    }
+                    if (it[slots[s] - 1].key == it[j].key) {
+                        repeat = true;
+                        break;
+                    }
+                }
+                if (repeat) {  // rows of a partition come in increasing order: this is its first repeat
+                    const int64_t r = it[j].row;
+                    int64_t cur = lowest.load();
+                    while (r < cur && !lowest.compare_exchange_weak(cur, r)) {
+                    }
+                    break;
+                }
+            }
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; t++) pool.emplace_back(check);
+        check();
+        for (auto &th : pool) th.join();
+    }
+    if (lowest.load() != INT64_MAX) *first = lowest.load();
     return FFX_OK;
 }
 
@@ -441,22 +520,77 @@ int ffx_ranking_order(const int32_t *q_rank, const float *score, int64_t n, int6
     if (n < 0 || (n > 0 && (!q_rank || !score || !order)))
         return fail(FFX_ERR_INVALID, "ffx_ranking_order: bad arguments");
     if (n >= (int64_t(1) << 32)) return fail(FFX_ERR_UNSUPPORTED, "ffx_ranking_order: more than 2^32 rows");
+    if (n == 0) return FFX_OK;
     // key: query rank ascending, then score DEscending (-0.0 == +0.0, NaN after every number),
-    // the incoming row order breaking ties (LSD radix passes are stable)
-    std::atomic<int> negative{0};
-    const int rc = radix_order(n, n_threads, order, [&](int64_t i) {
+    // the incoming row order breaking ties
+    auto desc_key = [&](int64_t i) {
         float f = score[i];
         uint32_t u;
         if (f == 0.0f) f = 0.0f;  // drops the sign of -0.0
         memcpy(&u, &f, 4);
         const uint32_t asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending in f
-        uint32_t desc = ~asc;
-        if (f != f) desc = 0xffffffffu;
-        if (q_rank[i] < 0) negative.store(1, std::memory_order_relaxed);
-        return (static_cast<uint64_t>(static_cast<uint32_t>(q_rank[i])) << 32) | desc;
+        return (f != f) ? 0xffffffffu : ~asc;
+    };
+    const int threads = worker_count(n_threads, n / 16);
+    const int64_t step = (n + threads - 1) / threads;
+    std::vector<int32_t> top(static_cast<size_t>(threads), 0), low(static_cast<size_t>(threads), 0);
+    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+        int32_t mx = 0, mn = 0;
+        for (int64_t i = lo; i < hi; i++) {
+            mx = std::max(mx, q_rank[i]);
+            mn = std::min(mn, q_rank[i]);
+        }
+        top[static_cast<size_t>(lo / step)] = mx;
+        low[static_cast<size_t>(lo / step)] = mn;
     });
-    if (negative.load()) return fail(FFX_ERR_INVALID, "ffx_ranking_order: negative query rank");
-    return rc;
+    if (*std::min_element(low.begin(), low.end()) < 0) return fail(FFX_ERR_INVALID, "ffx_ranking_order: negative query rank");
+    const int64_t n_ranks = static_cast<int64_t>(*std::max_element(top.begin(), top.end())) + 1;
+    if (n_ranks * threads > (int64_t(1) << 24))  // too many queries for per-thread histograms
+        return radix_order(n, n_threads, order, [&](int64_t i) {
+            return (static_cast<uint64_t>(static_cast<uint32_t>(q_rank[i])) << 32) | desc_key(i);
+        });
+    // one stable counting pass groups the rows by query; every query's block (its rows, in incoming
+    // order) is then sorted on its own, (score key, row) packed in one word
+    std::vector<int64_t> counts(static_cast<size_t>(threads * n_ranks), 0);
+    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+        int64_t *mine = counts.data() + (lo / step) * n_ranks;
+        for (int64_t i = lo; i < hi; i++) mine[q_rank[i]]++;
+    });
+    std::vector<int64_t> begin(static_cast<size_t>(n_ranks) + 1, 0);
+    int64_t at = 0;
+    for (int64_t r = 0; r < n_ranks; r++) {
+        begin[static_cast<size_t>(r)] = at;
+        for (int t = 0; t < threads; t++) {
+            int64_t &c = counts[static_cast<size_t>(t * n_ranks + r)];
+            const int64_t mine = c;
+            c = at;
+            at += mine;
+        }
+    }
+    begin[static_cast<size_t>(n_ranks)] = at;
+    raw_array<uint64_t> items(n);
+    parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
+        int64_t *cursor = counts.data() + (lo / step) * n_ranks;
+        for (int64_t i = lo; i < hi; i++)
+            items[static_cast<size_t>(cursor[q_rank[i]]++)] = (static_cast<uint64_t>(desc_key(i)) << 32) | static_cast<uint32_t>(i);
+    });
+    std::atomic<int64_t> next{0};
+    const int64_t kChunk = 16;
+    auto sort_blocks = [&]() {
+        for (int64_t r0 = next.fetch_add(kChunk); r0 < n_ranks; r0 = next.fetch_add(kChunk))
+            for (int64_t r = r0; r < std::min(n_ranks, r0 + kChunk); r++) {
+                const int64_t b = begin[static_cast<size_t>(r)], e = begin[static_cast<size_t>(r) + 1];
+                std::sort(items.begin() + b, items.begin() + e);
+                for (int64_t i = b; i < e; i++) order[i] = static_cast<int64_t>(items[static_cast<size_t>(i)] & 0xffffffffu);
+            }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; t++) pool.emplace_back(sort_blocks);
+        sort_blocks();
+        for (auto &th : pool) th.join();
+    }
+    return FFX_OK;
 }
 
 int ffx_order_u64(const uint64_t *keys, int64_t n, int64_t *order, int n_threads) {
@@ -624,9 +758,6 @@ struct ffx_factor {
     int64_t n_keys = 0, key_bytes = 0;
 };
 
-namespace {
-constexpr int kFactorBits = 6, kFactorParts = 1 << kFactorBits;
-}
 
 extern "C" {
 
@@ -635,6 +766,7 @@ int ffx_factorize(const int64_t *offsets, const char *data, int64_t n, int32_t *
     if (!out || !n_keys || !key_bytes || bad_strings(offsets, data, n) || (n > 0 && !codes))
         return fail(FFX_ERR_INVALID, "ffx_factorize: bad arguments");
     if (n >= (int64_t(1) << 31)) return fail(FFX_ERR_UNSUPPORTED, "ffx_factorize: more than 2^31 rows");
+    const int kFactorBits = partition_bits(n, 8), kFactorParts = 1 << kFactorBits;
     ffx_factor *f = new ffx_factor();
     f->offsets = offsets;
     f->data = data;
@@ -644,8 +776,8 @@ int ffx_factorize(const int64_t *offsets, const char *data, int64_t n, int32_t *
     const int threads = worker_count(n_threads, n / 8);
     const int64_t step = (n + threads - 1) / std::max(threads, 1);
     // pass 1: hash every row, count rows per (thread, partition)
-    std::vector<uint32_t> hash_lo(static_cast<size_t>(n));
-    std::vector<uint8_t> part(static_cast<size_t>(n));
+    raw_array<uint32_t> hash_lo(n);
+    raw_array<uint8_t> part(n);
     std::vector<int64_t> counts(static_cast<size_t>(threads) * kFactorParts, 0);
     parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
         int64_t *mine = counts.data() + static_cast<size_t>(step > 0 ? lo / step : 0) * kFactorParts;
@@ -672,7 +804,7 @@ int ffx_factorize(const int64_t *offsets, const char *data, int64_t n, int32_t *
         }
         part_begin[kFactorParts] = at;
     }
-    std::vector<uint32_t> rows(static_cast<size_t>(n));
+    raw_array<uint32_t> rows(n);
     parallel_ranges(n, threads, [&](int64_t lo, int64_t hi) {
         int64_t *cursor = counts.data() + static_cast<size_t>(step > 0 ? lo / step : 0) * kFactorParts;
         for (int64_t i = lo; i < hi; i++) rows[static_cast<size_t>(cursor[part[static_cast<size_t>(i)]]++)] = static_cast<uint32_t>(i);
@@ -736,8 +868,8 @@ int ffx_factorize(const int64_t *offsets, const char *data, int64_t n, int32_t *
 int ffx_factor_export(const ffx_factor *f, int64_t *key_offsets, char *key_data) {
     if (!f || !key_offsets || (f->key_bytes > 0 && !key_data)) return fail(FFX_ERR_INVALID, "ffx_factor_export: bad arguments");
     int64_t code = 0, at = 0;
-    for (int p = 0; p < kFactorParts; p++)
-        for (uint32_t r : f->first_row[static_cast<size_t>(p)]) {
+    for (size_t p = 0; p < f->first_row.size(); p++)
+        for (uint32_t r : f->first_row[p]) {
             const int64_t len = f->offsets[r + 1] - f->offsets[r];
             key_offsets[code++] = at;
             memcpy(key_data + at, f->data + f->offsets[r], static_cast<size_t>(len));
