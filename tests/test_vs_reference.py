@@ -23,15 +23,19 @@ REF = os.path.join(ROOT, "baseline", "_ref", "fast_forward")
 @pytest.mark.skipif(not os.path.isdir(REF), reason="baseline/_ref (the reference package) is not installed here")
 @pytest.mark.parametrize("seed,dim,variant", [(1, 768, "plain"), (2, 384, "plain"), (3, 100, "plain"),
                                               (4, 768, "scattered+batched"), (5, 768, "float64"),
-                                              (6, 100, "scattered+batched")])
-def test_frames_equal_the_reference(tmp_path, seed, dim, variant):
+                                              (6, 100, "scattered+batched"), (7, 768, "coded"),
+                                              (8, 100, "coded+scattered+batched"), (9, 384, "coded+float64")])
+def test_frames_equal_the_reference(tmp_path, monkeypatch, seed, dim, variant):
     import __graft_entry__ as g
 
     g.build()
     import fast_forward
+    import fast_forward.ranking as rk
     from fast_forward.encoder import TableEncoder
     from fast_forward.index import InMemoryIndex, Mode
 
+    if "coded" in variant:  # rankings on integer-coded columns, as at the large sizes (ranking._CODED_FROM)
+        monkeypatch.setattr(rk, "_CODED_FROM", 0)
     rng = np.random.default_rng(seed)
     n_docs, nq, C = 3000, 40, 600
     cnt = rng.integers(1, 9, n_docs)
@@ -43,8 +47,8 @@ def test_frames_equal_the_reference(tmp_path, seed, dim, variant):
         split = len(vectors) - len(vectors) // 4
         doc_ids[split:] = [f"d{int(x)}" for x in rng.integers(0, n_docs, len(vectors) - split)]
         extra = {"split": split, "batch_size": 7}
-    score_dtype = np.float64 if variant == "float64" else np.float32
-    if variant == "float64":
+    score_dtype = np.float64 if "float64" in variant else np.float32
+    if "float64" in variant:
         extra["score_dtype"] = "float64"
     qvecs = rng.standard_normal((nq, dim)).astype(np.float32)
     cols = {}
