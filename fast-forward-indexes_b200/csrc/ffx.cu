@@ -27,6 +27,7 @@
 #include "ffx_kernels.cuh"
 #include "ffx_score_tma.cuh"
 #include "ffx_score_any.cuh"
+#include "ffx_score_packed.cuh"
 #include "ffx_coalesce.cuh"
 #include "ffx_layout.h"
 
@@ -131,6 +132,7 @@ struct ffx_index {
     uint2 *doc_span = nullptr;
     int32_t *doc_rows = nullptr;
     int indirect = 0;
+    int64_t max_doc_rows = 1;  // rows of the longest document (bounds a candidate batch of the short-row kernel)
 
     // doc-id-range shard of a larger corpus (ffx_index_set_shard); off = whole corpus
     bool sharded = false;
@@ -441,12 +443,35 @@ int launch_score_any(const ffx::ScoreArgs &a, const ffx_any_plan &plan, bool fus
     return FFX_OK;
 }
 
+// ---- short rows (8 / 16 lanes per row): ffx_score_packed_kernel -------------------------------
+template <class Dot>
+int launch_score_packed(const ffx::ScoreArgs &a, const typename Dot::Plan &plan, int query_bytes, int slot_bytes, bool fuse,
+                        int grid, int warps, int ns, int batch, cudaStream_t st) {
+    const size_t smem = ffx::packed_smem_bytes(fuse ? a.cpad : 0, warps, ns, query_bytes, slot_bytes);
+    if (fuse) {
+        auto kern = ffx::ffx_score_packed_kernel<Dot, true>;
+        FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kern<<<grid, warps * 32, smem, st>>>(a, plan, ns, batch);
+        note_kernel(kern);
+    } else {
+        auto kern = ffx::ffx_score_packed_kernel<Dot, false>;
+        FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kern<<<grid, warps * 32, smem, st>>>(a, plan, ns, batch);
+        note_kernel(kern);
+    }
+    g_launches++;
+    FFX_CUDA(cudaGetLastError());
+    return FFX_OK;
+}
+
 int dispatch_score_any(const ffx_any_plan &p, const ScorePlan &sp, const ffx::ScoreArgs &a, bool fuse, int grid,
                        cudaStream_t st) {
+    if (p.cpl == 1 && p.lpr == 8)
+        return launch_score_packed<ffx::TreeDot<8>>(a, p, p.stride * 4, p.stride * 16, fuse, grid, sp.warps, sp.ns, sp.batch, st);
+    if (p.cpl == 1 && p.lpr == 16)
+        return launch_score_packed<ffx::TreeDot<16>>(a, p, p.stride * 4, p.stride * 8, fuse, grid, sp.warps, sp.ns, sp.batch, st);
 #define FFX_CASE(C, L) \
     if (p.cpl == C && p.lpr == L) return launch_score_any<C, L>(a, p, fuse, grid, sp.warps, sp.ns, sp.batch, st)
-    FFX_CASE(1, 8);
-    FFX_CASE(1, 16);
     FFX_CASE(1, 32);
     FFX_CASE(2, 32);
     FFX_CASE(4, 32);
@@ -521,8 +546,9 @@ int dispatch_score(const ffx_plan &p, const ScorePlan &sp, const ffx::ScoreArgs 
         FFX_CASE(8, 14);
         FFX_CASE(8, 16);
 #undef FFX_CASE
-#define FFX_CASE(S_, L) \
-    if (p.lanes == L && p.steps == S_) return launch_score_tma<1, S_, L>(a, fuse, grid, sp.warps, sp.ns, sp.batch, st)
+#define FFX_CASE(S_, L)                                                                                            \
+    if (p.lanes == L && p.steps == S_)                                                                             \
+        return launch_score_packed<ffx::LaneMajorDot<S_, L>>(a, {}, 0, 32 * S_ * 4, fuse, grid, sp.warps, sp.ns, sp.batch, st)
         FFX_CASE(8, 8);
         FFX_CASE(12, 8);
         FFX_CASE(16, 8);
@@ -947,6 +973,7 @@ int ffx_index_set_docs(ffx_index *idx, int64_t n_docs, const int64_t *doc_off,
     idx->doc_rows = nullptr;
     idx->n_docs = 0;
     idx->indirect = 0;
+    idx->max_doc_rows = 1;
     if (n_docs == 0) return FFX_OK;
 
     const int64_t total = doc_off[n_docs];
@@ -972,6 +999,7 @@ int ffx_index_set_docs(ffx_index *idx, int64_t n_docs, const int64_t *doc_off,
     for (int64_t d = 0; d < n_docs; d++) {
         const int64_t b = doc_off[d];
         const uint32_t cnt = static_cast<uint32_t>(doc_off[d + 1] - b);
+        idx->max_doc_rows = std::max<int64_t>(idx->max_doc_rows, cnt);
         const uint32_t first = contiguous ? static_cast<uint32_t>(doc_rows ? doc_rows[b] : b)
                                           : static_cast<uint32_t>(b);
         span[static_cast<size_t>(d)] = make_uint2(first, cnt);
@@ -1184,8 +1212,10 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     const float *topk_src = rank_scores ? rank_scores : out_int;  // input of a separate top-k pass
 
     // tiles: split a query over several CTAs when there are few queries
-    const ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4 * (32 / idx->plan.lanes),
-                                           idx->sharded, few_pairs, idx->plan.lanes != 32) : sp_any;
+    ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4 * (32 / idx->plan.lanes),
+                                     idx->sharded, few_pairs, idx->plan.lanes != 32) : sp_any;
+    // short-row kernel: positions inside a batch's flattened row sequence are 32-bit
+    sp.batch = static_cast<int>(std::min<int64_t>(sp.batch, std::max<int64_t>(1, 0x7fffffffll / idx->max_doc_rows)));
     int tiles = 1, tile = static_cast<int>(std::max<int64_t>(max_cand, 1));
     if (!fuse) {
         // enough CTAs for ~2 waves at the plan's occupancy, but a tile keeps every warp of its
