@@ -382,12 +382,27 @@ ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, 
         return p;
     }
     if (short_rows) {
-        // 256-1024 byte rows (D <= 256), 2 or 4 per warp step and ring slot (`row_bytes` is the slot
-        // here): deep rings keep enough bytes in flight
-        p.warps = fuse ? 8 : (few_pairs ? 2 : 4);
-        if (!fuse && few_pairs && g_tune.batch <= 0) p.batch = 8;
-        p.ns = std::min(16, ring_slots(keys, p.warps, row_bytes, fuse ? 2 : 4));
-        if (p.ns < 3) p.ns = std::min(16, ring_slots(keys, p.warps, row_bytes, 1));
+        // D <= 256 (ffx_score_packed_kernel): `row_bytes` is the ring slot of one warp step here — 4 .. 16
+        // rows, 3-4 KB.  Fused: the shape with the most slots in flight per SM, at least two per warp.
+        // Full batches of 32 candidates: a batch ends with a partly filled step.
+        if (g_tune.batch <= 0) p.batch = 32;
+        if (fuse) {
+            const int shapes[][2] = {{8, 2}, {16, 1}, {12, 1}, {8, 1}, {4, 1}};
+            int best = 0;
+            p.ns = 0;
+            for (const auto &shape : shapes) {
+                const int ns = std::min(6, ring_slots(keys, shape[0], row_bytes, shape[1]));
+                if (ns < 2 || ns * shape[0] * shape[1] <= best) continue;
+                best = ns * shape[0] * shape[1];
+                p.warps = shape[0];
+                p.ns = ns;
+            }
+        } else {
+            p.warps = few_pairs ? 2 : 4;
+            if (few_pairs && g_tune.batch <= 0) p.batch = 8;
+            p.ns = std::min(6, ring_slots(0, p.warps, row_bytes, 4));
+            if (p.ns < 2) p.ns = std::min(6, ring_slots(0, p.warps, row_bytes, 1));
+        }
         if (g_tune.tma_stages > 0) p.ns = std::min(p.ns, std::max(2, g_tune.tma_stages));
         p.tma = p.ns >= 2;
         return p;
@@ -466,10 +481,20 @@ int launch_score_packed(const ffx::ScoreArgs &a, const typename Dot::Plan &plan,
 
 int dispatch_score_any(const ffx_any_plan &p, const ScorePlan &sp, const ffx::ScoreArgs &a, bool fuse, int grid,
                        cudaStream_t st) {
-    if (p.cpl == 1 && p.lpr == 8)
-        return launch_score_packed<ffx::TreeDot<8>>(a, p, p.stride * 4, p.stride * 16, fuse, grid, sp.warps, sp.ns, sp.batch, st);
-    if (p.cpl == 1 && p.lpr == 16)
-        return launch_score_packed<ffx::TreeDot<16>>(a, p, p.stride * 4, p.stride * 8, fuse, grid, sp.warps, sp.ns, sp.batch, st);
+    if (p.cpl == 2 && p.lpr == 4)
+        return launch_score_packed<ffx::TreeDot<2, 4>>(a, p, p.stride * 4, p.stride * 32, fuse, grid, sp.warps, sp.ns, sp.batch, st);
+    if (p.cpl == 2 && p.lpr == 8)
+        return launch_score_packed<ffx::TreeDot<2, 8>>(a, p, p.stride * 4, p.stride * 16, fuse, grid, sp.warps, sp.ns, sp.batch, st);
+    if (g_tune.kernel == 3) {  // A/B: whole-warp rows through the packed kernel too
+#define FFX_CASE(C) \
+    if (p.cpl == C && p.lpr == 32) \
+        return launch_score_packed<ffx::TreeDot<C, 32>>(a, p, p.stride * 4, p.stride * 4, fuse, grid, sp.warps, sp.ns, sp.batch, st)
+        FFX_CASE(1);
+        FFX_CASE(2);
+        FFX_CASE(4);
+        FFX_CASE(8);
+#undef FFX_CASE
+    }
 #define FFX_CASE(C, L) \
     if (p.cpl == C && p.lpr == L) return launch_score_any<C, L>(a, p, fuse, grid, sp.warps, sp.ns, sp.batch, st)
     FFX_CASE(1, 32);
@@ -546,14 +571,15 @@ int dispatch_score(const ffx_plan &p, const ScorePlan &sp, const ffx::ScoreArgs 
         FFX_CASE(8, 14);
         FFX_CASE(8, 16);
 #undef FFX_CASE
-#define FFX_CASE(S_, L)                                                                                            \
-    if (p.lanes == L && p.steps == S_)                                                                             \
-        return launch_score_packed<ffx::LaneMajorDot<S_, L>>(a, {}, 0, 32 * S_ * 4, fuse, grid, sp.warps, sp.ns, sp.batch, st)
-        FFX_CASE(8, 8);
-        FFX_CASE(12, 8);
-        FFX_CASE(16, 8);
-        FFX_CASE(12, 16);
-        FFX_CASE(16, 16);
+#define FFX_CASE(S_, L, C)                                                                                   \
+    if (p.lanes == L && p.steps == S_ && ffx_short_row_cpl(p) == C)                                              \
+        return launch_score_packed<ffx::LaneMajorDot<S_, L, C>>(a, {}, 0, 32 * C * S_ * 4, fuse, grid, sp.warps, sp.ns, \
+                                                                sp.batch, st)
+        FFX_CASE(8, 8, 4);    // D = 64: 2 lanes per row, 16 rows per warp step
+        FFX_CASE(12, 8, 2);   // D = 96: 4 lanes, 8 rows
+        FFX_CASE(16, 8, 2);   // D = 128
+        FFX_CASE(12, 16, 2);  // D = 192: 8 lanes, 4 rows
+        FFX_CASE(16, 16, 2);  // D = 256
 #undef FFX_CASE
     }
     const size_t smem = fuse ? static_cast<size_t>(a.cpad) * 8 : 0;
@@ -701,7 +727,7 @@ const char *ffx_last_error(void) { return g_err.c_str(); }
 int ffx_set_option(const char *name, int value) {
     if (!name) return fail(FFX_ERR_INVALID, "ffx_set_option: NULL name");
     const std::string key(name);
-    if (key == "kernel" && value >= 0 && value <= 2) g_tune.kernel = value;
+    if (key == "kernel" && value >= 0 && value <= 3) g_tune.kernel = value;
     else if (key == "tma_stages" && value >= 0 && value <= 16) g_tune.tma_stages = value;
     else if (key == "batch" && value >= 0 && value <= 32) g_tune.batch = value;
     else if (key == "adc" && value >= 0 && value <= 3) g_tune.adc = value;
@@ -1212,7 +1238,9 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     const float *topk_src = rank_scores ? rank_scores : out_int;  // input of a separate top-k pass
 
     // tiles: split a query over several CTAs when there are few queries
-    ScorePlan sp = fast ? plan_score(mode, fuse, cpad, static_cast<int>(idx->dim) * 4 * (32 / idx->plan.lanes),
+    // (short rows: the ring slot of one warp step, 32 / (lanes per row) rows)
+    ScorePlan sp = fast ? plan_score(mode, fuse, cpad,
+                                     static_cast<int>(idx->dim) * 4 * (32 * ffx_short_row_cpl(idx->plan) / idx->plan.lanes),
                                      idx->sharded, few_pairs, idx->plan.lanes != 32) : sp_any;
     // short-row kernel: positions inside a batch's flattened row sequence are 32-bit
     sp.batch = static_cast<int>(std::min<int64_t>(sp.batch, std::max<int64_t>(1, 0x7fffffffll / idx->max_doc_rows)));

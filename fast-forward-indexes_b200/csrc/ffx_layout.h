@@ -42,6 +42,10 @@ static inline ffx_plan ffx_plan_for_dim(int64_t dim) {
     return ffx_plan{0, 0, 32};
 }
 
+// Short lane-major rows are CONSUMED by lanes / cpl lanes, each taking cpl adjacent chains (the
+// packed kernel, ffx_score_packed.cuh): about 32 elements per lane.
+static inline int ffx_short_row_cpl(const ffx_plan &p) { return p.lanes == 32 ? p.cpl : (p.steps <= 8 ? 4 : 2); }
+
 // staged float offset k inside a row  ->  original element index.  The i-th float4 of lane l
 // (of the `lanes` lanes sharing the row) sits at float offset (i*lanes + l)*4.
 FFX_HD static inline int ffx_orig_index(int cpl, int steps, int k, int lanes = 32) {
@@ -69,8 +73,8 @@ FFX_HD static inline int ffx_orig_index(int cpl, int steps, int k, int lanes = 3
 struct ffx_any_plan {
     int valid;       // 0: more than 32 leaf slots (D beyond ~4096): thread-per-pair kernel
     int dim, stride; // elements, stored floats per row
-    int lpr;         // lanes sharing one row: 8, 16, 32
-    int cpl;         // chains per lane: 1, 2, 4, 8
+    int lpr;         // lanes sharing one row: 4, 8, 32
+    int cpl;         // chains per lane: 1, 2, 4, 8 (2 for the short rows of one or two leaves)
     int n_slots;     // leaf slots, a power of two <= 32
     int max_steps;   // longest chain (groups of 8 in the longest leaf)
     int tail_slot, tail_start, tail_len;
@@ -117,8 +121,9 @@ static inline ffx_any_plan ffx_any_plan_for_dim(int64_t dim) {
             p.tail_len = tail;
         }
     }
+    // one or two leaves: two chains per lane, 4 or 8 lanes per row (8 / 4 rows per warp step)
     const int chains = 8 * p.n_slots;
-    p.lpr = chains >= 32 ? 32 : chains;
+    p.lpr = chains >= 32 ? 32 : chains / 2;
     p.cpl = chains / p.lpr;
     p.valid = 1;
     return p;

@@ -1,4 +1,5 @@
-// ffx_score_packed.cuh — the scoring kernel for SHORT rows (D <= 256: 8 or 16 lanes per row).
+// ffx_score_packed.cuh — the scoring kernel for SHORT rows (D <= 256: 2 .. 8 lanes per row) and for
+// every dimension without a uniform numpy tree.
 //
 // Same contract and arithmetic as ffx_score_tma_kernel / ffx_score_any_kernel (one warp-shared
 // ring of bulk-copied row slots per warp, candidate batches resolved ahead, fused interpolation
@@ -30,41 +31,95 @@ __host__ __device__ inline size_t packed_smem_bytes(int cpad_scores, int warps, 
     return keys + qv + static_cast<size_t>(warps) * ns * slot_bytes + static_cast<size_t>(warps) * ns * 8 + 128;
 }
 
-// D = LPR * S elements, one accumulator chain of S terms per lane (ffx_layout.h)
-template <int S, int LPR_>
+// Lane-major short rows (ffx_layout.h): the row is STORED for L0 = 8 or 16 lanes, stored lane c owning
+// accumulator chain c (S terms) in float4 pieces (i * L0 + c).  Here LPR = L0 / CPL lanes share a
+// row, each taking CPL adjacent chains — 32 / LPR = 4 .. 16 rows per warp step, CPL independent add
+// chains per lane.  Register k of a lane holds chain (k ^ x), x from the lane's place in its
+// quarter warp: the lanes of one 128-bit load phase then touch all eight 16-byte bank groups
+// (no shared-memory conflicts), and the in-lane combine (k, k + w) still pairs the chains numpy
+// pairs — fp32 addition commutes, the tree is unchanged.
+template <int S, int L0, int CPL>
 struct LaneMajorDot {
-    static constexpr int LPR = LPR_;
+    static constexpr int LPR = L0 / CPL;
     static constexpr int NV4 = S / 4;
+    static constexpr bool kPair = CPL == 1;  // one chain per lane: two ring slots per consumer iteration instead
+    static_assert(S % 4 == 0 && (L0 == 8 || L0 == 16) && (CPL == 1 || CPL == 2 || CPL == 4), "lane-major short rows");
     struct Plan {};
-    float q[S];
-    __device__ static uint32_t row_bytes(const Plan &) { return LPR * S * 4u; }
+    float q[CPL][S];
+    uint32_t piece[CPL];  // byte offset of chain k's first float4 inside a row
+    __device__ static uint32_t row_bytes(const Plan &) { return L0 * S * 4u; }
     __device__ static uint32_t query_bytes(const Plan &) { return 0; }
     __device__ void stage_query(const Plan &, const ScoreArgs &, int64_t, float *) const {}
     __device__ void init(const Plan &, const ScoreArgs &a, int64_t q_idx, int lane, uint32_t) {
-        const float *qv = a.qvecs + q_idx * (LPR * S);
-        const int g = lane % LPR;
+        const float *qv = a.qvecs + q_idx * (L0 * S);
+        const int x = ((lane & 7) * CPL) >> 3;
 #pragma unroll
-        for (int m = 0; m < S; m++) q[m] = __ldg(qv + (g >> 3) * (8 * S) + 8 * m + (g & 7));
+        for (int k = 0; k < CPL; k++) {
+            const int c = (lane % LPR) * CPL + (k ^ x);  // stored lane = chain
+            piece[k] = static_cast<uint32_t>(c) * 16u;
+#pragma unroll
+            for (int m = 0; m < S; m++) q[k][m] = __ldg(qv + (c >> 3) * (8 * S) + 8 * m + (c & 7));
+        }
+    }
+    __device__ void load(uint32_t row, float4 (&v)[CPL][NV4]) const {
+#pragma unroll
+        for (int i = 0; i < NV4; i++) {
+#pragma unroll
+            for (int k = 0; k < CPL; k++) v[k][i] = lds_f4(row + piece[k] + i * (L0 * 16));
+        }
     }
     // `row` = shared address of this lane group's row; every lane of the group returns the row's dot product
-    __device__ float operator()(uint32_t row, int lane) const {
-        float4 v[NV4];
-        const uint32_t src = row + (lane % LPR) * 16;
+    __device__ float operator()(uint32_t row, int) const {
+        float4 v[CPL][NV4];
+        load(row, v);
+        float acc[CPL];
 #pragma unroll
-        for (int i = 0; i < NV4; i++) v[i] = lds_f4(src + i * (LPR * 16));
-        float part = lane_chain_sum<1, S>(q, v);
+        for (int k = 0; k < CPL; k++) acc[k] = __fmul_rn(q[k][0], f4c(v[k][0], 0));
+#pragma unroll
+        for (int m = 1; m < S; m++) {
+#pragma unroll
+            for (int k = 0; k < CPL; k++) acc[k] = __fadd_rn(acc[k], __fmul_rn(q[k][m], f4c(v[k][m >> 2], m & 3)));
+        }
+#pragma unroll
+        for (int w = 1; w < CPL; w <<= 1) {
+#pragma unroll
+            for (int k = 0; k < CPL; k += 2 * w) acc[k] = __fadd_rn(acc[k], acc[k + w]);
+        }
+        float part = acc[0];
 #pragma unroll
         for (int o = 1; o < LPR; o <<= 1) part = __fadd_rn(part, __shfl_xor_sync(kFull, part, o));
         return __fadd_rn(0.f, part);
     }
+    // CPL == 1: two rows at once, their (order-bound) add chains and butterflies interleave
+    __device__ void pair(uint32_t row0, uint32_t row1, int, float &out0, float &out1) const {
+        float4 v0[CPL][NV4], v1[CPL][NV4];
+        load(row0, v0);
+        load(row1, v1);
+        float a0 = __fmul_rn(q[0][0], f4c(v0[0][0], 0)), a1 = __fmul_rn(q[0][0], f4c(v1[0][0], 0));
+#pragma unroll
+        for (int m = 1; m < S; m++) {
+            a0 = __fadd_rn(a0, __fmul_rn(q[0][m], f4c(v0[0][m >> 2], m & 3)));
+            a1 = __fadd_rn(a1, __fmul_rn(q[0][m], f4c(v1[0][m >> 2], m & 3)));
+        }
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) {
+            const float b0 = __shfl_xor_sync(kFull, a0, o), b1 = __shfl_xor_sync(kFull, a1, o);
+            a0 = __fadd_rn(a0, b0);
+            a1 = __fadd_rn(a1, b1);
+        }
+        out0 = __fadd_rn(0.f, a0);
+        out1 = __fadd_rn(0.f, a1);
+    }
 };
 
-// any D whose tree has one or two leaves: rows in original order (stride padded to 16 bytes)
-template <int LPR_>
+// any other D: the numpy tree as data (ffx_any_plan), rows in original order (stride padded to 16
+// bytes), CPL chains per lane
+template <int CPL, int LPR_>
 struct TreeDot {
     static constexpr int LPR = LPR_;
+    static constexpr bool kPair = false;
     using Plan = ffx_any_plan;
-    AnyQuery<1> q;
+    AnyQuery<CPL> q;
     uint32_t q_addr, my_byte, tail_byte;
     int my_steps, max_steps, tail_len;
     bool tail_mine;
@@ -77,18 +132,22 @@ struct TreeDot {
     // after the staged query vector is visible (__syncthreads)
     __device__ void init(const Plan &p, const ScoreArgs &, int64_t, int lane, uint32_t s_q_addr) {
         const int sub = lane % LPR;
-        const int slot = sub >> 3;
+        const int slot = (sub * CPL) >> 3;
         q_addr = s_q_addr;
-        my_byte = static_cast<uint32_t>(p.start[slot] + (sub & 7)) * 4u;
+        my_byte = static_cast<uint32_t>(p.start[slot] + ((sub * CPL) & 7)) * 4u;
         my_steps = p.steps[slot];
         max_steps = p.max_steps;
         tail_mine = slot == p.tail_slot;
         tail_byte = static_cast<uint32_t>(p.tail_start) * 4u;
         tail_len = p.tail_len;
-        any_load_query<1>(q, q_addr, my_byte, my_steps);
+        any_load_query<CPL>(q, q_addr, my_byte, my_steps);
     }
     __device__ float operator()(uint32_t row, int) const {
-        return any_row_dot<1, LPR>(row, q_addr, q, my_byte, my_steps, max_steps, tail_mine, tail_byte, tail_len);
+        return any_row_dot<CPL, LPR>(row, q_addr, q, my_byte, my_steps, max_steps, tail_mine, tail_byte, tail_len);
+    }
+    __device__ void pair(uint32_t row0, uint32_t row1, int lane, float &out0, float &out1) const {
+        out0 = (*this)(row0, lane);
+        out1 = (*this)(row1, lane);
     }
 };
 
@@ -106,7 +165,8 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_packed_kernel(con
                                                                            const int ns, const int batch) {
     constexpr int LPR = Dot::LPR;
     constexpr int RPS = 32 / LPR;  // rows per warp step = rows per ring slot
-    static_assert(LPR == 8 || LPR == 16, "short rows: 8 or 16 lanes per row");
+    constexpr bool kPair = Dot::kPair;
+    static_assert(LPR == 2 || LPR == 4 || LPR == 8 || LPR == 16 || LPR == 32, "lanes per row");
     const uint32_t ROWB = Dot::row_bytes(plan);
     const uint32_t SLOTB = ROWB * RPS;
 
@@ -275,21 +335,34 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_packed_kernel(con
     while (nbA > 0) {
         DocReduce red;
         red.init();
-        for (uint32_t r0 = 0; r0 < rowsA; r0 += RPS) {
+        for (uint32_t r0 = 0; r0 < rowsA;) {
+            // two steps (ring slots) per iteration while the batch has them; groups beyond the batch's
+            // last row — and the second slot of an odd last step — run on stale bytes: nobody's window
+            // holds their value
             top_up();
-            mbar_wait(bars + c_stage * 8, (c_phase >> c_stage) & 1u);
-            // groups beyond the step's last row run on stale bytes: nobody's window holds their value
-            const float part = dot(ring + c_stage * SLOTB + grp * ROWB, lane);
-            __syncwarp();  // every lane has consumed its row: the slot may be refilled
-            c_phase ^= 1u << c_stage;
-            c_stage = c_stage + 1 == ns ? 0 : c_stage + 1;
-            inflight--;
+            const bool two = kPair && r0 + RPS < rowsA;  // warp-uniform
+            const int s0 = c_stage;
+            const int s1 = s0 + 1 == ns ? 0 : s0 + 1;
+            float part0, part1 = 0.f;
+            mbar_wait(bars + s0 * 8, (c_phase >> s0) & 1u);
+            if constexpr (kPair) {
+                if (two) mbar_wait(bars + s1 * 8, (c_phase >> s1) & 1u);
+                dot.pair(ring + s0 * SLOTB + grp * ROWB, ring + s1 * SLOTB + grp * ROWB, lane, part0, part1);
+            } else {
+                part0 = dot(ring + s0 * SLOTB + grp * ROWB, lane);
+            }
+            __syncwarp();  // every lane has consumed its rows: the slots may be refilled
+            c_phase ^= (1u << s0) | (two ? 1u << s1 : 0u);
+            c_stage = two ? (s1 + 1 == ns ? 0 : s1 + 1) : s1;
+            inflight -= two ? 2 : 1;
             const int rel = static_cast<int>(r0 - A.first);  // row r0 + g is row rel + g of this lane's candidate
 #pragma unroll
-            for (int g = 0; g < RPS; g++) {
-                const float v = __shfl_sync(kFull, part, g * LPR);
+            for (int g = 0; g < (kPair ? 2 : 1) * RPS; g++) {
+                const float part = g < RPS ? part0 : part1;
+                const float v = RPS == 1 ? part : __shfl_sync(kFull, part, (g % RPS) * LPR);  // a whole-warp row: every lane has it
                 if (static_cast<uint32_t>(rel + g) < A.cnt) red.add(v, rel + g == 0, a.mode);
             }
+            r0 += two ? 2 * RPS : RPS;
         }
         const float my_ff = A.cnt ? red.finish(A.cnt, a.mode) : 0.f;
 

@@ -6,6 +6,9 @@ sys.path.insert(0, os.path.join(ROOT, "fast-forward-indexes_b200")); sys.path.in
 import bench
 from fast_forward import _ffx
 dev = torch.device("cuda", 0)
+for name in ("kernel", "tma_stages", "tma_warps", "batch"):  # A/B switches: FFX_OPT_kernel=3 ...
+    if os.environ.get("FFX_OPT_" + name):
+        _ffx.set_option(name, int(os.environ["FFX_OPT_" + name]))
 out = {}
 for D in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "384,768,1024,2048,3072,4096").split(",")]:
     n_docs = int(24e9 / (D * 4 * 6.25))  # ~24 GB of rows
