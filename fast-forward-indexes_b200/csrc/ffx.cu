@@ -292,18 +292,17 @@ int launch_score(const ffx::ScoreArgs &a, bool fuse, int grid, size_t smem, cuda
     return FFX_OK;
 }
 
-template <int CPL, int S, int LPR = 32>
+template <int CPL, int S>
 int launch_score_tma(const ffx::ScoreArgs &a, bool fuse, int grid, int warps, int ns, int batch,
                      cudaStream_t st) {
-    // a ring slot = what one warp step consumes: 32 lanes' worth of elements (a row, or 2 / 4 short rows)
     const size_t smem = ffx::tma_smem_bytes(fuse ? a.cpad : 0, warps, ns, 32 * CPL * S * 4);
     if (fuse) {
-        auto kern = ffx::ffx_score_tma_kernel<CPL, S, true, LPR>;
+        auto kern = ffx::ffx_score_tma_kernel<CPL, S, true>;
         FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         kern<<<grid, warps * 32, smem, st>>>(a, ns, batch);
         note_kernel(kern);
     } else {
-        auto kern = ffx::ffx_score_tma_kernel<CPL, S, false, LPR>;
+        auto kern = ffx::ffx_score_tma_kernel<CPL, S, false>;
         FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         kern<<<grid, warps * 32, smem, st>>>(a, ns, batch);
         note_kernel(kern);
@@ -362,6 +361,8 @@ int ring_slots(int cpad_scores, int warps, int row_bytes, int ctas_per_sm) {
     return ns;
 }
 
+int any_ring_slots(int keys, int warps, int row_bytes, int slot_bytes, int ctas_per_sm);
+
 ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, bool few_pairs, bool short_rows) {
     ScorePlan p;
     // candidates a warp publishes per batch: few rows per candidate (single-row modes, or a shard
@@ -387,11 +388,12 @@ ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, 
         // Full batches of 32 candidates: a batch ends with a partly filled step.
         if (g_tune.batch <= 0) p.batch = 32;
         if (fuse) {
+            // (ties go to two CTAs: one query's top-k epilogue overlaps the other's row stream)
             const int shapes[][2] = {{8, 2}, {16, 1}, {12, 1}, {8, 1}, {4, 1}};
             int best = 0;
             p.ns = 0;
             for (const auto &shape : shapes) {
-                const int ns = std::min(6, ring_slots(keys, shape[0], row_bytes, shape[1]));
+                const int ns = std::min(6, any_ring_slots(keys, shape[0], 0, row_bytes, shape[1]));
                 if (ns < 2 || ns * shape[0] * shape[1] <= best) continue;
                 best = ns * shape[0] * shape[1];
                 p.warps = shape[0];
@@ -400,8 +402,8 @@ ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, 
         } else {
             p.warps = few_pairs ? 2 : 4;
             if (few_pairs && g_tune.batch <= 0) p.batch = 8;
-            p.ns = std::min(6, ring_slots(0, p.warps, row_bytes, 4));
-            if (p.ns < 2) p.ns = std::min(6, ring_slots(0, p.warps, row_bytes, 1));
+            p.ns = std::min(6, any_ring_slots(0, p.warps, 0, row_bytes, 4));
+            if (p.ns < 2) p.ns = std::min(6, any_ring_slots(0, p.warps, 0, row_bytes, 1));
         }
         if (g_tune.tma_stages > 0) p.ns = std::min(p.ns, std::max(2, g_tune.tma_stages));
         p.tma = p.ns >= 2;
@@ -437,28 +439,7 @@ ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, 
     return p;
 }
 
-// ---- dimensions without a lane-major plan: ffx_score_any_kernel ------------------------------
-template <int CPL, int LPR>
-int launch_score_any(const ffx::ScoreArgs &a, const ffx_any_plan &plan, bool fuse, int grid, int warps, int ns,
-                     int batch, cudaStream_t st) {
-    const size_t smem = ffx::any_smem_bytes(fuse ? a.cpad : 0, warps, ns, plan.stride * 4, plan.stride * 4 * (32 / plan.lpr));
-    if (fuse) {
-        auto kern = ffx::ffx_score_any_kernel<CPL, LPR, true>;
-        FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        kern<<<grid, warps * 32, smem, st>>>(a, plan, ns, batch);
-        note_kernel(kern);
-    } else {
-        auto kern = ffx::ffx_score_any_kernel<CPL, LPR, false>;
-        FFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        kern<<<grid, warps * 32, smem, st>>>(a, plan, ns, batch);
-        note_kernel(kern);
-    }
-    g_launches++;
-    FFX_CUDA(cudaGetLastError());
-    return FFX_OK;
-}
-
-// ---- short rows (8 / 16 lanes per row): ffx_score_packed_kernel -------------------------------
+// ---- short rows and dimensions without a lane-major plan: ffx_score_packed_kernel ----------------
 template <class Dot>
 int launch_score_packed(const ffx::ScoreArgs &a, const typename Dot::Plan &plan, int query_bytes, int slot_bytes, bool fuse,
                         int grid, int warps, int ns, int batch, cudaStream_t st) {
@@ -485,22 +466,13 @@ int dispatch_score_any(const ffx_any_plan &p, const ScorePlan &sp, const ffx::Sc
         return launch_score_packed<ffx::TreeDot<2, 4>>(a, p, p.stride * 4, p.stride * 32, fuse, grid, sp.warps, sp.ns, sp.batch, st);
     if (p.cpl == 2 && p.lpr == 8)
         return launch_score_packed<ffx::TreeDot<2, 8>>(a, p, p.stride * 4, p.stride * 16, fuse, grid, sp.warps, sp.ns, sp.batch, st);
-    if (g_tune.kernel == 3) {  // A/B: whole-warp rows through the packed kernel too
 #define FFX_CASE(C) \
     if (p.cpl == C && p.lpr == 32) \
         return launch_score_packed<ffx::TreeDot<C, 32>>(a, p, p.stride * 4, p.stride * 4, fuse, grid, sp.warps, sp.ns, sp.batch, st)
-        FFX_CASE(1);
-        FFX_CASE(2);
-        FFX_CASE(4);
-        FFX_CASE(8);
-#undef FFX_CASE
-    }
-#define FFX_CASE(C, L) \
-    if (p.cpl == C && p.lpr == L) return launch_score_any<C, L>(a, p, fuse, grid, sp.warps, sp.ns, sp.batch, st)
-    FFX_CASE(1, 32);
-    FFX_CASE(2, 32);
-    FFX_CASE(4, 32);
-    FFX_CASE(8, 32);
+    FFX_CASE(1);
+    FFX_CASE(2);
+    FFX_CASE(4);
+    FFX_CASE(8);
 #undef FFX_CASE
     return fail(FFX_ERR_UNSUPPORTED, "no kernel for tree plan (%d chains per lane, %d lanes per row)", p.cpl, p.lpr);
 }
@@ -509,7 +481,7 @@ int dispatch_score_any(const ffx_any_plan &p, const ScorePlan &sp, const ffx::Sc
 // top-k sorts its 64-bit keys inside the drained ring)
 int any_ring_slots(int keys, int warps, int row_bytes, int slot_bytes, int ctas_per_sm) {
     const size_t budget = kSmemBudget / ctas_per_sm - 1024;  // static shared memory of the fused epilogue: 2.3 KB
-    const size_t fixed = ffx::any_smem_bytes(keys, warps, 0, row_bytes, slot_bytes);
+    const size_t fixed = ffx::packed_smem_bytes(keys, warps, 0, row_bytes, slot_bytes);
     if (fixed >= budget) return 0;
     int ns = static_cast<int>((budget - fixed) / (static_cast<size_t>(warps) * (slot_bytes + 8)));
     ns = std::min(ns, 32);
@@ -727,7 +699,7 @@ const char *ffx_last_error(void) { return g_err.c_str(); }
 int ffx_set_option(const char *name, int value) {
     if (!name) return fail(FFX_ERR_INVALID, "ffx_set_option: NULL name");
     const std::string key(name);
-    if (key == "kernel" && value >= 0 && value <= 3) g_tune.kernel = value;
+    if (key == "kernel" && value >= 0 && value <= 2) g_tune.kernel = value;
     else if (key == "tma_stages" && value >= 0 && value <= 16) g_tune.tma_stages = value;
     else if (key == "batch" && value >= 0 && value <= 32) g_tune.batch = value;
     else if (key == "adc" && value >= 0 && value <= 3) g_tune.adc = value;
@@ -1240,7 +1212,7 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     // tiles: split a query over several CTAs when there are few queries
     // (short rows: the ring slot of one warp step, 32 / (lanes per row) rows)
     ScorePlan sp = fast ? plan_score(mode, fuse, cpad,
-                                     static_cast<int>(idx->dim) * 4 * (32 * ffx_short_row_cpl(idx->plan) / idx->plan.lanes),
+                                     static_cast<int>(idx->dim) * 4 * ffx_rows_per_step(idx->plan),
                                      idx->sharded, few_pairs, idx->plan.lanes != 32) : sp_any;
     // short-row kernel: positions inside a batch's flattened row sequence are 32-bit
     sp.batch = static_cast<int>(std::min<int64_t>(sp.batch, std::max<int64_t>(1, 0x7fffffffll / idx->max_doc_rows)));

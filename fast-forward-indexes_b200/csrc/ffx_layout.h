@@ -44,7 +44,9 @@ static inline ffx_plan ffx_plan_for_dim(int64_t dim) {
 
 // Short lane-major rows are CONSUMED by lanes / cpl lanes, each taking cpl adjacent chains (the
 // packed kernel, ffx_score_packed.cuh): about 32 elements per lane.
-static inline int ffx_short_row_cpl(const ffx_plan &p) { return p.lanes == 32 ? p.cpl : (p.steps <= 8 ? 4 : 2); }
+static inline int ffx_short_row_cpl(const ffx_plan &p) { return p.steps <= 8 ? 4 : 2; }
+// rows per warp step (= per ring slot): 1 for whole-warp rows
+static inline int ffx_rows_per_step(const ffx_plan &p) { return p.lanes == 32 ? 1 : 32 * ffx_short_row_cpl(p) / p.lanes; }
 
 // staged float offset k inside a row  ->  original element index.  The i-th float4 of lane l
 // (of the `lanes` lanes sharing the row) sits at float offset (i*lanes + l)*4.

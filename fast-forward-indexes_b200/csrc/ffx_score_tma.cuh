@@ -101,22 +101,19 @@ __device__ __forceinline__ float lane_chain_sum_streamed(uint32_t q_addr, uint32
     return acc[0];
 }
 
-// LPR = lanes that share one row: 32, or 16 / 8 for short rows (D <= 256), where 2 / 4 rows of a
-// document are consumed per warp step, one per lane group.
+// A warp per row (D >= 384 with a uniform tree); LPR stays in the signature (always 32) so that the
+// kernel's name in launch lists and tests is stable.  Shorter rows: ffx_score_packed.cuh.
 template <int CPL, int S, bool FUSE, int LPR = 32>
 __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const ScoreArgs a, const int ns,
                                                                         const int batch) {
     constexpr int EPL = CPL * S;
     constexpr int NV4 = EPL / 4;
     constexpr uint32_t ROWB = static_cast<uint32_t>(LPR) * EPL * 4u;
-    constexpr int RPS = 32 / LPR;                        // rows per warp step (short rows)
-    // a ring slot holds what ONE warp step consumes: a row, or — short rows — the up to RPS consecutive
-    // rows of a document that the lane groups take together (one bulk copy, one barrier per step)
-    constexpr uint32_t SLOTB = ROWB * RPS;
-    constexpr bool kPairRows = LPR == 32 && EPL <= 32;   // two rows of registers per lane only while they fit
+    constexpr uint32_t SLOTB = ROWB;                     // a ring slot holds one row
+    constexpr bool kPairRows = EPL <= 32;                // two rows of registers per lane only while they fit
     constexpr bool kStream = EPL > 64;                   // query vector in shared memory, rows streamed against it
     static_assert(EPL % 4 == 0, "lane slice must be whole float4s");
-    static_assert(LPR == 32 || CPL == 1, "short rows: one chain per lane");
+    static_assert(LPR == 32, "a warp per row");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_next;
@@ -288,38 +285,17 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
                 break;
             }
             if (!have) break;
-            if constexpr (RPS > 1) {
-                // the next min(RPS, rows left) rows of the document into one slot
-                const uint32_t nr = min(static_cast<uint32_t>(RPS), pcnt - pk);
+            uint32_t row = pstart + pk;
+            if (indirect) {
+                if ((pk & 31u) == 0)
+                    p_rows = (pk + lane < pcnt) ? static_cast<uint32_t>(__ldg(a.doc_rows + pstart + pk + lane)) : 0u;
+                row = __shfl_sync(kFull, p_rows, pk & 31u);
+            }
+            pk++;
+            if (lane == 0) {
                 const uint32_t bar = bars + p_stage * 8;
-                if (lane == 0) mbar_expect_tx(bar, nr * ROWB);
-                if (!indirect) {
-                    if (lane == 0)
-                        bulk_g2s(ring + p_stage * SLOTB, rows_base + static_cast<size_t>(pstart + pk) * ROWB, nr * ROWB, bar);
-                } else {
-                    for (uint32_t g = 0; g < nr; g++, pk++) {
-                        if ((pk & 31u) == 0 || g == 0)
-                            p_rows = ((pk & ~31u) + lane < pcnt) ? static_cast<uint32_t>(__ldg(a.doc_rows + pstart + (pk & ~31u) + lane)) : 0u;
-                        const uint32_t row = __shfl_sync(kFull, p_rows, pk & 31u);
-                        if (lane == 0)
-                            bulk_g2s(ring + p_stage * SLOTB + g * ROWB, rows_base + static_cast<size_t>(row) * ROWB, ROWB, bar);
-                    }
-                    pk -= nr;
-                }
-                pk += nr;
-            } else {
-                uint32_t row = pstart + pk;
-                if (indirect) {
-                    if ((pk & 31u) == 0)
-                        p_rows = (pk + lane < pcnt) ? static_cast<uint32_t>(__ldg(a.doc_rows + pstart + pk + lane)) : 0u;
-                    row = __shfl_sync(kFull, p_rows, pk & 31u);
-                }
-                pk++;
-                if (lane == 0) {
-                    const uint32_t bar = bars + p_stage * 8;
-                    mbar_expect_tx(bar, ROWB);
-                    bulk_g2s(ring + p_stage * ROWB, rows_base + static_cast<size_t>(row) * ROWB, ROWB, bar);
-                }
+                mbar_expect_tx(bar, ROWB);
+                bulk_g2s(ring + p_stage * ROWB, rows_base + static_cast<size_t>(row) * ROWB, ROWB, bar);
             }
             p_stage = p_stage + 1 == ns ? 0 : p_stage + 1;
             inflight++;
@@ -334,32 +310,6 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1) ffx_score_tma_kernel(const 
             DocReduce red;
             red.init();
             for (uint32_t ck = 0; ck < cnt;) {
-                if constexpr (LPR < 32) {
-                    // short rows: lane group g takes row ck + g of the document, all from ring slot
-                    // c_stage (one copy, one barrier per step); the butterfly stays inside the group
-                    top_up();
-                    const int nr = static_cast<int>(min(static_cast<uint32_t>(RPS), cnt - ck));  // warp-uniform
-                    const int grp = lane / LPR, sub = lane % LPR;
-                    float part = 0.f;
-                    mbar_wait(bars + c_stage * 8, (c_phase >> c_stage) & 1u);
-                    if (grp < nr) {
-                        float4 v[NV4];
-                        const uint32_t src = ring + c_stage * SLOTB + grp * ROWB + sub * 16;
-#pragma unroll
-                        for (int i = 0; i < NV4; i++) v[i] = lds_f4(src + i * (LPR * 16));
-                        part = lane_chain_sum<CPL, S>(q, v);
-                    }
-#pragma unroll
-                    for (int o = 1; o < LPR; o <<= 1) part = __fadd_rn(part, __shfl_xor_sync(kFull, part, o));
-                    part = __fadd_rn(0.f, part);
-                    __syncwarp();  // the rows are in registers: the slot may be refilled
-                    c_phase ^= 1u << c_stage;
-                    for (int g = 0; g < nr; g++) red.add(__shfl_sync(kFull, part, g * LPR), ck + g == 0, a.mode);
-                    c_stage = c_stage + 1 == ns ? 0 : c_stage + 1;
-                    inflight--;
-                    ck += nr;
-                    continue;
-                }
                 // two rows of the document per step: their multiply/reduce chains interleave
                 top_up();
                 const bool two = kPairRows && ck + 1 < cnt;  // warp-uniform

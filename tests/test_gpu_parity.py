@@ -276,18 +276,14 @@ def test_long_and_short_rows_fused_path(ffx, oracle_c, dim):
     idx.close()
 
 
-@pytest.mark.parametrize("route", ["auto", "packed"])
 @pytest.mark.parametrize("dim", [5, 50, 100, 130, 200, 260, 300, 1000, 1280, 2000, 4000])
-def test_any_dimension_kernel_fused_and_tiled(ffx, oracle_c, dim, route):
-    """Dimensions without a uniform numpy tree (the tree as data: leaves of different lengths and
-    depths, a tail after the last leaf, row stride padded to 16 bytes) — ffx_score_packed_kernel
-    with TreeDot for rows shared by 8 / 16 lanes (D <= 256), ffx_score_any_kernel above (or, route
-    "packed", the packed kernel for those too): fused one-CTA-per-query launches, tiled launches,
-    scattered documents, ring depths and batch sizes — bit for bit against the plain-C oracle; rows
-    read back unchanged."""
-    if route == "packed" and dim <= 256:
-        pytest.skip("short rows always take the packed kernel")
-    kernel_name = "ffx_score_packed_kernel" if dim <= 256 or route == "packed" else "ffx_score_any_kernel"
+def test_any_dimension_kernel_fused_and_tiled(ffx, oracle_c, dim):
+    """Dimensions without a uniform numpy tree (ffx_score_packed_kernel with TreeDot, the tree as
+    data: leaves of different lengths and depths, a tail after the last leaf, row stride padded to
+    16 bytes; 4 / 8 / 32 lanes per row): fused one-CTA-per-query launches, tiled launches, scattered
+    documents, ring depths and batch sizes — bit for bit against the plain-C oracle; rows read back
+    unchanged."""
+    kernel_name = "ffx_score_packed_kernel<ffx::TreeDot<"
     rng = np.random.default_rng(dim)
     for contiguous in (True, False):
         off, rows, vec = make_corpus(rng, 500, 7, dim, contiguous)
@@ -311,7 +307,6 @@ def test_any_dimension_kernel_fused_and_tiled(ffx, oracle_c, dim, route):
             for stages, batch in ((0, 0), (2, 5), (7, 32)):
                 ffx.set_option("tma_stages", stages)
                 ffx.set_option("batch", batch)
-                ffx.set_option("kernel", 3 if route == "packed" else 0)
                 try:
                     for sub in (nq, 9):  # fused and tiled launches
                         n_sub = int(q_off[sub])
@@ -325,7 +320,6 @@ def test_any_dimension_kernel_fused_and_tiled(ffx, oracle_c, dim, route):
                 finally:
                     ffx.set_option("tma_stages", 0)
                     ffx.set_option("batch", 0)
-                    ffx.set_option("kernel", 0)
         idx.close()
 
 

@@ -191,7 +191,7 @@ def test_early_stopping(api, golden_kat):
 def test_early_stopping_random_golden(api, golden_es, key):
     """Seeded early-stopping cases against the reference's frames: es21 (D=768) runs the whole
     depth walk in one launch (ffx_rerank_early_stop), es22 (D=100, a dimension without a uniform
-    summation tree: ffx_score_any_kernel) as a stream-ordered sequence of launches per depth."""
+    summation tree: ffx_score_packed_kernel with TreeDot) as a stream-ordered sequence of launches per depth."""
     from fast_forward import _ffx
 
     meta, arrays = golden_es
