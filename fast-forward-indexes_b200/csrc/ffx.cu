@@ -466,10 +466,11 @@ int dispatch_score_any(const ffx_any_plan &p, const ScorePlan &sp, const ffx::Sc
         return launch_score_packed<ffx::TreeDot<2, 4>>(a, p, p.stride * 4, p.stride * 32, fuse, grid, sp.warps, sp.ns, sp.batch, st);
     if (p.cpl == 2 && p.lpr == 8)
         return launch_score_packed<ffx::TreeDot<2, 8>>(a, p, p.stride * 4, p.stride * 16, fuse, grid, sp.warps, sp.ns, sp.batch, st);
+    if (p.cpl == 2 && p.lpr == 16)
+        return launch_score_packed<ffx::TreeDot<2, 16>>(a, p, p.stride * 4, p.stride * 8, fuse, grid, sp.warps, sp.ns, sp.batch, st);
 #define FFX_CASE(C) \
     if (p.cpl == C && p.lpr == 32) \
         return launch_score_packed<ffx::TreeDot<C, 32>>(a, p, p.stride * 4, p.stride * 4, fuse, grid, sp.warps, sp.ns, sp.batch, st)
-    FFX_CASE(1);
     FFX_CASE(2);
     FFX_CASE(4);
     FFX_CASE(8);

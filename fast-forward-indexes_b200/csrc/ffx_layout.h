@@ -75,7 +75,7 @@ FFX_HD static inline int ffx_orig_index(int cpl, int steps, int k, int lanes = 3
 struct ffx_any_plan {
     int valid;       // 0: more than 32 leaf slots (D beyond ~4096): thread-per-pair kernel
     int dim, stride; // elements, stored floats per row
-    int lpr;         // lanes sharing one row: 4, 8, 32
+    int lpr;         // lanes sharing one row: 4, 8, 16, 32
     int cpl;         // chains per lane: 1, 2, 4, 8 (2 for the short rows of one or two leaves)
     int n_slots;     // leaf slots, a power of two <= 32
     int max_steps;   // longest chain (groups of 8 in the longest leaf)
@@ -123,9 +123,10 @@ static inline ffx_any_plan ffx_any_plan_for_dim(int64_t dim) {
             p.tail_len = tail;
         }
     }
-    // one or two leaves: two chains per lane, 4 or 8 lanes per row (8 / 4 rows per warp step)
+    // up to four leaf slots (D <= 512): two chains per lane, 4 / 8 / 16 lanes per row (8 / 4 / 2 rows
+    // per warp step) — at least ~16 elements per lane and step
     const int chains = 8 * p.n_slots;
-    p.lpr = chains >= 32 ? 32 : chains / 2;
+    p.lpr = chains >= 64 ? 32 : chains / 2;
     p.cpl = chains / p.lpr;
     p.valid = 1;
     return p;
