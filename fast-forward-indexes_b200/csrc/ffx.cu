@@ -28,6 +28,8 @@
 #include "ffx_score_tma.cuh"
 #include "ffx_score_any.cuh"
 #include "ffx_score_packed.cuh"
+
+#include <nvtx3/nvToolsExt.h>
 #include "ffx_coalesce.cuh"
 #include "ffx_layout.h"
 
@@ -86,6 +88,14 @@ struct Tuning {
 // which ADC kernel scores this index: 3 = XOR-swizzled (M % 32 == 0), 2 = warp-per-row (M = 64..128), 1 = generic
 int adc_kind(const ffx_index *idx);
 Tuning g_tune;
+
+// NVTX range over a C-ABI call (header-only NVTX 3: a no-op unless a tool is attached)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 struct Scratch {
     void *p = nullptr;
@@ -862,6 +872,7 @@ int ffx_index_reserve(ffx_index *idx, int64_t capacity_rows) {
 
 int ffx_index_stage_rows(ffx_index *idx, int64_t row0, int64_t nrows, const void *rows,
                          int src_on_device) {
+    NvtxRange nvtx_range("ffx_index_stage_rows");
     if (!idx || (!rows && nrows > 0) || row0 < 0 || nrows < 0)
         return fail(FFX_ERR_INVALID, "ffx_index_stage_rows: bad arguments");
     if (row0 + nrows > idx->capacity)
@@ -961,6 +972,7 @@ int ffx_index_has_fast_path(const ffx_index *idx) {
 
 int ffx_index_set_docs(ffx_index *idx, int64_t n_docs, const int64_t *doc_off,
                        const int64_t *doc_rows) {
+    NvtxRange nvtx_range("ffx_index_set_docs");
     if (!idx || n_docs < 0 || (n_docs > 0 && !doc_off))
         return fail(FFX_ERR_INVALID, "ffx_index_set_docs: bad arguments");
     if (n_docs > 0x7fffffffll) return fail(FFX_ERR_INVALID, "ffx_index_set_docs: too many documents");
@@ -1407,6 +1419,7 @@ int ffx_rerank(ffx_index *idx, int mode, const float *qvecs, int64_t nq, const i
                const int32_t *cand, const float *lex, double alpha, int k, int64_t max_cand,
                float *out_ff, float *out_int, float *out_topk_score, int32_t *out_topk_pos,
                void *stream) {
+    NvtxRange nvtx_range("ffx_rerank");
     return rerank_impl(idx, mode, qvecs, nq, q_off, cand, lex, alpha, k, max_cand, out_ff, out_int,
                        out_topk_score, out_topk_pos, stream, nullptr);
 }
@@ -1415,6 +1428,7 @@ int ffx_rerank_host(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
                     const int64_t *q_off, const int32_t *cand, const float *lex, double alpha,
                     int k, float *out_ff, float *out_int, float *out_topk_score,
                     int32_t *out_topk_pos) {
+    NvtxRange nvtx_range("ffx_rerank_host");
     if (!idx) return fail(FFX_ERR_INVALID, "ffx_rerank_host: NULL index");
     if (nq < 0) return fail(FFX_ERR_INVALID, "ffx_rerank_host: nq < 0");
     if (nq == 0) return FFX_OK;
@@ -1583,6 +1597,7 @@ int ffx_rerank_early_stop(ffx_index *idx, int mode, const float *qvecs, int64_t 
                           const int32_t *cand, const float *lex, double alpha, int cutoff,
                           const int32_t *depths, int n_depths, int64_t max_cand, float *out_ff,
                           float *out_int, int32_t *out_scored, void *stream) {
+    NvtxRange nvtx_range("ffx_rerank_early_stop");
     if (!idx) return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop: NULL index");
     if (mode < FFX_MODE_PASSAGE || mode > FFX_MODE_AVEP)
         return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop: unknown mode %d", mode);
@@ -1654,6 +1669,7 @@ int ffx_rerank_early_stop_host(ffx_index *idx, int mode, const float *qvecs, int
                                const int64_t *q_off, const int32_t *cand, const float *lex,
                                double alpha, int cutoff, const int32_t *depths, int n_depths,
                                float *out_ff, float *out_int, int32_t *out_scored) {
+    NvtxRange nvtx_range("ffx_rerank_early_stop_host");
     if (!idx) return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop_host: NULL index");
     if (nq < 0) return fail(FFX_ERR_INVALID, "ffx_rerank_early_stop_host: nq < 0");
     if (nq == 0) return FFX_OK;
@@ -1867,6 +1883,7 @@ int ffx_sgemm(int device, int trans_a, int64_t m, int64_t n, int64_t k, const fl
 
 int ffx_index_coalesce(ffx_index *idx, int64_t doc0, int64_t n_docs, const int64_t *doc_off, double delta,
                        float *out_vectors, int32_t *out_groups) {
+    NvtxRange nvtx_range("ffx_index_coalesce");
     if (!idx || doc0 < 0 || n_docs < 0 || !doc_off || !out_groups)
         return fail(FFX_ERR_INVALID, "ffx_index_coalesce: bad arguments");
     if (idx->row_kind != FFX_ROWS_F32) return fail(FFX_ERR_STATE, "ffx_index_coalesce: the index holds codes, not vectors");
@@ -1989,6 +2006,7 @@ int ffx_interpolate_topk_host(ffx_index *idx, const float *lex, const float *ff,
 
 int ffx_merge_topk(int device, const float *shard_scores, const int32_t *shard_pos, int n_shards,
                    int64_t nq, int k, float *out_score, int32_t *out_pos, void *stream) {
+    NvtxRange nvtx_range("ffx_merge_topk");
     if (n_shards <= 0 || nq < 0 || k <= 0 || !shard_scores || !shard_pos || !out_score || !out_pos)
         return fail(FFX_ERR_INVALID, "ffx_merge_topk: bad arguments");
     if (nq == 0) return FFX_OK;
@@ -2014,6 +2032,7 @@ int ffx_merge_topk(int device, const float *shard_scores, const int32_t *shard_p
 
 int ffx_merge_topk_host(ffx_index *idx, const float *shard_scores, const int32_t *shard_pos, int n_shards,
                         int64_t nq, int k, float *out_score, int32_t *out_pos) {
+    NvtxRange nvtx_range("ffx_merge_topk_host");
     if (!idx) return fail(FFX_ERR_INVALID, "ffx_merge_topk_host: NULL index");
     if (n_shards <= 0 || nq < 0 || k <= 0 || !shard_scores || !shard_pos || !out_score || !out_pos)
         return fail(FFX_ERR_INVALID, "ffx_merge_topk_host: bad arguments");
