@@ -538,6 +538,12 @@ ScorePlan plan_score_any(const ffx_any_plan &p, int mode, bool fuse, int cpad, b
 int dispatch_score(const ffx_plan &p, const ScorePlan &sp, const ffx::ScoreArgs &a, bool fuse, int grid,
                    cudaStream_t st) {
     if (sp.tma) {
+        if (g_tune.kernel == 3 && p.lanes == 32 && p.cpl == 1) {  // A/B: D = 384 / 512 as two rows per warp step
+            if (p.steps == 12)
+                return launch_score_packed<ffx::LaneMajorDot<12, 32, 2>>(a, {}, 0, 32 * 2 * 12 * 4, fuse, grid, sp.warps, sp.ns, sp.batch, st);
+            if (p.steps == 16)
+                return launch_score_packed<ffx::LaneMajorDot<16, 32, 2>>(a, {}, 0, 32 * 2 * 16 * 4, fuse, grid, sp.warps, sp.ns, sp.batch, st);
+        }
 #define FFX_CASE(C, S_) \
     if (p.lanes == 32 && p.cpl == C && p.steps == S_) \
         return launch_score_tma<C, S_>(a, fuse, grid, sp.warps, sp.ns, sp.batch, st)
@@ -710,7 +716,7 @@ const char *ffx_last_error(void) { return g_err.c_str(); }
 int ffx_set_option(const char *name, int value) {
     if (!name) return fail(FFX_ERR_INVALID, "ffx_set_option: NULL name");
     const std::string key(name);
-    if (key == "kernel" && value >= 0 && value <= 2) g_tune.kernel = value;
+    if (key == "kernel" && value >= 0 && value <= 3) g_tune.kernel = value;
     else if (key == "tma_stages" && value >= 0 && value <= 16) g_tune.tma_stages = value;
     else if (key == "batch" && value >= 0 && value <= 32) g_tune.batch = value;
     else if (key == "adc" && value >= 0 && value <= 3) g_tune.adc = value;
@@ -1224,9 +1230,10 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
 
     // tiles: split a query over several CTAs when there are few queries
     // (short rows: the ring slot of one warp step, 32 / (lanes per row) rows)
+    const bool ab_packed = g_tune.kernel == 3 && idx->plan.lanes == 32 && idx->plan.cpl == 1;
     ScorePlan sp = fast ? plan_score(mode, fuse, cpad,
-                                     static_cast<int>(idx->dim) * 4 * ffx_rows_per_step(idx->plan),
-                                     idx->sharded, few_pairs, idx->plan.lanes != 32) : sp_any;
+                                     static_cast<int>(idx->dim) * 4 * (ab_packed ? 2 : ffx_rows_per_step(idx->plan)),
+                                     idx->sharded, few_pairs, idx->plan.lanes != 32 || ab_packed) : sp_any;
     // short-row kernel: positions inside a batch's flattened row sequence are 32-bit
     sp.batch = static_cast<int>(std::min<int64_t>(sp.batch, std::max<int64_t>(1, 0x7fffffffll / idx->max_doc_rows)));
     int tiles = 1, tile = static_cast<int>(std::max<int64_t>(max_cand, 1));

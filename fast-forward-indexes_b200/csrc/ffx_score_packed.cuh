@@ -43,7 +43,7 @@ struct LaneMajorDot {
     static constexpr int LPR = L0 / CPL;
     static constexpr int NV4 = S / 4;
     static constexpr bool kPair = CPL == 1;  // one chain per lane: two ring slots per consumer iteration instead
-    static_assert(S % 4 == 0 && (L0 == 8 || L0 == 16) && (CPL == 1 || CPL == 2 || CPL == 4), "lane-major short rows");
+    static_assert(S % 4 == 0 && (L0 == 8 || L0 == 16 || L0 == 32) && (CPL == 1 || CPL == 2 || CPL == 4), "lane-major rows");
     struct Plan {};
     float q[CPL][S];
     uint32_t piece[CPL];  // byte offset of chain k's first float4 inside a row

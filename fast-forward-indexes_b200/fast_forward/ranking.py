@@ -174,7 +174,9 @@ class Ranking:
     @property
     def has_queries(self) -> bool:
         """Whether query texts are attached."""
-        return "query" in self._df.columns
+        if self._frame is None:  # integer-coded columns: no pandas frame is built for the answer
+            return self._cols.queries is not None
+        return "query" in self._frame.columns
 
     @property
     def q_ids(self) -> set[str]:
