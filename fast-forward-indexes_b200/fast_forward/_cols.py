@@ -21,6 +21,7 @@ the per-pair candidate array is cached on the columns, so a second `index(rankin
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import pandas as pd
@@ -42,6 +43,25 @@ def _series(arr) -> pd.Series:
 
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+_TAKE_FROM = 1 << 20
+
+
+def _take(values, indices: np.ndarray):
+    """`values.take(indices)` for a (long) integer index array: pyarrow gathers strings on one
+    thread, so long gathers are cut into slices taken concurrently (the GIL is released) and come
+    back as one chunked array."""
+    n = len(indices)
+    threads = min(os.cpu_count() or 1, 32, n // _TAKE_FROM)
+    if threads < 2:
+        return values.take(pa.array(indices))
+    from concurrent.futures import ThreadPoolExecutor
+
+    step = -(-n // threads)
+    with ThreadPoolExecutor(threads) as pool:
+        parts = list(pool.map(lambda lo: values.take(pa.array(indices[lo:lo + step])), range(0, n, step)))
+    return pa.chunked_array(parts)
 
 
 class IdTable:
@@ -162,11 +182,11 @@ class Cols:
         """The frame the reference keeps in `Ranking._df`: q_id, id (pandas `str`), score[, query],
         RangeIndex."""
         block = np.repeat(np.arange(self.nq, dtype=np.int32), self.counts())
-        data = {"q_id": _series(self.q_keys.take(pa.array(block))),
-                "id": _series(self.ids.keys.take(pa.array(self.id_code))),
+        data = {"q_id": _series(_take(self.q_keys, block)),
+                "id": _series(_take(self.ids.keys, self.id_code)),
                 "score": np.array(self.score, copy=True)}
         if self.queries is not None:
-            data["query"] = _series(self.queries.take(pa.array(block)))
+            data["query"] = _series(_take(self.queries, block))
         return pd.DataFrame(data, copy=False)
 
     # ---- derived rankings ---------------------------------------------------------------
