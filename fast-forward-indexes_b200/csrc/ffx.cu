@@ -357,6 +357,7 @@ int launch_adc(const ffx::AdcArgs &a, unsigned grid, size_t smem, cudaStream_t s
 //   tiled (few queries)     : 4 warps per CTA, 4 CTAs/SM
 struct ScorePlan {
     bool tma = false;
+    bool packed = false;  // ffx_score_packed_kernel with LaneMajorDot (rows of up to 512 elements)
     int warps = 8, ns = 0, batch = 16;
 };
 
@@ -417,6 +418,7 @@ ScorePlan plan_score(int mode, bool fuse, int cpad, int row_bytes, bool sparse, 
         }
         if (g_tune.tma_stages > 0) p.ns = std::min(p.ns, std::max(2, g_tune.tma_stages));
         p.tma = p.ns >= 2;
+        p.packed = true;
         return p;
     }
     if (g_tune.kernel == 1) return p;
@@ -537,13 +539,22 @@ ScorePlan plan_score_any(const ffx_any_plan &p, int mode, bool fuse, int cpad, b
 
 int dispatch_score(const ffx_plan &p, const ScorePlan &sp, const ffx::ScoreArgs &a, bool fuse, int grid,
                    cudaStream_t st) {
+    if (sp.tma && sp.packed) {
+        // rows of up to 512 elements: several rows per warp step (ffx_score_packed_kernel)
+#define FFX_CASE(S_, L, C)                                                                                   \
+    if (p.lanes == L && p.steps == S_ && ffx_packed_cpl(p) == C)                                                 \
+        return launch_score_packed<ffx::LaneMajorDot<S_, L, C>>(a, {}, 0, 32 * C * S_ * 4, fuse, grid, sp.warps, sp.ns, \
+                                                                sp.batch, st)
+        FFX_CASE(8, 8, 4);    // D = 64: 2 lanes per row, 16 rows per warp step
+        FFX_CASE(12, 8, 2);   // D = 96: 4 lanes, 8 rows
+        FFX_CASE(16, 8, 2);   // D = 128
+        FFX_CASE(12, 16, 2);  // D = 192: 8 lanes, 4 rows
+        FFX_CASE(16, 16, 2);  // D = 256
+        FFX_CASE(12, 32, 2);  // D = 384: 16 lanes, 2 rows
+        FFX_CASE(16, 32, 2);  // D = 512
+#undef FFX_CASE
+    }
     if (sp.tma) {
-        if (g_tune.kernel == 3 && p.lanes == 32 && p.cpl == 1) {  // A/B: D = 384 / 512 as two rows per warp step
-            if (p.steps == 12)
-                return launch_score_packed<ffx::LaneMajorDot<12, 32, 2>>(a, {}, 0, 32 * 2 * 12 * 4, fuse, grid, sp.warps, sp.ns, sp.batch, st);
-            if (p.steps == 16)
-                return launch_score_packed<ffx::LaneMajorDot<16, 32, 2>>(a, {}, 0, 32 * 2 * 16 * 4, fuse, grid, sp.warps, sp.ns, sp.batch, st);
-        }
 #define FFX_CASE(C, S_) \
     if (p.lanes == 32 && p.cpl == C && p.steps == S_) \
         return launch_score_tma<C, S_>(a, fuse, grid, sp.warps, sp.ns, sp.batch, st)
@@ -559,16 +570,6 @@ int dispatch_score(const ffx_plan &p, const ScorePlan &sp, const ffx::ScoreArgs 
         FFX_CASE(8, 12);
         FFX_CASE(8, 14);
         FFX_CASE(8, 16);
-#undef FFX_CASE
-#define FFX_CASE(S_, L, C)                                                                                   \
-    if (p.lanes == L && p.steps == S_ && ffx_short_row_cpl(p) == C)                                              \
-        return launch_score_packed<ffx::LaneMajorDot<S_, L, C>>(a, {}, 0, 32 * C * S_ * 4, fuse, grid, sp.warps, sp.ns, \
-                                                                sp.batch, st)
-        FFX_CASE(8, 8, 4);    // D = 64: 2 lanes per row, 16 rows per warp step
-        FFX_CASE(12, 8, 2);   // D = 96: 4 lanes, 8 rows
-        FFX_CASE(16, 8, 2);   // D = 128
-        FFX_CASE(12, 16, 2);  // D = 192: 8 lanes, 4 rows
-        FFX_CASE(16, 16, 2);  // D = 256
 #undef FFX_CASE
     }
     const size_t smem = fuse ? static_cast<size_t>(a.cpad) * 8 : 0;
@@ -716,7 +717,7 @@ const char *ffx_last_error(void) { return g_err.c_str(); }
 int ffx_set_option(const char *name, int value) {
     if (!name) return fail(FFX_ERR_INVALID, "ffx_set_option: NULL name");
     const std::string key(name);
-    if (key == "kernel" && value >= 0 && value <= 3) g_tune.kernel = value;
+    if (key == "kernel" && value >= 0 && value <= 2) g_tune.kernel = value;
     else if (key == "tma_stages" && value >= 0 && value <= 16) g_tune.tma_stages = value;
     else if (key == "batch" && value >= 0 && value <= 32) g_tune.batch = value;
     else if (key == "adc" && value >= 0 && value <= 3) g_tune.adc = value;
@@ -1230,10 +1231,11 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
 
     // tiles: split a query over several CTAs when there are few queries
     // (short rows: the ring slot of one warp step, 32 / (lanes per row) rows)
-    const bool ab_packed = g_tune.kernel == 3 && idx->plan.lanes == 32 && idx->plan.cpl == 1;
+    // (options kernel = 1 / 2 pick the register-staged / TMA-staged whole-warp kernels where they exist)
+    const bool packed = ffx_packed_cpl(idx->plan) != 0 && !(g_tune.kernel != 0 && idx->plan.lanes == 32);
     ScorePlan sp = fast ? plan_score(mode, fuse, cpad,
-                                     static_cast<int>(idx->dim) * 4 * (ab_packed ? 2 : ffx_rows_per_step(idx->plan)),
-                                     idx->sharded, few_pairs, idx->plan.lanes != 32 || ab_packed) : sp_any;
+                                     static_cast<int>(idx->dim) * 4 * (packed ? ffx_rows_per_step(idx->plan) : 1),
+                                     idx->sharded, few_pairs, packed) : sp_any;
     // short-row kernel: positions inside a batch's flattened row sequence are 32-bit
     sp.batch = static_cast<int>(std::min<int64_t>(sp.batch, std::max<int64_t>(1, 0x7fffffffll / idx->max_doc_rows)));
     int tiles = 1, tile = static_cast<int>(std::max<int64_t>(max_cand, 1));

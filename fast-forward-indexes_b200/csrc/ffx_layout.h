@@ -42,11 +42,19 @@ static inline ffx_plan ffx_plan_for_dim(int64_t dim) {
     return ffx_plan{0, 0, 32};
 }
 
-// Short lane-major rows are CONSUMED by lanes / cpl lanes, each taking cpl adjacent chains (the
-// packed kernel, ffx_score_packed.cuh): about 32 elements per lane.
-static inline int ffx_short_row_cpl(const ffx_plan &p) { return p.steps <= 8 ? 4 : 2; }
-// rows per warp step (= per ring slot): 1 for whole-warp rows
-static inline int ffx_rows_per_step(const ffx_plan &p) { return p.lanes == 32 ? 1 : 32 * ffx_short_row_cpl(p) / p.lanes; }
+// Rows of up to 512 elements are CONSUMED by the packed kernel (ffx_score_packed.cuh): lanes / cpl
+// lanes per row, each taking cpl adjacent chains (24 - 32 elements per lane), 32 * cpl / lanes rows
+// per warp step.  0 = not a packed shape (a whole warp per row, ffx_score_tma.cuh).
+static inline int ffx_packed_cpl(const ffx_plan &p) {
+    if (p.cpl == 0) return 0;
+    if (p.lanes == 32) return p.cpl == 1 ? 2 : 0;  // D = 384, 512: 16 lanes per row
+    return p.steps <= 8 ? 4 : 2;                   // D = 64: 2 lanes; 96 .. 256: 4 or 8 lanes
+}
+// rows per warp step (= per ring slot)
+static inline int ffx_rows_per_step(const ffx_plan &p) {
+    const int cpl = ffx_packed_cpl(p);
+    return cpl ? 32 * cpl / p.lanes : 1;
+}
 
 // staged float offset k inside a row  ->  original element index.  The i-th float4 of lane l
 // (of the `lanes` lanes sharing the row) sits at float offset (i*lanes + l)*4.

@@ -276,14 +276,16 @@ def test_long_and_short_rows_fused_path(ffx, oracle_c, dim):
     idx.close()
 
 
-@pytest.mark.parametrize("dim", [5, 50, 100, 130, 200, 260, 300, 1000, 1280, 2000, 4000])
-def test_any_dimension_kernel_fused_and_tiled(ffx, oracle_c, dim):
-    """Dimensions without a uniform numpy tree (ffx_score_packed_kernel with TreeDot, the tree as
-    data: leaves of different lengths and depths, a tail after the last leaf, row stride padded to
-    16 bytes; 4 / 8 / 32 lanes per row): fused one-CTA-per-query launches, tiled launches, scattered
-    documents, ring depths and batch sizes — bit for bit against the plain-C oracle; rows read back
-    unchanged."""
-    kernel_name = "ffx_score_packed_kernel<ffx::TreeDot<"
+@pytest.mark.parametrize("dim", [5, 50, 100, 130, 200, 260, 300, 1000, 1280, 2000, 4000, 64, 128, 192, 384, 512])
+def test_packed_kernel_fused_and_tiled(ffx, oracle_c, dim):
+    """ffx_score_packed_kernel under its default options.  Dimensions without a uniform numpy tree
+    (TreeDot, the tree as data: leaves of different lengths and depths, a tail after the last leaf,
+    row stride padded to 16 bytes; 4 / 8 / 16 / 32 lanes per row) and the lane-major rows of up to
+    512 elements (LaneMajorDot: 2 .. 16 lanes per row, 16 .. 2 rows per warp step): fused
+    one-CTA-per-query launches, tiled launches, scattered documents, ring depths and batch sizes —
+    bit for bit against the plain-C oracle; rows read back unchanged."""
+    kernel_name = "ffx_score_packed_kernel<ffx::" + ("LaneMajorDot<" if dim in (64, 128, 192, 384, 512) else "TreeDot<")
+    ffx.set_option("kernel", 0)  # the fixture's kernel = 1 / 2 would pick the whole-warp kernels at D = 384 / 512
     rng = np.random.default_rng(dim)
     for contiguous in (True, False):
         off, rows, vec = make_corpus(rng, 500, 7, dim, contiguous)

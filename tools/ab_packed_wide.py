@@ -1,5 +1,5 @@
-"""A/B: D = 384 / 512 through ffx_score_packed_kernel (two rows per warp step) against the TMA-staged
-kernel — outputs must be identical bit for bit; prints both kernels' names."""
+"""A/B: D = 384 / 512 through ffx_score_packed_kernel (the default: two rows per warp step) against the
+TMA-staged whole-warp kernel (option kernel = 2) — outputs must be identical bit for bit."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -19,11 +19,11 @@ for dim in (384, 512):
     qv = rng.standard_normal((nq, dim)).astype(np.float32)
     q_off = (np.arange(nq + 1) * C).astype(np.int64)
     lex = rng.uniform(0, 20, nq * C).astype(np.float32)
-    for mode in (0, 1, 2, 3):
-        pool = len(vec) if mode == 0 else n_docs
+    for mode in (1, 2, 3, 4):
+        pool = len(vec) if mode == 1 else n_docs
         cand = np.concatenate([rng.choice(pool, C, replace=False) for _ in range(nq)]).astype(np.int32)
         outs, names = [], []
-        for kernel in (0, 3):
+        for kernel in (2, 0):
             _ffx.set_option("kernel", kernel)
             for sub in (nq, 7):
                 o = idx.rerank_host(mode, qv[:sub], q_off[:sub + 1], cand[:sub * C], lex[:sub * C], 0.3, 50, want_ff=True, want_int=True)
