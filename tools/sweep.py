@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--nq-list", default="", help="comma-separated query counts: time every config at each (wave-tail study)")
     ap.add_argument("configs", nargs="+")
     args = ap.parse_args()
     import torch
@@ -38,6 +39,8 @@ def main():
     mode = bench.MODES[wl["mode"]]
     cands, k = wl["cands"], wl["k"]
     nq = wl["nq"] if args.scale == 1 else max(296, int(wl["nq"] * args.scale))
+    nq_list = [int(x) for x in args.nq_list.split(",") if x]
+    nq = max([nq] + nq_list)
     n_docs, cnt = bench.build_corpus(wl, args.scale, 0, 1)
     if n_docs is not None:
         off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
@@ -74,7 +77,7 @@ def main():
     algo = rows_touched * bench.DIM * 4 + nq * cands * 16 + nq * (bench.DIM * 4 + k * 8)
     stream = torch.cuda.current_stream()
     ref_pos = None
-    for cfg in args.configs:
+    for cfg, n_run in [(c, n) for c in args.configs for n in (nq_list or [nq])]:
         kern, warps, stages, batch = (int(x) for x in cfg.split(":"))
         _ffx.set_option("kernel", kern)
         _ffx.set_option("tma_warps", warps)
@@ -82,7 +85,7 @@ def main():
         _ffx.set_option("batch", batch)
 
         def step():
-            idx.rerank_device(mode, qv.data_ptr(), nq, q_off.data_ptr(), cand.data_ptr(), lex.data_ptr(), 0.1, k,
+            idx.rerank_device(mode, qv.data_ptr(), n_run, q_off.data_ptr(), cand.data_ptr(), lex.data_ptr(), 0.1, k,
                               cands, 0, 0, ts.data_ptr(), tp.data_ptr(), stream.cuda_stream)
 
         for _ in range(3):
@@ -99,8 +102,8 @@ def main():
         pos = tp[:64].cpu().numpy()
         same = "" if ref_pos is None else (" same-output" if (pos == ref_pos).all() else " OUTPUT-DIFFERS")
         ref_pos = pos if ref_pos is None else ref_pos
-        print(f"{cfg:>12s}  {ms:9.3f} ms  {nq * cands / ms / 1e3:9.1f} Mpairs/s  {algo / ms / 1e6:8.1f} GB/s{same}",
-              flush=True)
+        print(f"{cfg:>12s}  nq {n_run:6d}  {ms:9.3f} ms  {n_run * cands / ms / 1e3:9.1f} Mpairs/s  "
+              f"{algo * n_run / nq / ms / 1e6:8.1f} GB/s{same}", flush=True)
 
 
 if __name__ == "__main__":
