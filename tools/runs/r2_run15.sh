@@ -14,7 +14,7 @@ print(d['ms_per_step'], d['value'], d['roofline'], d['e2e'], d['clocks'])
 print(d.get('api_e2e')); print(d['cpu_baseline'])
 PY
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_ref_final.json 2> gpurun_out/r2_bench_ref_final.err; echo "ref rc=$?"; cat gpurun_out/r2_bench_ref_final.json
-for w in c4_opq_adc c2_msmarco_passage c1_memory_small; do
+for w in c4_opq_avep c2_msmarco_passage c1_passage_10k; do
   python bench.py --workload $w --steps 20 --warmup 5 > gpurun_out/r2_bench_${w}_final.json 2> gpurun_out/r2_bench_${w}_final.err; echo "$w rc=$?"
   python -c "import json; d=json.loads(open('gpurun_out/r2_bench_${w}_final.json').read().strip().splitlines()[-1]); print(d['ms_per_step'], d['value'], d['e2e'], d['roofline'])"
 done
