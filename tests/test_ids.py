@@ -177,6 +177,18 @@ def test_host_sort_and_match_routines_at_multithreaded_sizes():
             again[b] = again[a]
             _ffx.check(lib.ffx_first_repeat(ptr(again), n, C.byref(first)))
             assert first.value == b
+    # more distinct queries than per-thread histograms are kept for: the LSD radix route
+    n = 400_000
+    q_rank = rng.integers(0, 20_000_000, n).astype(np.int32)
+    q_rank[0:n - 1:3] = q_rank[1:n:3][: len(q_rank[0:n - 1:3])]  # some queries with several rows
+    score = rng.choice(np.array([0.5, 1.5, -2.25], np.float32), n)
+    order = np.empty(n, np.int64)
+    _ffx.check(lib.ffx_ranking_order(ptr(q_rank), ptr(score), n, ptr(order), 0))
+    assert (order == np.lexsort((np.arange(n), -score.astype(np.float64), q_rank))).all()
+    bad = q_rank.copy()
+    bad[17] = -1
+    assert lib.ffx_ranking_order(ptr(bad), ptr(score), n, ptr(order), 0) != 0  # negative rank: refused
+
     nan_scores = np.array([1.0, np.nan, 2.0, np.nan, -1.0], np.float32)
     order = np.empty(5, np.int64)
     _ffx.check(lib.ffx_ranking_order(ptr(np.zeros(5, np.int32)), ptr(nan_scores), 5, ptr(order), 0))
