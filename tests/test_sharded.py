@@ -24,10 +24,11 @@ def test_plan_doc_shards_balances_rows():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dim,nq", [(768, 300), (768, 9), (100, 9)])
+@pytest.mark.parametrize("dim,nq", [(768, 300), (768, 9), (100, 9), (128, 300), (384, 300), (100, 300), (64, 9)])
 @pytest.mark.parametrize("mode", ["MAXP", "AVEP", "PASSAGE"])
 def test_shards_on_one_gpu_equal_the_whole(dim, nq, mode):
-    """fused (nq=300), tiled (nq=9) and generic (dim=100) kernels, 3 shards."""
+    """fused (nq=300) and tiled (nq=9) launches of the whole-warp kernel (768) and of the packed
+    kernel (lane-major 64 / 128 / 384, tree-as-data 100), 3 shards."""
     import torch
 
     import __graft_entry__ as g
