@@ -63,10 +63,11 @@ class RowStore:
 
     def check_new_passages(self, psg_ids: Sequence[str | None]) -> None:
         """RuntimeError if a passage id exists already or repeats in the batch (memory.py:93-94)."""
-        psg_ids = _ids.as_id_list(psg_ids)
-        dup = self.psgs.insert_unique(psg_ids, self.count, dry_run=True) if psg_ids else -1
+        if not hasattr(psg_ids, "__getitem__"):
+            psg_ids = _ids.as_id_list(psg_ids)
+        dup = self.psgs.insert_unique(psg_ids, self.count, dry_run=True) if len(psg_ids) else -1
         if dup >= 0:
-            raise RuntimeError(f"Passage ID {psg_ids[dup]} already exists.")
+            raise RuntimeError(f"Passage ID {_ids.first_text(psg_ids, dup)} already exists.")
 
     # ---- growth -------------------------------------------------------------------------
     def reserve_for(self, n_new: int, width: int, dtype, first_capacity: int, grow_by: int) -> None:
@@ -104,10 +105,11 @@ class RowStore:
         else:
             self._row_doc_parts.append(np.full(n, -1, np.int64))
         if psg_ids is not None and len(psg_ids):
-            psg_ids = _ids.as_id_list(psg_ids)
-            dup = self.psgs.insert_unique(psg_ids, base)
+            if not hasattr(psg_ids, "__getitem__"):  # a generator: the error message indexes it
+                psg_ids = _ids.as_id_list(psg_ids)
+            dup = self.psgs.insert_unique(psg_ids, base)  # columns stay columns (no Python list of a million ids)
             if dup >= 0:
-                raise RuntimeError(f"Passage ID {psg_ids[dup]} already exists.")
+                raise RuntimeError(f"Passage ID {_ids.first_text(psg_ids, dup)} already exists.")
         self._maps_stale = True
         self.version += 1
 
