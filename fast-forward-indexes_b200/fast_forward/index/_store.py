@@ -116,8 +116,25 @@ class RowStore:
     def adopt_id_columns(self, doc_col, psg_col) -> None:
         """Name all `count` rows at once from two id columns (None = no id): the vectorised
         replacement for the O(N) Python loop of index/disk.py:408-417."""
-        self.docs, self.psgs, self._row_doc_parts = _ids.IdDict(), _ids.IdDict(), []
-        self.record_ids(doc_col, psg_col, 0, self.count)
+        self.adopt_prepared(*self.prepare_id_columns(doc_col, psg_col, self.count))
+
+    @staticmethod
+    def prepare_id_columns(doc_col, psg_col, n: int):
+        """The dictionaries and the row -> document table of `n` rows named by two id columns.
+        Touches no store: a loader runs it on a thread of its own while the rows stream to the
+        device (the C++ dictionary calls release the GIL)."""
+        docs, psgs = _ids.IdDict(), _ids.IdDict()
+        row_doc = docs.insert_ordinal(doc_col) if doc_col is not None and len(doc_col) else np.full(n, -1, np.int64)
+        if psg_col is not None and len(psg_col):
+            dup = psgs.insert_unique(psg_col, 0)
+            if dup >= 0:
+                raise RuntimeError(f"Passage ID {_ids.first_text(psg_col, dup)} already exists.")
+        return docs, psgs, row_doc
+
+    def adopt_prepared(self, docs, psgs, row_doc) -> None:
+        self.docs, self.psgs, self._row_doc_parts = docs, psgs, [row_doc]
+        self._maps_stale = True
+        self.version += 1
 
     # ---- id mapping ---------------------------------------------------------------------
     def _row_doc(self) -> np.ndarray:

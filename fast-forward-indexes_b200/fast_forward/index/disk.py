@@ -311,15 +311,31 @@ class OnDiskIndex(Index):
             # one HDF5 chunk (a contiguous byte range of the file) per staging step, read in place
             codes = index._quantizer is not None and meta["dtype"] == np.uint8
             by_ids = hasattr(index._store, "shards")  # doc shards place every row by its ids
+            naming = None
             if by_ids:
                 doc_col, psg_col = _text_ids(fp.read("doc_ids", 0, total)), _text_ids(fp.read("psg_ids", 0, total))
-            for row0, block in fp.spans("vectors", 0, total):
-                rows = block if codes or block.dtype == np.float32 else block.astype(np.float32)
-                ids = (doc_col.slice(row0, len(rows)), psg_col.slice(row0, len(rows))) if by_ids else (None, None)
-                index._store.append(rows, ids[0], ids[1], first_capacity=total, grow_by=index._chunk_size)
-            # the O(N) Python loop of disk.py:408-417, as two calls into the C++ id dictionaries
-            if not by_ids:
-                index._store.adopt_id_columns(_text_ids(fp.read("doc_ids", 0, total)), _text_ids(fp.read("psg_ids", 0, total)))
+            else:
+                # the O(N) Python loop of disk.py:408-417, as two calls into the C++ id dictionaries — on a
+                # thread of their own, next to the row stream (both sides release the GIL)
+                from concurrent.futures import ThreadPoolExecutor
+
+                def name_rows():
+                    with _h5.H5File(index_file) as ids_fp:  # a handle of its own: the reader's object cache is not shared
+                        return RowStore.prepare_id_columns(_text_ids(ids_fp.read("doc_ids", 0, total)),
+                                                           _text_ids(ids_fp.read("psg_ids", 0, total)), total)
+
+                pool = ThreadPoolExecutor(1)
+                naming = pool.submit(name_rows)
+            try:
+                for row0, block in fp.spans("vectors", 0, total):
+                    rows = block if codes or block.dtype == np.float32 else block.astype(np.float32)
+                    ids = (doc_col.slice(row0, len(rows)), psg_col.slice(row0, len(rows))) if by_ids else (None, None)
+                    index._store.append(rows, ids[0], ids[1], first_capacity=total, grow_by=index._chunk_size)
+                if naming is not None:
+                    index._store.adopt_prepared(*naming.result())
+            finally:
+                if naming is not None:
+                    pool.shutdown(wait=True)
 
     @classmethod
     def _stage_h5py(cls, index: "OnDiskIndex", h5py, index_file: Path) -> None:
