@@ -877,6 +877,29 @@ int ffx_index_reserve(ffx_index *idx, int64_t capacity_rows) {
     return FFX_OK;
 }
 
+int ffx_index_copy_rows(ffx_index *dst, ffx_index *src) {
+    NvtxRange nvtx_range("ffx_index_copy_rows");
+    if (!dst || !src || dst == src) return fail(FFX_ERR_INVALID, "ffx_index_copy_rows: bad arguments");
+    if (dst->row_kind != src->row_kind || dst->dim != src->dim)
+        return fail(FFX_ERR_INVALID, "ffx_index_copy_rows: the two indexes hold different kinds of rows");
+    if (dst->num_rows != 0) return fail(FFX_ERR_STATE, "ffx_index_copy_rows: the destination is not empty");
+    FFX_TRY(bind(src));
+    FFX_TRY(settle(src));
+    FFX_CUDA(cudaStreamSynchronize(src->stream));
+    if (src->num_rows == 0) return FFX_OK;
+    FFX_TRY(ffx_index_reserve(dst, src->num_rows));
+    FFX_TRY(bind(dst));
+    // the store's own layout (lane-major / padded) is the same on both sides: a plain byte copy
+    const size_t bytes = static_cast<size_t>(src->num_rows) * src->row_bytes;
+    if (dst->device == src->device)
+        FFX_CUDA(cudaMemcpyAsync(dst->store, src->store, bytes, cudaMemcpyDeviceToDevice, dst->stream));
+    else
+        FFX_CUDA(cudaMemcpyPeerAsync(dst->store, dst->device, src->store, src->device, bytes, dst->stream));
+    FFX_CUDA(cudaStreamSynchronize(dst->stream));
+    dst->num_rows = src->num_rows;
+    return FFX_OK;
+}
+
 int ffx_index_stage_rows(ffx_index *idx, int64_t row0, int64_t nrows, const void *rows,
                          int src_on_device) {
     NvtxRange nvtx_range("ffx_index_stage_rows");

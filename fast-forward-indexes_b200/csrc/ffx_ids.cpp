@@ -378,6 +378,12 @@ int ffx_dict_lookup(const ffx_dict *d, const int64_t *offsets, const char *data,
     return FFX_OK;
 }
 
+int ffx_dict_clone(const ffx_dict *d, ffx_dict **out) {
+    if (!d || !out) return fail(FFX_ERR_INVALID, "ffx_dict_clone: bad arguments");
+    *out = new ffx_dict(*d);
+    return FFX_OK;
+}
+
 int ffx_dict_export(const ffx_dict *d, int64_t *offsets, char *data, int64_t *values) {
     if (!d || !offsets) return fail(FFX_ERR_INVALID, "ffx_dict_export: bad arguments");
     memcpy(offsets, d->key_off.data(), d->key_off.size() * sizeof(int64_t));

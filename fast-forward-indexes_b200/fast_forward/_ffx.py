@@ -30,6 +30,7 @@ SYMBOLS = {
     "ffx_index_create": (_I, [_I, _I, _L, _L, C.POINTER(_P)]),
     "ffx_index_destroy": (_I, [_P]),
     "ffx_index_reserve": (_I, [_P, _L]),
+    "ffx_index_copy_rows": (_I, [_P, _P]),
     "ffx_index_stage_rows": (_I, [_P, _L, _L, _P, _I]),
     "ffx_index_read_rows": (_I, [_P, _P, _L, _P]),
     "ffx_index_num_rows": (_L, [_P]),
@@ -84,6 +85,7 @@ SYMBOLS = {
     "ffx_dict_insert_unique": (_I, [_P, _P, _P, _P, _L, _L, _L, _I, C.POINTER(_L)]),
     "ffx_dict_lookup": (_I, [_P, _P, _P, _P, _L, _L, _P, C.POINTER(_L), _I]),
     "ffx_dict_export": (_I, [_P, _P, _P, _P]),
+    "ffx_dict_clone": (_I, [_P, C.POINTER(_P)]),
     "ffx_csr_build": (_I, [_P, _L, _L, _P, _P]),
     "ffx_factorize": (_I, [_P, _P, _L, _P, C.POINTER(_P), C.POINTER(_L), C.POINTER(_L), _I]),
     "ffx_factor_export": (_I, [_P, _P, _P]),
@@ -297,6 +299,10 @@ class DeviceIndex:
 
     def reserve(self, capacity: int):
         check(lib().ffx_index_reserve(self.handle, int(capacity)))
+
+    def copy_rows_from(self, other: "DeviceIndex"):
+        """ffx_index_copy_rows: all rows of `other` into this (empty) index, device to device."""
+        check(lib().ffx_index_copy_rows(self.handle, other.handle))
 
     def stage(self, row0: int, rows: np.ndarray):
         dt = np.float32 if self.row_kind == ROWS_F32 else np.uint8

@@ -98,6 +98,13 @@ class IdDict:
     def __len__(self) -> int:
         return int(_ffx.lib().ffx_dict_size(self._h))
 
+    def clone(self) -> "IdDict":
+        """A deep copy (ffx_dict_clone)."""
+        other = IdDict.__new__(IdDict)
+        other._h = C.c_void_p()
+        _ffx.check(_ffx.lib().ffx_dict_clone(self._h, C.byref(other._h)))
+        return other
+
     # ---- building ---------------------------------------------------------------------------
     def insert_ordinal(self, values) -> np.ndarray:
         """Document ids: ordinal (order of first appearance) per value, -1 for None."""

@@ -49,6 +49,22 @@ class RowStore:
         self._reverse = None  # (count, doc keys, psg keys, row -> psg key)
         self._pq_of: object | None = None  # quantizer whose tables are on the device
 
+    def clone(self) -> "RowStore | None":
+        """A store with the same rows and ids, copied device to device (OnDiskIndex.to_memory: the
+        on-disk index is resident in HBM already); None where only the generic row-by-row route
+        applies (the multi-device stores)."""
+        if type(self) is not RowStore:
+            return None
+        other = RowStore(self.device)
+        if self.dev is not None:
+            other.dev = _ffx.DeviceIndex(self.dev.dim, capacity=max(self.count, 1), row_kind=self.dev.row_kind,
+                                         device=self.device)
+            other.dev.copy_rows_from(self.dev)
+        other.count = self.count
+        other.docs, other.psgs = self.docs.clone(), self.psgs.clone()
+        other._row_doc_parts = [self._row_doc().copy()]
+        return other
+
     # ---- properties -------------------------------------------------------------------
     @property
     def width(self) -> int | None:

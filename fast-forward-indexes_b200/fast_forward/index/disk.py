@@ -246,6 +246,12 @@ class OnDiskIndex(Index):
                               init_size=max(len(self), 1), device=self._store.device,
                               devices=getattr(self._store, "devices", None),
                               shard="doc" if hasattr(self._store, "shards") else "query")
+        copy = self._store.clone()
+        if copy is not None:
+            # the rows are in HBM already: one device-to-device copy and two dictionary copies instead of
+            # reading every row back and adding it again
+            index._store = copy
+            return index
         for rows, doc_ids, psg_ids in self._batch_iter(batch_size or max(self._store.count, 1)):
             index._add(rows, doc_ids=doc_ids, psg_ids=psg_ids)
         return index

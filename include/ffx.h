@@ -82,6 +82,13 @@ int ffx_index_create(int device, int row_kind, int64_t dim, int64_t capacity_row
 int ffx_index_destroy(ffx_index *idx);
 /* Grow the store (index/memory.py:103-108, the alloc_size chunk growth); keeps contents. */
 int ffx_index_reserve(ffx_index *idx, int64_t capacity_rows);
+
+/* Copies all stored rows of `src` into the EMPTY index `dst` (same row kind and dimension; same or
+ * another device: device-to-device / peer copy of the store as it is laid out, no host round
+ * trip) — the rows of `OnDiskIndex.to_memory()` (index/disk.py:177-205), whose on-disk index is
+ * already resident in HBM here.  Document tables and PQ tables are not copied (ffx_index_set_docs /
+ * ffx_index_set_pq on the copy). */
+int ffx_index_copy_rows(ffx_index *dst, ffx_index *src);
 /* Replaces the chunk copy of `InMemoryIndex._add` (index/memory.py:97-119) and the slice
  * loop of `OnDiskIndex.to_memory` (index/disk.py:190-204): rows [row0, row0+nrows) take
  * `rows` (row-major, fp32 or uint8 per row_kind).  Host sources go through a pinned double
@@ -185,6 +192,9 @@ int ffx_factorize(const int64_t *offsets, const char *data, int64_t n, int32_t *
                   int64_t *key_bytes, int n_threads);
 int ffx_factor_export(const ffx_factor *f, int64_t *key_offsets, char *key_data);
 void ffx_factor_free(ffx_factor *f);
+
+/* A deep copy of a dictionary (the id tables of `OnDiskIndex.to_memory()`). */
+int ffx_dict_clone(const ffx_dict *d, ffx_dict **out);
 
 /* A column of fixed-width, NUL-padded byte ids (HDF5 `S{max_id_length}` datasets, "" = no id:
  * index/disk.py:152-165,414-417) as Arrow string buffers for the dictionaries above:

@@ -39,6 +39,12 @@ class FakeDeviceIndex:
     def read_rows(self, rows):
         return self.rows[np.asarray(rows, np.int64)].copy()
 
+    def copy_rows_from(self, other):
+        assert self.n == 0 and self.dim == other.dim and self.row_kind == other.row_kind
+        self.reserve(other.n)
+        self.rows[:other.n] = other.rows[:other.n]
+        self.n = other.n
+
     def set_docs(self, doc_off, doc_rows=None):
         self.off = np.asarray(doc_off, np.int64)
         self.doc_rows = np.arange(self.off[-1]) if doc_rows is None else np.asarray(doc_rows, np.int64)

@@ -83,6 +83,15 @@ def test_create_score_reload(api, tmp_path, golden_kat):
     assert isinstance(mem, api.InMemoryIndex) and len(mem) == 5 and mem.doc_ids == set(DOC)
     mem.mode = api.Mode.MAXP
     assert mem(rank) == index(rank)
+    # a deep copy (rows device to device, id dictionaries cloned): the two indexes grow apart
+    assert mem._store.dev is not loaded._store.dev and mem.psg_ids == set(PSG)
+    mem.add(V[:1] * 3, doc_ids=["d0"], psg_ids=["p-extra"])
+    assert len(mem) == 6 and len(loaded) == 5 and "p-extra" not in loaded.psg_ids
+    loaded.mode = api.Mode.MAXP
+    assert loaded(rank) == index(rank)
+    mem.mode = api.Mode.PASSAGE
+    vecs, ids = mem._get_vectors(PSG + ["p-extra"])
+    assert np.array_equal(vecs[:5], V) and np.array_equal(vecs[5], V[0] * 3) and ids == PSG + ["p-extra"]
     empty = api.OnDiskIndex(tmp_path / "empty.h5")
     assert len(api.OnDiskIndex.load(tmp_path / "empty.h5")) == 0 and empty.dim is None
 

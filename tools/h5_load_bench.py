@@ -51,6 +51,14 @@ for trial in ("first", "second"):
     got = index._store.read(np.array([0, n // 2, n - 1]))
     assert (got == vec[[0, n // 2, n - 1]]).all()
     assert len(index) == n and len(index.doc_ids) == (n + 5) // 6
+    if trial == "second":  # OnDiskIndex.to_memory(): a device-to-device copy of the rows + two dictionary copies
+        t = time.perf_counter()
+        mem = index.to_memory()
+        mem._store.dev.sync()
+        dt = time.perf_counter() - t
+        out["to_memory"] = {"seconds": round(dt, 3), "GB_per_s": round(size / 1e9 / dt, 2)}
+        assert (mem._store.read(np.array([0, n // 2, n - 1])) == vec[[0, n // 2, n - 1]]).all() and len(mem) == n
+        del mem
     del index
 
 # the pieces: rows only, ids only
