@@ -77,6 +77,7 @@ constexpr size_t kSmemBudget = 227 * 1024 - 2048;  // opt-in shared memory per C
 
 // Tuning / diagnostic knobs (ffx_set_option).  0 = automatic.
 struct Tuning {
+    int adc_lut = 0;     // XOR-swizzled ADC tables: 1 = built inside the scoring kernel, 2 = thread-per-entry kernel
     int kernel = 0;      // 1: register-staged ffx_score_kernel, 2: TMA-staged ffx_score_tma_kernel
     int tma_stages = 0;  // ring slots per warp
     int tma_warps = 0;   // warps per CTA of the TMA-staged kernel (8..16)
@@ -721,6 +722,7 @@ int ffx_set_option(const char *name, int value) {
     else if (key == "tma_stages" && value >= 0 && value <= 16) g_tune.tma_stages = value;
     else if (key == "batch" && value >= 0 && value <= 32) g_tune.batch = value;
     else if (key == "adc" && value >= 0 && value <= 3) g_tune.adc = value;
+    else if (key == "adc_lut" && value >= 0 && value <= 2) g_tune.adc_lut = value;
     else if (key == "chunk_waves" && value >= 0 && value <= 64) g_tune.chunk_waves = value;
     else if (key == "tma_warps" && (value == 0 || (value >= 1 && value <= 16))) g_tune.tma_warps = value;
     else return fail(FFX_ERR_INVALID, "ffx_set_option: unknown option or bad value (%s=%d)", name, value);
@@ -1240,7 +1242,7 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
     // (ffx_adc_xor_lut_kernel) when they fit the scratch budget, else inside the scoring kernel
     size_t off_lut = 0;
     const size_t lut_floats = pq ? static_cast<size_t>(idx->M) * idx->Ks : 0;
-    const bool lut_ahead = pq && max_cand > 0 && adc_kind(idx) == 3 && (lut_floats * 4) % 16 == 0 &&
+    const bool lut_ahead = pq && max_cand > 0 && adc_kind(idx) == 3 && (lut_floats * 4) % 16 == 0 && g_tune.adc_lut != 1 &&
                            (lut_buf || static_cast<size_t>(nq) * lut_floats * 4 <= kAdcLutScratch);
     if (lut_ahead && !lut_buf) {
         total = (total + 255) & ~static_cast<size_t>(255);
@@ -1333,13 +1335,26 @@ static int rerank_impl(ffx_index *idx, int mode, const float *qvecs, int64_t nq,
                 w.topk_pos = out_topk_pos;
                 if (lut_ahead) {
                     float *lut = lut_buf ? lut_buf : reinterpret_cast<float *>(work + off_lut);
-                    const dim3 grid_l(static_cast<unsigned>((lut_floats + ffx::kAdcLutThreads - 1) / ffx::kAdcLutThreads),
-                                      static_cast<unsigned>((nq + ffx::kAdcLutQueries - 1) / ffx::kAdcLutQueries));
-                    switch (idx->Ds) {
-                        case 4: ffx::ffx_adc_xor_lut_kernel<4><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
-                        case 8: ffx::ffx_adc_xor_lut_kernel<8><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
-                        case 16: ffx::ffx_adc_xor_lut_kernel<16><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
-                        default: ffx::ffx_adc_xor_lut_kernel<0><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
+                    const unsigned q_blocks = static_cast<unsigned>((nq + ffx::kAdcLutQueries - 1) / ffx::kAdcLutQueries);
+                    const bool tiled = g_tune.adc_lut != 2 && idx->Ks % 32 == 0 && (idx->Ds == 4 || idx->Ds == 8 || idx->Ds == 16) &&
+                                       (reinterpret_cast<uintptr_t>(qeff) & 15) == 0 && q_blocks <= 65535u;
+                    if (tiled) {
+                        // a 32 x 32 tile of one table per CTA, query slices broadcast
+                        const dim3 grid_t(static_cast<unsigned>(idx->M / 32 * (idx->Ks / 32)), q_blocks);
+                        switch (idx->Ds) {
+                            case 4: ffx::ffx_adc_xor_lut_tile_kernel<4><<<grid_t, ffx::kAdcLutTileThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, nq, lut); break;
+                            case 8: ffx::ffx_adc_xor_lut_tile_kernel<8><<<grid_t, ffx::kAdcLutTileThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, nq, lut); break;
+                            default: ffx::ffx_adc_xor_lut_tile_kernel<16><<<grid_t, ffx::kAdcLutTileThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, nq, lut); break;
+                        }
+                    } else {
+                        const dim3 grid_l(static_cast<unsigned>((lut_floats + ffx::kAdcLutThreads - 1) / ffx::kAdcLutThreads),
+                                          static_cast<unsigned>((nq + ffx::kAdcLutQueries - 1) / ffx::kAdcLutQueries));
+                        switch (idx->Ds) {
+                            case 4: ffx::ffx_adc_xor_lut_kernel<4><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
+                            case 8: ffx::ffx_adc_xor_lut_kernel<8><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
+                            case 16: ffx::ffx_adc_xor_lut_kernel<16><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
+                            default: ffx::ffx_adc_xor_lut_kernel<0><<<grid_l, ffx::kAdcLutThreads, 0, st>>>(idx->cw_x, qeff, idx->M, idx->Ks, idx->Ds, nq, lut); break;
+                        }
                     }
                     g_launches++;
                     FFX_CUDA(cudaGetLastError());

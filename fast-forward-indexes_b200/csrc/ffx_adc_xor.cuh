@@ -118,6 +118,67 @@ __global__ void __launch_bounds__(kAdcLutThreads) ffx_adc_xor_lut_kernel(const f
     }
 }
 
+// The same tables with the query slices BROADCAST instead of gathered: a CTA owns a 32 x 32 tile of one
+// table (32 codewords c, the 32 sub-quantizers b of table j3 — 4 KB of consecutive entries), lane =
+// codeword, warp = sub-quantizer (4 of them per warp), so that the 32 lanes of a warp read the SAME
+// 32-byte query slice (one L1 wavefront instead of eight: the thread-per-entry kernel above keeps the
+// L1 data pipe 95 % busy, profiles/r2_adc_lut_raw.csv).  The tile goes through shared memory
+// (stride 33: conflict-free both ways) and leaves as four 128-byte rows per warp.  Same arithmetic
+// per entry: fmaf over d, ascending, from 0.  Needs Ks % 32 == 0 and DS in {4, 8, 16}.
+constexpr int kAdcLutTileThreads = 256;
+
+template <int DS>
+__global__ void __launch_bounds__(kAdcLutTileThreads) ffx_adc_xor_lut_tile_kernel(const float *cw_x, const float *qeff, int M,
+                                                                                int Ks, int64_t nq, float *lut) {
+    __shared__ float tile[2][32 * 33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tiles_per_table = Ks / 32;
+    const int j3 = blockIdx.x / tiles_per_table;
+    const int c0 = (blockIdx.x % tiles_per_table) * 32;
+    const int64_t e0 = (static_cast<int64_t>(j3) * Ks + c0) * 32;  // first entry of the tile
+    const int64_t total = static_cast<int64_t>(M) * Ks;
+    const int64_t D = static_cast<int64_t>(M) * DS;
+    float c[4][DS];
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const int b = warp + 8 * p;
+        const float *cw = cw_x + (e0 + static_cast<int64_t>(lane) * 32 + b) * DS;
+#pragma unroll
+        for (int d = 0; d < DS; d += 4) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4 *>(cw + d));
+            c[p][d] = c4.x, c[p][d + 1] = c4.y, c[p][d + 2] = c4.z, c[p][d + 3] = c4.w;
+        }
+    }
+    const int64_t q0 = static_cast<int64_t>(blockIdx.y) * kAdcLutQueries;
+    const int64_t q1 = q0 + kAdcLutQueries < nq ? q0 + kAdcLutQueries : nq;
+    for (int64_t q = q0; q < q1; q++) {
+        float *t = tile[(q - q0) & 1];
+        const float *qrow = qeff + q * D + static_cast<int64_t>(32 * j3) * DS;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const int b = warp + 8 * p;
+            const float *qm = qrow + b * DS;  // warp-uniform: a broadcast load
+            float acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < DS; d += 4) {
+                const float4 q4 = __ldg(reinterpret_cast<const float4 *>(qm + d));
+                acc = fmaf(q4.x, c[p][d], acc);
+                acc = fmaf(q4.y, c[p][d + 1], acc);
+                acc = fmaf(q4.z, c[p][d + 2], acc);
+                acc = fmaf(q4.w, c[p][d + 3], acc);
+            }
+            t[lane * 33 + b] = acc;  // entry (c = c0 + lane, b)
+        }
+        __syncthreads();  // (the other tile buffer is free again: its readers passed the previous barrier)
+        float *out = lut + q * total + e0;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const int row = warp + 8 * p;  // codeword c0 + row: 32 consecutive entries
+            __stcs(out + row * 32 + lane, t[row * 33 + lane]);
+        }
+    }
+}
+
 // [table][slots: warps x 32 x M][mbarriers][FUSE: cpad interpolated scores]; the sort keys of the
 // fused top-k overlay table + slots once they are dead
 __host__ __device__ inline size_t adc_xor_smem_bytes(int M, int Ks, int cpad_scores) {

@@ -600,6 +600,38 @@ def test_long_lists_sorted_by_the_radix_epilogue(ffx, oracle_c, lo, hi):
     idx.close()
 
 
+@pytest.mark.parametrize("M,Ks,Ds", [(96, 256, 8), (32, 64, 4), (64, 256, 16), (64, 100, 8)])
+def test_adc_tables_are_the_same_from_all_three_builders(ffx, M, Ks, Ds):
+    """The per-query tables of the XOR-swizzled ADC kernel come from a tiled kernel (query slices
+    broadcast), a thread-per-entry kernel (shapes the tiles do not cover, here Ks = 100) or are
+    built inside the scoring kernel: same fmaf chain per entry, so the scores agree bit for bit."""
+    rng = np.random.default_rng(M + Ks + Ds)
+    off, rows, _ = make_corpus(rng, 400, 6, 4, True)
+    n_rows = int(off[-1])
+    idx = ffx.DeviceIndex(M, capacity=n_rows, row_kind=ffx.ROWS_PQ_U8)
+    idx.stage(0, rng.integers(0, Ks, (n_rows, M)).astype(np.uint8))
+    idx.set_docs(off)
+    D = M * Ds
+    R = np.linalg.qr(rng.standard_normal((D, D)))[0].astype(np.float32)
+    idx.set_pq(rng.standard_normal((M, Ks, Ds)).astype(np.float32), R)
+    nq = 333  # not a multiple of the 32 queries a table CTA walks
+    qv = rng.standard_normal((nq, D)).astype(np.float32)
+    q_off, cand, _ = make_pairs(rng, nq, 400, 1, 90)
+    lex = rng.uniform(0, 20, len(cand)).astype(np.float32)
+    outs = []
+    try:
+        for how in (0, 1, 2):
+            ffx.set_option("adc_lut", how)
+            for mode in (fo.MODE_MAXP, fo.MODE_AVEP):
+                outs.append(idx.rerank_host(mode, qv, q_off, cand, lex, 0.2, 30, want_ff=True, want_int=True))
+                assert "ffx_adc_xor_kernel" in ffx.last_kernel()
+    finally:
+        ffx.set_option("adc_lut", 0)
+        idx.close()
+    for a, b in ((0, 2), (0, 4), (1, 3), (1, 5)):
+        assert (bits(outs[a]["ff"]) == bits(outs[b]["ff"])).all() and (outs[a]["topk_pos"] == outs[b]["topk_pos"]).all()
+
+
 def test_adc_fused_launches_are_bit_reproducible(ffx):
     """The XOR ADC kernel refills a warp's code slots with bulk copies (async proxy) right after
     the lanes have loaded their rows through the generic proxy; without a cross-proxy fence a copy
