@@ -32,7 +32,7 @@ def api():
     a.ff, a.Ranking, a.InMemoryIndex, a.OnDiskIndex, a.Mode, a.LambdaEncoder, a.NanoOPQ = \
         fast_forward, fast_forward.Ranking, InMemoryIndex, OnDiskIndex, Mode, LambdaEncoder, NanoOPQ
     n_gpu = _ffx.device_count()
-    a.devices = [0, 1, 2][:min(n_gpu, 3)] if n_gpu >= 2 else [0, 0, 0]
+    a.devices = list(range(min(n_gpu, 8))) if n_gpu >= 2 else [0, 0, 0]  # every GPU of the box
     if n_gpu < 2:
         os.environ["FFX_ALLOW_DUPLICATE_DEVICES"] = "1"
     return a
