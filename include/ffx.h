@@ -60,14 +60,18 @@ int ffx_device_count(void);
 
 /* Tuning / diagnostics (process-wide; 0 restores the automatic choice).  Not part of the
  * reference contract — it has no kernels to tune.
- *   "kernel"      1 = register-staged scoring kernel, 2 = TMA-staged (default when it fits)
+ *   "kernel"      1 = register-staged scoring kernel, 2 = TMA-staged whole-warp kernel, where they exist
+ *                 (D >= 384 with a uniform summation tree); default: the packed kernel for rows of up to
+ *                 512 elements and for every dimension without a uniform tree, the TMA-staged one above
  *   "tma_stages"  ring slots per warp of the TMA-staged kernel (capped by shared memory)
  *   "batch"       candidates a warp takes per grab (1..32)
  *   "tma_warps"   warps per CTA of the TMA-staged kernel
  *   "chunk_waves" ffx_rerank_host: queries per pipelined chunk, in units of 2 x #SMs (default 1)
  *   "adc"         1 = generic thread-per-row ADC kernel, 2 = warp-per-row with conflict-free tables
  *                 (M = 64..128), 3 = XOR-swizzled thread-per-row (M % 32 == 0, M <= 128); a kernel the
- *                 shape does not allow falls back to the next one */
+ *                 shape does not allow falls back to the next one
+ *   "adc_lut"     tables of the XOR-swizzled ADC kernel: 1 = built inside the scoring kernel, 2 = by the
+ *                 thread-per-entry kernel; default: ahead of the launch by the tiled kernel */
 int ffx_set_option(const char *name, int value);
 
 /* Pinned host memory for buffers that cross PCIe every call (candidate lists, query
