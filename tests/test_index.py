@@ -455,3 +455,4 @@ def test_one_very_long_list_among_many_short_ones(api, monkeypatch):
     dense = (index(r), index.rerank(r, 0.3, 10), index.rerank(r, 0.3), r.interpolate(index(r), 0.3).cut(7))
     for a, b in zip(skewed, dense):
         pd.testing.assert_frame_equal(a._df, b._df)
+
