@@ -35,7 +35,6 @@ def test_chunk_indexer_matches_the_reference_class():
     if os.path.exists(path):
         spec = importlib.util.spec_from_file_location("_reference_index_util", path)
         module = importlib.util.module_from_spec(spec)
-        saved = sys.modules.get("fast_forward.index")
         spec.loader.exec_module(module)  # imports Mode from fast_forward.index: ours, same members
         ref = module.ChunkIndexer(chunks, docs, psgs)
     for mode in (Mode.MAXP, Mode.FIRSTP, Mode.AVEP, Mode.PASSAGE):
