@@ -309,8 +309,8 @@ def from_frame(df: pd.DataFrame, is_sorted: bool, queries=None):
     if q_col is None or id_col is None:
         return None
     n = len(df)
-    q_code, q_uniques = pd.factorize(q_col)
-    id_code, id_keys = _ids.factorize(id_col)  # all host cores; the numbering is arbitrary
+    q_code, q_uniques = _ids.factorize(q_col)  # all host cores; the numbering is arbitrary
+    id_code, id_keys = _ids.factorize(id_col)
     n_ids = len(id_keys)
     pair = q_code.astype(np.int64) * n_ids + id_code
     first = C.c_int64(-1)
@@ -322,7 +322,7 @@ def from_frame(df: pd.DataFrame, is_sorted: bool, queries=None):
     score = np.ascontiguousarray(df["score"].to_numpy(), dtype=np.float32)  # cast, then order (ranking.py:107-117)
     alive = ~np.isnan(score)
     rows = None if alive.all() else np.flatnonzero(alive)
-    q_names = np.asarray(q_uniques, dtype=object)
+    q_names = np.asarray(q_uniques.to_pylist(), dtype=object)
     if not is_sorted:
         q_rank_of = np.empty(len(q_names), np.int32)
         q_rank_of[np.argsort(q_names, kind="stable")[::-1]] = np.arange(len(q_names), dtype=np.int32)
