@@ -138,3 +138,40 @@ def test_skewed_lists_and_lazy_early_stopping_ids_on_the_fake_device(api, monkey
                                   index(api.Ranking(frame, queries=queries), **kw)._df)
     with pytest.raises(IndexError, match="ID unknown-late not found in the index."):
         index(api.Ranking(late, queries=queries), early_stopping=4, early_stopping_alpha=0.0, early_stopping_depths=[8, 20, 40])
+
+
+def test_on_disk_round_trip_and_to_memory_on_a_fake_device(api, tmp_path):
+    """`OnDiskIndex` -> file -> `OnDiskIndex.load` (id columns adopted on their own thread beside the
+    row stream) -> `to_memory()` (rows copied device to device, dictionaries cloned) with the fake
+    device: same contents, same frames, and the copies grow apart."""
+    from pathlib import Path
+
+    from fast_forward.index import OnDiskIndex
+
+    rng = np.random.default_rng(3)
+    dim, nq = 16, 6
+    vec, doc_ids, psg_ids = build(api, rng, [0], "query", dim, n_docs=60)
+    qv = {f"query {i}": rng.standard_normal(dim).astype(np.float32) for i in range(nq)}
+    queries = {f"q{i}": f"query {i}" for i in range(nq)}
+    enc = api.LambdaEncoder(lambda t: qv[t])
+    path = Path(tmp_path) / "index.h5"
+    disk = fill(OnDiskIndex(path, enc, init_size=32, chunk_size=32), vec, doc_ids, psg_ids, pieces=3)
+    loaded = OnDiskIndex.load(path, enc)
+    assert len(loaded) == len(disk) == len(vec)
+    assert loaded.doc_ids == disk.doc_ids and loaded.psg_ids == disk.psg_ids
+    mem = loaded.to_memory()
+    assert isinstance(mem, api.InMemoryIndex) and len(mem) == len(vec)
+    assert mem._store.dev is not loaded._store.dev and mem.doc_ids == disk.doc_ids and mem.psg_ids == disk.psg_ids
+    docs = sorted(d for d in disk.doc_ids)
+    ids = [docs[i] for i in rng.integers(0, len(docs), nq * 20)]
+    frame = pd.DataFrame({"q_id": np.repeat([f"q{i}" for i in range(nq)], 20), "id": ids,
+                          "score": rng.uniform(0, 10, nq * 20).astype(np.float32)}).drop_duplicates(["q_id", "id"])
+    r = api.Ranking(frame, queries=queries)
+    for mode in (api.Mode.MAXP, api.Mode.AVEP, api.Mode.FIRSTP):
+        disk.mode = loaded.mode = mem.mode = mode
+        want = disk(r)
+        assert loaded(r) == want and mem(r) == want
+    mem.add(vec[:2], doc_ids=["brand-new", "brand-new"], psg_ids=["px1", "px2"])
+    assert len(mem) == len(vec) + 2 and len(loaded) == len(vec) and "brand-new" not in loaded.doc_ids
+    with pytest.raises(RuntimeError):
+        mem.add(vec[:1], psg_ids=["px1"])  # the cloned dictionary knows its own additions
